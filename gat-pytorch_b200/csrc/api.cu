@@ -1,0 +1,59 @@
+// Library-wide entry points: version, last-error string, GEMM dispatch.
+#include "common.cuh"
+#include <string.h>
+
+namespace gat {
+
+static thread_local char g_last_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+int gemm_simt(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b,
+              int64_t ldb, float* c, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t simt_workspace_bytes(int64_t m, int64_t n, int64_t k);
+
+int gemm_tc(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b,
+            int64_t ldb, float* c, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t tc_workspace_bytes(int ta, int tb, int64_t m, int64_t n, int64_t k);
+bool tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc);
+
+}  // namespace gat
+
+extern "C" int gat_version(void) { return 100; }
+
+extern "C" const char* gat_last_error(void) { return gat::g_last_error; }
+
+extern "C" int gat_gemm_tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                                     int64_t ldc) {
+  return gat::tc_supported(ta, tb, m, n, k, lda, ldb, ldc) ? 1 : 0;
+}
+
+extern "C" size_t gat_gemm_workspace_bytes(int ta, int tb, int64_t m, int64_t n, int64_t k, int algo) {
+  size_t simt = gat::simt_workspace_bytes(m, n, k);
+  if (algo == 1) return simt;
+  size_t tc = gat::tc_workspace_bytes(ta, tb, m, n, k);
+  return simt > tc ? simt : tc;
+}
+
+extern "C" int gat_gemm(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda,
+                        const float* b, int64_t ldb, float* c, int64_t ldc, int algo, void* workspace,
+                        size_t workspace_bytes, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(m >= 0 && n >= 0 && k >= 0, "gat_gemm: negative dimension");
+  GAT_CHECK_ARG(algo >= 0 && algo <= 2, "gat_gemm: unknown algo %d", algo);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool tc_ok = tc_supported(ta, tb, m, n, k, lda, ldb, ldc);
+  if (algo == 2 && !tc_ok) {
+    set_error("gat_gemm: tcgen05 path does not support this shape/alignment (m=%lld n=%lld k=%lld)", (long long)m,
+              (long long)n, (long long)k);
+    return GAT_EUNSUPPORTED;
+  }
+  if (algo == 2 || (algo == 0 && tc_ok))
+    return gemm_tc(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
+  return gemm_simt(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
+}

@@ -1,0 +1,304 @@
+// Kernel 3a (global max of the logits) and Kernel 3 (fused edge forward), plus the head merge.
+// Replaces gat_layer.py:70-132: no (E', NH, F) tensor is ever materialised.
+#include "edge_common.cuh"
+
+namespace gat {
+
+// ------------------------------------------------------------------------------------------
+// Kernel 3a: M = max_{e,h} (s_src[src_e,h] + s_tgt[dst_e,h])      (gat_layer.py:85)
+// 8 lanes per destination row; s_src (n*NH floats) is L2-resident, so DRAM traffic is ~ col only.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+edge_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
+                const float* __restrict__ s_src, const float* __restrict__ s_tgt, int nh, float* __restrict__ gmax) {
+  __shared__ float warp_max[8];
+  const int tid = threadIdx.x, gl = tid & 7;
+  const int64_t row = (int64_t)blockIdx.x * 32 + (tid >> 3);
+  float m = -INFINITY;
+  if (row < n) {
+    float st[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) st[h] = h < nh ? __ldg(s_tgt + row * nh + h) : 0.f;
+    const int start = rowptr[row], end = rowptr[row + 1];
+    for (int e = start + gl; e < end; e += 8) {
+      const float* ss = s_src + (int64_t)__ldg(col + e) * nh;
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h)
+        if (h < nh) m = fmaxf(m, __ldg(ss + h) + st[h]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) warp_max[tid >> 5] = m;
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, warp_max[w]);
+    if (m > -INFINITY) atomic_max_float(gmax, m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 3: fused forward over destination rows.
+// ------------------------------------------------------------------------------------------
+struct EdgeFwdParams {
+  const int32_t* rowptr; const int32_t* col; const int32_t* eid; int64_t n;
+  const float* wh; int nh; int dp; int chunks; int chunks_per_head;
+  const float* s_src; const float* s_tgt; const float* gmax;
+  int const_attention; float dropout_p; uint64_t seed; uint64_t offset;
+  float* out; float* alpha_out; float* z_out;
+  int32_t* tie_dst; int32_t* tie_src; unsigned long long* tie_total;
+};
+
+__device__ __forceinline__ void edge_probs(const EdgeFwdParams& P, int e, bool valid, const float (&st)[kMaxHeads],
+                                           float gmax, int& src, float (&p)[kMaxHeads], unsigned& tiemask) {
+  tiemask = 0;
+  src = 0;
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) p[h] = 0.f;
+  if (!valid) return;
+  src = __ldg(P.col + e);
+  if (P.const_attention) {
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) p[h] = h < P.nh ? 1.f : 0.f;   // exp(0), gat_layer.py:89-96
+    return;
+  }
+  const float* ss = P.s_src + (int64_t)src * P.nh;
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) {
+    if (h < P.nh) {
+      float l = __ldg(ss + h) + st[h];
+      p[h] = attn_exp(l, gmax);
+      if (l == gmax) tiemask |= 1u << h;
+    }
+  }
+}
+
+template <int G, int SLOTS>
+__global__ void __launch_bounds__(kEdgeThreads)
+edge_fwd_kernel(const EdgeFwdParams P) {
+  constexpr int U = SLOTS >= 4 ? 2 : (SLOTS >= 2 ? 4 : 8);
+  __shared__ int sh_src[kEdgeThreads];
+  __shared__ float sh_w[kEdgeThreads * kMaxHeads];
+  const int tid = threadIdx.x, lane = tid & 31, gl = tid & (G - 1), gbase = tid - gl;
+  const unsigned gmask = group_mask<G>(lane);
+  const int64_t row = (int64_t)blockIdx.x * (kEdgeThreads / G) + tid / G;
+  if (row >= P.n) return;
+  const int nh = P.nh;
+
+  int head[SLOTS];
+  bool ok[SLOTS];
+  float4 acc[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    int c = s * G + gl;
+    ok[s] = c < P.chunks;
+    head[s] = ok[s] ? c / P.chunks_per_head : 0;
+    acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int start = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
+  float st[kMaxHeads];
+  float gmax = 0.f;
+  if (!P.const_attention) {
+    gmax = __ldg(P.gmax);
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) st[h] = h < nh ? __ldg(P.s_tgt + row * nh + h) : 0.f;
+  } else {
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) st[h] = 0.f;
+  }
+
+  // ---- phase A: softmax denominators Z[h] = sum_e p[e,h]  (gat_layer.py:99-103)
+  float p[kMaxHeads], z[kMaxHeads];
+  int my_src = 0;
+  unsigned tiemask = 0;
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) z[h] = 0.f;
+  for (int base = start; base < end; base += G) {
+    edge_probs(P, base + gl, base + gl < end, st, gmax, my_src, p, tiemask);
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) z[h] += p[h];
+  }
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h)
+    if (h < nh) z[h] = group_sum<G>(z[h], gmask);
+  if (P.z_out && gl == 0) {
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h)
+      if (h < nh) P.z_out[row * nh + h] = z[h];
+  }
+  const bool single = (end - start) <= G;   // p[] of the only batch is still in registers
+
+  // ---- phase B: alpha, dropout, weighted gather-accumulate  (gat_layer.py:106-127)
+  for (int base = start; base < end; base += G) {
+    const int e = base + gl;
+    const bool valid = e < end;
+    if (!single) edge_probs(P, e, valid, st, gmax, my_src, p, tiemask);
+    if (valid) {
+      float w[kMaxHeads];
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h) w[h] = h < nh ? p[h] / (z[h] + kSoftmaxEps) : 0.f;
+      int edge_id = 0;
+      if (P.alpha_out || P.dropout_p > 0.f) edge_id = __ldg(P.eid + e);
+      if (P.alpha_out) {
+        float* ao = P.alpha_out + (int64_t)edge_id * nh;
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+          if (h < nh) ao[h] = w[h];
+      }
+      if (P.tie_total && tiemask) {
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h) {
+          if (tiemask & (1u << h)) {
+            atomicAdd(P.tie_dst + row * nh + h, 1);
+            atomicAdd(P.tie_src + (int64_t)my_src * nh + h, 1);
+            atomicAdd(P.tie_total, 1ull);
+          }
+        }
+      }
+      if (P.dropout_p > 0.f) {
+        float m[kMaxHeads];
+        dropout_scales(P.seed, P.offset, (uint32_t)edge_id, nh, P.dropout_p, m);
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+          if (h < nh) w[h] *= m[h];
+      }
+      sh_src[tid] = my_src;
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h) sh_w[tid * kMaxHeads + h] = w[h];
+    }
+    __syncwarp(gmask);
+    const int cnt = min(G, end - base);
+    for (int t = 0; t < cnt; t += U) {
+      float4 v[U][SLOTS];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool on = t + u < cnt;
+        const int sidx = on ? sh_src[gbase + t + u] : 0;
+        const float* rowp = P.wh + (int64_t)sidx * P.dp + gl * 4;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s)
+          v[u][s] = (on && ok[s]) ? ldg4(rowp + s * G * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (t + u < cnt) {
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
+            const float w = sh_w[(gbase + t + u) * kMaxHeads + head[s]];
+            acc[s].x = fmaf(w, v[u][s].x, acc[s].x);
+            acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
+            acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
+            acc[s].w = fmaf(w, v[u][s].w, acc[s].w);
+          }
+        }
+      }
+    }
+    __syncwarp(gmask);
+  }
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s)
+    if (ok[s]) *reinterpret_cast<float4*>(P.out + row * P.dp + (s * G + gl) * 4) = acc[s];
+}
+
+// ------------------------------------------------------------------------------------------
+// Head merge: padded (n, NH, Fp) -> (n, NH*F) or head mean (n, F)   (gat_layer.py:129-132)
+// ------------------------------------------------------------------------------------------
+__global__ void head_merge_fwd_kernel(const float* __restrict__ o, int64_t n, int nh, int f, int fp, int concat,
+                                      float* __restrict__ out) {
+  const int width = concat ? nh * f : f;
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * width) return;
+  int64_t i = idx / width;
+  int c = (int)(idx % width);
+  const float* r = o + i * (int64_t)nh * fp;
+  if (concat) {
+    out[idx] = r[(c / f) * fp + (c % f)];
+  } else {
+    float s = 0.f;
+    for (int h = 0; h < nh; ++h) s += r[h * fp + c];
+    out[idx] = s / (float)nh;   // torch.mean(dim=1): sum then divide
+  }
+}
+
+__global__ void head_merge_bwd_kernel(const float* __restrict__ g, int64_t n, int nh, int f, int fp, int concat,
+                                      float* __restrict__ go) {
+  const int dp = nh * fp;
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * dp) return;
+  int64_t i = idx / dp;
+  int c = (int)(idx % dp), h = c / fp, j = c % fp;
+  float v = 0.f;
+  if (j < f) v = concat ? g[i * (int64_t)nh * f + h * f + j] : g[i * (int64_t)f + j] / (float)nh;
+  go[idx] = v;
+}
+
+}  // namespace gat
+
+extern "C" int gat_edge_max(const int32_t* rowptr, const int32_t* col, int64_t n, const float* s_src,
+                            const float* s_tgt, int nh, float* gmax, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(nh >= 1 && nh <= kMaxHeads, "gat_edge_max: num_heads %d not in [1, %d]", nh, kMaxHeads);
+  if (n == 0) return GAT_OK;
+  edge_max_kernel<<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(rowptr, col, n, s_src, s_tgt, nh, gmax);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
+                            const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
+                            const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
+                            float* out, float* alpha_out, float* z_out,
+                            int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
+                            gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(nh >= 1 && nh <= kMaxHeads, "gat_edge_fwd: num_heads %d not in [1, %d]", nh, kMaxHeads);
+  GAT_CHECK_ARG(fp > 0 && fp % 4 == 0, "gat_edge_fwd: padded head width %d must be a positive multiple of 4", fp);
+  GAT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "gat_edge_fwd: dropout %f not in [0, 1)", dropout_p);
+  GAT_CHECK_ARG(const_attention || (s_src && s_tgt && gmax), "gat_edge_fwd: score buffers missing");
+  GAT_CHECK_ARG((tie_total == nullptr) == (tie_dst == nullptr) && (tie_total == nullptr) == (tie_src == nullptr),
+                "gat_edge_fwd: tie buffers must be given together");
+  if (n == 0) return GAT_OK;
+  EdgeFwdParams P;
+  P.rowptr = rowptr; P.col = col; P.eid = eid; P.n = n; P.wh = wh; P.nh = nh; P.dp = nh * fp;
+  P.chunks = nh * fp / 4; P.chunks_per_head = fp / 4;
+  P.s_src = s_src; P.s_tgt = s_tgt; P.gmax = gmax; P.const_attention = const_attention;
+  P.dropout_p = dropout_p; P.seed = seed; P.offset = offset;
+  P.out = out; P.alpha_out = alpha_out; P.z_out = z_out;
+  P.tie_dst = const_attention ? nullptr : tie_dst; P.tie_src = const_attention ? nullptr : tie_src;
+  P.tie_total = const_attention ? nullptr : tie_total;
+  GroupShape shape = pick_group(P.chunks);
+  if (shape.slots < 0) {
+    set_error("gat_edge_fwd: row width %d floats exceeds the supported 1024", P.dp);
+    return GAT_EUNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(G_, S_)                                                                      \
+  edge_fwd_kernel<G_, S_><<<(unsigned)((n + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)), kEdgeThreads, 0, st>>>(P)
+  GAT_DISPATCH_GROUP(shape, LAUNCH);
+#undef LAUNCH
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_head_merge_fwd(const float* o_padded, int64_t n, int nh, int f, int fp, int concat, float* out,
+                                  gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(nh >= 1 && f >= 1 && fp >= f, "gat_head_merge_fwd: bad shape");
+  int64_t total = n * (concat ? nh * f : f);
+  if (total == 0) return GAT_OK;
+  head_merge_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(o_padded, n, nh, f, fp, concat, out);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_head_merge_bwd(const float* grad_out, int64_t n, int nh, int f, int fp, int concat, float* go_padded,
+                                  gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(nh >= 1 && f >= 1 && fp >= f, "gat_head_merge_bwd: bad shape");
+  int64_t total = n * (int64_t)nh * fp;
+  if (total == 0) return GAT_OK;
+  head_merge_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad_out, n, nh, f, fp, concat, go_padded);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
