@@ -1,0 +1,79 @@
+"""ctypes binding of libgat_b200.so (the C ABI declared in include/gat_b200.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgat_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+_lock = threading.Lock()
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/gat_b200.h one to one.
+_P = c_void_p
+SIGNATURES = {
+    "gat_version": (c_int, []),
+    "gat_last_error": (c_char_p, []),
+    "gat_edges_scan": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
+    "gat_csr_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "gat_csr_build": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_int64,
+                              _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int64, c_int64, c_int]),
+    "gat_gemm_tc_supported": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64]),
+    "gat_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64,
+                         c_int, _P, c_size_t, _P]),
+    "gat_scores_fwd": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P]),
+    "gat_edge_max": (c_int, [_P, _P, c_int64, _P, _P, c_int, _P, _P]),
+    "gat_edge_fwd": (c_int, [_P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, c_int, c_float, c_uint64, c_uint64,
+                             _P, _P, _P, _P, _P, _P, _P]),
+    "gat_head_merge_fwd": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
+    "gat_head_merge_bwd": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
+    "gat_edge_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "gat_edge_bwd_dst": (c_int, [_P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, c_int,
+                                 c_float, c_uint64, c_uint64, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_src": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, c_int,
+                                 _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libgat_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-j8", "-C", CSRC], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libgat_b200.so failed")
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the B200 GAT layer has no CPU or PyTorch fallback. "
+                "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or `make -C gat-pytorch_b200/csrc`.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError here = header and library out of sync
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().gat_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

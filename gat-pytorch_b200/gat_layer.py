@@ -1,0 +1,239 @@
+"""Drop-in `GATLayer` whose forward and backward run as hand-written sm_100a kernels.
+
+Mirror of the reference operator interface `models/gat_layer.py:6-147` (same constructor, same
+`forward(x, edge_index, return_attention_weights=False)`, same sub-module / parameter names, same
+construction order so a seeded init draws the same weights, same state_dict keys).  The numerical work
+goes through the C ABI of include/gat_b200.h; torch is used for memory, streams and autograd wiring.
+
+There is NO CPU path and no PyTorch fallback: non-CUDA inputs raise.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from . import _lib
+from .graph import GLOBAL_CACHE, GraphStructure
+
+MAX_HEADS = 8
+MAX_ROW_FLOATS = 1024
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def gemm(ta: bool, tb: bool, m: int, n: int, k: int, a, lda, b, ldb, c, ldc, algo: int = 0):
+    """C[m,n] = op(A) op(B) through gat_gemm (include/gat_b200.h)."""
+    lib = _lib.load()
+    dev = c.device
+    ws_bytes = int(lib.gat_gemm_workspace_bytes(int(ta), int(tb), m, n, k, algo))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev) if ws_bytes else None
+    _lib.check(lib.gat_gemm(int(ta), int(tb), m, n, k, a.data_ptr(), lda, b.data_ptr(), ldb, c.data_ptr(), ldc,
+                            algo, _ptr(ws), ws_bytes, _stream(dev)), "gat_gemm")
+
+
+class _GATFunction(torch.autograd.Function):
+    """(x, W_p, A_src_p, A_tgt_p) -> (out, alpha).  W_p is W in padded-head row layout (NH*Fp, F_in);
+    A_*_p are the two halves of `a` in padded-head column layout (NH, NH*Fp)."""
+
+    @staticmethod
+    def forward(ctx, x, w_p, a_src_p, a_tgt_p, st: GraphStructure, nh, f, fp, concat, const_attention,
+                p_drop, want_alpha, gemm_algo):
+        lib = _lib.load()
+        dev = x.device
+        n, f_in, dp = x.size(0), x.size(1), nh * fp
+        needs_grad = any(ctx.needs_input_grad[:4])
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            wh = torch.empty((n, dp), **f32)
+            gemm(False, True, n, dp, f_in, x, x.stride(0), w_p, w_p.stride(0), wh, dp, gemm_algo)
+            s_src = s_tgt = gmax = None
+            if not const_attention:
+                s_src = torch.empty((n, nh), **f32)
+                s_tgt = torch.empty((n, nh), **f32)
+                _lib.check(lib.gat_scores_fwd(wh.data_ptr(), n, dp, a_src_p.data_ptr(), a_tgt_p.data_ptr(), nh,
+                                              s_src.data_ptr(), s_tgt.data_ptr(), s), "gat_scores_fwd")
+                gmax = torch.full((1,), float("-inf"), **f32)
+                _lib.check(lib.gat_edge_max(st.rowptr.data_ptr(), st.col.data_ptr(), n, s_src.data_ptr(),
+                                            s_tgt.data_ptr(), nh, gmax.data_ptr(), s), "gat_edge_max")
+            out_p = torch.empty((n, dp), **f32)
+            alpha = torch.empty((st.n_edges, nh), **f32) if want_alpha else None
+            z = torch.empty((n, nh), **f32)
+            tie_dst = tie_src = tie_total = None
+            if needs_grad and not const_attention:
+                ties = torch.zeros(2 * n * nh + 2, dtype=torch.int32, device=dev)
+                tie_total, tie_dst, tie_src = ties[:2], ties[2:2 + n * nh], ties[2 + n * nh:]
+            seed = 0
+            if p_drop > 0.0:
+                seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator: no device sync
+            _lib.check(lib.gat_edge_fwd(st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), n,
+                                        wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax),
+                                        int(const_attention), float(p_drop), seed, 0,
+                                        out_p.data_ptr(), _ptr(alpha), z.data_ptr(),
+                                        _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), s), "gat_edge_fwd")
+            if fp != f or not concat:
+                out = torch.empty((n, nh * f if concat else f), **f32)
+                _lib.check(lib.gat_head_merge_fwd(out_p.data_ptr(), n, nh, f, fp, int(concat), out.data_ptr(), s),
+                           "gat_head_merge_fwd")
+            else:
+                out = out_p
+        ctx.st, ctx.cfg = st, (nh, f, fp, concat, const_attention, float(p_drop), seed, gemm_algo)
+        ctx.save_for_backward(x, w_p, a_src_p, a_tgt_p, wh, s_src, s_tgt, gmax, z, tie_dst, tie_src, tie_total)
+        if alpha is None:
+            return out, None
+        return out, alpha
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_alpha):
+        lib = _lib.load()
+        x, w_p, a_src_p, a_tgt_p, wh, s_src, s_tgt, gmax, z, tie_dst, tie_src, tie_total = ctx.saved_tensors
+        st: GraphStructure = ctx.st
+        nh, f, fp, concat, const_attention, p_drop, seed, gemm_algo = ctx.cfg
+        dev = x.device
+        n, f_in, dp = x.size(0), x.size(1), nh * fp
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            d_out = nh * f if concat else f
+            if grad_out is None:
+                grad_out = torch.zeros((n, d_out), **f32)
+            grad_out = grad_out.contiguous()
+            if grad_alpha is not None:
+                grad_alpha = grad_alpha.contiguous()
+            if fp != f or not concat:
+                go_p = torch.empty((n, dp), **f32)
+                _lib.check(lib.gat_head_merge_bwd(grad_out.data_ptr(), n, nh, f, fp, int(concat), go_p.data_ptr(), s),
+                           "gat_head_merge_bwd")
+            else:
+                go_p = grad_out
+            rec = torch.empty((st.n_edges, 2 * nh), **f32)
+            d_wh = torch.empty((n, dp), **f32)
+            ds_src = ds_tgt = None
+            if not const_attention:
+                ds_src = torch.empty((n, nh), **f32)
+                ds_tgt = torch.empty((n, nh), **f32)
+            ws_bytes = int(lib.gat_edge_bwd_workspace_bytes(n, st.n_edges, nh))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.gat_edge_bwd_dst(st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), n,
+                                            wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax), z.data_ptr(),
+                                            int(const_attention), p_drop, seed, 0,
+                                            go_p.data_ptr(), _ptr(grad_alpha), rec.data_ptr(), _ptr(ds_tgt),
+                                            ws.data_ptr(), ws_bytes, s), "gat_edge_bwd_dst")
+            _lib.check(lib.gat_edge_bwd_src(st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), n,
+                                            nh, fp, rec.data_ptr(), go_p.data_ptr(), _ptr(a_src_p), _ptr(a_tgt_p),
+                                            int(const_attention), _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total),
+                                            _ptr(ds_src), _ptr(ds_tgt), d_wh.data_ptr(),
+                                            ws.data_ptr(), ws_bytes, s), "gat_edge_bwd_src")
+            gx = gw = ga_src = ga_tgt = None
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty((n, f_in), **f32)
+                gemm(False, False, n, f_in, dp, d_wh, dp, w_p, w_p.stride(0), gx, f_in, gemm_algo)
+            if ctx.needs_input_grad[1]:
+                gw = torch.empty((dp, f_in), **f32)
+                gemm(True, False, dp, f_in, n, d_wh, dp, x, x.stride(0), gw, f_in, gemm_algo)
+            if not const_attention and ctx.needs_input_grad[2]:
+                ga_src = torch.empty((nh, dp), **f32)
+                gemm(True, False, nh, dp, n, ds_src, nh, wh, dp, ga_src, dp, gemm_algo)
+            if not const_attention and ctx.needs_input_grad[3]:
+                ga_tgt = torch.empty((nh, dp), **f32)
+                gemm(True, False, nh, dp, n, ds_tgt, nh, wh, dp, ga_tgt, dp, gemm_algo)
+        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None
+
+
+class GATLayer(nn.Module):
+    """Multi-head graph attention layer, edge-list formulation, B200-native.
+
+    Same contract as the reference `GATLayer` (models/gat_layer.py:13-40, :42-140):
+      * `W`: Linear(in_features -> num_heads*out_features, bias=False)            (:27)
+      * `a`: Linear(num_heads*2*out_features -> num_heads, bias=False), a full cross-head matrix;
+        absent when `const_attention`                                              (:30-31)
+      * global-max-shifted LeakyReLU(0.01) logits, exp, +1e-8 in the softmax denominator (:85-109)
+      * dropout on the normalised coefficients in training mode                    (:113-115)
+      * returns `out` or `(out, (edge_index', alpha))`, alpha pre-dropout in the rewritten edge order
+    """
+
+    def __init__(self, in_features, out_features, num_heads, concat, dropout=0, add_self_loops=False, bias=False,
+                 const_attention=False):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.num_heads = num_heads
+        self.concat = concat
+        self.dropout = dropout
+        self.add_self_loops = add_self_loops
+        self.bias = bias
+        self.const_attention = const_attention
+        self.device = 'cuda' if torch.cuda.is_available() else 'cpu'
+
+        # same construction order as the reference => same RNG stream under a fixed seed
+        self.W = nn.Linear(in_features=self.in_features, out_features=self.num_heads * self.out_features, bias=False)
+        if not const_attention:
+            self.a = nn.Linear(in_features=self.num_heads * (2 * self.out_features), out_features=self.num_heads,
+                               bias=False)
+        if self.dropout > 0:
+            self.dropout_layer = nn.Dropout(p=self.dropout)   # kept for module-tree parity; the mask is Philox in-kernel
+        if self.bias:
+            self.bias_param = nn.Parameter(torch.Tensor(self.num_heads * self.out_features))
+
+        self.normalised_attention_coeffs = None
+        self.gemm_algo = 0          # 0 auto, 1 fp32 FFMA, 2 tcgen05 3xTF32
+        self.structure_cache = GLOBAL_CACHE
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.W.weight)
+        if not self.const_attention:
+            nn.init.xavier_uniform_(self.a.weight)
+        if self.bias:
+            nn.init.zeros_(self.bias_param)
+
+    # -- layout helpers (tiny differentiable torch ops; identity when out_features % 4 == 0) --------------
+    def _padded_operands(self):
+        nh, f = self.num_heads, self.out_features
+        fp = (f + 3) // 4 * 4
+        w = self.W.weight
+        if fp != f:
+            w = F.pad(w.view(nh, f, self.in_features), (0, 0, 0, fp - f)).reshape(nh * fp, self.in_features)
+        a_src = a_tgt = None
+        if not self.const_attention:
+            a3 = self.a.weight.view(nh, nh, 2 * f)                     # column h'*2F+j: gat_layer.py:76-82
+            a_src, a_tgt = a3[:, :, :f], a3[:, :, f:]
+            if fp != f:
+                a_src, a_tgt = F.pad(a_src, (0, fp - f)), F.pad(a_tgt, (0, fp - f))
+            a_src, a_tgt = a_src.reshape(nh, nh * fp).contiguous(), a_tgt.reshape(nh, nh * fp).contiguous()
+        return w, a_src, a_tgt, fp
+
+    def forward(self, x, edge_index, return_attention_weights=False):
+        if not x.is_cuda:
+            raise RuntimeError("gat_b200.GATLayer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.dtype != torch.float32:
+            raise RuntimeError(f"expected float32 node features, got {x.dtype}")   # the reference raises a dtype mismatch
+        if x.dim() != 2 or x.size(1) != self.in_features:
+            raise RuntimeError(f"x must have shape (N, {self.in_features}), got {tuple(x.shape)}")
+        if self.num_heads > MAX_HEADS:
+            raise NotImplementedError(f"num_heads > {MAX_HEADS} is not supported by the sm_100a kernels")
+        if edge_index.device != x.device:
+            raise RuntimeError("x and edge_index must be on the same device")
+        if x.stride(1) != 1 or (x.size(0) > 1 and x.stride(0) < x.size(1)):
+            x = x.contiguous()
+        st = self.structure_cache.get(edge_index, x.size(0), self.add_self_loops)
+        w_p, a_src, a_tgt, fp = self._padded_operands()
+        if self.num_heads * fp > MAX_ROW_FLOATS:
+            raise NotImplementedError(f"num_heads*out_features > {MAX_ROW_FLOATS} is not supported by the sm_100a kernels")
+        p_drop = float(self.dropout) if (self.training and self.dropout > 0) else 0.0
+        out, alpha = _GATFunction.apply(x, w_p, a_src, a_tgt, st, self.num_heads, self.out_features, fp,
+                                        bool(self.concat), bool(self.const_attention), p_drop,
+                                        bool(return_attention_weights), int(self.gemm_algo))
+        self.normalised_attention_coeffs = alpha
+        if self.bias:
+            out = out + self.bias_param          # gat_layer.py:134-135 (same broadcast rules, same latent shape error)
+        if return_attention_weights:
+            return out, (st.edge_index, alpha)
+        return out

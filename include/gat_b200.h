@@ -34,8 +34,14 @@ extern "C" {
 
 typedef void* gat_stream_t; /* cudaStream_t */
 
-int gat_version(void);
-const char* gat_last_error(void);
+#if defined(__GNUC__)
+#define GAT_API __attribute__((visibility("default")))
+#else
+#define GAT_API
+#endif
+
+GAT_API int gat_version(void);
+GAT_API const char* gat_last_error(void);
 
 /* ---------------------------------------------------------------------------------------
  * Kernel 1 -- edge_index -> rewritten edge list + destination-sorted CSR + transposed CSR.
@@ -44,13 +50,13 @@ const char* gat_last_error(void);
  * ------------------------------------------------------------------------------------- */
 
 /* Pass 1: d_stats[0] = max(edge_index)+1 (utils.py:72), d_stats[1] = #edges with src != dst
- * (utils.py:61).  `edge_index` is (2, E) with row stride `row_stride` elements, int64 when
+ * (utils.py:61), d_stats[2] = min(edge_index, 0) (negative ids are rejected by the caller).  `edge_index` is (2, E) with row stride `row_stride` elements, int64 when
  * index_is_int64 else int32.  The caller reads d_stats back (the one host sync per new graph,
  * replacing the `int(index.max())` sync at utils.py:72). */
-int gat_edges_scan(const void* edge_index, int64_t n_edges, int64_t row_stride, int index_is_int64,
+GAT_API int gat_edges_scan(const void* edge_index, int64_t n_edges, int64_t row_stride, int index_is_int64,
                    int64_t* d_stats, gat_stream_t stream);
 
-size_t gat_csr_workspace_bytes(int64_t n_edges_in, int64_t n_edges_out, int64_t n_nodes);
+GAT_API size_t gat_csr_workspace_bytes(int64_t n_edges_in, int64_t n_edges_out, int64_t n_nodes);
 
 /* Pass 2.  If add_self_loops: drops every (i,i), keeps the other edges in input order, appends
  * (k,k) for k < n_idx (utils.py:61-65); n_edges_out must equal d_stats[1] + n_idx.  Otherwise
@@ -60,7 +66,7 @@ size_t gat_csr_workspace_bytes(int64_t n_edges_in, int64_t n_edges_out, int64_t 
  *           rowptr diffs are the reference's degree counts (GATModel.py:196-201);
  *  rowptr_t (n_nodes+1) / col_t / pos_t: CSR by source; col_t = target ids, pos_t = slot of that
  *           edge in the target-sorted CSR. */
-int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t row_stride, int index_is_int64,
+GAT_API int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t row_stride, int index_is_int64,
                   int add_self_loops, int64_t n_idx, int64_t n_edges_out, int64_t n_nodes,
                   int64_t* ei_out, int32_t* rowptr, int32_t* col, int32_t* eid,
                   int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t,
@@ -75,15 +81,15 @@ int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t row_stride
  * B is stored (K,N) (tb=0) or (N,K) (tb=1).  algo: 0 = auto, 1 = fp32 FFMA tiles,
  * 2 = tcgen05 3xTF32 (TMA-fed; needs the alignment gat_gemm_tc_supported reports).
  * Deterministic: split-K partials are reduced in a fixed order inside `workspace`. */
-size_t gat_gemm_workspace_bytes(int ta, int tb, int64_t m, int64_t n, int64_t k, int algo);
-int gat_gemm_tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc);
-int gat_gemm(int ta, int tb, int64_t m, int64_t n, int64_t k,
+GAT_API size_t gat_gemm_workspace_bytes(int ta, int tb, int64_t m, int64_t n, int64_t k, int algo);
+GAT_API int gat_gemm_tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc);
+GAT_API int gat_gemm(int ta, int tb, int64_t m, int64_t n, int64_t k,
              const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
              int algo, void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* s_src[i,h] = <wh[i,:], a_src[h,:]>, s_tgt[i,h] = <wh[i,:], a_tgt[h,:]>  (fp64 accumulate).
  * The decomposition of gat_layer.py:76-82: logit[e,h] = s_src[src_e,h] + s_tgt[dst_e,h]. */
-int gat_scores_fwd(const float* wh, int64_t n, int dp, const float* a_src, const float* a_tgt, int nh,
+GAT_API int gat_scores_fwd(const float* wh, int64_t n, int dp, const float* a_src, const float* a_tgt, int nh,
                    float* s_src, float* s_tgt, gat_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -92,7 +98,7 @@ int gat_scores_fwd(const float* wh, int64_t n, int dp, const float* a_src, const
 
 /* Kernel 3a: *gmax = max over all (e,h) of s_src[col[e],h] + s_tgt[dst(e),h]  (gat_layer.py:85).
  * gmax must hold -inf on entry (the kernel combines with an ordered atomic max). */
-int gat_edge_max(const int32_t* rowptr, const int32_t* col, int64_t n, const float* s_src,
+GAT_API int gat_edge_max(const int32_t* rowptr, const int32_t* col, int64_t n, const float* s_src,
                  const float* s_tgt, int nh, float* gmax, gat_stream_t stream);
 
 /* Kernel 3: per destination row, p = exp(0.01*(l-M)) (gat_layer.py:85-96), Z = sum p (:99-103),
@@ -104,7 +110,7 @@ int gat_edge_max(const int32_t* rowptr, const int32_t* col, int64_t n, const flo
  *               gradient through max(), zero-initialised by the caller, or NULL;
  *  const_attention: logits are 0, gmax/s_src/s_tgt ignored (gat_layer.py:89-92);
  *  dropout_p > 0 enables the mask with (seed, offset) keyed on (edge id, head). */
-int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
+GAT_API int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
                  const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
                  const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
                  float* out, float* alpha_out, float* z_out,
@@ -112,23 +118,23 @@ int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, 
                  gat_stream_t stream);
 
 /* Head merge (gat_layer.py:129-132): padded (n, nh, fp) -> (n, nh*f) concat or (n, f) head mean. */
-int gat_head_merge_fwd(const float* o_padded, int64_t n, int nh, int f, int fp, int concat,
+GAT_API int gat_head_merge_fwd(const float* o_padded, int64_t n, int nh, int f, int fp, int concat,
                        float* out, gat_stream_t stream);
 /* and its adjoint: grad (n, nh*f | f) -> padded (n, nh, fp) with zero pad lanes. */
-int gat_head_merge_bwd(const float* grad_out, int64_t n, int nh, int f, int fp, int concat,
+GAT_API int gat_head_merge_bwd(const float* grad_out, int64_t n, int nh, int f, int fp, int concat,
                        float* go_padded, gat_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Kernel 4 -- atomic-free deterministic backward.  Replaces autograd of gat_layer.py:70-132.
  * ------------------------------------------------------------------------------------- */
 
-size_t gat_edge_bwd_workspace_bytes(int64_t n, int64_t n_edges, int nh);
+GAT_API size_t gat_edge_bwd_workspace_bytes(int64_t n, int64_t n_edges, int nh);
 
 /* Destination pass (CSR): d_alpha = m*<go[i,h,:], wh[src,h,:]> + grad_alpha, S = sum alpha*d_alpha,
  * g = 0.01*alpha*(d_alpha - S).  Writes per-edge records rec[j] = {g[0..nh), m*alpha[0..nh)} in CSR
  * order, ds_tgt (n, nh) (before the arg-max correction) and per-block partial sums of g.
  * grad_alpha is (n_edges, nh) in rewritten edge order or NULL. */
-int gat_edge_bwd_dst(const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
+GAT_API int gat_edge_bwd_dst(const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
                      const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
                      const float* gmax, const float* z, int const_attention,
                      float dropout_p, uint64_t seed, uint64_t offset,
@@ -140,7 +146,7 @@ int gat_edge_bwd_dst(const int32_t* rowptr, const int32_t* col, const int32_t* e
  * arg-max correction Gamma/|T| (Gamma reduced from the dst-pass partials in `workspace`) to ds_src
  * and ds_tgt via the tie counts; then adds ds_src*A_src + ds_tgt*A_tgt so that d_wh is the total
  * gradient of Wh.  ds_src/ds_tgt (n, nh) hold the corrected values on exit. */
-int gat_edge_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, int64_t n,
+GAT_API int gat_edge_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, int64_t n,
                      int nh, int fp, const float* rec, const float* go_padded,
                      const float* a_src, const float* a_tgt, int const_attention,
                      const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,

@@ -1,0 +1,231 @@
+"""Parity of the CUDA path (through the C ABI, via the drop-in GATLayer) against the oracle and the
+golden vectors minted from the reference.  Bar: integer work bit-exact; fp32 within 1e-5 tensor-relative
+(max|got-want| / max|want|) of the fp64 oracle, as BASELINE.json's north_star states.  Cases whose own
+fp32 reference noise exceeds that (eps-dominated softmax) carry their tolerance below.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import gat_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASE_NAMES = [c["name"] for c in cases.adversarial_cases()] + [
+    f"{m}_L{i}" for m in ("cora", "pubmed", "ppi", "pattern", "products") for i in range(len(cases.synth.LAYER_SHAPES[m]))]
+
+TOL = 1e-5
+# looser where the reference's fp32 run itself is further than 1e-5 from its fp64 run (value = measured
+# reference fp32 noise, see tests/test_oracle_golden.py) -- the CUDA path must be no worse than that.
+TOL_OVERRIDE = {"adv_eps_dominated": 2e-3, "pattern_L2": 5e-5, "pattern_L3": 5e-5}
+
+
+def make_layer(case, device="cuda", gemm_algo=0, dropout=0.0):
+    from gat_pytorch_b200 import GATLayer
+    layer = GATLayer(case["x"].shape[1], case["f"], case["nh"], case["concat"], dropout=dropout,
+                     add_self_loops=case["add_self_loops"], bias=case["bias"] is not None,
+                     const_attention=case["const_attention"]).to(device)
+    layer.gemm_algo = gemm_algo
+    with torch.no_grad():
+        layer.W.weight.copy_(torch.from_numpy(case["W"]))
+        if not case["const_attention"]:
+            layer.a.weight.copy_(torch.from_numpy(case["a"]))
+        if case["bias"] is not None:
+            layer.bias_param.copy_(torch.from_numpy(case["bias"]))
+    return layer
+
+
+def run_cuda(case, gemm_algo=0):
+    layer = make_layer(case, gemm_algo=gemm_algo)
+    x = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+    ei = torch.from_numpy(case["edge_index"]).cuda()
+    out, (ei2, alpha) = layer(x, ei, return_attention_weights=True)
+    go, ga = cases.upstream_grads(case, out.shape[0], out.shape[1], alpha.shape[0])
+    loss = (out * torch.from_numpy(go).cuda()).sum()
+    if alpha.requires_grad:
+        loss = loss + (alpha * torch.from_numpy(ga).cuda()).sum()
+    loss.backward()
+    res = dict(out=out, alpha=alpha, gx=x.grad, gW=layer.W.weight.grad)
+    if not case["const_attention"]:
+        res["ga"] = layer.a.weight.grad
+    if case["bias"] is not None:
+        res["gb"] = layer.bias_param.grad.reshape(-1, 1)
+    return {k: v.detach().cpu().numpy() for k, v in res.items()}, ei2.cpu().numpy()
+
+
+def run_oracle(case):
+    fw = O.forward(case["x"], case["edge_index"].astype(np.int64), case["W"], case["a"], case["nh"], case["f"], case["concat"],
+                   case["add_self_loops"], case["bias"], case["const_attention"])
+    go, ga = cases.upstream_grads(case, fw["out"].shape[0], fw["out"].shape[1], fw["alpha"].shape[0])
+    gr = O.backward(fw, go, None if case["const_attention"] else ga)
+    res = dict(out=fw["out"], alpha=fw["alpha"], gx=gr["x"], gW=gr["W"])
+    if not case["const_attention"]:
+        res["ga"] = gr["a"]
+    if case["bias"] is not None:
+        res["gb"] = gr["bias"].reshape(-1, 1)
+    return fw, res
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_layer_matches_oracle_and_golden(name, small_cases, golden):
+    case = small_cases[name]
+    got, ei2 = run_cuda(case)
+    fw, want = run_oracle(case)
+    assert ei2.dtype == case["edge_index"].dtype
+    assert np.array_equal(ei2, fw["edge_index"]), "rewritten edge list must be bit-exact (utils.py:47-67)"
+    tol = TOL_OVERRIDE.get(name, TOL)
+    errs = {k: O.rel_err(got[k], want[k]) for k in want}
+    assert all(e <= tol for e in errs.values()), errs
+    # and against the reference's own fp32 outputs (sampled rows), within the same bar + the reference's noise
+    for k in want:
+        if name == "adv_int32" and k.startswith("g"):
+            continue   # the reference's int32 gradients are wrong under torch 2.11 (see test_oracle_golden.py)
+        g2 = got[k].reshape(got[k].shape[0], -1)
+        sample = g2[np.ix_(cases.sample_idx(g2.shape[0], 64), cases.sample_idx(g2.shape[1], 160))]
+        scale = max(float(golden[f"{name}/f64/{k}_max"]), 1e-30)
+        ref32 = golden[f"{name}/f32/{k}"]
+        err = np.abs(sample - ref32).max() / scale if sample.size else 0.0
+        assert err <= 2 * tol, (k, err)
+
+
+@pytest.mark.parametrize("name", ["adv_concat", "cora_L0", "pattern_L0", "products_L1"])
+def test_structure_bit_exact(name, small_cases):
+    """Kernel 1 against the oracle's stable argsort / bincount."""
+    from gat_pytorch_b200 import build_structure
+    case = small_cases[name]
+    n = case["x"].shape[0]
+    ei = torch.from_numpy(case["edge_index"]).cuda()
+    st = build_structure(ei, n, True)
+    want_ei = O.add_remaining_self_loops(case["edge_index"])
+    assert np.array_equal(st.edge_index.cpu().numpy(), want_ei)
+    rowptr, col, eid = O.csr_by_target(want_ei, n)
+    rowptr_t, col_t, pos_t = O.csr_by_source(want_ei, n, eid)
+    for got, want in [(st.rowptr, rowptr), (st.col, col), (st.eid, eid), (st.rowptr_t, rowptr_t), (st.col_t, col_t), (st.pos_t, pos_t)]:
+        assert np.array_equal(got.cpu().numpy().astype(np.int64), want)
+    assert np.array_equal(st.in_degrees().cpu().numpy(), O.in_degrees(want_ei, n))
+    # idempotent: the rewritten list maps to the same structure (GATModel.py:166 feeds it to the next layer)
+    st2 = build_structure(st.edge_index, n, True)
+    assert torch.equal(st2.edge_index, st.edge_index) and torch.equal(st2.col, st.col)
+    # no rewrite requested: list used as is
+    st3 = build_structure(ei, n, False)
+    assert st3.n_edges == ei.size(1) and st3.edge_index is ei
+
+
+def test_out_of_range_index_raises():
+    from gat_pytorch_b200 import build_structure
+    ei = torch.tensor([[0, 5], [1, 2]], device="cuda")
+    with pytest.raises(IndexError):
+        build_structure(ei, 4, True)
+
+
+def test_trailing_isolated_nodes_are_zero(small_cases):
+    case = small_cases["adv_concat"]
+    got, _ = run_cuda(case)
+    assert np.all(got["out"][-5:] == 0.0)   # nodes that never appear in edge_index get no self-loop
+
+
+def test_deterministic_bitwise(small_cases):
+    """Atomic-free backward: two runs give identical bits (replaces a race detector)."""
+    for name in ("adv_wide", "products_L1", "pattern_L0"):
+        a, _ = run_cuda(small_cases[name])
+        b, _ = run_cuda(small_cases[name])
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (name, k)
+
+
+def test_eval_forward_without_attention_matches(small_cases):
+    case = small_cases["cora_L0"]
+    layer = make_layer(case).eval()
+    x = torch.from_numpy(case["x"]).cuda()
+    ei = torch.from_numpy(case["edge_index"]).cuda()
+    with torch.no_grad():
+        out = layer(x, ei)
+        out2, (_, alpha) = layer(x, ei, return_attention_weights=True)
+    assert torch.equal(out, out2)
+    fw = O.forward(case["x"], case["edge_index"], case["W"], case["a"], case["nh"], case["f"], True, True)
+    assert O.rel_err(out.cpu().numpy(), fw["out"]) <= TOL
+
+
+def test_dropout_statistics_and_backward_mask(small_cases):
+    """Philox cannot bit-match nn.Dropout: check keep-rate, unbiasedness, pre-dropout alpha,
+    and that backward regenerates the forward's mask (gradient check against the oracle with that mask)."""
+    case = small_cases["products_L0"]
+    p = 0.6
+    layer = make_layer(case, dropout=p).train()
+    x = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+    ei = torch.from_numpy(case["edge_index"]).cuda()
+    torch.manual_seed(123)
+    out, (ei2, alpha) = layer(x, ei, return_attention_weights=True)
+    fw = O.forward(case["x"], case["edge_index"], case["W"], case["a"], case["nh"], case["f"], True, True)
+    assert O.rel_err(alpha.detach().cpu().numpy(), fw["alpha"]) <= TOL          # returned alpha is pre-dropout
+    # recover the mask from out = sum m*alpha*Wh: use a probe with one-hot features instead
+    torch.manual_seed(123)
+    out_b, _ = layer(x, ei, return_attention_weights=True)
+    assert torch.equal(out, out_b)                                               # same seed -> same mask
+    torch.manual_seed(124)
+    out_c, _ = layer(x, ei, return_attention_weights=True)
+    assert not torch.equal(out, out_c)
+    # unbiased: mean over many masks approaches the eval output
+    acc = torch.zeros_like(out)
+    reps = 200
+    with torch.no_grad():
+        for _ in range(reps):
+            acc += layer(x, ei)
+    mean = (acc / reps).cpu().numpy()
+    err = np.abs(mean - fw["out"]).mean() / np.abs(fw["out"]).mean()
+    assert err < 0.08, err
+
+
+def test_dropout_gradient_uses_forward_mask():
+    """Linear probe: with Wh = identity-like features the output reveals the mask; backward must use it."""
+    from gat_pytorch_b200 import GATLayer
+    torch.manual_seed(0)
+    n, nh, f = 64, 2, 4
+    rng = np.random.default_rng(5)
+    ei_np = rng.integers(0, n, size=(2, 600)).astype(np.int64)
+    layer = GATLayer(8, f, nh, True, dropout=0.5, add_self_loops=True).cuda().train()
+    x = torch.randn(n, 8, device="cuda", requires_grad=True)
+    ei = torch.from_numpy(ei_np).cuda()
+    torch.manual_seed(77)
+    out, (ei2, alpha) = layer(x, ei, return_attention_weights=True)
+    go = torch.randn_like(out)
+    (out * go).sum().backward()
+    gx = x.grad.clone()
+    # finite-difference directional derivative with the SAME mask (same seed)
+    d = torch.randn_like(x)
+    eps = 1e-2
+    with torch.no_grad():
+        torch.manual_seed(77)
+        op = layer(x + eps * d, ei)
+        torch.manual_seed(77)
+        om = layer(x - eps * d, ei)
+    fd = ((op - om) * go).sum().item() / (2 * eps)
+    an = (gx * d).sum().item()
+    assert abs(fd - an) <= 2e-2 * max(abs(fd), abs(an), 1e-3), (fd, an)
+
+
+def test_cpu_input_raises(small_cases):
+    from gat_pytorch_b200 import GATLayer
+    layer = GATLayer(4, 2, 2, True)
+    with pytest.raises(RuntimeError):
+        layer(torch.randn(3, 4), torch.zeros((2, 2), dtype=torch.long))
+    layer = layer.cuda()
+    with pytest.raises(RuntimeError):
+        layer(torch.randn(3, 4, device="cuda", dtype=torch.float64), torch.zeros((2, 2), dtype=torch.long, device="cuda"))
+
+
+def test_gemm_all_layouts():
+    """gat_gemm (fp32 FFMA path) against torch fp64 matmul for every transposition and ragged sizes."""
+    from gat_pytorch_b200.gat_layer import gemm
+    torch.manual_seed(1)
+    for (m, n, k) in [(1, 1, 1), (70, 33, 129), (257, 64, 1433), (8, 256, 20000), (300, 100, 5000)]:
+        for ta in (False, True):
+            for tb in (False, True):
+                a = torch.randn((k, m) if ta else (m, k), device="cuda")
+                b = torch.randn((n, k) if tb else (k, n), device="cuda")
+                c = torch.empty((m, n), device="cuda")
+                gemm(ta, tb, m, n, k, a, a.stride(0), b, b.stride(0), c, n, algo=1)
+                want = (a.double().T if ta else a.double()) @ (b.double().T if tb else b.double())
+                err = (c.double() - want).abs().max().item() / want.abs().max().item()
+                assert err < 2e-6, (m, n, k, ta, tb, err)
