@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- GAT layer fwd+bwd edges/s on the ogbn-products-shaped synthetic graph.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME] [--scale S]
+
+One "step" = forward + backward of the 3-layer, 4-head GAT of BASELINE.json configs[4]
+(100 -> 4x64 -> 4x64 -> 4x47 mean; hidden width per SURVEY.md section 8) over the whole graph
+(2 449 029 nodes, 61 859 140 edges, E' = edges after the self-loop rewrite), with the reference's
+inter-layer glue (layer -> ELU, GATModel.py:120-151).  metric = layer-edges/s = L * E' / t
+(BASELINE.md section 2).  Prints ONE JSON line on rank 0.
+
+  value    device-resident inputs, graph structure cached (steady-state training step)
+  e2e      same step through the public GATLayer API starting from PINNED HOST buffers: H2D of x and
+           edge_index, CSR/CSR^T build for the freshly uploaded graph, fwd+bwd, D2H of the loss
+  roofline dominant kernel (edge backward, destination pass) timed live with CUDA events inside the
+           timed region; algorithmic bytes per SURVEY.md section 8-d / DESIGN.md
+  cpu_baseline / --impl reference: the torch CPU port of the reference layer (oracle/torch_port.py; the
+           reference is Python and cannot travel to the GPU box) on all host cores, on a 1/128-scale
+           products-shaped graph (the reference formulation cannot allocate full scale)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+METRIC = "gat_layer_fwd_bwd_edges_per_s"
+UNIT = "edges/s"
+CPU_SCALE = 1.0 / 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="products")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ----------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------
+def load_synth():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gat_b200_synth", os.path.join(ROOT, "gat-pytorch_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_workload(name, scale):
+    synth = load_synth()
+    gen = synth.GENERATORS[name]
+    x, ei = gen(scale=scale) if name == "products" else gen()
+    shapes = synth.LAYER_SHAPES[name]
+    if name in ("products", "ppi"):
+        weights = synth.seeded_weights(name)
+    else:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "ckpt_weights.npz"))
+        tag = {"cora": "Cora", "citeseer": "Citeseer", "pubmed": "Pubmed", "pattern": "PATTERN"}[name]
+        weights = [(z[f"{tag}.gat_layer_list.{i}.W.weight"], z[f"{tag}.gat_layer_list.{i}.a.weight"]) for i in range(len(shapes))]
+    return x, ei, shapes, weights
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons every 100 ms while the timed region runs (NVML)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while self.nv is not None and not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU reference arm (torch port of the reference formulation)
+# ----------------------------------------------------------------------------------------------
+def cpu_port_step_fn(name, scale):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port
+    x, ei, shapes, weights = make_workload(name, scale)
+    torch.set_num_threads(os.cpu_count() or 1)
+    xt, eit = torch.from_numpy(x), torch.from_numpy(ei)
+    ws = [(torch.from_numpy(w).requires_grad_(True), torch.from_numpy(a).requires_grad_(True)) for w, a in weights]
+    e_prime = int(torch_port.rewrite_edges(eit).size(1))
+
+    def step():
+        for w, a in ws:
+            w.grad = a.grad = None
+        return torch_port.model_step(xt, eit, ws, shapes)
+
+    return step, e_prime, len(shapes), x.shape[0]
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    step, e_prime, n_layers, n = cpu_port_step_fn(args.workload, CPU_SCALE if args.workload == "products" else 1.0)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n_layers * e_prime / dt
+    sample = (f"{args.workload}-shaped graph at scale 1/128 (N={n}, E'={e_prime}), {n_layers}-layer fwd+bwd, "
+              f"torch {torch.__version__} CPU, {torch.get_num_threads()} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, gpus):
+    return {"workload": f"{name}-shaped synthetic graph, 3-layer 4-head GAT (100->4x64->4x64->4x47 mean), fwd+bwd, "
+                        "value = layers*E'/t" if name == "products" else f"{name}-shaped synthetic graph, all layers fwd+bwd",
+            "graph": name, "partition": "single GPU" if gpus == 1 else f"destination-range over {gpus} GPUs",
+            "l2_policy": "inputs larger than L2 (per-layer feature matrix 2.5 GB vs 126 MB L2); no flush"}
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def algorithmic_bytes(kernel, e, n, nh, d, d_out):
+    """SURVEY.md section 8-d per-launch byte counts (fp32, int32 indices)."""
+    if kernel == "gat_edge_fwd":
+        return e * (4 + 4 * nh + 4 * d) + n * (8 + 8 * nh + 4 * d_out)
+    if kernel == "gat_edge_bwd_dst":
+        return e * (4 + 8 * nh + 4 * d) + n * (8 + 4 * d_out + 12 * nh)
+    if kernel == "gat_edge_bwd_src":
+        return e * (8 + 12 * nh + 4 * d_out) + n * (8 + 4 * d + 4 * nh)
+    raise KeyError(kernel)
+
+
+def run_b200(args):
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import gat_pytorch_b200 as g
+    from gat_pytorch_b200 import _lib
+    lib = _lib.load()
+
+    x_np, ei_np, shapes, weights = make_workload(args.workload, args.scale)
+    n = x_np.shape[0]
+    x_host = torch.from_numpy(x_np).pin_memory()
+    ei_host = torch.from_numpy(ei_np).pin_memory()
+
+    if world > 1:
+        from gat_pytorch_b200.partition import PartitionedGAT
+        model = PartitionedGAT(shapes, weights, x_host, ei_host, dev)
+        step_resident, step_e2e, e_prime = model.step_resident, model.step_e2e, model.n_edges_global
+    else:
+        layers = []
+        for (f_in, nh, f, concat), (w, a) in zip(shapes, weights):
+            layer = g.GATLayer(f_in, f, nh, concat, dropout=0.0, add_self_loops=True).to(dev)
+            with torch.no_grad():
+                layer.W.weight.copy_(torch.from_numpy(w))
+                layer.a.weight.copy_(torch.from_numpy(a))
+            layers.append(layer)
+
+        def fwd_bwd(x, ei):
+            h = x
+            for i, layer in enumerate(layers):
+                layer.W.weight.grad = layer.a.weight.grad = None
+                h = layer(h, ei)
+                if i != len(layers) - 1:
+                    h = F.elu(h)
+            loss = h.square().mean()
+            loss.backward()
+            return loss
+
+        x_dev, ei_dev = x_host.to(dev), ei_host.to(dev)
+        e_prime = g.GLOBAL_CACHE.get(ei_dev, n, True).n_edges
+
+        def step_resident():
+            return fwd_bwd(x_dev, ei_dev)
+
+        def step_e2e():
+            g.GLOBAL_CACHE.clear()                       # a freshly uploaded graph: structure is rebuilt
+            xd = x_host.to(dev, non_blocking=True)
+            eid = ei_host.to(dev, non_blocking=True)
+            return float(fwd_bwd(xd, eid).item())        # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_layers = len(shapes)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.gat_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with _lib.KernelTimer() as kt:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step_resident()
+        ev1.record()
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = int(lib.gat_launch_count() - launches0)
+    clocks = sampler.stop()
+    kernels = kt.summary()
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n_layers * e_prime / (ms_step * 1e-3)
+
+    # ---- end-to-end from pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        step_e2e()
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step_e2e()
+        ev1.record()
+        barrier()
+        ms_e2e = ev0.elapsed_time(ev1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        e2e = {"value": n_layers * e_prime / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(x_host.numel() * 4 + ei_host.numel() * 8), "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e / args.steps}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (hidden-layer shape), timed live above
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    f_in, nh, f, concat = shapes[min(1, n_layers - 1)]
+    fp = (f + 3) // 4 * 4
+    d = nh * fp
+    n_local = n if world == 1 else model.n_local
+    e_local = e_prime if world == 1 else model.n_edges_local
+    per_kernel = {}
+    for kname in ("gat_edge_fwd", "gat_edge_bwd_dst", "gat_edge_bwd_src"):
+        rec = kernels.get((kname, (nh, fp)))
+        if rec:
+            b = algorithmic_bytes(kname, e_local, n_local, nh, d, d)
+            gbs = b / (rec["ms_avg"] * 1e-3) / 1e9
+            per_kernel[kname] = {"ms_avg": rec["ms_avg"], "calls": rec["calls"], "algorithmic_bytes": b, "GBps": gbs, "frac": gbs / peak}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_avg"]) if per_kernel else None
+    roofline = None
+    if dom:
+        pk = per_kernel[dom]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": pk["GBps"], "peak": peak, "unit": "GB/s", "frac": pk["frac"],
+                    "traffic": traffic, "peak_source": peak_src, "ms_avg": pk["ms_avg"], "algorithmic_bytes": pk["algorithmic_bytes"]}
+    total_kernel_ms = sum(v["ms_total"] for v in kernels.values())
+    breakdown = {f"{k[0]}{'' if k[1] is None else list(k[1])}": round(v["ms_total"] / args.steps, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_total"])}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        step, e_cpu, l_cpu, n_cpu = cpu_port_step_fn(args.workload, CPU_SCALE if args.workload == "products" else 1.0)
+        step()
+        best = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            step()
+            best = min(best, time.perf_counter() - t0)
+        cpu_baseline = {"value": l_cpu * e_cpu / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{args.workload}-shaped graph at scale {'1/128' if args.workload == 'products' else '1'} "
+                                  f"(N={n_cpu}, E'={e_cpu}), {l_cpu}-layer fwd+bwd, best of 2 after 1 warm-up, "
+                                  f"oracle/torch_port.py on {torch.get_num_threads()} threads"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(workload_config(args.workload, world), n_nodes=n, n_edges_rewritten=e_prime,
+                                                 scale=args.scale, layers=[list(s) for s in shapes]),
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "kernels_ms_per_step": breakdown, "edge_kernels": per_kernel,
+            "kernel_time_share_of_step": total_kernel_ms / ms_total if ms_total else None}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+    if dist_env()[2] > 1 and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

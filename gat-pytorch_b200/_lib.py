@@ -22,6 +22,7 @@ _P = c_void_p
 SIGNATURES = {
     "gat_version": (c_int, []),
     "gat_last_error": (c_char_p, []),
+    "gat_launch_count": (ctypes.c_ulonglong, []),
     "gat_edges_scan": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
     "gat_csr_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "gat_csr_build": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_int64,
@@ -40,7 +41,8 @@ SIGNATURES = {
     "gat_edge_bwd_dst": (c_int, [_P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, c_int,
                                  c_float, c_uint64, c_uint64, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_src": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, c_int,
-                                 _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+                                 _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_gamma": (c_int, [_P, c_size_t, _P, _P]),
 }
 
 
@@ -77,3 +79,49 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().gat_last_error()
         raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+class KernelTimer:
+    """Optional per-entry-point CUDA-event timing (bench.py's live roofline measurement).  While active,
+    every C-ABI call made through `call()` is bracketed by two events on the current stream; no
+    synchronisation happens until `summary()`."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _timer
+        _timer = self
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = None
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, tag, e0, e1 in self.records:
+            d = out.setdefault((name, tag), [0, 0.0])
+            d[0] += 1
+            d[1] += e0.elapsed_time(e1)
+        return {k: dict(calls=v[0], ms_total=v[1], ms_avg=v[1] / v[0]) for k, v in out.items()}
+
+
+_timer = None
+
+
+def call(name: str, *args, tag=None):
+    """Invoke C-ABI entry point `name`; raise on a non-zero status."""
+    fn = getattr(load(), name)
+    if _timer is None:
+        rc = fn(*args)
+    else:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _timer.records.append((name, tag, e0, e1))
+    check(rc, name)

@@ -1,10 +1,14 @@
 // Library-wide entry points: version, last-error string, GEMM dispatch.
 #include "common.cuh"
 #include <string.h>
+#include <atomic>
 
 namespace gat {
 
 static thread_local char g_last_error[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -27,6 +31,8 @@ bool tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, 
 extern "C" int gat_version(void) { return 100; }
 
 extern "C" const char* gat_last_error(void) { return gat::g_last_error; }
+
+extern "C" unsigned long long gat_launch_count(void) { return gat::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int gat_gemm_tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
                                      int64_t ldc) {

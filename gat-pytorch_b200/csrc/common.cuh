@@ -9,6 +9,7 @@
 namespace gat {
 
 void set_error(const char* fmt, ...);
+void count_launch();   // bumps the counter behind gat_launch_count()
 
 #define GAT_CHECK_ARG(cond, ...)            \
   do {                                      \
@@ -29,6 +30,7 @@ void set_error(const char* fmt, ...);
 
 #define GAT_LAUNCH_CHECK()                                                              \
   do {                                                                                  \
+    gat::count_launch();                                                                \
     cudaError_t _e = cudaGetLastError();                                                \
     if (_e != cudaSuccess) {                                                            \
       gat::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

@@ -239,7 +239,8 @@ struct EdgeBwdSrcParams {
   const int32_t* rowptr_t; const int32_t* col_t; const int32_t* pos_t; int64_t n;
   int nh; int dp; int chunks; int chunks_per_head;
   const float* rec; const float* go; const float* a_src; const float* a_tgt; int const_attention;
-  const int32_t* tie_dst; const int32_t* tie_src; const BwdHeader* header;
+  const int32_t* tie_dst; const int32_t* tie_src; const BwdHeader* header; const float* corr_override;
+  int64_t tgt_lo; int64_t tgt_hi;   // rows that this call owns as TARGETS (ds_tgt / tie_dst are indexed row - tgt_lo)
   float* ds_src; float* ds_tgt; float* d_wh;
 };
 
@@ -314,7 +315,9 @@ edge_bwd_src_kernel(const EdgeBwdSrcParams P) {
 
   if (!P.const_attention) {
     // ds_src = sum g - |T_src|*Gamma/|T|;  ds_tgt -= |T_dst|*Gamma/|T|   (gradient through max(), section 9.2)
-    const float corr = P.header->corr;
+    const float corr = P.corr_override ? __ldg(P.corr_override) : P.header->corr;
+    const bool own_tgt = row >= P.tgt_lo && row < P.tgt_hi;   // single GPU: always; partitioned: owner rank only
+    const int64_t trow = row - P.tgt_lo;
     float dss[kMaxHeads], dst_[kMaxHeads];
 #pragma unroll
     for (int h = 0; h < kMaxHeads; ++h) {
@@ -322,17 +325,22 @@ edge_bwd_src_kernel(const EdgeBwdSrcParams P) {
       if (h < nh) {
         float g = group_sum<G>(gsum[h], gmask);
         int ts = P.tie_src ? __ldg(P.tie_src + row * nh + h) : 0;
-        int td = P.tie_dst ? __ldg(P.tie_dst + row * nh + h) : 0;
         dss[h] = ts ? g - (float)ts * corr : g;
-        float t = P.ds_tgt[row * nh + h];
-        dst_[h] = td ? t - (float)td * corr : t;
+        if (own_tgt) {
+          int td = P.tie_dst ? __ldg(P.tie_dst + trow * nh + h) : 0;
+          float t = P.ds_tgt[trow * nh + h];
+          dst_[h] = td ? t - (float)td * corr : t;
+        }
       }
     }
     __syncwarp(gmask);   // every lane has read ds_tgt before lane 0 overwrites it
     if (gl == 0) {
 #pragma unroll
       for (int h = 0; h < kMaxHeads; ++h)
-        if (h < nh) { P.ds_src[row * nh + h] = dss[h]; P.ds_tgt[row * nh + h] = dst_[h]; }
+        if (h < nh) {
+          P.ds_src[row * nh + h] = dss[h];
+          if (own_tgt) P.ds_tgt[trow * nh + h] = dst_[h];
+        }
     }
     // d_wh_total = d_wh + ds_src * A_src + ds_tgt * A_tgt
 #pragma unroll
@@ -410,10 +418,22 @@ extern "C" int gat_edge_bwd_dst(const int32_t* rowptr, const int32_t* col, const
   return GAT_OK;
 }
 
+extern "C" int gat_edge_bwd_gamma(void* workspace, size_t workspace_bytes, double* gamma_out, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(workspace && gamma_out && workspace_bytes >= kBwdHeaderBytes, "gat_edge_bwd_gamma: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdHeader* header = (BwdHeader*)workspace;
+  gamma_finalize_kernel<<<1, 1024, 0, st>>>(header, (const double*)((char*)workspace + kBwdHeaderBytes), nullptr);
+  GAT_LAUNCH_CHECK();
+  GAT_CUDA(cudaMemcpyAsync(gamma_out, &header->gamma, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return GAT_OK;
+}
+
 extern "C" int gat_edge_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, int64_t n,
                                 int nh, int fp, const float* rec, const float* go_padded,
                                 const float* a_src, const float* a_tgt, int const_attention,
                                 const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                                const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
                                 float* ds_src, float* ds_tgt, float* d_wh,
                                 void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
@@ -427,7 +447,7 @@ extern "C" int gat_edge_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, c
   if (n == 0) return GAT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   BwdHeader* header = (BwdHeader*)workspace;
-  if (!const_attention) {
+  if (!const_attention && corr_override == nullptr) {
     gamma_finalize_kernel<<<1, 1024, 0, st>>>(header, (const double*)((char*)workspace + kBwdHeaderBytes), tie_total);
     GAT_LAUNCH_CHECK();
   }
@@ -435,7 +455,8 @@ extern "C" int gat_edge_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, c
   P.rowptr_t = rowptr_t; P.col_t = col_t; P.pos_t = pos_t; P.n = n; P.nh = nh; P.dp = nh * fp;
   P.chunks = nh * fp / 4; P.chunks_per_head = fp / 4;
   P.rec = rec; P.go = go_padded; P.a_src = a_src; P.a_tgt = a_tgt; P.const_attention = const_attention;
-  P.tie_dst = tie_dst; P.tie_src = tie_src; P.header = header;
+  P.tie_dst = tie_dst; P.tie_src = tie_src; P.header = header; P.corr_override = corr_override;
+  P.tgt_lo = tgt_lo; P.tgt_hi = tgt_hi;
   P.ds_src = ds_src; P.ds_tgt = ds_tgt; P.d_wh = d_wh;
   GroupShape shape = pick_group(P.chunks);
   if (shape.slots < 0) {

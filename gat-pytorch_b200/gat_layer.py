@@ -34,8 +34,8 @@ def gemm(ta: bool, tb: bool, m: int, n: int, k: int, a, lda, b, ldb, c, ldc, alg
     dev = c.device
     ws_bytes = int(lib.gat_gemm_workspace_bytes(int(ta), int(tb), m, n, k, algo))
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev) if ws_bytes else None
-    _lib.check(lib.gat_gemm(int(ta), int(tb), m, n, k, a.data_ptr(), lda, b.data_ptr(), ldb, c.data_ptr(), ldc,
-                            algo, _ptr(ws), ws_bytes, _stream(dev)), "gat_gemm")
+    _lib.call("gat_gemm", int(ta), int(tb), m, n, k, a.data_ptr(), lda, b.data_ptr(), ldb, c.data_ptr(), ldc,
+              algo, _ptr(ws), ws_bytes, _stream(dev), tag=(int(ta), int(tb), m, n, k))
 
 
 class _GATFunction(torch.autograd.Function):
@@ -58,11 +58,11 @@ class _GATFunction(torch.autograd.Function):
             if not const_attention:
                 s_src = torch.empty((n, nh), **f32)
                 s_tgt = torch.empty((n, nh), **f32)
-                _lib.check(lib.gat_scores_fwd(wh.data_ptr(), n, dp, a_src_p.data_ptr(), a_tgt_p.data_ptr(), nh,
-                                              s_src.data_ptr(), s_tgt.data_ptr(), s), "gat_scores_fwd")
+                _lib.call("gat_scores_fwd", wh.data_ptr(), n, dp, a_src_p.data_ptr(), a_tgt_p.data_ptr(), nh,
+                                              s_src.data_ptr(), s_tgt.data_ptr(), s)
                 gmax = torch.full((1,), float("-inf"), **f32)
-                _lib.check(lib.gat_edge_max(st.rowptr.data_ptr(), st.col.data_ptr(), n, s_src.data_ptr(),
-                                            s_tgt.data_ptr(), nh, gmax.data_ptr(), s), "gat_edge_max")
+                _lib.call("gat_edge_max", st.rowptr.data_ptr(), st.col.data_ptr(), n, s_src.data_ptr(),
+                                            s_tgt.data_ptr(), nh, gmax.data_ptr(), s)
             out_p = torch.empty((n, dp), **f32)
             alpha = torch.empty((st.n_edges, nh), **f32) if want_alpha else None
             z = torch.empty((n, nh), **f32)
@@ -73,15 +73,14 @@ class _GATFunction(torch.autograd.Function):
             seed = 0
             if p_drop > 0.0:
                 seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator: no device sync
-            _lib.check(lib.gat_edge_fwd(st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), n,
+            _lib.call("gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), n,
                                         wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax),
                                         int(const_attention), float(p_drop), seed, 0,
                                         out_p.data_ptr(), _ptr(alpha), z.data_ptr(),
-                                        _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), s), "gat_edge_fwd")
+                                        _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), s, tag=(nh, fp))
             if fp != f or not concat:
                 out = torch.empty((n, nh * f if concat else f), **f32)
-                _lib.check(lib.gat_head_merge_fwd(out_p.data_ptr(), n, nh, f, fp, int(concat), out.data_ptr(), s),
-                           "gat_head_merge_fwd")
+                _lib.call("gat_head_merge_fwd", out_p.data_ptr(), n, nh, f, fp, int(concat), out.data_ptr(), s)
             else:
                 out = out_p
         ctx.st, ctx.cfg = st, (nh, f, fp, concat, const_attention, float(p_drop), seed, gemm_algo)
@@ -109,8 +108,7 @@ class _GATFunction(torch.autograd.Function):
                 grad_alpha = grad_alpha.contiguous()
             if fp != f or not concat:
                 go_p = torch.empty((n, dp), **f32)
-                _lib.check(lib.gat_head_merge_bwd(grad_out.data_ptr(), n, nh, f, fp, int(concat), go_p.data_ptr(), s),
-                           "gat_head_merge_bwd")
+                _lib.call("gat_head_merge_bwd", grad_out.data_ptr(), n, nh, f, fp, int(concat), go_p.data_ptr(), s)
             else:
                 go_p = grad_out
             rec = torch.empty((st.n_edges, 2 * nh), **f32)
@@ -121,16 +119,16 @@ class _GATFunction(torch.autograd.Function):
                 ds_tgt = torch.empty((n, nh), **f32)
             ws_bytes = int(lib.gat_edge_bwd_workspace_bytes(n, st.n_edges, nh))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            _lib.check(lib.gat_edge_bwd_dst(st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), n,
+            _lib.call("gat_edge_bwd_dst", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), n,
                                             wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax), z.data_ptr(),
                                             int(const_attention), p_drop, seed, 0,
                                             go_p.data_ptr(), _ptr(grad_alpha), rec.data_ptr(), _ptr(ds_tgt),
-                                            ws.data_ptr(), ws_bytes, s), "gat_edge_bwd_dst")
-            _lib.check(lib.gat_edge_bwd_src(st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), n,
+                                            ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+            _lib.call("gat_edge_bwd_src", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), n,
                                             nh, fp, rec.data_ptr(), go_p.data_ptr(), _ptr(a_src_p), _ptr(a_tgt_p),
                                             int(const_attention), _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total),
-                                            _ptr(ds_src), _ptr(ds_tgt), d_wh.data_ptr(),
-                                            ws.data_ptr(), ws_bytes, s), "gat_edge_bwd_src")
+                                            None, 0, n, _ptr(ds_src), _ptr(ds_tgt), d_wh.data_ptr(),
+                                            ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
             gx = gw = ga_src = ga_tgt = None
             if ctx.needs_input_grad[0]:
                 gx = torch.empty((n, f_in), **f32)

@@ -56,7 +56,7 @@ def build_structure(edge_index: torch.Tensor, n_nodes: int, add_self_loops: bool
     with torch.cuda.device(dev):
         st = _stream(dev)
         stats = torch.empty(3, dtype=torch.int64, device=dev)
-        _lib.check(lib.gat_edges_scan(ei.data_ptr(), n_in, ei.stride(0), is64, stats.data_ptr(), st), "gat_edges_scan")
+        _lib.call("gat_edges_scan", ei.data_ptr(), n_in, ei.stride(0), is64, stats.data_ptr(), st)
         n_idx, n_keep, vmin = (int(v) for v in stats.tolist())   # the one host sync per new graph
         if vmin < 0:
             raise IndexError("edge_index contains negative node ids")
@@ -70,11 +70,11 @@ def build_structure(edge_index: torch.Tensor, n_nodes: int, add_self_loops: bool
         ei_out = torch.empty((2, n_out), dtype=torch.int64, device=dev) if add_self_loops else None
         ws_bytes = int(lib.gat_csr_workspace_bytes(n_in, n_out, n_nodes))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-        _lib.check(lib.gat_csr_build(ei.data_ptr(), n_in, ei.stride(0), is64, int(add_self_loops), n_idx, n_out, n_nodes,
+        _lib.call("gat_csr_build", ei.data_ptr(), n_in, ei.stride(0), is64, int(add_self_loops), n_idx, n_out, n_nodes,
                                      ei_out.data_ptr() if ei_out is not None else None,
                                      rowptr.data_ptr(), col.data_ptr(), eid.data_ptr(),
                                      rowptr_t.data_ptr(), col_t.data_ptr(), pos_t.data_ptr(),
-                                     ws.data_ptr(), ws_bytes, st), "gat_csr_build")
+                                     ws.data_ptr(), ws_bytes, st)
     if ei_out is None:
         ei_ret = edge_index
     else:

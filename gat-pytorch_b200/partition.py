@@ -1,0 +1,289 @@
+"""Destination-range partitioned GAT layer: one process per GPU, torch.distributed for the plumbing.
+
+New functionality defined by BASELINE.json (the reference is single-device):
+nodes are range-partitioned by DESTINATION over the ranks of one box; rank r owns rows
+[lo, hi) = [r*R, min((r+1)*R, N)), R = ceil(N/P): its slice of x, the CSR rows of its targets (global
+source ids) and the transposed CSR of ITS edges.  W and a are replicated.  Per layer:
+
+  forward   local GEMM -> Wh[lo:hi], s_src[lo:hi], s_tgt[lo:hi]
+            ALL-GATHER   Wh and s_src  -> (P*R, .) on every rank          (the one exchange step)
+            ALL-REDUCE(max) of the logit max M (mandatory: the softmax is not shift invariant)
+            local fused edge kernel over the owned rows
+  backward  local dst pass; ALL-REDUCE(sum) of (Gamma, |T|) for the gradient through max()
+            local src pass -> partial dWh for ALL sources; REDUCE-SCATTER(sum) to the owners
+            local GEMMs; ALL-REDUCE(sum) of dW, dA_src, dA_tgt
+
+The forward is bit-identical to the single-GPU forward (same rows, same edge order inside a row, same
+M); parameter gradients agree to fp32 reduction-order noise.  Equal node ranges are used so that the
+all-gather is uniform; with the id-permuted synthetic graphs this is also edge-balanced.
+
+The numerical work goes through a `backend` object with one method per C-ABI entry point.  The product
+backend is `CudaBackend` (libgat_b200.so; raises without CUDA).  tests/ inject an oracle-based backend to
+exercise the partition plan and the collective choreography on CPU with gloo, world_size 2.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import _lib
+from .graph import build_structure
+
+
+@dataclass
+class Plan:
+    world: int
+    rank: int
+    n: int            # global node count
+    rows_per_rank: int
+    lo: int
+    hi: int
+
+    @property
+    def n_pad(self) -> int:
+        return self.rows_per_rank * self.world
+
+    @property
+    def rows(self) -> int:
+        return self.hi - self.lo
+
+
+def make_plan(n: int, world: int, rank: int) -> Plan:
+    r = (n + world - 1) // world
+    return Plan(world, rank, n, r, min(rank * r, n), min((rank + 1) * r, n))
+
+
+def local_edge_list(edge_index: torch.Tensor, n_idx: int, lo: int, hi: int, add_self_loops: bool = True) -> torch.Tensor:
+    """The sub-sequence of the REWRITTEN edge list (utils.py:47-67) whose target lies in [lo, hi): kept
+    edges in input order, then the loops (k,k) for k in [lo, min(hi, n_idx)).  Rows of the resulting CSR
+    are therefore identical, edge for edge, to the same rows of the global CSR."""
+    src, dst = edge_index[0], edge_index[1]
+    keep = (dst >= lo) & (dst < hi)
+    if add_self_loops:
+        keep &= src != dst
+        loops = torch.arange(lo, max(min(hi, n_idx), lo), dtype=edge_index.dtype, device=edge_index.device)
+        return torch.cat([edge_index[:, keep], torch.stack([loops, loops])], dim=1)
+    return edge_index[:, keep]
+
+
+# ----------------------------------------------------------------------------------------------
+# product backend: the C ABI
+# ----------------------------------------------------------------------------------------------
+class CudaBackend:
+    """One method per entry point of include/gat_b200.h; tensors in, tensors out."""
+
+    def __init__(self, gemm_algo: int = 0):
+        self.gemm_algo = gemm_algo
+        self.lib = _lib.load()
+
+    @staticmethod
+    def _s(dev):
+        return torch.cuda.current_stream(dev).cuda_stream
+
+    def build_structure(self, edges_local, n_global):
+        return build_structure(edges_local.contiguous(), n_global, False)
+
+    def n_edges(self, st):
+        return st.n_edges
+
+    def gemm(self, ta, tb, m, n, k, a, lda, b, ldb, c, ldc):
+        from .gat_layer import gemm
+        gemm(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, self.gemm_algo)
+
+    def scores(self, wh, rows, dp, a_src, a_tgt, nh, s_src, s_tgt):
+        _lib.call("gat_scores_fwd", wh.data_ptr(), rows, dp, a_src.data_ptr(), a_tgt.data_ptr(), nh,
+                  s_src.data_ptr(), s_tgt.data_ptr(), self._s(wh.device))
+
+    def edge_max(self, st, plan, s_src_full, s_tgt_local, nh, gmax):
+        _lib.call("gat_edge_max", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), plan.rows,
+                  s_src_full.data_ptr(), s_tgt_local.data_ptr(), nh, gmax.data_ptr(), self._s(gmax.device))
+
+    def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total):
+        p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
+        _lib.call("gat_edge_fwd", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(), plan.rows,
+                  wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(), s_tgt_local.data_ptr(), gmax.data_ptr(),
+                  0, 0.0, 0, 0, out_p.data_ptr(), None, z.data_ptr(), p(tie_dst), p(tie_src), p(tie_total),
+                  self._s(out_p.device), tag=(nh, fp))
+
+    def edge_bwd_dst(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z, go_p, rec, ds_tgt):
+        ws_bytes = int(self.lib.gat_edge_bwd_workspace_bytes(plan.rows, st.n_edges, nh))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=go_p.device)
+        _lib.call("gat_edge_bwd_dst", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(), plan.rows,
+                  wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(), s_tgt_local.data_ptr(), gmax.data_ptr(), z.data_ptr(),
+                  0, 0.0, 0, 0, go_p.data_ptr(), None, rec.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes,
+                  self._s(go_p.device), tag=(nh, fp))
+        gamma = torch.empty(1, dtype=torch.float64, device=go_p.device)
+        _lib.call("gat_edge_bwd_gamma", ws.data_ptr(), ws_bytes, gamma.data_ptr(), self._s(go_p.device))
+        return gamma
+
+    def edge_bwd_src(self, st, plan, nh, fp, rec, go_p, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
+        dp = nh * fp
+        ws_bytes = int(self.lib.gat_edge_bwd_workspace_bytes(plan.n, st.n_edges, nh))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=go_p.device)
+        go_base = go_p.data_ptr() - 4 * dp * plan.lo       # col_t holds GLOBAL target ids, all in [lo, hi)
+        _lib.call("gat_edge_bwd_src", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), plan.n,
+                  nh, fp, rec.data_ptr(), go_base, a_src.data_ptr(), a_tgt.data_ptr(), 0,
+                  tie_dst.data_ptr(), tie_src.data_ptr(), None, corr.data_ptr(), plan.lo, plan.hi,
+                  ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(), ws.data_ptr(), ws_bytes,
+                  self._s(go_p.device), tag=(nh, fp))
+
+
+# ----------------------------------------------------------------------------------------------
+# the partitioned layer
+# ----------------------------------------------------------------------------------------------
+class _PartitionedGATFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_local, w_p, a_src_p, a_tgt_p, st, plan: Plan, nh, fp, backend, group):
+        dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
+        rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
+        wh_slab = torch.zeros((R, dp), **f32)
+        s_src_slab = torch.zeros((R, nh), **f32)
+        s_tgt = torch.empty((max(rows, 1), nh), **f32)
+        if rows:
+            backend.gemm(False, True, rows, dp, f_in, x_local, x_local.stride(0), w_p, w_p.stride(0), wh_slab, dp)
+            backend.scores(wh_slab, rows, dp, a_src_p, a_tgt_p, nh, s_src_slab, s_tgt)
+        wh_full = torch.empty((plan.n_pad, dp), **f32)
+        s_src_full = torch.empty((plan.n_pad, nh), **f32)
+        dist.all_gather_into_tensor(wh_full, wh_slab, group=group)          # the feature exchange (NVLink)
+        dist.all_gather_into_tensor(s_src_full, s_src_slab, group=group)
+        gmax = torch.full((1,), float("-inf"), **f32)
+        if rows:
+            backend.edge_max(st, plan, s_src_full, s_tgt, nh, gmax)
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)            # ONE global max, gat_layer.py:85
+        out_p = torch.zeros((max(rows, 1), dp), **f32)[:rows]
+        z = torch.zeros((max(rows, 1), nh), **f32)
+        ties = torch.zeros(2 + max(rows, 1) * nh + plan.n_pad * nh, dtype=torch.int32, device=dev)
+        tie_total, tie_dst, tie_src = ties[:2], ties[2:2 + max(rows, 1) * nh], ties[2 + max(rows, 1) * nh:]
+        if rows:
+            backend.edge_fwd(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, out_p, z, tie_dst, tie_src, tie_total)
+        ctx.misc = (st, plan, nh, fp, backend, group)
+        ctx.save_for_backward(x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total)
+        return out_p
+
+    @staticmethod
+    def backward(ctx, go_p):
+        x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total = ctx.saved_tensors
+        st, plan, nh, fp, backend, group = ctx.misc
+        dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
+        rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
+        go_p = go_p.contiguous()
+        rec = torch.empty((max(backend.n_edges(st), 1), 2 * nh), **f32)
+        ds_tgt = torch.zeros((max(rows, 1), nh), **f32)
+        gamma = torch.zeros(1, dtype=torch.float64, device=dev)
+        if rows:
+            gamma = backend.edge_bwd_dst(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, rec, ds_tgt)
+        red = torch.stack([gamma[0], tie_total.view(torch.int64)[0].to(torch.float64)])
+        dist.all_reduce(red, group=group)                                   # (Gamma, |T|) over ranks
+        corr = torch.where(red[1] > 0, red[0] / red[1].clamp(min=1.0), torch.zeros_like(red[0])).to(torch.float32).reshape(1)
+        d_wh_part = torch.zeros((plan.n_pad, dp), **f32)
+        ds_src_part = torch.zeros((plan.n_pad, nh), **f32)
+        backend.edge_bwd_src(st, plan, nh, fp, rec, go_p, a_src_p, a_tgt_p, tie_dst, tie_src, corr, ds_src_part, ds_tgt, d_wh_part)
+        d_wh = torch.empty((R, dp), **f32)
+        dist.reduce_scatter_tensor(d_wh, d_wh_part, group=group)            # transpose of the all-gather
+        gx = None
+        if ctx.needs_input_grad[0] and rows:
+            gx = torch.empty((rows, f_in), **f32)
+            backend.gemm(False, False, rows, f_in, dp, d_wh, dp, w_p, w_p.stride(0), gx, f_in)
+        elif ctx.needs_input_grad[0]:
+            gx = torch.zeros((0, f_in), **f32)
+        gw = torch.zeros((dp, f_in), **f32)
+        ga_src = torch.zeros((nh, dp), **f32)
+        ga_tgt = torch.zeros((nh, dp), **f32)
+        if rows:
+            backend.gemm(True, False, dp, f_in, rows, d_wh, dp, x_local, x_local.stride(0), gw, f_in)
+            backend.gemm(True, False, nh, dp, rows, ds_tgt, nh, wh_full[plan.lo:], dp, ga_tgt, dp)
+        backend.gemm(True, False, nh, dp, plan.n, ds_src_part, nh, wh_full, dp, ga_src, dp)
+        flat = torch.cat([gw.reshape(-1), ga_src.reshape(-1), ga_tgt.reshape(-1)])
+        dist.all_reduce(flat, group=group)                                  # the gradient all-reduce
+        gw, ga_src, ga_tgt = flat[:gw.numel()].view_as(gw), flat[gw.numel():gw.numel() + ga_src.numel()].view_as(ga_src), \
+            flat[gw.numel() + ga_src.numel():].view_as(ga_tgt)
+        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None
+
+
+class PartitionedGATLayer(torch.nn.Module):
+    """`GATLayer` semantics (add_self_loops=True, dropout 0, attention not returned) for one rank's rows.
+    forward(x_local, st, plan) -> out_local.  Parameters are replicated; their .grad is the global sum."""
+
+    def __init__(self, in_features, out_features, num_heads, concat, backend=None, group=None):
+        super().__init__()
+        self.in_features, self.out_features, self.num_heads, self.concat = in_features, out_features, num_heads, concat
+        self.W = torch.nn.Linear(in_features, num_heads * out_features, bias=False)
+        self.a = torch.nn.Linear(num_heads * 2 * out_features, num_heads, bias=False)
+        torch.nn.init.xavier_uniform_(self.W.weight)
+        torch.nn.init.xavier_uniform_(self.a.weight)
+        self.backend, self.group = backend, group
+
+    def _padded_operands(self):
+        nh, f = self.num_heads, self.out_features
+        fp = (f + 3) // 4 * 4
+        w = self.W.weight
+        if fp != f:
+            w = F.pad(w.view(nh, f, self.in_features), (0, 0, 0, fp - f)).reshape(nh * fp, self.in_features)
+        a3 = self.a.weight.view(nh, nh, 2 * f)
+        a_src, a_tgt = a3[:, :, :f], a3[:, :, f:]
+        if fp != f:
+            a_src, a_tgt = F.pad(a_src, (0, fp - f)), F.pad(a_tgt, (0, fp - f))
+        return w, a_src.reshape(nh, nh * fp).contiguous(), a_tgt.reshape(nh, nh * fp).contiguous(), fp
+
+    def forward(self, x_local, st, plan: Plan):
+        if self.backend is None:
+            self.backend = CudaBackend()
+        w_p, a_src, a_tgt, fp = self._padded_operands()
+        nh, f = self.num_heads, self.out_features
+        out_p = _PartitionedGATFunction.apply(x_local.contiguous(), w_p, a_src, a_tgt, st, plan, nh, fp, self.backend, self.group)
+        o = out_p.view(-1, nh, fp)[:, :, :f]
+        return o.reshape(-1, nh * f) if self.concat else o.mean(dim=1)      # gat_layer.py:129-132
+
+
+class PartitionedGAT:
+    """bench.py's multi-GPU model: the stacked layers of one config over a partitioned graph."""
+
+    def __init__(self, shapes, weights, x_host, ei_host, dev, backend=None):
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.dev, self.x_host, self.ei_host = dev, x_host, ei_host
+        self.plan = make_plan(x_host.size(0), self.world, self.rank)
+        self.backend = backend or CudaBackend()
+        self.layers = []
+        for (f_in, nh, f, concat), (w, a) in zip(shapes, weights):
+            layer = PartitionedGATLayer(f_in, f, nh, concat, self.backend).to(dev)
+            with torch.no_grad():
+                layer.W.weight.copy_(torch.as_tensor(w))
+                layer.a.weight.copy_(torch.as_tensor(a))
+            self.layers.append(layer)
+        self.x_local_host = x_host[self.plan.lo:self.plan.hi].contiguous()
+        if x_host.is_pinned():
+            self.x_local_host = self.x_local_host.pin_memory()
+        self.x_local, self.st = self._upload()
+        counts = torch.tensor([self.backend.n_edges(self.st)], dtype=torch.int64, device=dev)
+        dist.all_reduce(counts)
+        self.n_edges_local, self.n_edges_global, self.n_local = self.backend.n_edges(self.st), int(counts.item()), self.plan.rows
+
+    def _upload(self):
+        x_local = self.x_local_host.to(self.dev, non_blocking=True)
+        ei = self.ei_host.to(self.dev, non_blocking=True)
+        n_idx = int(ei.max().item()) + 1
+        local = local_edge_list(ei, n_idx, self.plan.lo, self.plan.hi, True)
+        return x_local, self.backend.build_structure(local, self.plan.n)
+
+    def _fwd_bwd(self, x_local, st):
+        h = x_local
+        for i, layer in enumerate(self.layers):
+            layer.W.weight.grad = layer.a.weight.grad = None
+            h = layer(h, st, self.plan)
+            if i != len(self.layers) - 1:
+                h = F.elu(h)
+        loss = h.square().sum() / (self.plan.n * h.size(1))     # this rank's share of the global mean
+        loss.backward()
+        return loss
+
+    def step_resident(self):
+        return self._fwd_bwd(self.x_local, self.st)
+
+    def step_e2e(self):
+        x_local, st = self._upload()
+        loss = self._fwd_bwd(x_local, st).detach().clone()
+        dist.all_reduce(loss)
+        return float(loss.item())

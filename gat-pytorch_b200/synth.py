@@ -36,14 +36,19 @@ SKIP = {
 DROPOUT = {"cora": 0.6, "citeseer": 0.6, "pubmed": 0.6, "ppi": 0.0, "pattern": 0.0, "products": 0.0}
 
 
+def _powerlaw_ranks(rng, n, size, exponent, offset):
+    """Ranks in [0, n) with density ~ (rank+offset)^-exponent: analytic inverse CDF of the continuous
+    power law on [offset, n+offset), floored (no O(n) table, so 3e7 draws take well under a second)."""
+    a, b, q = float(offset), float(n + offset), 1.0 - exponent
+    t = (rng.random(size) * (b ** q - a ** q) + a ** q) ** (1.0 / q)
+    return np.clip((t - a).astype(np.int64), 0, n - 1)
+
+
 def _symmetric_powerlaw_pairs(rng, n, n_pairs, exponent, offset):
-    """Chung-Lu style undirected pairs: endpoints drawn with probability ~ (rank+offset)^-exponent."""
-    w = (np.arange(n, dtype=np.float64) + offset) ** (-exponent)
-    cdf = np.cumsum(w)
-    cdf /= cdf[-1]
+    """Chung-Lu style undirected pairs: both endpoints drawn with probability ~ (rank+offset)^-exponent."""
     perm = rng.permutation(n)  # decouple degree from node id
-    u = perm[np.searchsorted(cdf, rng.random(n_pairs), side="right").clip(0, n - 1)]
-    v = perm[np.searchsorted(cdf, rng.random(n_pairs), side="right").clip(0, n - 1)]
+    u = perm[_powerlaw_ranks(rng, n, n_pairs, exponent, offset)]
+    v = perm[_powerlaw_ranks(rng, n, n_pairs, exponent, offset)]
     clash = u == v
     v[clash] = (v[clash] + 1 + rng.integers(0, n - 1, size=int(clash.sum()))) % n
     return u.astype(np.int64), v.astype(np.int64)
@@ -52,9 +57,10 @@ def _symmetric_powerlaw_pairs(rng, n, n_pairs, exponent, offset):
 def _directed_both_ways(u, v, n, sort=True):
     src = np.concatenate([u, v])
     dst = np.concatenate([v, u])
-    if sort:  # PyG datasets are coalesced: ordered by (src, dst)
-        order = np.argsort(src * np.int64(n) + dst, kind="stable")
-        src, dst = src[order], dst[order]
+    if sort:  # PyG datasets are coalesced: ordered by (src, dst); duplicates are kept
+        key = src * np.int64(n) + dst
+        key.sort()
+        src, dst = key // np.int64(n), key % np.int64(n)
     return np.stack([src, dst]).astype(np.int64)
 
 

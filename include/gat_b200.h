@@ -42,6 +42,8 @@ typedef void* gat_stream_t; /* cudaStream_t */
 
 GAT_API int gat_version(void);
 GAT_API const char* gat_last_error(void);
+/* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
+GAT_API unsigned long long gat_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * Kernel 1 -- edge_index -> rewritten edge list + destination-sorted CSR + transposed CSR.
@@ -145,13 +147,21 @@ GAT_API int gat_edge_bwd_dst(const int32_t* rowptr, const int32_t* col, const in
 /* Source pass (transposed CSR): d_wh[j,h,:] = sum_e m*alpha*go[dst_e,h,:]; ds_src = sum g; applies the
  * arg-max correction Gamma/|T| (Gamma reduced from the dst-pass partials in `workspace`) to ds_src
  * and ds_tgt via the tie counts; then adds ds_src*A_src + ds_tgt*A_tgt so that d_wh is the total
- * gradient of Wh.  ds_src/ds_tgt (n, nh) hold the corrected values on exit. */
+ * gradient of Wh.  ds_src/ds_tgt (n, nh) hold the corrected values on exit.
+ * Rows are SOURCE nodes 0..n-1.  [tgt_lo, tgt_hi) is the range of nodes this call also owns as targets:
+ * ds_tgt and tie_dst have tgt_hi - tgt_lo rows and only those rows receive the ds_tgt*A_tgt term. */
 GAT_API int gat_edge_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, int64_t n,
                      int nh, int fp, const float* rec, const float* go_padded,
                      const float* a_src, const float* a_tgt, int const_attention,
                      const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                     const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
                      float* ds_src, float* ds_tgt, float* d_wh,
                      void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
+/* Partitioned graphs only: *gamma_out = this rank's sum of g (fixed-order reduction of the dst-pass partials).
+ * The caller all-reduces gamma and tie_total over ranks and hands Gamma/|T| to gat_edge_bwd_src as
+ * `corr_override` (a device scalar).  On one GPU pass corr_override = NULL, tgt_lo = 0, tgt_hi = n. */
+GAT_API int gat_edge_bwd_gamma(void* workspace, size_t workspace_bytes, double* gamma_out, gat_stream_t stream);
 
 #ifdef __cplusplus
 }

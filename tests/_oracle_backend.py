@@ -1,0 +1,83 @@
+"""CPU stand-in for the C-ABI backend of gat-pytorch_b200/partition.py -- TEST INFRASTRUCTURE.
+
+Implements each backend method with dense torch/numpy maths in the reference's formulation (per-edge
+gather / scatter), so the gloo world_size-2 test can exercise the partition plan and the collective
+choreography without a GPU.  Mirrors the semantics documented in include/gat_b200.h.
+"""
+import torch
+
+SLOPE, EPS = 0.01, 1e-8
+
+
+class OracleBackend:
+    def build_structure(self, edges_local, n_global):
+        return {"src": edges_local[0].long(), "dst": edges_local[1].long(), "n": n_global}
+
+    def n_edges(self, st):
+        return int(st["src"].numel())
+
+    def gemm(self, ta, tb, m, n, k, a, lda, b, ldb, c, ldc):
+        a2 = a.reshape(-1)[: (k if ta else m) * lda].view(-1, lda)
+        b2 = b.reshape(-1)[: (n if tb else k) * ldb].view(-1, ldb)
+        A = a2[:k, :m].T if ta else a2[:m, :k]
+        B = b2[:n, :k].T if tb else b2[:k, :n]
+        c.reshape(-1)[: m * ldc].view(-1, ldc)[:m, :n] = (A.double() @ B.double()).float()
+
+    def scores(self, wh, rows, dp, a_src, a_tgt, nh, s_src, s_tgt):
+        s_src[:rows] = (wh[:rows].double() @ a_src.double().T).float()
+        s_tgt[:rows] = (wh[:rows].double() @ a_tgt.double().T).float()
+
+    def _logits(self, st, plan, s_src_full, s_tgt_local):
+        return s_src_full[st["src"]] + s_tgt_local[st["dst"] - plan.lo]
+
+    def edge_max(self, st, plan, s_src_full, s_tgt_local, nh, gmax):
+        l = self._logits(st, plan, s_src_full, s_tgt_local)
+        if l.numel():
+            gmax[0] = torch.maximum(gmax[0], l.max())
+
+    def _alpha(self, st, plan, s_src_full, s_tgt_local, gmax, rows, nh):
+        l = self._logits(st, plan, s_src_full, s_tgt_local)
+        t = l - gmax
+        p = torch.exp(torch.where(t >= 0, t, t * SLOPE))
+        z = torch.zeros((rows, nh)).index_add_(0, st["dst"] - plan.lo, p)
+        return l, p, z
+
+    def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total):
+        rows = plan.rows
+        l, p, zz = self._alpha(st, plan, s_src_full, s_tgt_local, gmax, rows, nh)
+        z[:rows] = zz
+        alpha = p / (zz[st["dst"] - plan.lo] + EPS)
+        msg = alpha[:, :, None] * wh_full[st["src"]].view(-1, nh, fp)
+        out_p.zero_()
+        out_p.view(-1, nh, fp).index_add_(0, st["dst"] - plan.lo, msg)
+        tie = (l == gmax).to(torch.int32)
+        tie_dst.view(-1, nh).index_add_(0, st["dst"] - plan.lo, tie)
+        tie_src.view(-1, nh).index_add_(0, st["src"], tie)
+        tie_total.view(torch.int64)[0] = int(tie.sum())
+
+    def edge_bwd_dst(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z, go_p, rec, ds_tgt):
+        rows = plan.rows
+        dl = st["dst"] - plan.lo
+        l, p, _ = self._alpha(st, plan, s_src_full, s_tgt_local, gmax, rows, nh)
+        alpha = p / (z[:rows][dl] + EPS)
+        d_alpha = (go_p.view(-1, nh, fp)[dl] * wh_full[st["src"]].view(-1, nh, fp)).sum(-1)
+        s = torch.zeros((rows, nh)).index_add_(0, dl, alpha * d_alpha)
+        g = SLOPE * alpha * (d_alpha - s[dl])
+        rec[: g.size(0), :nh] = g
+        rec[: g.size(0), nh:] = alpha
+        ds_tgt.zero_()
+        ds_tgt[:rows].index_add_(0, dl, g)
+        return g.double().sum().reshape(1)
+
+    def edge_bwd_src(self, st, plan, nh, fp, rec, go_p, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
+        e = st["src"].numel()
+        g, w = rec[:e, :nh], rec[:e, nh:]
+        dl = st["dst"] - plan.lo
+        d_wh.zero_()
+        d_wh.view(-1, nh, fp).index_add_(0, st["src"], w[:, :, None] * go_p.view(-1, nh, fp)[dl])
+        ds_src.zero_()
+        ds_src.index_add_(0, st["src"], g)
+        ds_src -= tie_src.view(-1, nh).float() * corr
+        ds_tgt[: plan.rows] -= tie_dst.view(-1, nh)[: plan.rows].float() * corr
+        d_wh += ds_src @ a_src
+        d_wh[plan.lo:plan.hi] += ds_tgt[: plan.rows] @ a_tgt

@@ -173,8 +173,10 @@ def test_dropout_statistics_and_backward_mask(small_cases):
         for _ in range(reps):
             acc += layer(x, ei)
     mean = (acc / reps).cpu().numpy()
-    err = np.abs(mean - fw["out"]).mean() / np.abs(fw["out"]).mean()
-    assert err < 0.08, err
+    # per-element noise of a 200-sample mean at p=0.6 is ~sqrt(p/(1-p)/reps) ~ 9 %; the BIAS must vanish
+    noise = np.abs(mean - fw["out"]).mean() / np.abs(fw["out"]).mean()
+    bias = abs((mean - fw["out"]).sum()) / np.abs(fw["out"]).sum()
+    assert noise < 0.2 and bias < 0.01, (noise, bias)
 
 
 def test_dropout_gradient_uses_forward_mask():

@@ -1,0 +1,128 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/gat_b200.h
+declares, the drop-in module mirrors the reference's constructor contract, the product path refuses
+to run without CUDA, and the synthetic generators are deterministic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gat_b200.h")).read()
+    return sorted(set(re.findall(r"GAT_API\s+[\w\s\*]+?\b(gat_\w+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for must in ["gat_edges_scan", "gat_csr_build", "gat_gemm", "gat_scores_fwd", "gat_edge_max", "gat_edge_fwd",
+                 "gat_edge_bwd_dst", "gat_edge_bwd_src", "gat_last_error", "gat_version"]:
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from gat_pytorch_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), s
+    bound = _lib.load()
+    assert set(_lib.SIGNATURES) == set(declared_symbols())
+    assert bound.gat_version() >= 100
+    assert bound.gat_last_error() is not None
+
+
+def test_constructor_contract_matches_reference():
+    """Reference: models/gat_layer.py:13-40 -- attribute names, sub-modules, state_dict keys and init RNG order."""
+    from gat_pytorch_b200 import GATLayer
+    torch.manual_seed(0)
+    layer = GATLayer(in_features=10, out_features=3, num_heads=4, concat=True, dropout=0.5, add_self_loops=True, bias=True)
+    assert list(layer.state_dict().keys()) == ["bias_param", "W.weight", "a.weight"]
+    assert layer.W.weight.shape == (12, 10) and layer.a.weight.shape == (4, 24) and layer.bias_param.shape == (12,)
+    assert isinstance(layer.dropout_layer, torch.nn.Dropout) and layer.normalised_attention_coeffs is None
+    for attr in ["in_features", "out_features", "num_heads", "concat", "dropout", "add_self_loops", "bias", "const_attention", "device"]:
+        assert hasattr(layer, attr)
+    # same RNG stream as constructing Linear(W) then Linear(a) then xavier on both (gat_layer.py:27-40,142-147)
+    torch.manual_seed(0)
+    w = torch.nn.Linear(10, 12, bias=False)
+    a = torch.nn.Linear(24, 4, bias=False)
+    torch.nn.init.xavier_uniform_(w.weight)
+    torch.nn.init.xavier_uniform_(a.weight)
+    assert torch.equal(layer.W.weight, w.weight) and torch.equal(layer.a.weight, a.weight)
+    const = GATLayer(10, 3, 4, False, const_attention=True)
+    assert not hasattr(const, "a") and list(const.state_dict().keys()) == ["W.weight"]
+
+
+def test_checkpoint_weights_load():
+    """State-dict keys of the committed checkpoints load into the drop-in layer."""
+    from gat_pytorch_b200 import GATLayer
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ckpt_weights.npz"))
+    layer = GATLayer(1433, 8, 8, True, dropout=0.6, add_self_loops=True)
+    sd = {"W.weight": torch.from_numpy(z["Cora.gat_layer_list.0.W.weight"]), "a.weight": torch.from_numpy(z["Cora.gat_layer_list.0.a.weight"])}
+    layer.load_state_dict(sd, strict=True)
+
+
+def test_no_cpu_fallback():
+    from gat_pytorch_b200 import GATLayer, build_structure
+    layer = GATLayer(4, 2, 2, True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layer(torch.randn(3, 4), torch.zeros((2, 2), dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        build_structure(torch.zeros((2, 2), dtype=torch.long), 3, True)
+
+
+def test_product_path_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "gat-pytorch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "gat_oracle" not in text and "torch_port" not in text, fn
+
+
+def test_overlay_resolves_models_gat_layer():
+    import importlib
+    import sys
+    overlay = os.path.join(ROOT, "gat-pytorch_b200", "overlay")
+    sys.path.insert(0, overlay)
+    try:
+        sys.modules.pop("models", None)
+        sys.modules.pop("models.gat_layer", None)
+        mod = importlib.import_module("models.gat_layer")
+        from gat_pytorch_b200 import GATLayer
+        assert mod.GATLayer is GATLayer
+    finally:
+        sys.path.remove(overlay)
+        sys.modules.pop("models", None)
+        sys.modules.pop("models.gat_layer", None)
+
+
+def test_synth_is_deterministic_and_shaped():
+    from gat_pytorch_b200 import synth
+    x1, e1 = synth.cora()
+    x2, e2 = synth.cora()
+    assert np.array_equal(x1, x2) and np.array_equal(e1, e2)
+    assert x1.shape == (2708, 1433) and e1.shape == (2, 10556) and not np.any(e1[0] == e1[1])
+    assert set(np.unique(x1)) <= {0.0, 1.0}
+    xp, ep = synth.products(scale=1 / 512)
+    assert xp.shape[1] == 100 and ep.shape[0] == 2 and ep.max() < xp.shape[0]
+    # symmetric: every (u,v) has its (v,u)
+    fwd = set(map(tuple, ep.T[:2000].tolist()))
+    allp = set(map(tuple, ep.T.tolist()))
+    assert all((v, u) in allp for (u, v) in fwd)
+
+
+def test_torch_port_matches_oracle(small_cases):
+    """The CPU-baseline port (oracle/torch_port.py) computes what the oracle computes."""
+    import gat_oracle as O
+    import torch_port
+    case = small_cases["adv_concat"]
+    out, ei2, alpha = torch_port.layer_forward(torch.from_numpy(case["x"]), torch.from_numpy(case["edge_index"]),
+                                               torch.from_numpy(case["W"]), torch.from_numpy(case["a"]), case["nh"], case["f"], True, True)
+    fw = O.forward(case["x"], case["edge_index"], case["W"], case["a"], case["nh"], case["f"], True, True)
+    assert np.array_equal(ei2.numpy(), fw["edge_index"])
+    assert O.rel_err(out.numpy(), fw["out"]) < 1e-5 and O.rel_err(alpha.numpy(), fw["alpha"]) < 1e-5
