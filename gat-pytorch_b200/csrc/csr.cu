@@ -106,6 +106,24 @@ __global__ void gather_csrt_kernel(const int32_t* __restrict__ perm_t, const int
   }
 }
 
+// Scheduling order for the persistent edge kernels: rows longer than `thresh` first (in row order), then
+// the rest in row order.  Purely a performance hint -- results do not depend on it.
+__global__ void long_flag_kernel(const int32_t* __restrict__ rowptr, int64_t n, int thresh, int* __restrict__ flags) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r < n) flags[r] = (rowptr[r + 1] - rowptr[r]) > thresh;
+}
+
+__global__ void order_scatter_kernel(const int* __restrict__ flags, const int* __restrict__ scan, int64_t n,
+                                     int32_t* __restrict__ order) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int n_long = scan[n - 1] + flags[n - 1];
+  const int before = scan[r];
+  order[flags[r] ? before : n_long + (int)r - before] = (int32_t)r;
+}
+
+constexpr int kLongRowThreshold = 256;
+
 static int key_bits(int64_t n_nodes) {
   int b = 1;
   while (((int64_t)1 << b) < n_nodes) ++b;
@@ -115,17 +133,18 @@ static int key_bits(int64_t n_nodes) {
 struct CsrWorkspace {
   size_t off_src32, off_dst32, off_keys_out, off_iota, off_perm, off_slot, off_flags, off_pos, off_cub, cub_bytes, total;
 };
+static inline int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
 
 static int plan_workspace(int64_t e_in, int64_t e_out, int64_t n_nodes, CsrWorkspace* w) {
   size_t sort_bytes = 0, scan_bytes = 0;
   cudaError_t e1 = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
                                                   (const int32_t*)nullptr, (int32_t*)nullptr, (int)e_out, 0, key_bits(n_nodes));
-  cudaError_t e2 = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)e_in);
+  cudaError_t e2 = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)max64(e_in, n_nodes));
   if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
   size_t eb = (size_t)(e_out > 0 ? e_out : 1) * sizeof(int32_t);
-  size_t ib = (size_t)(e_in > 0 ? e_in : 1) * sizeof(int);
+  size_t ib = (size_t)(max64(max64(e_in, n_nodes), 1)) * sizeof(int);   // flags/pos also serve the row-order scan
   w->off_src32 = take(eb); w->off_dst32 = take(eb); w->off_keys_out = take(eb); w->off_iota = take(eb);
   w->off_perm = take(eb); w->off_slot = take(eb); w->off_flags = take(ib); w->off_pos = take(ib);
   w->cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
@@ -137,8 +156,8 @@ static int plan_workspace(int64_t e_in, int64_t e_out, int64_t n_nodes, CsrWorks
 template <typename T>
 static int csr_build_impl(const T* src, const T* dst, int64_t e_in, int add_self_loops, int64_t n_idx, int64_t e_out,
                           int64_t n_nodes, int64_t* ei_out, int32_t* rowptr, int32_t* col, int32_t* eid,
-                          int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t, char* ws, const CsrWorkspace& w,
-                          cudaStream_t st) {
+                          int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t, int32_t* row_order, int32_t* row_order_t,
+                          char* ws, const CsrWorkspace& w, cudaStream_t st) {
   int32_t* src32 = (int32_t*)(ws + w.off_src32);
   int32_t* dst32 = (int32_t*)(ws + w.off_dst32);
   int32_t* keys_out = (int32_t*)(ws + w.off_keys_out);
@@ -184,6 +203,18 @@ static int csr_build_impl(const T* src, const T* dst, int64_t e_in, int add_self
     gather_csrt_kernel<<<blocks(e_out), T256, 0, st>>>(perm, dst32, slot, e_out, col_t, pos_t);
     GAT_LAUNCH_CHECK();
   }
+  if (n_nodes > 0) {
+    const int32_t* rps[2] = {rowptr, rowptr_t};
+    int32_t* outs[2] = {row_order, row_order_t};
+    for (int i = 0; i < 2; ++i) {
+      if (!outs[i]) continue;
+      long_flag_kernel<<<blocks(n_nodes), T256, 0, st>>>(rps[i], n_nodes, kLongRowThreshold, flags);
+      GAT_LAUNCH_CHECK();
+      GAT_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flags, pos, (int)n_nodes, st));
+      order_scatter_kernel<<<blocks(n_nodes), T256, 0, st>>>(flags, pos, n_nodes, outs[i]);
+      GAT_LAUNCH_CHECK();
+    }
+  }
   return GAT_OK;
 }
 
@@ -220,6 +251,7 @@ extern "C" int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t
                              int add_self_loops, int64_t n_idx, int64_t n_edges_out, int64_t n_nodes,
                              int64_t* ei_out, int32_t* rowptr, int32_t* col, int32_t* eid,
                              int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t,
+                             int32_t* row_order, int32_t* row_order_t,
                              void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
   GAT_CHECK_ARG(n_edges_in >= 0 && n_edges_out >= 0 && n_nodes >= 0, "gat_csr_build: negative size");
@@ -240,9 +272,9 @@ extern "C" int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t
   if (index_is_int64) {
     const int64_t* p = (const int64_t*)edge_index;
     return csr_build_impl<int64_t>(p, p + row_stride, n_edges_in, add_self_loops, n_idx, n_edges_out, n_nodes, ei_out,
-                                   rowptr, col, eid, rowptr_t, col_t, pos_t, (char*)workspace, w, st);
+                                   rowptr, col, eid, rowptr_t, col_t, pos_t, row_order, row_order_t, (char*)workspace, w, st);
   }
   const int32_t* p = (const int32_t*)edge_index;
   return csr_build_impl<int32_t>(p, p + row_stride, n_edges_in, add_self_loops, n_idx, n_edges_out, n_nodes, ei_out,
-                                 rowptr, col, eid, rowptr_t, col_t, pos_t, (char*)workspace, w, st);
+                                 rowptr, col, eid, rowptr_t, col_t, pos_t, row_order, row_order_t, (char*)workspace, w, st);
 }

@@ -33,11 +33,13 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 }
 
 // Per-head dropout keep-scales of one edge (Philox keyed on the edge's position in the rewritten list).
+template <int NHT>
 __device__ __forceinline__ void dropout_scales(uint64_t seed, uint64_t offset, uint32_t edge, int nh, float p,
-                                               float (&m)[kMaxHeads]) {
+                                               float (&m)[NHT]) {
+  static_assert(NHT % 4 == 0, "head bound must be a multiple of 4");
   const float keep = 1.0f / (1.0f - p);
 #pragma unroll
-  for (int b = 0; b < kMaxHeads / 4; ++b) {
+  for (int b = 0; b < NHT / 4; ++b) {
     if (b * 4 < nh) {
       uint4 r = philox4x32(seed, offset, edge, (uint32_t)b);
       m[b * 4 + 0] = ((float)(r.x >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : keep;
@@ -61,6 +63,33 @@ __device__ __forceinline__ float atomic_max_float(float* addr, float value) {
                         : __uint_as_float(atomicMin((unsigned int*)addr, __float_as_uint(value)));
 }
 
+// Persistent-grid row scheduler.  Rows are handed out to WARPS from a global counter in the order given by
+// `order` (long rows first, built by gat_csr_build), so a hub row starts at t=0 and short rows fill in
+// behind it; which warp computes a row never changes the row's result, so the output stays deterministic.
+struct RowSched {
+  const int32_t* order;      // permutation of [0, n) or nullptr for natural order
+  unsigned int* counter;     // zeroed before the launch
+  int64_t n;
+};
+
+template <int G>
+__device__ __forceinline__ bool grab_rows(const RowSched& S, int lane, int64_t& base) {
+  constexpr int kRowsPerGrab = (32 / G) * (G == 32 ? 4 : 2);
+  __syncwarp();
+  unsigned int b = 0;
+  if (lane == 0) b = atomicAdd(S.counter, (unsigned int)kRowsPerGrab);
+  b = __shfl_sync(0xffffffffu, b, 0);
+  base = (int64_t)b;
+  return base < S.n;
+}
+
+template <int G>
+__device__ __forceinline__ int64_t sched_row(const RowSched& S, int64_t base, int k, int lane) {
+  const int64_t idx = base + (int64_t)k * (32 / G) + lane / G;
+  if (idx >= S.n) return -1;
+  return S.order ? (int64_t)__ldg(S.order + idx) : idx;
+}
+
 // Host-side choice of (G, SLOTS) for a padded row of `chunks` float4s.
 struct GroupShape { int g, slots; };
 static inline GroupShape pick_group(int chunks) {
@@ -80,19 +109,36 @@ static inline GroupShape pick_group(int chunks) {
   return s;
 }
 
-#define GAT_DISPATCH_GROUP(shape, LAUNCH)                                         \
+#define GAT_DISPATCH_GROUP_NHT(shape, NHT_, LAUNCH)                               \
   do {                                                                            \
-    if ((shape).g == 1) { LAUNCH(1, 1); }                                         \
-    else if ((shape).g == 2) { LAUNCH(2, 1); }                                    \
-    else if ((shape).g == 4) { LAUNCH(4, 1); }                                    \
-    else if ((shape).g == 8) { LAUNCH(8, 1); }                                    \
-    else if ((shape).g == 16) { LAUNCH(16, 1); }                                  \
-    else if ((shape).slots == 1) { LAUNCH(32, 1); }                               \
-    else if ((shape).slots == 2) { LAUNCH(32, 2); }                               \
-    else if ((shape).slots == 3) { LAUNCH(32, 3); }                               \
-    else if ((shape).slots == 4) { LAUNCH(32, 4); }                               \
-    else if ((shape).slots == 6) { LAUNCH(32, 6); }                               \
-    else { LAUNCH(32, 8); }                                                       \
+    if ((shape).g == 1) { LAUNCH(1, 1, NHT_); }                                   \
+    else if ((shape).g == 2) { LAUNCH(2, 1, NHT_); }                              \
+    else if ((shape).g == 4) { LAUNCH(4, 1, NHT_); }                              \
+    else if ((shape).g == 8) { LAUNCH(8, 1, NHT_); }                              \
+    else if ((shape).g == 16) { LAUNCH(16, 1, NHT_); }                            \
+    else if ((shape).slots == 1) { LAUNCH(32, 1, NHT_); }                         \
+    else if ((shape).slots == 2) { LAUNCH(32, 2, NHT_); }                         \
+    else if ((shape).slots == 3) { LAUNCH(32, 3, NHT_); }                         \
+    else if ((shape).slots == 4) { LAUNCH(32, 4, NHT_); }                         \
+    else if ((shape).slots == 6) { LAUNCH(32, 6, NHT_); }                         \
+    else { LAUNCH(32, 8, NHT_); }                                                 \
   } while (0)
+
+// NHT = compile-time bound on the head count (4 or 8): halves the per-head register arrays for NH <= 4.
+#define GAT_DISPATCH_GROUP(shape, nh, LAUNCH)                                     \
+  do {                                                                            \
+    if ((nh) <= 4) GAT_DISPATCH_GROUP_NHT(shape, 4, LAUNCH);                      \
+    else GAT_DISPATCH_GROUP_NHT(shape, 8, LAUNCH);                                \
+  } while (0)
+
+// Persistent grid: enough CTAs to fill every SM at the kernel's occupancy, never more than the work.
+template <typename K>
+static inline unsigned persistent_grid(K kernel, int threads, size_t dyn_smem, int64_t work_blocks) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  int64_t g = (int64_t)per_sm * kNumSMs;
+  if (g > work_blocks) g = work_blocks;
+  return (unsigned)(g < 1 ? 1 : g);
+}
 
 }  // namespace gat

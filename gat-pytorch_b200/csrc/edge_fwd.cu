@@ -39,10 +39,10 @@ edge_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 3: fused forward over destination rows.
+// Kernel 3: fused forward over destination rows (persistent grid, rows handed out per warp).
 // ------------------------------------------------------------------------------------------
 struct EdgeFwdParams {
-  const int32_t* rowptr; const int32_t* col; const int32_t* eid; int64_t n;
+  const int32_t* rowptr; const int32_t* col; const int32_t* eid; RowSched sched;
   const float* wh; int nh; int dp; int chunks; int chunks_per_head;
   const float* s_src; const float* s_tgt; const float* gmax;
   int const_attention; float dropout_p; uint64_t seed; uint64_t offset;
@@ -50,22 +50,23 @@ struct EdgeFwdParams {
   int32_t* tie_dst; int32_t* tie_src; unsigned long long* tie_total;
 };
 
-__device__ __forceinline__ void edge_probs(const EdgeFwdParams& P, int e, bool valid, const float (&st)[kMaxHeads],
-                                           float gmax, int& src, float (&p)[kMaxHeads], unsigned& tiemask) {
+template <int NHT>
+__device__ __forceinline__ void edge_probs(const EdgeFwdParams& P, int e, bool valid, const float (&st)[NHT],
+                                           float gmax, int& src, float (&p)[NHT], unsigned& tiemask) {
   tiemask = 0;
   src = 0;
 #pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h) p[h] = 0.f;
+  for (int h = 0; h < NHT; ++h) p[h] = 0.f;
   if (!valid) return;
   src = __ldg(P.col + e);
   if (P.const_attention) {
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) p[h] = h < P.nh ? 1.f : 0.f;   // exp(0), gat_layer.py:89-96
+    for (int h = 0; h < NHT; ++h) p[h] = h < P.nh ? 1.f : 0.f;   // exp(0), gat_layer.py:89-96
     return;
   }
   const float* ss = P.s_src + (int64_t)src * P.nh;
 #pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h) {
+  for (int h = 0; h < NHT; ++h) {
     if (h < P.nh) {
       float l = __ldg(ss + h) + st[h];
       p[h] = attn_exp(l, gmax);
@@ -74,18 +75,12 @@ __device__ __forceinline__ void edge_probs(const EdgeFwdParams& P, int e, bool v
   }
 }
 
-template <int G, int SLOTS>
-__global__ void __launch_bounds__(kEdgeThreads)
-edge_fwd_kernel(const EdgeFwdParams P) {
+template <int G, int SLOTS, int NHT>
+__device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64_t row, const int tid, const int gl,
+                                             const int gbase, const unsigned gmask, const float gmax,
+                                             int* sh_src, float* sh_w) {
   constexpr int U = SLOTS >= 4 ? 2 : (SLOTS >= 2 ? 4 : 8);
-  __shared__ int sh_src[kEdgeThreads];
-  __shared__ float sh_w[kEdgeThreads * kMaxHeads];
-  const int tid = threadIdx.x, lane = tid & 31, gl = tid & (G - 1), gbase = tid - gl;
-  const unsigned gmask = group_mask<G>(lane);
-  const int64_t row = (int64_t)blockIdx.x * (kEdgeThreads / G) + tid / G;
-  if (row >= P.n) return;
   const int nh = P.nh;
-
   int head[SLOTS];
   bool ok[SLOTS];
   float4 acc[SLOTS];
@@ -97,34 +92,27 @@ edge_fwd_kernel(const EdgeFwdParams P) {
     acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const int start = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
-  float st[kMaxHeads];
-  float gmax = 0.f;
-  if (!P.const_attention) {
-    gmax = __ldg(P.gmax);
+  float st[NHT];
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) st[h] = h < nh ? __ldg(P.s_tgt + row * nh + h) : 0.f;
-  } else {
-#pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) st[h] = 0.f;
-  }
+  for (int h = 0; h < NHT; ++h) st[h] = (!P.const_attention && h < nh) ? __ldg(P.s_tgt + row * nh + h) : 0.f;
 
   // ---- phase A: softmax denominators Z[h] = sum_e p[e,h]  (gat_layer.py:99-103)
-  float p[kMaxHeads], z[kMaxHeads];
+  float p[NHT], z[NHT];
   int my_src = 0;
   unsigned tiemask = 0;
 #pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h) z[h] = 0.f;
+  for (int h = 0; h < NHT; ++h) z[h] = 0.f;
   for (int base = start; base < end; base += G) {
-    edge_probs(P, base + gl, base + gl < end, st, gmax, my_src, p, tiemask);
+    edge_probs<NHT>(P, base + gl, base + gl < end, st, gmax, my_src, p, tiemask);
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) z[h] += p[h];
+    for (int h = 0; h < NHT; ++h) z[h] += p[h];
   }
 #pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h)
+  for (int h = 0; h < NHT; ++h)
     if (h < nh) z[h] = group_sum<G>(z[h], gmask);
   if (P.z_out && gl == 0) {
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h)
+    for (int h = 0; h < NHT; ++h)
       if (h < nh) P.z_out[row * nh + h] = z[h];
   }
   const bool single = (end - start) <= G;   // p[] of the only batch is still in registers
@@ -133,22 +121,22 @@ edge_fwd_kernel(const EdgeFwdParams P) {
   for (int base = start; base < end; base += G) {
     const int e = base + gl;
     const bool valid = e < end;
-    if (!single) edge_probs(P, e, valid, st, gmax, my_src, p, tiemask);
+    if (!single) edge_probs<NHT>(P, e, valid, st, gmax, my_src, p, tiemask);
     if (valid) {
-      float w[kMaxHeads];
+      float w[NHT];
 #pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h) w[h] = h < nh ? p[h] / (z[h] + kSoftmaxEps) : 0.f;
+      for (int h = 0; h < NHT; ++h) w[h] = h < nh ? p[h] / (z[h] + kSoftmaxEps) : 0.f;
       int edge_id = 0;
       if (P.alpha_out || P.dropout_p > 0.f) edge_id = __ldg(P.eid + e);
       if (P.alpha_out) {
         float* ao = P.alpha_out + (int64_t)edge_id * nh;
 #pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h)
+        for (int h = 0; h < NHT; ++h)
           if (h < nh) ao[h] = w[h];
       }
       if (P.tie_total && tiemask) {
 #pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h) {
+        for (int h = 0; h < NHT; ++h) {
           if (tiemask & (1u << h)) {
             atomicAdd(P.tie_dst + row * nh + h, 1);
             atomicAdd(P.tie_src + (int64_t)my_src * nh + h, 1);
@@ -157,15 +145,15 @@ edge_fwd_kernel(const EdgeFwdParams P) {
         }
       }
       if (P.dropout_p > 0.f) {
-        float m[kMaxHeads];
-        dropout_scales(P.seed, P.offset, (uint32_t)edge_id, nh, P.dropout_p, m);
+        float m[NHT];
+        dropout_scales<NHT>(P.seed, P.offset, (uint32_t)edge_id, nh, P.dropout_p, m);
 #pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h)
+        for (int h = 0; h < NHT; ++h)
           if (h < nh) w[h] *= m[h];
       }
       sh_src[tid] = my_src;
 #pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h) sh_w[tid * kMaxHeads + h] = w[h];
+      for (int h = 0; h < NHT; ++h) sh_w[tid * NHT + h] = w[h];
     }
     __syncwarp(gmask);
     const int cnt = min(G, end - base);
@@ -185,7 +173,7 @@ edge_fwd_kernel(const EdgeFwdParams P) {
         if (t + u < cnt) {
 #pragma unroll
           for (int s = 0; s < SLOTS; ++s) {
-            const float w = sh_w[(gbase + t + u) * kMaxHeads + head[s]];
+            const float w = sh_w[(gbase + t + u) * NHT + head[s]];
             acc[s].x = fmaf(w, v[u][s].x, acc[s].x);
             acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
             acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
@@ -199,6 +187,24 @@ edge_fwd_kernel(const EdgeFwdParams P) {
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s)
     if (ok[s]) *reinterpret_cast<float4*>(P.out + row * P.dp + (s * G + gl) * 4) = acc[s];
+}
+
+template <int G, int SLOTS, int NHT>
+__global__ void __launch_bounds__(kEdgeThreads, (SLOTS <= 2 ? 3 : (SLOTS <= 4 ? 2 : 1)))
+edge_fwd_kernel(const EdgeFwdParams P) {
+  __shared__ int sh_src[kEdgeThreads];
+  __shared__ float sh_w[kEdgeThreads * NHT];
+  const int tid = threadIdx.x, lane = tid & 31, gl = tid & (G - 1), gbase = tid - gl;
+  const unsigned gmask = group_mask<G>(lane);
+  const float gmax = P.const_attention ? 0.f : __ldg(P.gmax);
+  int64_t base;
+  while (grab_rows<G>(P.sched, lane, base)) {
+#pragma unroll 1
+    for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
+      const int64_t row = sched_row<G>(P.sched, base, k, lane);
+      if (row >= 0) edge_fwd_row<G, SLOTS, NHT>(P, row, tid, gl, gbase, gmask, gmax, sh_src, sh_w);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -245,14 +251,17 @@ extern "C" int gat_edge_max(const int32_t* rowptr, const int32_t* col, int64_t n
   return GAT_OK;
 }
 
-extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
+extern "C" size_t gat_edge_fwd_workspace_bytes(void) { return 256; }
+
+extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n,
                             const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
                             const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
                             float* out, float* alpha_out, float* z_out,
                             int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
-                            gat_stream_t stream) {
+                            void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
   GAT_CHECK_ARG(nh >= 1 && nh <= kMaxHeads, "gat_edge_fwd: num_heads %d not in [1, %d]", nh, kMaxHeads);
+  GAT_CHECK_ARG(workspace != nullptr && workspace_bytes >= gat_edge_fwd_workspace_bytes(), "gat_edge_fwd: workspace too small");
   GAT_CHECK_ARG(fp > 0 && fp % 4 == 0, "gat_edge_fwd: padded head width %d must be a positive multiple of 4", fp);
   GAT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "gat_edge_fwd: dropout %f not in [0, 1)", dropout_p);
   GAT_CHECK_ARG(const_attention || (s_src && s_tgt && gmax), "gat_edge_fwd: score buffers missing");
@@ -260,7 +269,8 @@ extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int
                 "gat_edge_fwd: tie buffers must be given together");
   if (n == 0) return GAT_OK;
   EdgeFwdParams P;
-  P.rowptr = rowptr; P.col = col; P.eid = eid; P.n = n; P.wh = wh; P.nh = nh; P.dp = nh * fp;
+  P.rowptr = rowptr; P.col = col; P.eid = eid; P.wh = wh; P.nh = nh; P.dp = nh * fp;
+  P.sched.order = row_order; P.sched.counter = (unsigned int*)workspace; P.sched.n = n;
   P.chunks = nh * fp / 4; P.chunks_per_head = fp / 4;
   P.s_src = s_src; P.s_tgt = s_tgt; P.gmax = gmax; P.const_attention = const_attention;
   P.dropout_p = dropout_p; P.seed = seed; P.offset = offset;
@@ -273,9 +283,11 @@ extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int
     return GAT_EUNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(G_, S_)                                                                      \
-  edge_fwd_kernel<G_, S_><<<(unsigned)((n + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)), kEdgeThreads, 0, st>>>(P)
-  GAT_DISPATCH_GROUP(shape, LAUNCH);
+  GAT_CUDA(cudaMemsetAsync(workspace, 0, sizeof(unsigned int), st));
+#define LAUNCH(G_, S_, N_)                                                                  \
+  edge_fwd_kernel<G_, S_, N_><<<persistent_grid(edge_fwd_kernel<G_, S_, N_>, kEdgeThreads, 0,       \
+                                                (n + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)), kEdgeThreads, 0, st>>>(P)
+  GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
 #undef LAUNCH
   GAT_LAUNCH_CHECK();
   return GAT_OK;

@@ -73,11 +73,13 @@ class _GATFunction(torch.autograd.Function):
             seed = 0
             if p_drop > 0.0:
                 seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator: no device sync
-            _lib.call("gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), n,
+            fws = torch.empty(int(lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=dev)
+            _lib.call("gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), n,
                                         wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax),
                                         int(const_attention), float(p_drop), seed, 0,
                                         out_p.data_ptr(), _ptr(alpha), z.data_ptr(),
-                                        _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), s, tag=(nh, fp))
+                                        _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), fws.data_ptr(), fws.numel(), s,
+                                        tag=(nh, fp))
             if fp != f or not concat:
                 out = torch.empty((n, nh * f if concat else f), **f32)
                 _lib.call("gat_head_merge_fwd", out_p.data_ptr(), n, nh, f, fp, int(concat), out.data_ptr(), s)
@@ -119,12 +121,13 @@ class _GATFunction(torch.autograd.Function):
                 ds_tgt = torch.empty((n, nh), **f32)
             ws_bytes = int(lib.gat_edge_bwd_workspace_bytes(n, st.n_edges, nh))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            _lib.call("gat_edge_bwd_dst", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), n,
+            _lib.call("gat_edge_bwd_dst", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), n,
                                             wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax), z.data_ptr(),
                                             int(const_attention), p_drop, seed, 0,
                                             go_p.data_ptr(), _ptr(grad_alpha), rec.data_ptr(), _ptr(ds_tgt),
                                             ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
-            _lib.call("gat_edge_bwd_src", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), n,
+            _lib.call("gat_edge_bwd_src", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(),
+                                            st.order_t.data_ptr(), n,
                                             nh, fp, rec.data_ptr(), go_p.data_ptr(), _ptr(a_src_p), _ptr(a_tgt_p),
                                             int(const_attention), _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total),
                                             None, 0, n, _ptr(ds_src), _ptr(ds_tgt), d_wh.data_ptr(),

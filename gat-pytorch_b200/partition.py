@@ -103,15 +103,16 @@ class CudaBackend:
 
     def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total):
         p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
-        _lib.call("gat_edge_fwd", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(), plan.rows,
+        fws = torch.empty(int(self.lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=out_p.device)
+        _lib.call("gat_edge_fwd", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(), None, plan.rows,
                   wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(), s_tgt_local.data_ptr(), gmax.data_ptr(),
                   0, 0.0, 0, 0, out_p.data_ptr(), None, z.data_ptr(), p(tie_dst), p(tie_src), p(tie_total),
-                  self._s(out_p.device), tag=(nh, fp))
+                  fws.data_ptr(), fws.numel(), self._s(out_p.device), tag=(nh, fp))
 
     def edge_bwd_dst(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z, go_p, rec, ds_tgt):
         ws_bytes = int(self.lib.gat_edge_bwd_workspace_bytes(plan.rows, st.n_edges, nh))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=go_p.device)
-        _lib.call("gat_edge_bwd_dst", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(), plan.rows,
+        _lib.call("gat_edge_bwd_dst", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(), None, plan.rows,
                   wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(), s_tgt_local.data_ptr(), gmax.data_ptr(), z.data_ptr(),
                   0, 0.0, 0, 0, go_p.data_ptr(), None, rec.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes,
                   self._s(go_p.device), tag=(nh, fp))
@@ -124,7 +125,8 @@ class CudaBackend:
         ws_bytes = int(self.lib.gat_edge_bwd_workspace_bytes(plan.n, st.n_edges, nh))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=go_p.device)
         go_base = go_p.data_ptr() - 4 * dp * plan.lo       # col_t holds GLOBAL target ids, all in [lo, hi)
-        _lib.call("gat_edge_bwd_src", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), plan.n,
+        _lib.call("gat_edge_bwd_src", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(),
+                  st.order_t.data_ptr(), plan.n,
                   nh, fp, rec.data_ptr(), go_base, a_src.data_ptr(), a_tgt.data_ptr(), 0,
                   tie_dst.data_ptr(), tie_src.data_ptr(), None, corr.data_ptr(), plan.lo, plan.hi,
                   ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(), ws.data_ptr(), ws_bytes,

@@ -67,11 +67,14 @@ GAT_API size_t gat_csr_workspace_bytes(int64_t n_edges_in, int64_t n_edges_out, 
  *  rowptr   (n_nodes+1) / col / eid (n_edges_out): CSR by target, stable in edge order;
  *           rowptr diffs are the reference's degree counts (GATModel.py:196-201);
  *  rowptr_t (n_nodes+1) / col_t / pos_t: CSR by source; col_t = target ids, pos_t = slot of that
- *           edge in the target-sorted CSR. */
+ *           edge in the target-sorted CSR;
+ *  row_order / row_order_t (n_nodes) or NULL: scheduling permutations for the persistent edge kernels
+ *           (rows with more than 256 edges first); a performance hint only, results do not depend on it. */
 GAT_API int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t row_stride, int index_is_int64,
                   int add_self_loops, int64_t n_idx, int64_t n_edges_out, int64_t n_nodes,
                   int64_t* ei_out, int32_t* rowptr, int32_t* col, int32_t* eid,
                   int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t,
+                  int32_t* row_order, int32_t* row_order_t,
                   void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -111,13 +114,16 @@ GAT_API int gat_edge_max(const int32_t* rowptr, const int32_t* col, int64_t n, c
  *  tie_dst/tie_src (n, nh) int32 + tie_total (1) uint64: arg-max-set bookkeeping for the
  *               gradient through max(), zero-initialised by the caller, or NULL;
  *  const_attention: logits are 0, gmax/s_src/s_tgt ignored (gat_layer.py:89-92);
- *  dropout_p > 0 enables the mask with (seed, offset) keyed on (edge id, head). */
-GAT_API int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
+ *  dropout_p > 0 enables the mask with (seed, offset) keyed on (edge id, head);
+ *  row_order: scheduling permutation from gat_csr_build or NULL (natural order);
+ *  workspace: gat_edge_fwd_workspace_bytes() bytes (the persistent grid's row counter). */
+GAT_API size_t gat_edge_fwd_workspace_bytes(void);
+GAT_API int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n,
                  const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
                  const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
                  float* out, float* alpha_out, float* z_out,
                  int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
-                 gat_stream_t stream);
+                 void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* Head merge (gat_layer.py:129-132): padded (n, nh, fp) -> (n, nh*f) concat or (n, f) head mean. */
 GAT_API int gat_head_merge_fwd(const float* o_padded, int64_t n, int nh, int f, int fp, int concat,
@@ -136,7 +142,7 @@ GAT_API size_t gat_edge_bwd_workspace_bytes(int64_t n, int64_t n_edges, int nh);
  * g = 0.01*alpha*(d_alpha - S).  Writes per-edge records rec[j] = {g[0..nh), m*alpha[0..nh)} in CSR
  * order, ds_tgt (n, nh) (before the arg-max correction) and per-block partial sums of g.
  * grad_alpha is (n_edges, nh) in rewritten edge order or NULL. */
-GAT_API int gat_edge_bwd_dst(const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t n,
+GAT_API int gat_edge_bwd_dst(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n,
                      const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
                      const float* gmax, const float* z, int const_attention,
                      float dropout_p, uint64_t seed, uint64_t offset,
@@ -150,7 +156,7 @@ GAT_API int gat_edge_bwd_dst(const int32_t* rowptr, const int32_t* col, const in
  * gradient of Wh.  ds_src/ds_tgt (n, nh) hold the corrected values on exit.
  * Rows are SOURCE nodes 0..n-1.  [tgt_lo, tgt_hi) is the range of nodes this call also owns as targets:
  * ds_tgt and tie_dst have tgt_hi - tgt_lo rows and only those rows receive the ds_tgt*A_tgt term. */
-GAT_API int gat_edge_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, int64_t n,
+GAT_API int gat_edge_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t, int64_t n,
                      int nh, int fp, const float* rec, const float* go_padded,
                      const float* a_src, const float* a_tgt, int const_attention,
                      const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
