@@ -1,15 +1,305 @@
-// tcgen05 / TMA 3xTF32 GEMM (algo 2).  Placeholder until the kernel lands: reports "unsupported" so
-// that algo 0 (auto) routes everything to the exact fp32 FFMA path.
+// Kernel 2: tcgen05 / TMA projection GEMM with fp32-grade accuracy ("3xTF32").
+//
+//   C[M,N] = A[M,K] * B[N,K]^T        A, B row-major fp32, both K-major (gat_gemm ta=0, tb=1)
+//
+// tcgen05 has no fp32 MMA kind, and plain TF32 (~5e-4) cannot meet the 1e-5 parity bar, so
+// every operand tile is split IN SHARED MEMORY into hi = tf32(v) and lo = v - hi, and three MMAs accumulate
+// hi*lo + lo*hi + hi*hi into the same fp32 TMEM accumulator.  The global operands are read exactly once, as
+// fp32, by TMA (no pre-split pass, no extra HBM traffic).
+//
+// CTA = one 128 x BN output tile, 192 threads, warp-specialised:
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes of 32 fp32 = 128 B per row) -> smem stage
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8)
+//   warps 2..5  splitters (hi/lo in place, position preserving, so the swizzle is irrelevant), then the epilogue:
+//               tcgen05.ld 32x32b from TMEM -> registers -> 32-byte row segments to global
+// mbarrier pipeline per stage: full (TMA -> splitters), ready (splitters -> MMA), empty (tcgen05.commit -> TMA).
+// Every wait is bounded and traps instead of hanging.
 #include "common.cuh"
+#include <cuda.h>
 
 namespace gat {
 
-bool tc_supported(int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t) { return false; }
+namespace tc {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;        // tf32
+constexpr int kThreads = 192;
+constexpr int kSplitThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (spins > (1u << 26)) __trap();   // a broken pipeline must fault, not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO unused (1), SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N>>3, M>>4.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_round(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+template <int BN>
+struct Smem {
+  static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
+  static constexpr int kABytes = BM * BK * 4;     // 16 KB
+  static constexpr int kBBytes = BN * BK * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // raw/hi + lo for both operands
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K) {
+  using S = Smem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr int kTmemCols = BN < 32 ? 32 : BN;   // BN is a power of two here
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024 B alignment
+  uint64_t* bars = (uint64_t*)(smem + kStages * S::kStageBytes);
+  uint64_t* full = bars;                    // TMA landed
+  uint64_t* ready = bars + kStages;         // hi/lo split done
+  uint64_t* empty = bars + 2 * kStages;     // MMAs that read the stage have completed
+  uint64_t* accum = bars + 3 * kStages;     // all MMAs of the tile have completed
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 3 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  const int num_kb = (int)((K + BK - 1) / BK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], kSplitThreads); mbar_init(&empty[s], 1); }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        if (kb >= kStages) mbar_wait(&empty[s], ((kb / kStages) - 1) & 1);
+        uint8_t* st = smem + s * S::kStageBytes;
+        mbar_expect_tx(&full[s], S::kABytes + S::kBBytes);
+        tma_load_2d(st, &map_a, &full[s], kb * BK, (int)m0);
+        tma_load_2d(st + 2 * S::kABytes, &map_b, &full[s], kb * BK, (int)n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(&ready[s], (kb / kStages) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * S::kStageBytes), a_lo = a_hi + S::kABytes;
+        const uint32_t b_hi = a_hi + 2 * S::kABytes, b_lo = b_hi + S::kBBytes;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint32_t off = k * UMMA_K * 4;   // bytes along the 128-byte swizzled row
+          // small cross terms first, then the leading term
+          umma_tf32(tmem_base, make_desc_k_sw128(a_hi + off), make_desc_k_sw128(b_lo + off), idesc, (kb | k) != 0);
+          umma_tf32(tmem_base, make_desc_k_sw128(a_lo + off), make_desc_k_sw128(b_hi + off), idesc, 1);
+          umma_tf32(tmem_base, make_desc_k_sw128(a_hi + off), make_desc_k_sw128(b_hi + off), idesc, 1);
+        }
+        umma_commit(&empty[s]);                  // implies tcgen05.fence::before_thread_sync
+      }
+      umma_commit(accum);
+    }
+  } else {
+    // ===== splitters (warps 2..5), then epilogue =====
+    const int t = threadIdx.x - 64;              // 0..127
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages;
+      mbar_wait(&full[s], (kb / kStages) & 1);
+      float4* a_hi = (float4*)(smem + s * S::kStageBytes);
+      float4* a_lo = (float4*)(smem + s * S::kStageBytes + S::kABytes);
+      float4* b_hi = (float4*)(smem + s * S::kStageBytes + 2 * S::kABytes);
+      float4* b_lo = (float4*)(smem + s * S::kStageBytes + 2 * S::kABytes + S::kBBytes);
+#pragma unroll 4
+      for (int i = t; i < S::kABytes / 16; i += kSplitThreads) {
+        float4 v = a_hi[i], h, l;
+        h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        a_hi[i] = h; a_lo[i] = l;
+      }
+#pragma unroll 4
+      for (int i = t; i < S::kBBytes / 16; i += kSplitThreads) {
+        float4 v = b_hi[i], h, l;
+        h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        b_hi[i] = h; b_lo[i] = l;
+      }
+      fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&ready[s]);
+    }
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int64_t row = m0 + q * 32 + lane;
+    float* crow = C + row * ldc + n0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 8) {
+      uint32_t r[8];
+      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+      if (row < M) {
+        if (n0 + c + 8 <= N) {
+          *reinterpret_cast<float4*>(crow + c) = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+          *reinterpret_cast<float4*>(crow + c + 4) = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (n0 + c + j < N) crow[c + j] = __uint_as_float(r[j]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major (rows x cols, leading dimension ld elements); box = box_rows x 32 columns, SWIZZLE_128B,
+// out-of-bounds elements read as zero (so M, N and K tails need no special casing).
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("gat_gemm: cuTensorMapEncodeTiled is unavailable"); return GAT_EUNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gat_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r); return GAT_EINVAL; }
+  return GAT_OK;
+}
+
+template <int BN>
+static int launch_nt(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb, float* c,
+                     int64_t ldc, cudaStream_t st) {
+  CUtensorMap map_a, map_b;
+  int rc = make_map(&map_a, a, m, k, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&map_b, b, n, k, ldb, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GAT_CUDA(cudaFuncSetAttribute(gemm_tc_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN));
+  gemm_tc_nt_kernel<BN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+}  // namespace tc
+
+bool tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc) {
+  if (ta != 0 || tb != 1) return false;                        // K-major x K-major only (the forward projection layout)
+  if (lda % 4 || ldb % 4 || ldc % 4) return false;             // TMA global strides / float4 stores need 16-byte multiples
+  if (m < 1 || n < 8 || k < 1) return false;
+  if (m >= ((int64_t)1 << 31) || n >= ((int64_t)1 << 31) || k >= ((int64_t)1 << 31)) return false;
+  return true;
+}
+
 size_t tc_workspace_bytes(int, int, int64_t, int64_t, int64_t) { return 0; }
-int gemm_tc(int, int, int64_t, int64_t, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t,
-            void*, size_t, cudaStream_t) {
-  set_error("gat_gemm: tcgen05 path not built");
-  return GAT_EUNSUPPORTED;
+
+int gemm_tc(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb,
+            float* c, int64_t ldc, void*, size_t, cudaStream_t st) {
+  if (!tc_supported(ta, tb, m, n, k, lda, ldb, ldc) || ((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) % 16) {
+    set_error("gat_gemm: tcgen05 path needs ta=0, tb=1 and 16-byte aligned pointers / leading dimensions");
+    return GAT_EUNSUPPORTED;
+  }
+  if (n > 128) return tc::launch_nt<256>(m, n, k, a, lda, b, ldb, c, ldc, st);
+  if (n > 64) return tc::launch_nt<128>(m, n, k, a, lda, b, ldb, c, ldc, st);
+  return tc::launch_nt<64>(m, n, k, a, lda, b, ldb, c, ldc, st);
 }
 
 }  // namespace gat

@@ -1,4 +1,4 @@
-// Per-node attention score terms (Kernel 2 epilogue, standalone form).
+// Per-node attention score terms and their adjoint (the "a" half of Kernel 2).
 //
 // The reference multiplies the (E', NH*2F) pair tensor by the full cross-head matrix `a`
 // (gat_layer.py:76-82).  That product decomposes exactly into per-node terms
@@ -6,59 +6,116 @@
 // with A_src/A_tgt the (NH, NH*F) halves of `a`.  The dot products are
 // accumulated in fp64 from the fp32 Wh: with the committed PATTERN weights the logits reach
 // +-1.9e3 and sit at the fp32 noise floor of the 1e-5 parity bar, so this
-// tiny contraction (2*NH columns) is kept more accurate than fp32.
+// tiny contraction (2*NH columns) is kept more accurate than fp32.  Both kernels stream Wh once
+// (HBM-bound: 4*n*dp bytes) with persistent grids.
 #include "common.cuh"
 
 namespace gat {
 
-constexpr int kScoreKC = 128;  // columns of Wh staged per step
-constexpr int kScoreRows = 32; // rows per CTA
+constexpr int kScoreMaxJ = 16;     // 2 * max heads
 
+// ---- forward: one warp per row, lanes over float4 chunks, 2*NH fp64 partial sums per lane ----
+template <int NJ>   // NJ = compile-time bound on 2*nh (8 or 16)
 __global__ void __launch_bounds__(256)
-scores_kernel(const float* __restrict__ wh, int64_t n, int dp, const float* __restrict__ a_src,
-              const float* __restrict__ a_tgt, int nh, float* __restrict__ s_src, float* __restrict__ s_tgt) {
-  __shared__ float wh_s[kScoreRows][kScoreKC + 1];
-  __shared__ float a_s[16][kScoreKC + 1];  // rows 0..nh-1 = A_src, nh..2nh-1 = A_tgt
-  const int tid = threadIdx.x;
-  const int nj = 2 * nh;                      // <= 16
-  const int64_t row0 = (int64_t)blockIdx.x * kScoreRows;
-  // thread -> (row r, output column j); 256 threads cover 32 rows x 8 columns per pass
-  const int r = tid >> 3, jl = tid & 7;
-  double acc0 = 0.0, acc1 = 0.0;              // columns jl and jl+8
-  for (int k0 = 0; k0 < dp; k0 += kScoreKC) {
-    int kc = min(kScoreKC, dp - k0);
-    for (int idx = tid; idx < kScoreRows * kScoreKC; idx += 256) {
-      int rr = idx / kScoreKC, kk = idx % kScoreKC;
-      int64_t gr = row0 + rr;
-      wh_s[rr][kk] = (gr < n && kk < kc) ? wh[gr * dp + k0 + kk] : 0.f;
+scores_fwd_kernel(const float* __restrict__ wh, int64_t n, int dp, const float* __restrict__ a_src,
+                  const float* __restrict__ a_tgt, int nh, float* __restrict__ s_src, float* __restrict__ s_tgt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  const int chunks = dp >> 2, nj = 2 * nh;
+  for (int64_t row = warp; row < n; row += nwarps) {
+    double acc[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[j] = 0.0;
+    const float* wr = wh + row * dp;
+    for (int c = lane; c < chunks; c += 32) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wr) + c);
+      const double w0 = w.x, w1 = w.y, w2 = w.z, w3 = w.w;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (j < nj) {
+          const float* ap = (j < nh ? a_src + (int64_t)j * dp : a_tgt + (int64_t)(j - nh) * dp);
+          const float4 a = __ldg(reinterpret_cast<const float4*>(ap) + c);
+          acc[j] = fma(w0, (double)a.x, acc[j]);
+          acc[j] = fma(w1, (double)a.y, acc[j]);
+          acc[j] = fma(w2, (double)a.z, acc[j]);
+          acc[j] = fma(w3, (double)a.w, acc[j]);
+        }
+      }
     }
-    for (int idx = tid; idx < nj * kScoreKC; idx += 256) {
-      int j = idx / kScoreKC, kk = idx % kScoreKC;
-      float v = 0.f;
-      if (kk < kc) v = (j < nh) ? a_src[(int64_t)j * dp + k0 + kk] : a_tgt[(int64_t)(j - nh) * dp + k0 + kk];
-      a_s[j][kk] = v;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (j < nj) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      }
     }
-    __syncthreads();
-    if (jl < nj) {
-#pragma unroll 4
-      for (int kk = 0; kk < kc; ++kk) acc0 = fma((double)wh_s[r][kk], (double)a_s[jl][kk], acc0);
-    }
-    if (jl + 8 < nj) {
-#pragma unroll 4
-      for (int kk = 0; kk < kc; ++kk) acc1 = fma((double)wh_s[r][kk], (double)a_s[jl + 8][kk], acc1);
-    }
-    __syncthreads();
-  }
-  int64_t gr = row0 + r;
-  if (gr < n) {
-    if (jl < nj) {
-      if (jl < nh) s_src[gr * nh + jl] = (float)acc0; else s_tgt[gr * nh + (jl - nh)] = (float)acc0;
-    }
-    int j1 = jl + 8;
-    if (j1 < nj) {
-      if (j1 < nh) s_src[gr * nh + j1] = (float)acc1; else s_tgt[gr * nh + (j1 - nh)] = (float)acc1;
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (j < nj) {
+          if (j < nh) s_src[row * nh + j] = (float)acc[j]; else s_tgt[row * nh + (j - nh)] = (float)acc[j];
+        }
+      }
     }
   }
+}
+
+// ---- backward: dA_src = ds_src^T Wh, dA_tgt = ds_tgt^T Wh  (NH x dp each), one streaming pass over Wh ----
+// Thread t owns float4 chunk (t % CP) of dp and walks rows sub, sub+RS, ... of its CTA's row slice, with
+// CP = next power of two >= dp/4 and RS = 256/CP row sub-groups; per-(CTA, sub-group) fp32 partials go to the
+// workspace and are summed in fp64 in a fixed order by scores_bwd_reduce_kernel (deterministic).
+constexpr int kScoreBwdBlocks = 592;
+
+template <int NHT>
+__global__ void __launch_bounds__(256)
+scores_bwd_partial_kernel(const float* __restrict__ wh, int64_t n, int dp, int nh, int cp_log2,
+                          const float* __restrict__ ds_src, const float* __restrict__ ds_tgt, float* __restrict__ partial) {
+  const int cp = 1 << cp_log2, rs = 256 >> cp_log2;
+  const int c = threadIdx.x & (cp - 1), sub = threadIdx.x >> cp_log2;
+  const int chunks = dp >> 2;
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
+  float4 as[NHT], at[NHT];
+#pragma unroll
+  for (int h = 0; h < NHT; ++h) { as[h] = make_float4(0.f, 0.f, 0.f, 0.f); at[h] = as[h]; }
+  if (c < chunks) {
+    for (int64_t i = lo + sub; i < hi; i += rs) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wh + i * dp) + c);
+#pragma unroll
+      for (int h = 0; h < NHT; ++h) {
+        if (h < nh) {
+          const float a = __ldg(ds_src + i * nh + h), b = __ldg(ds_tgt + i * nh + h);
+          as[h].x = fmaf(a, w.x, as[h].x); as[h].y = fmaf(a, w.y, as[h].y); as[h].z = fmaf(a, w.z, as[h].z); as[h].w = fmaf(a, w.w, as[h].w);
+          at[h].x = fmaf(b, w.x, at[h].x); at[h].y = fmaf(b, w.y, at[h].y); at[h].z = fmaf(b, w.z, at[h].z); at[h].w = fmaf(b, w.w, at[h].w);
+        }
+      }
+    }
+    // partial layout: [block][sub][2*nh][dp]
+    float* p = partial + (((int64_t)blockIdx.x * rs + sub) * 2 * nh) * dp + c * 4;
+#pragma unroll
+    for (int h = 0; h < NHT; ++h) {
+      if (h < nh) {
+        *reinterpret_cast<float4*>(p + (int64_t)h * dp) = as[h];
+        *reinterpret_cast<float4*>(p + (int64_t)(nh + h) * dp) = at[h];
+      }
+    }
+  }
+}
+
+__global__ void scores_bwd_reduce_kernel(const float* __restrict__ partial, int slabs, int nh, int dp,
+                                         float* __restrict__ da_src, float* __restrict__ da_tgt) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 2*nh*dp
+  if (idx >= 2 * nh * dp) return;
+  double s = 0.0;
+  for (int b = 0; b < slabs; ++b) s += (double)partial[(int64_t)b * 2 * nh * dp + idx];
+  const int j = idx / dp, d = idx - j * dp;
+  if (j < nh) da_src[(int64_t)j * dp + d] = (float)s; else da_tgt[(int64_t)(j - nh) * dp + d] = (float)s;
+}
+
+static int cp_log2_for(int chunks) {
+  int l = 0;
+  while ((1 << l) < chunks) ++l;
+  return l;
 }
 
 }  // namespace gat
@@ -67,10 +124,37 @@ extern "C" int gat_scores_fwd(const float* wh, int64_t n, int dp, const float* a
                               float* s_src, float* s_tgt, gat_stream_t stream) {
   using namespace gat;
   GAT_CHECK_ARG(nh >= 1 && nh <= 8, "gat_scores_fwd: num_heads %d not in [1, 8]", nh);
-  GAT_CHECK_ARG(dp > 0 && n >= 0, "gat_scores_fwd: bad shape");
+  GAT_CHECK_ARG(dp > 0 && dp % 4 == 0 && n >= 0, "gat_scores_fwd: bad shape");
   if (n == 0) return GAT_OK;
-  unsigned blocks = (unsigned)((n + kScoreRows - 1) / kScoreRows);
-  scores_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(wh, n, dp, a_src, a_tgt, nh, s_src, s_tgt);
+  int64_t want = (n + 7) / 8;
+  unsigned blocks = (unsigned)(want < kNumSMs * 8 ? want : kNumSMs * 8);
+  if (nh <= 4) scores_fwd_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(wh, n, dp, a_src, a_tgt, nh, s_src, s_tgt);
+  else scores_fwd_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(wh, n, dp, a_src, a_tgt, nh, s_src, s_tgt);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" size_t gat_scores_bwd_workspace_bytes(int dp, int nh) {
+  int rs = 256 >> gat::cp_log2_for(dp / 4);
+  return (size_t)gat::kScoreBwdBlocks * rs * 2 * nh * dp * sizeof(float);
+}
+
+extern "C" int gat_scores_bwd(const float* wh, int64_t n, int dp, int nh, const float* ds_src, const float* ds_tgt,
+                              float* da_src, float* da_tgt, void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(nh >= 1 && nh <= 8, "gat_scores_bwd: num_heads %d not in [1, 8]", nh);
+  GAT_CHECK_ARG(dp > 0 && dp % 4 == 0 && dp <= 1024 && n >= 0, "gat_scores_bwd: bad shape");
+  if (workspace == nullptr || workspace_bytes < gat_scores_bwd_workspace_bytes(dp, nh)) {
+    set_error("gat_scores_bwd: workspace too small");
+    return GAT_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int l2 = cp_log2_for(dp / 4), rs = 256 >> l2;
+  if (nh <= 4) scores_bwd_partial_kernel<4><<<kScoreBwdBlocks, 256, 0, st>>>(wh, n, dp, nh, l2, ds_src, ds_tgt, (float*)workspace);
+  else scores_bwd_partial_kernel<8><<<kScoreBwdBlocks, 256, 0, st>>>(wh, n, dp, nh, l2, ds_src, ds_tgt, (float*)workspace);
+  GAT_LAUNCH_CHECK();
+  const int total = 2 * nh * dp;
+  scores_bwd_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, kScoreBwdBlocks * rs, nh, dp, da_src, da_tgt);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }

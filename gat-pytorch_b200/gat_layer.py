@@ -139,12 +139,13 @@ class _GATFunction(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 gw = torch.empty((dp, f_in), **f32)
                 gemm(True, False, dp, f_in, n, d_wh, dp, x, x.stride(0), gw, f_in, gemm_algo)
-            if not const_attention and ctx.needs_input_grad[2]:
+            if not const_attention and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
                 ga_src = torch.empty((nh, dp), **f32)
-                gemm(True, False, nh, dp, n, ds_src, nh, wh, dp, ga_src, dp, gemm_algo)
-            if not const_attention and ctx.needs_input_grad[3]:
                 ga_tgt = torch.empty((nh, dp), **f32)
-                gemm(True, False, nh, dp, n, ds_tgt, nh, wh, dp, ga_tgt, dp, gemm_algo)
+                sb = int(lib.gat_scores_bwd_workspace_bytes(dp, nh))
+                sws = torch.empty(sb, dtype=torch.uint8, device=dev)
+                _lib.call("gat_scores_bwd", wh.data_ptr(), n, dp, nh, ds_src.data_ptr(), ds_tgt.data_ptr(),
+                          ga_src.data_ptr(), ga_tgt.data_ptr(), sws.data_ptr(), sb, s)
         return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None
 
 

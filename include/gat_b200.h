@@ -97,6 +97,12 @@ GAT_API int gat_gemm(int ta, int tb, int64_t m, int64_t n, int64_t k,
 GAT_API int gat_scores_fwd(const float* wh, int64_t n, int dp, const float* a_src, const float* a_tgt, int nh,
                    float* s_src, float* s_tgt, gat_stream_t stream);
 
+/* Adjoint of gat_scores_fwd w.r.t. the attention matrix: da_src = ds_src^T wh, da_tgt = ds_tgt^T wh, (nh, dp)
+ * each, one streaming pass over wh with a fixed-order two-stage reduction (deterministic). */
+GAT_API size_t gat_scores_bwd_workspace_bytes(int dp, int nh);
+GAT_API int gat_scores_bwd(const float* wh, int64_t n, int dp, int nh, const float* ds_src, const float* ds_tgt,
+                           float* da_src, float* da_tgt, void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Kernel 3 -- fused edge forward.  Replaces gat_layer.py:70-132.
  * ------------------------------------------------------------------------------------- */
