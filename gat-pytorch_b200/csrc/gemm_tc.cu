@@ -186,14 +186,16 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int i = t; i < S::kABytes / 16; i += kSplitThreads) {
         float4 v = a_hi[i], h, l;
         h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        // lo is rounded too: the tensor core would otherwise TRUNCATE its low 13 bits, a one-sided error that
+        // accumulates linearly over K
+        l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
         a_hi[i] = h; a_lo[i] = l;
       }
 #pragma unroll 4
       for (int i = t; i < S::kBBytes / 16; i += kSplitThreads) {
         float4 v = b_hi[i], h, l;
         h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
         b_hi[i] = h; b_lo[i] = l;
       }
       fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)

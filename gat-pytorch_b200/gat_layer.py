@@ -135,7 +135,8 @@ class _GATFunction(torch.autograd.Function):
             gx = gw = ga_src = ga_tgt = None
             if ctx.needs_input_grad[0]:
                 gx = torch.empty((n, f_in), **f32)
-                gemm(False, False, n, f_in, dp, d_wh, dp, w_p, w_p.stride(0), gx, f_in, gemm_algo)
+                w_t = w_p.t().contiguous()      # (f_in, dp): makes dX = dWh * W a K-major x K-major product (tcgen05 path)
+                gemm(False, True, n, f_in, dp, d_wh, dp, w_t, dp, gx, f_in, gemm_algo)
             if ctx.needs_input_grad[1]:
                 gw = torch.empty((dp, f_in), **f32)
                 gemm(True, False, dp, f_in, n, d_wh, dp, x, x.stride(0), gw, f_in, gemm_algo)

@@ -188,7 +188,8 @@ class _PartitionedGATFunction(torch.autograd.Function):
         gx = None
         if ctx.needs_input_grad[0] and rows:
             gx = torch.empty((rows, f_in), **f32)
-            backend.gemm(False, False, rows, f_in, dp, d_wh, dp, w_p, w_p.stride(0), gx, f_in)
+            w_t = w_p.t().contiguous()
+            backend.gemm(False, True, rows, f_in, dp, d_wh, dp, w_t, dp, gx, f_in)
         elif ctx.needs_input_grad[0]:
             gx = torch.zeros((0, f_in), **f32)
         gw = torch.zeros((dp, f_in), **f32)

@@ -231,3 +231,23 @@ def test_gemm_all_layouts():
                 want = (a.double().T if ta else a.double()) @ (b.double().T if tb else b.double())
                 err = (c.double() - want).abs().max().item() / want.abs().max().item()
                 assert err < 2e-6, (m, n, k, ta, tb, err)
+
+
+def test_gemm_tcgen05_3xtf32():
+    """Kernel 2 (tcgen05 + TMA, hi/lo split in shared memory) against torch fp64: fp32-grade accuracy on
+    ragged M/N/K tails, every N tile width."""
+    from gat_pytorch_b200 import _lib
+    from gat_pytorch_b200.gat_layer import gemm
+    lib = _lib.load()
+    torch.manual_seed(2)
+    for (m, n, k) in [(128, 64, 32), (300, 192, 100), (1000, 72, 520), (4097, 256, 1024), (257, 128, 36), (5000, 1024, 48),
+                      (20000, 256, 256)]:
+        assert lib.gat_gemm_tc_supported(0, 1, m, n, k, k, k, n)
+        a = torch.randn((m, k), device="cuda")
+        b = torch.randn((n, k), device="cuda")
+        c = torch.full((m, n), float("nan"), device="cuda")
+        gemm(False, True, m, n, k, a, k, b, k, c, n, algo=2)
+        want = a.double() @ b.double().T
+        err = ((c.double() - want).abs().max() / want.abs().max()).item()
+        assert err < 3e-6, (m, n, k, err)
+    assert not lib.gat_gemm_tc_supported(0, 1, 100, 64, 1433, 1433, 1433, 64)     # Cora: K*4 bytes is not a 16-byte multiple
