@@ -91,6 +91,13 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ P, int splits, in
   C[(idx / N) * ldc + (idx % N)] = s;
 }
 
+namespace tc {
+void splitk_reduce_launch(const float* partial, int splits, int64_t m, int64_t n, float* c, int64_t ldc, cudaStream_t st) {
+  const int64_t total = m * n;
+  splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, m, n, c, ldc);
+}
+}  // namespace tc
+
 struct SimtPlan { int bm, bn, splits; int64_t k_chunk; };
 
 SimtPlan simt_plan(int64_t m, int64_t n, int64_t k) {

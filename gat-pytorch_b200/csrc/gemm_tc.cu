@@ -1,6 +1,7 @@
 // Kernel 2: tcgen05 / TMA projection GEMM with fp32-grade accuracy ("3xTF32").
 //
-//   C[M,N] = A[M,K] * B[N,K]^T        A, B row-major fp32, both K-major (gat_gemm ta=0, tb=1)
+//   NT:  C[M,N] = A[M,K] * B[N,K]^T    A, B row-major fp32, both K-major   (gat_gemm ta=0, tb=1: Wh = x W^T, dX = dWh W)
+//   TN:  C[M,N] = A[K,M]^T * B[K,N]    A, B row-major fp32, both MN-major  (gat_gemm ta=1, tb=0: dW = dWh^T x), split-K
 //
 // tcgen05 has no fp32 MMA kind, and plain TF32 (~5e-4) cannot meet the 1e-5 parity bar, so
 // every operand tile is split IN SHARED MEMORY into hi = tf32(v) and lo = v - hi, and three MMAs accumulate
@@ -67,9 +68,17 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N>>3, M>>4.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// MN-major, SWIZZLE_128B: an atom is 32 MN-elements (128 B) x 8 K-rows (1024 B, swizzled); atoms tile along MN with
+// stride LBO and along K with stride SBO.  A TMA box of {32 MN-elements, BK k-rows} lands as BK/8 atoms stacked
+// along K (SBO = 1024 B); consecutive boxes along MN are BK*128 B apart (LBO).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majorness bits 15/16, N>>3, M>>4.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, bool mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((mn_major ? 1u : 0u) << 15) | ((mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -104,13 +113,18 @@ struct Smem {
   static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// MN = false: NT product, one CTA per output tile, whole K.   MN = true: TN product, blockIdx.z = K split, the CTA
+// writes its partial tile to C + blockIdx.z * split_stride (reduced in a fixed order by splitk_reduce_kernel).
+template <int BN, bool MN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, int kb_per_split, int64_t split_stride) {
   using S = Smem<BN>;
   constexpr int kStages = S::kStages;
-  constexpr int kTmemCols = BN < 32 ? 32 : BN;   // BN is a power of two here
+  // two accumulators: [0, BN) leading term hi*hi, [BN, 2BN) cross terms hi*lo + lo*hi.  The tensor core rounds its
+  // fp32 accumulator toward zero at every step, a one-sided error proportional to the accumulator's magnitude; keeping
+  // the (2^-12 smaller) cross terms apart cuts the number of roundings the large accumulator sees by 3x.
+  constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // BN is a power of two here
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024 B alignment
   uint64_t* bars = (uint64_t*)(smem + kStages * S::kStageBytes);
@@ -122,7 +136,10 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
-  const int num_kb = (int)((K + BK - 1) / BK);
+  const int total_kb = (int)((K + BK - 1) / BK);
+  const int kb_begin = MN ? (int)blockIdx.z * kb_per_split : 0;
+  const int num_kb = MN ? max(0, min(kb_per_split, total_kb - kb_begin)) : total_kb;
+  C += (int64_t)blockIdx.z * split_stride;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], kSplitThreads); mbar_init(&empty[s], 1); }
@@ -146,14 +163,24 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (kb >= kStages) mbar_wait(&empty[s], ((kb / kStages) - 1) & 1);
         uint8_t* st = smem + s * S::kStageBytes;
         mbar_expect_tx(&full[s], S::kABytes + S::kBBytes);
-        tma_load_2d(st, &map_a, &full[s], kb * BK, (int)m0);
-        tma_load_2d(st + 2 * S::kABytes, &map_b, &full[s], kb * BK, (int)n0);
+        if (!MN) {
+          tma_load_2d(st, &map_a, &full[s], kb * BK, (int)m0);
+          tma_load_2d(st + 2 * S::kABytes, &map_b, &full[s], kb * BK, (int)n0);
+        } else {
+          const int krow = (kb_begin + kb) * BK;
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(st + j * (BK * 128), &map_a, &full[s], (int)m0 + 32 * j, krow);
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_2d(st + 2 * S::kABytes + j * (BK * 128), &map_b, &full[s], (int)n0 + 32 * j, krow);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN, MN);
+      const uint32_t tmem_main = tmem_base, tmem_cross = tmem_base + BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         mbar_wait(&ready[s], (kb / kStages) & 1);
@@ -162,15 +189,23 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t b_hi = a_hi + 2 * S::kABytes, b_lo = b_hi + S::kBBytes;
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint32_t off = k * UMMA_K * 4;   // bytes along the 128-byte swizzled row
-          // small cross terms first, then the leading term
-          umma_tf32(tmem_base, make_desc_k_sw128(a_hi + off), make_desc_k_sw128(b_lo + off), idesc, (kb | k) != 0);
-          umma_tf32(tmem_base, make_desc_k_sw128(a_lo + off), make_desc_k_sw128(b_hi + off), idesc, 1);
-          umma_tf32(tmem_base, make_desc_k_sw128(a_hi + off), make_desc_k_sw128(b_hi + off), idesc, 1);
+          const uint32_t first = (kb | k) != 0;
+          if (!MN) {
+            const uint32_t off = k * UMMA_K * 4;   // bytes along the 128-byte swizzled row
+            umma_tf32(tmem_cross, make_desc_k_sw128(a_hi + off), make_desc_k_sw128(b_lo + off), idesc, first);
+            umma_tf32(tmem_cross, make_desc_k_sw128(a_lo + off), make_desc_k_sw128(b_hi + off), idesc, 1);
+            umma_tf32(tmem_main, make_desc_k_sw128(a_hi + off), make_desc_k_sw128(b_hi + off), idesc, first);
+          } else {
+            const uint32_t off = k * 1024;         // one 8-row swizzle atom per UMMA_K
+            constexpr uint32_t lbo = BK * 128;
+            umma_tf32(tmem_cross, make_desc_mn_sw128(a_hi + off, lbo), make_desc_mn_sw128(b_lo + off, lbo), idesc, first);
+            umma_tf32(tmem_cross, make_desc_mn_sw128(a_lo + off, lbo), make_desc_mn_sw128(b_hi + off, lbo), idesc, 1);
+            umma_tf32(tmem_main, make_desc_mn_sw128(a_hi + off, lbo), make_desc_mn_sw128(b_hi + off, lbo), idesc, first);
+          }
         }
         umma_commit(&empty[s]);                  // implies tcgen05.fence::before_thread_sync
       }
-      umma_commit(accum);
+      if (num_kb > 0) umma_commit(accum);
     }
   } else {
     // ===== splitters (warps 2..5), then epilogue =====
@@ -202,24 +237,33 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_arrive(&ready[s]);
     }
     // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
-    mbar_wait(accum, 0);
+    if (num_kb > 0) mbar_wait(accum, 0);
     tc_fence_after();
     const int q = warp & 3;
     const int64_t row = m0 + q * 32 + lane;
     float* crow = C + row * ldc + n0;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 8) {
-      uint32_t r[8];
-      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
+      uint32_t r[8], x[8];
+      float v[8];
+      if (num_kb > 0) {
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c), x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(x[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
       if (row < M) {
         if (n0 + c + 8 <= N) {
-          *reinterpret_cast<float4*>(crow + c) = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
-          *reinterpret_cast<float4*>(crow + c + 4) = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+          *reinterpret_cast<float4*>(crow + c) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(crow + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (n0 + c + j < N) crow[c + j] = __uint_as_float(r[j]);
+            if (n0 + c + j < N) crow[c + j] = v[j];
         }
       }
     }
@@ -262,46 +306,99 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   return GAT_OK;
 }
 
-template <int BN>
-static int launch_nt(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb, float* c,
-                     int64_t ldc, cudaStream_t st) {
+struct TnPlan { int splits; int kb_per_split; };
+static TnPlan tn_plan(int64_t m, int64_t n, int64_t k, int bn) {
+  const int64_t tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
+  const int total_kb = (int)((k + BK - 1) / BK);
+  int64_t want = (kNumSMs + tiles - 1) / tiles;            // one wave of CTAs
+  if (want > total_kb) want = total_kb;
+  if (want < 1) want = 1;
+  TnPlan p;
+  p.kb_per_split = (int)((total_kb + want - 1) / want);
+  p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  if (p.splits < 1) p.splits = 1;
+  return p;
+}
+
+void splitk_reduce_launch(const float* partial, int splits, int64_t m, int64_t n, float* c, int64_t ldc, cudaStream_t st);
+
+template <int BN, bool MN>
+static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb, float* c,
+                  int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   CUtensorMap map_a, map_b;
-  int rc = make_map(&map_a, a, m, k, lda, BM);
-  if (rc) return rc;
-  rc = make_map(&map_b, b, n, k, ldb, BN);
+  int rc;
+  if (!MN) {
+    rc = make_map(&map_a, a, m, k, lda, BM);
+    if (!rc) rc = make_map(&map_b, b, n, k, ldb, BN);
+  } else {   // stored (K, M) and (K, N): boxes of 32 MN-elements x BK k-rows
+    rc = make_map(&map_a, a, k, m, lda, BK);
+    if (!rc) rc = make_map(&map_b, b, k, n, ldb, BK);
+  }
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    GAT_CUDA(cudaFuncSetAttribute(gemm_tc_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal));
+    GAT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal));
     attr_set = true;
   }
-  dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN));
-  gemm_tc_nt_kernel<BN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k);
+  if (!MN) {
+    dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), 1);
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, 0, 0);
+    GAT_LAUNCH_CHECK();
+    return GAT_OK;
+  }
+  TnPlan p = tn_plan(m, n, k, BN);
+  dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), (unsigned)p.splits);
+  if (p.splits == 1) {
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, p.kb_per_split, 0);
+    GAT_LAUNCH_CHECK();
+    return GAT_OK;
+  }
+  const size_t need = (size_t)p.splits * m * n * sizeof(float);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("gat_gemm: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return GAT_EWORKSPACE;
+  }
+  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, (float*)workspace, n, m, n, k, p.kb_per_split, m * n);
+  GAT_LAUNCH_CHECK();
+  splitk_reduce_launch((const float*)workspace, p.splits, m, n, c, ldc, st);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }
 
+static int bn_for(int64_t n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
+
 }  // namespace tc
 
 bool tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc) {
-  if (ta != 0 || tb != 1) return false;                        // K-major x K-major only (the forward projection layout)
+  const bool nt = (ta == 0 && tb == 1), tn = (ta == 1 && tb == 0);
+  if (!nt && !tn) return false;
   if (lda % 4 || ldb % 4 || ldc % 4) return false;             // TMA global strides / float4 stores need 16-byte multiples
   if (m < 1 || n < 8 || k < 1) return false;
   if (m >= ((int64_t)1 << 31) || n >= ((int64_t)1 << 31) || k >= ((int64_t)1 << 31)) return false;
   return true;
 }
 
-size_t tc_workspace_bytes(int, int, int64_t, int64_t, int64_t) { return 0; }
+size_t tc_workspace_bytes(int ta, int tb, int64_t m, int64_t n, int64_t k) {
+  if (!(ta == 1 && tb == 0) || m < 1 || n < 1 || k < 1) return 0;
+  tc::TnPlan p = tc::tn_plan(m, n, k, tc::bn_for(n));
+  return p.splits > 1 ? (size_t)p.splits * m * n * sizeof(float) : 0;
+}
 
 int gemm_tc(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb,
-            float* c, int64_t ldc, void*, size_t, cudaStream_t st) {
+            float* c, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (!tc_supported(ta, tb, m, n, k, lda, ldb, ldc) || ((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) % 16) {
-    set_error("gat_gemm: tcgen05 path needs ta=0, tb=1 and 16-byte aligned pointers / leading dimensions");
+    set_error("gat_gemm: tcgen05 path needs (ta,tb) = (0,1) or (1,0) and 16-byte aligned pointers / leading dimensions");
     return GAT_EUNSUPPORTED;
   }
-  if (n > 128) return tc::launch_nt<256>(m, n, k, a, lda, b, ldb, c, ldc, st);
-  if (n > 64) return tc::launch_nt<128>(m, n, k, a, lda, b, ldb, c, ldc, st);
-  return tc::launch_nt<64>(m, n, k, a, lda, b, ldb, c, ldc, st);
+  const int bn = tc::bn_for(n);
+  if (ta == 0) {
+    if (bn == 256) return tc::launch<256, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
+    if (bn == 128) return tc::launch<128, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
+    return tc::launch<64, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
+  }
+  if (bn == 256) return tc::launch<256, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
+  if (bn == 128) return tc::launch<128, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
+  return tc::launch<64, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
 }
 
 }  // namespace gat
