@@ -60,7 +60,7 @@ extern "C" int gat_gemm(int ta, int tb, int64_t m, int64_t n, int64_t k, const f
     return GAT_EUNSUPPORTED;
   }
   // auto: tensor cores once the problem is big enough to fill the machine; tiny problems stay on the FFMA path
-  const bool big = (double)m * (double)n * (double)k >= 1.6e7 && m >= 512;
+  const bool big = (double)m * (double)n * (double)k >= 1.6e7 && (ta ? k >= 4096 : m >= 512);
   if (algo == 2 || (algo == 0 && tc_ok && big))
     return gemm_tc(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
   return gemm_simt(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);

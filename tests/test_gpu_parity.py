@@ -250,4 +250,14 @@ def test_gemm_tcgen05_3xtf32():
         want = a.double() @ b.double().T
         err = ((c.double() - want).abs().max() / want.abs().max()).item()
         assert err < 3e-6, (m, n, k, err)
+    # TN: both operands MN-major, split-K with a fixed-order reduction (dW = dWh^T x)
+    for (m, n, k) in [(128, 64, 32), (256, 256, 4096), (192, 256, 10000), (256, 100, 5000), (64, 72, 3333), (260, 136, 70000)]:
+        assert lib.gat_gemm_tc_supported(1, 0, m, n, k, m, n, n)
+        a = torch.randn((k, m), device="cuda")
+        b = torch.randn((k, n), device="cuda")
+        c = torch.full((m, n), float("nan"), device="cuda")
+        gemm(True, False, m, n, k, a, m, b, n, c, n, algo=2)
+        want = a.double().T @ b.double()
+        err = ((c.double() - want).abs().max() / want.abs().max()).item()
+        assert err < 3e-6, ("TN", m, n, k, err)
     assert not lib.gat_gemm_tc_supported(0, 1, 100, 64, 1433, 1433, 1433, 64)     # Cora: K*4 bytes is not a 16-byte multiple

@@ -36,3 +36,14 @@ for (m, n, k) in [(2449029, 256, 256), (2449029, 256, 100), (2449029, 192, 256)]
     e2, t2 = run(m, n, k, False, True, 2, reps=5)
     e1, t1 = run(m, n, k, False, True, 1, reps=3)
     print(f"NT m={m} n={n} k={k}: tc {t2:.3f} ms err {e2:.2e} | ffma {t1:.3f} ms err {e1:.2e} | {2*m*n*k/t2/1e9:.1f} TFLOP/s(fp32-equivalent)", flush=True)
+
+print("---- TN (MN-major operands, split-K) ----", flush=True)
+for (m, n, k) in [(128, 64, 32), (256, 256, 4096), (192, 256, 10000), (256, 100, 5000), (64, 72, 3333), (1024, 1024, 4800), (260, 136, 70000)]:
+    ok = lib.gat_gemm_tc_supported(1, 0, m, n, k, m, n, n)
+    e2, _ = run(m, n, k, True, False, 2) if ok else (None, None)
+    e1, _ = run(m, n, k, True, False, 1)
+    print(f"TN m={m} n={n} k={k}: tc_supported={ok} err_tc={e2} err_ffma={e1}", flush=True)
+for (m, n, k) in [(256, 256, 2449029), (192, 256, 2449029), (256, 100, 2449029)]:
+    e2, t2 = run(m, n, k, True, False, 2, reps=5)
+    e1, t1 = run(m, n, k, True, False, 1, reps=3)
+    print(f"TN m={m} n={n} k={k}: tc {t2:.3f} ms err {e2:.2e} | ffma {t1:.3f} ms err {e1:.2e}", flush=True)
