@@ -68,12 +68,13 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// MN-major, SWIZZLE_128B: an atom is 32 MN-elements (128 B) x 8 K-rows (1024 B, swizzled); atoms tile along MN with
-// stride LBO and along K with stride SBO.  A TMA box of {32 MN-elements, BK k-rows} lands as BK/8 atoms stacked
-// along K (SBO = 1024 B); consecutive boxes along MN are BK*128 B apart (LBO).
-__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+// MN-major tf32: the only layout the tensor core accepts is SWIZZLE_128B_BASE32B (layout type 1; TMA mode
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): an atom is 32 MN-elements (128 B) x 4 K-rows (512 B, 32-byte chunks XORed with
+// the row index); atoms tile along MN with stride LBO and along K with stride SBO.  A TMA box of {32 MN-elements, BK
+// k-rows} lands as BK/4 atoms stacked along K (SBO = 512 B); consecutive boxes along MN are BK*128 B apart (LBO).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majorness bits 15/16, N>>3, M>>4.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, bool mn_major) {
@@ -118,7 +119,8 @@ struct Smem {
 template <int BN, bool MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, int kb_per_split, int64_t split_stride) {
+               float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, int kb_per_split, int64_t split_stride,
+               uint32_t mn_lbo, uint32_t mn_sbo) {
   using S = Smem<BN>;
   constexpr int kStages = S::kStages;
   // two accumulators: [0, BN) leading term hi*hi, [BN, 2BN) cross terms hi*lo + lo*hi.  The tensor core rounds its
@@ -197,10 +199,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             umma_tf32(tmem_main, make_desc_k_sw128(a_hi + off), make_desc_k_sw128(b_hi + off), idesc, first);
           } else {
             const uint32_t off = k * 1024;         // one 8-row swizzle atom per UMMA_K
-            constexpr uint32_t lbo = BK * 128;
-            umma_tf32(tmem_cross, make_desc_mn_sw128(a_hi + off, lbo), make_desc_mn_sw128(b_lo + off, lbo), idesc, first);
-            umma_tf32(tmem_cross, make_desc_mn_sw128(a_lo + off, lbo), make_desc_mn_sw128(b_hi + off, lbo), idesc, 1);
-            umma_tf32(tmem_main, make_desc_mn_sw128(a_hi + off, lbo), make_desc_mn_sw128(b_hi + off, lbo), idesc, first);
+            umma_tf32(tmem_cross, make_desc_mn_sw128(a_hi + off, mn_lbo, mn_sbo), make_desc_mn_sw128(b_lo + off, mn_lbo, mn_sbo), idesc, first);
+            umma_tf32(tmem_cross, make_desc_mn_sw128(a_lo + off, mn_lbo, mn_sbo), make_desc_mn_sw128(b_hi + off, mn_lbo, mn_sbo), idesc, 1);
+            umma_tf32(tmem_main, make_desc_mn_sw128(a_hi + off, mn_lbo, mn_sbo), make_desc_mn_sw128(b_hi + off, mn_lbo, mn_sbo), idesc, first);
           }
         }
         umma_commit(&empty[s]);                  // implies tcgen05.fence::before_thread_sync
@@ -293,7 +294,8 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D fp32 row-major (rows x cols, leading dimension ld elements); box = box_rows x 32 columns, SWIZZLE_128B,
 // out-of-bounds elements read as zero (so M, N and K tails need no special casing).
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    bool atom32 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("gat_gemm: cuTensorMapEncodeTiled is unavailable"); return GAT_EUNSUPPORTED; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -301,7 +303,8 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("gat_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r); return GAT_EINVAL; }
   return GAT_OK;
 }
@@ -331,8 +334,8 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
     rc = make_map(&map_a, a, m, k, lda, BM);
     if (!rc) rc = make_map(&map_b, b, n, k, ldb, BN);
   } else {   // stored (K, M) and (K, N): boxes of 32 MN-elements x BK k-rows
-    rc = make_map(&map_a, a, k, m, lda, BK);
-    if (!rc) rc = make_map(&map_b, b, k, n, ldb, BK);
+    rc = make_map(&map_a, a, k, m, lda, BK, true);
+    if (!rc) rc = make_map(&map_b, b, k, n, ldb, BK, true);
   }
   if (rc) return rc;
   static bool attr_set = false;
@@ -342,14 +345,15 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
   }
   if (!MN) {
     dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), 1);
-    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, 0, 0);
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, 0, 0, 0, 0);
     GAT_LAUNCH_CHECK();
     return GAT_OK;
   }
   TnPlan p = tn_plan(m, n, k, BN);
+  const uint32_t mn_lbo = BK * 128, mn_sbo = 512;   // measured on B200: the swapped assignment gives wrong products
   dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), (unsigned)p.splits);
   if (p.splits == 1) {
-    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, p.kb_per_split, 0);
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, p.kb_per_split, 0, mn_lbo, mn_sbo);
     GAT_LAUNCH_CHECK();
     return GAT_OK;
   }
@@ -358,7 +362,7 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
     set_error("gat_gemm: workspace too small (%zu < %zu)", workspace_bytes, need);
     return GAT_EWORKSPACE;
   }
-  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, (float*)workspace, n, m, n, k, p.kb_per_split, m * n);
+  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, (float*)workspace, n, m, n, k, p.kb_per_split, m * n, mn_lbo, mn_sbo);
   GAT_LAUNCH_CHECK();
   splitk_reduce_launch((const float*)workspace, p.splits, m, n, c, ldc, st);
   GAT_LAUNCH_CHECK();
