@@ -86,9 +86,9 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ P, int splits, in
                                      float* __restrict__ C, int64_t ldc) {
   int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= M * N) return;
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += P[(int64_t)z * M * N + idx];
-  C[(idx / N) * ldc + (idx % N)] = s;
+  double s = 0.0;
+  for (int z = 0; z < splits; ++z) s += (double)P[(int64_t)z * M * N + idx];
+  C[(idx / N) * ldc + (idx % N)] = (float)s;
 }
 
 namespace tc {

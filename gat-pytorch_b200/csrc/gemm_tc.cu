@@ -313,11 +313,16 @@ struct TnPlan { int splits; int kb_per_split; };
 static TnPlan tn_plan(int64_t m, int64_t n, int64_t k, int bn) {
   const int64_t tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
   const int total_kb = (int)((k + BK - 1) / BK);
-  int64_t want = (kNumSMs + tiles - 1) / tiles;            // one wave of CTAs
+  int64_t want = (kNumSMs + tiles - 1) / tiles;            // at least one wave of CTAs
   if (want > total_kb) want = total_kb;
   if (want < 1) want = 1;
   TnPlan p;
   p.kb_per_split = (int)((total_kb + want - 1) / want);
+  // The tensor core rounds its fp32 accumulator toward zero at every MMA, so the error of one accumulator grows
+  // linearly with the number of k-steps (measured: 7e-5 after 4136 steps, ~1e-6 after 128).  Cap the steps per
+  // split; the partials are then summed in fp64 by splitk_reduce_kernel.
+  constexpr int kMaxKbPerSplit = 64;
+  if (p.kb_per_split > kMaxKbPerSplit) p.kb_per_split = kMaxKbPerSplit;
   p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (p.splits < 1) p.splits = 1;
   return p;

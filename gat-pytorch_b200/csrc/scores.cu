@@ -14,46 +14,57 @@ namespace gat {
 
 constexpr int kScoreMaxJ = 16;     // 2 * max heads
 
-// ---- forward: one warp per row, lanes over float4 chunks, 2*NH fp64 partial sums per lane ----
-template <int NJ>   // NJ = compile-time bound on 2*nh (8 or 16)
+// ---- forward: one warp per R rows, lanes over float4 chunks, R x 2*NH fp64 partial sums per lane.  The A values of
+// a chunk are loaded (L1-resident) and converted once and applied to R rows, so the L1 traffic per Wh byte drops R x.
+template <int NJ, int R>   // NJ = compile-time bound on 2*nh (8 or 16)
 __global__ void __launch_bounds__(256)
 scores_fwd_kernel(const float* __restrict__ wh, int64_t n, int dp, const float* __restrict__ a_src,
                   const float* __restrict__ a_tgt, int nh, float* __restrict__ s_src, float* __restrict__ s_tgt) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
   const int chunks = dp >> 2, nj = 2 * nh;
-  for (int64_t row = warp; row < n; row += nwarps) {
-    double acc[NJ];
+  for (int64_t row0 = warp * R; row0 < n; row0 += nwarps * R) {
+    double acc[R][NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[j] = 0.0;
-    const float* wr = wh + row * dp;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc[r][j] = 0.0;
     for (int c = lane; c < chunks; c += 32) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(wr) + c);
-      const double w0 = w.x, w1 = w.y, w2 = w.z, w3 = w.w;
+      float4 w[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        w[r] = (row0 + r < n) ? __ldg(reinterpret_cast<const float4*>(wh + (row0 + r) * dp) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         if (j < nj) {
           const float* ap = (j < nh ? a_src + (int64_t)j * dp : a_tgt + (int64_t)(j - nh) * dp);
           const float4 a = __ldg(reinterpret_cast<const float4*>(ap) + c);
-          acc[j] = fma(w0, (double)a.x, acc[j]);
-          acc[j] = fma(w1, (double)a.y, acc[j]);
-          acc[j] = fma(w2, (double)a.z, acc[j]);
-          acc[j] = fma(w3, (double)a.w, acc[j]);
+          const double a0 = a.x, a1 = a.y, a2 = a.z, a3 = a.w;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            acc[r][j] = fma((double)w[r].x, a0, acc[r][j]);
+            acc[r][j] = fma((double)w[r].y, a1, acc[r][j]);
+            acc[r][j] = fma((double)w[r].z, a2, acc[r][j]);
+            acc[r][j] = fma((double)w[r].w, a3, acc[r][j]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      if (j < nj) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-      }
-    }
-    if (lane == 0) {
+    for (int r = 0; r < R; ++r) {
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         if (j < nj) {
-          if (j < nh) s_src[row * nh + j] = (float)acc[j]; else s_tgt[row * nh + (j - nh)] = (float)acc[j];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc[r][j] += __shfl_xor_sync(0xffffffffu, acc[r][j], o);
+        }
+      }
+      if (lane == 0 && row0 + r < n) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          if (j < nj) {
+            if (j < nh) s_src[(row0 + r) * nh + j] = (float)acc[r][j]; else s_tgt[(row0 + r) * nh + (j - nh)] = (float)acc[r][j];
+          }
         }
       }
     }
@@ -126,10 +137,10 @@ extern "C" int gat_scores_fwd(const float* wh, int64_t n, int dp, const float* a
   GAT_CHECK_ARG(nh >= 1 && nh <= 8, "gat_scores_fwd: num_heads %d not in [1, 8]", nh);
   GAT_CHECK_ARG(dp > 0 && dp % 4 == 0 && n >= 0, "gat_scores_fwd: bad shape");
   if (n == 0) return GAT_OK;
-  int64_t want = (n + 7) / 8;
-  unsigned blocks = (unsigned)(want < kNumSMs * 8 ? want : kNumSMs * 8);
-  if (nh <= 4) scores_fwd_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(wh, n, dp, a_src, a_tgt, nh, s_src, s_tgt);
-  else scores_fwd_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(wh, n, dp, a_src, a_tgt, nh, s_src, s_tgt);
+  int64_t want = (n + 31) / 32;
+  unsigned blocks = (unsigned)(want < kNumSMs * 6 ? (want < 1 ? 1 : want) : kNumSMs * 6);
+  if (nh <= 4) scores_fwd_kernel<8, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(wh, n, dp, a_src, a_tgt, nh, s_src, s_tgt);
+  else scores_fwd_kernel<16, 2><<<blocks, 256, 0, (cudaStream_t)stream>>>(wh, n, dp, a_src, a_tgt, nh, s_src, s_tgt);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }
