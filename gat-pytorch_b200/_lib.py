@@ -31,10 +31,12 @@ SIGNATURES = {
     "gat_gemm_tc_supported": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64]),
     "gat_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64,
                          c_int, _P, c_size_t, _P]),
+    "gat_project_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, _P, _P,
+                                c_int, _P, c_size_t, _P]),
     "gat_scores_fwd": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P]),
     "gat_scores_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gat_scores_bwd": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "gat_edge_max": (c_int, [_P, _P, c_int64, _P, _P, c_int, _P, _P]),
+    "gat_edge_max": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int, _P, _P, c_size_t, _P]),
     "gat_edge_fwd_workspace_bytes": (c_size_t, []),
     "gat_edge_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, c_int, c_float, c_uint64, c_uint64,
                              _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),

@@ -25,6 +25,9 @@ int gemm_tc(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int
             int64_t ldb, float* c, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t tc_workspace_bytes(int ta, int tb, int64_t m, int64_t n, int64_t k);
 bool tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc);
+bool tc_project_supported(int64_t n_rows, int64_t dp, int64_t k, int64_t ldx, int64_t ldw);
+int gemm_tc_project(int64_t n_rows, int64_t dp, int64_t k, const float* x, int64_t ldx, const float* w, int64_t ldw,
+                    float* wh, const float* a_src, const float* a_tgt, int nh, float* s_src, float* s_tgt, cudaStream_t st);
 
 }  // namespace gat
 
@@ -64,4 +67,26 @@ extern "C" int gat_gemm(int ta, int tb, int64_t m, int64_t n, int64_t k, const f
   if (algo == 2 || (algo == 0 && tc_ok && big))
     return gemm_tc(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
   return gemm_simt(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
+}
+
+// Kernel 2 as the north star names it: the projection GEMM that also emits the per-node score terms.
+extern "C" int gat_project_fwd(const float* x, int64_t n, int64_t f_in, int64_t ldx, const float* w, int64_t ldw, int dp,
+                               const float* a_src, const float* a_tgt, int nh, float* wh, float* s_src, float* s_tgt,
+                               int algo, void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(n >= 0 && f_in >= 1 && dp >= 4 && dp % 4 == 0, "gat_project_fwd: bad shape");
+  GAT_CHECK_ARG(algo >= 0 && algo <= 2, "gat_project_fwd: unknown algo %d", algo);
+  GAT_CHECK_ARG((a_src == nullptr) == (a_tgt == nullptr), "gat_project_fwd: attention halves must be given together");
+  if (n == 0) return GAT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool want_scores = a_src != nullptr;
+  const bool big = (double)n * dp * (double)f_in >= 1.6e7 && n >= 512;
+  const bool fused_ok = want_scores && tc_project_supported(n, dp, f_in, ldx, ldw) &&
+                        ((uintptr_t)x | (uintptr_t)w | (uintptr_t)wh | (uintptr_t)a_src | (uintptr_t)a_tgt) % 16 == 0;
+  if (fused_ok && (algo == 2 || (algo == 0 && big)))
+    return gemm_tc_project(n, dp, f_in, x, ldx, w, ldw, wh, a_src, a_tgt, nh, s_src, s_tgt, st);
+  int rc = gat_gemm(0, 1, n, dp, f_in, x, ldx, w, ldw, wh, dp, algo == 2 && !tc_supported(0, 1, n, dp, f_in, ldx, ldw, dp) ? 0 : algo,
+                    workspace, workspace_bytes, stream);
+  if (rc != GAT_OK || !want_scores) return rc;
+  return gat_scores_fwd(wh, n, dp, a_src, a_tgt, nh, s_src, s_tgt, stream);
 }

@@ -6,35 +6,52 @@ namespace gat {
 
 // ------------------------------------------------------------------------------------------
 // Kernel 3a: M = max_{e,h} (s_src[src_e,h] + s_tgt[dst_e,h])      (gat_layer.py:85)
-// 8 lanes per destination row; s_src (n*NH floats) is L2-resident, so DRAM traffic is ~ col only.
+// Persistent grid, one warp per destination row handed out long rows first (same scheduler as Kernel 3);
+// s_src (n*NH floats) is L2-resident, so DRAM traffic is ~ col only.  max() is order independent, so the
+// float atomic max keeps the result deterministic.
 // ------------------------------------------------------------------------------------------
+struct EdgeMaxParams {
+  const int32_t* rowptr; const int32_t* col; RowSched sched;
+  const float* s_src; const float* s_tgt; int nh; float* gmax;
+};
+
 __global__ void __launch_bounds__(256)
-edge_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n,
-                const float* __restrict__ s_src, const float* __restrict__ s_tgt, int nh, float* __restrict__ gmax) {
+edge_max_kernel(const EdgeMaxParams P) {
   __shared__ float warp_max[8];
-  const int tid = threadIdx.x, gl = tid & 7;
-  const int64_t row = (int64_t)blockIdx.x * 32 + (tid >> 3);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nh = P.nh;
   float m = -INFINITY;
-  if (row < n) {
-    float st[kMaxHeads];
+  int64_t base;
+  while (grab_rows<32>(P.sched, lane, base)) {
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const int64_t row = sched_row<32>(P.sched, base, k, lane);
+      if (row < 0) continue;
+      float st[kMaxHeads];
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) st[h] = h < nh ? __ldg(s_tgt + row * nh + h) : 0.f;
-    const int start = rowptr[row], end = rowptr[row + 1];
-    for (int e = start + gl; e < end; e += 8) {
-      const float* ss = s_src + (int64_t)__ldg(col + e) * nh;
+      for (int h = 0; h < kMaxHeads; ++h) st[h] = h < nh ? __ldg(P.s_tgt + row * nh + h) : 0.f;
+      const int start = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
+      for (int e = start + lane; e < end; e += 32) {
+        const float* ss = P.s_src + (int64_t)__ldg(P.col + e) * nh;
+        if (nh == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(ss));
+          m = fmaxf(m, fmaxf(fmaxf(v.x + st[0], v.y + st[1]), fmaxf(v.z + st[2], v.w + st[3])));
+        } else {
 #pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h)
-        if (h < nh) m = fmaxf(m, __ldg(ss + h) + st[h]);
+          for (int h = 0; h < kMaxHeads; ++h)
+            if (h < nh) m = fmaxf(m, __ldg(ss + h) + st[h]);
+        }
+      }
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((tid & 31) == 0) warp_max[tid >> 5] = m;
+  if (lane == 0) warp_max[tid >> 5] = m;
   __syncthreads();
   if (tid == 0) {
 #pragma unroll
     for (int w = 1; w < 8; ++w) m = fmaxf(m, warp_max[w]);
-    if (m > -INFINITY) atomic_max_float(gmax, m);
+    if (m > -INFINITY) atomic_max_float(P.gmax, m);
   }
 }
 
@@ -241,12 +258,21 @@ __global__ void head_merge_bwd_kernel(const float* __restrict__ g, int64_t n, in
 
 }  // namespace gat
 
-extern "C" int gat_edge_max(const int32_t* rowptr, const int32_t* col, int64_t n, const float* s_src,
-                            const float* s_tgt, int nh, float* gmax, gat_stream_t stream) {
+extern "C" int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, int64_t n,
+                            const float* s_src, const float* s_tgt, int nh, float* gmax,
+                            void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
   GAT_CHECK_ARG(nh >= 1 && nh <= kMaxHeads, "gat_edge_max: num_heads %d not in [1, %d]", nh, kMaxHeads);
+  GAT_CHECK_ARG(workspace != nullptr && workspace_bytes >= 256, "gat_edge_max: workspace too small");
   if (n == 0) return GAT_OK;
-  edge_max_kernel<<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(rowptr, col, n, s_src, s_tgt, nh, gmax);
+  cudaStream_t st = (cudaStream_t)stream;
+  // the row counter lives in the second word of the shared 256-byte workspace (gat_edge_fwd uses the first)
+  unsigned int* counter = (unsigned int*)workspace + 16;
+  GAT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+  EdgeMaxParams P;
+  P.rowptr = rowptr; P.col = col; P.sched.order = row_order; P.sched.counter = counter; P.sched.n = n;
+  P.s_src = s_src; P.s_tgt = s_tgt; P.nh = nh; P.gmax = gmax;
+  edge_max_kernel<<<persistent_grid(edge_max_kernel, 256, 0, (n + 7) / 8), 256, 0, st>>>(P);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }

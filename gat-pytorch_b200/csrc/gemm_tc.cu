@@ -120,7 +120,10 @@ template <int BN, bool MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, int kb_per_split, int64_t split_stride,
-               uint32_t mn_lbo, uint32_t mn_sbo) {
+               uint32_t mn_lbo, uint32_t mn_sbo,
+               // fused score epilogue (NT only, one N tile): s_src = C A_src^T, s_tgt = C A_tgt^T in fp64, or nullptr
+               const float* __restrict__ a_src, const float* __restrict__ a_tgt, int nh,
+               float* __restrict__ s_src, float* __restrict__ s_tgt) {
   using S = Smem<BN>;
   constexpr int kStages = S::kStages;
   // two accumulators: [0, BN) leading term hi*hi, [BN, 2BN) cross terms hi*lo + lo*hi.  The tensor core rounds its
@@ -243,6 +246,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int q = warp & 3;
     const int64_t row = m0 + q * 32 + lane;
     float* crow = C + row * ldc + n0;
+    // Fused score terms: the attention halves (2*nh x N floats) are staged in the now idle pipeline memory; every
+    // epilogue thread owns one full row of Wh (this CTA covers all N columns), so s = Wh A^T needs no reduction.
+    const bool fuse = (!MN) && a_src != nullptr;
+    float* a_s = reinterpret_cast<float*>(smem);
+    const int nj = 2 * nh;
+    double sacc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sacc[j] = 0.0;
+    if (fuse) {
+      for (int i = t; i < nj * BN; i += kSplitThreads) {
+        const int j = i / BN, col = i - j * BN;
+        float v = 0.f;
+        if (col < N) v = (j < nh) ? __ldg(a_src + (int64_t)j * N + col) : __ldg(a_tgt + (int64_t)(j - nh) * N + col);
+        a_s[i] = v;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kSplitThreads) : "memory");
+    }
 #pragma unroll 1
     for (int c = 0; c < BN; c += 8) {
       uint32_t r[8], x[8];
@@ -257,6 +277,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
       }
+      if (fuse) {
+        double dv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dv[i] = (double)v[i];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j < nj) {
+            const float4 a0 = *reinterpret_cast<const float4*>(a_s + j * BN + c);
+            const float4 a1 = *reinterpret_cast<const float4*>(a_s + j * BN + c + 4);
+            double sj = sacc[j];
+            sj = fma(dv[0], (double)a0.x, sj); sj = fma(dv[1], (double)a0.y, sj);
+            sj = fma(dv[2], (double)a0.z, sj); sj = fma(dv[3], (double)a0.w, sj);
+            sj = fma(dv[4], (double)a1.x, sj); sj = fma(dv[5], (double)a1.y, sj);
+            sj = fma(dv[6], (double)a1.z, sj); sj = fma(dv[7], (double)a1.w, sj);
+            sacc[j] = sj;
+          }
+        }
+      }
       if (row < M) {
         if (n0 + c + 8 <= N) {
           *reinterpret_cast<float4*>(crow + c) = make_float4(v[0], v[1], v[2], v[3]);
@@ -265,6 +303,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (n0 + c + j < N) crow[c + j] = v[j];
+        }
+      }
+    }
+    if (fuse && row < M) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < nj) {
+          if (j < nh) s_src[row * nh + j] = (float)sacc[j]; else s_tgt[row * nh + (j - nh)] = (float)sacc[j];
         }
       }
     }
@@ -330,9 +376,11 @@ static TnPlan tn_plan(int64_t m, int64_t n, int64_t k, int bn) {
 
 void splitk_reduce_launch(const float* partial, int splits, int64_t m, int64_t n, float* c, int64_t ldc, cudaStream_t st);
 
+struct ScoreFuse { const float* a_src; const float* a_tgt; int nh; float* s_src; float* s_tgt; };
+
 template <int BN, bool MN>
 static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb, float* c,
-                  int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                  int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st, ScoreFuse f = ScoreFuse{nullptr, nullptr, 0, nullptr, nullptr}) {
   CUtensorMap map_a, map_b;
   int rc;
   if (!MN) {
@@ -350,7 +398,7 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
   }
   if (!MN) {
     dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), 1);
-    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, 0, 0, 0, 0);
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, 0, 0, 0, 0, f.a_src, f.a_tgt, f.nh, f.s_src, f.s_tgt);
     GAT_LAUNCH_CHECK();
     return GAT_OK;
   }
@@ -358,7 +406,7 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
   const uint32_t mn_lbo = BK * 128, mn_sbo = 512;   // measured on B200: the swapped assignment gives wrong products
   dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), (unsigned)p.splits);
   if (p.splits == 1) {
-    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, p.kb_per_split, 0, mn_lbo, mn_sbo);
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, p.kb_per_split, 0, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr);
     GAT_LAUNCH_CHECK();
     return GAT_OK;
   }
@@ -367,7 +415,7 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
     set_error("gat_gemm: workspace too small (%zu < %zu)", workspace_bytes, need);
     return GAT_EWORKSPACE;
   }
-  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, (float*)workspace, n, m, n, k, p.kb_per_split, m * n, mn_lbo, mn_sbo);
+  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, (float*)workspace, n, m, n, k, p.kb_per_split, m * n, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr);
   GAT_LAUNCH_CHECK();
   splitk_reduce_launch((const float*)workspace, p.splits, m, n, c, ldc, st);
   GAT_LAUNCH_CHECK();
@@ -391,6 +439,25 @@ size_t tc_workspace_bytes(int ta, int tb, int64_t m, int64_t n, int64_t k) {
   if (!(ta == 1 && tb == 0) || m < 1 || n < 1 || k < 1) return 0;
   tc::TnPlan p = tc::tn_plan(m, n, k, tc::bn_for(n));
   return p.splits > 1 ? (size_t)p.splits * m * n * sizeof(float) : 0;
+}
+
+// Forward projection with the score epilogue fused: wh = x W^T, s_src = wh A_src^T, s_tgt = wh A_tgt^T.  Needs the whole
+// row of wh in one CTA (dp <= 256) and dense attention halves (leading dimension dp).
+bool tc_project_supported(int64_t n_rows, int64_t dp, int64_t k, int64_t ldx, int64_t ldw) {
+  return dp <= 256 && dp % 4 == 0 && tc_supported(0, 1, n_rows, dp, k, ldx, ldw, dp);
+}
+
+int gemm_tc_project(int64_t n_rows, int64_t dp, int64_t k, const float* x, int64_t ldx, const float* w, int64_t ldw,
+                    float* wh, const float* a_src, const float* a_tgt, int nh, float* s_src, float* s_tgt, cudaStream_t st) {
+  if (!tc_project_supported(n_rows, dp, k, ldx, ldw) || ((uintptr_t)x | (uintptr_t)w | (uintptr_t)wh | (uintptr_t)a_src | (uintptr_t)a_tgt) % 16) {
+    set_error("gat_project_fwd: fused tcgen05 path unsupported for this shape/alignment");
+    return GAT_EUNSUPPORTED;
+  }
+  tc::ScoreFuse f{a_src, a_tgt, nh, s_src, s_tgt};
+  const int bn = tc::bn_for(dp);
+  if (bn == 256) return tc::launch<256, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f);
+  if (bn == 128) return tc::launch<128, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f);
+  return tc::launch<64, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f);
 }
 
 int gemm_tc(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb,

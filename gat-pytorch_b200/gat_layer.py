@@ -53,16 +53,21 @@ class _GATFunction(torch.autograd.Function):
             s = _stream(dev)
             f32 = dict(dtype=torch.float32, device=dev)
             wh = torch.empty((n, dp), **f32)
-            gemm(False, True, n, dp, f_in, x, x.stride(0), w_p, w_p.stride(0), wh, dp, gemm_algo)
             s_src = s_tgt = gmax = None
+            fws = torch.empty(int(lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=dev)
             if not const_attention:
                 s_src = torch.empty((n, nh), **f32)
                 s_tgt = torch.empty((n, nh), **f32)
-                _lib.call("gat_scores_fwd", wh.data_ptr(), n, dp, a_src_p.data_ptr(), a_tgt_p.data_ptr(), nh,
-                                              s_src.data_ptr(), s_tgt.data_ptr(), s)
+            gws_bytes = int(lib.gat_gemm_workspace_bytes(0, 1, n, dp, f_in, gemm_algo))
+            gws = torch.empty(gws_bytes, dtype=torch.uint8, device=dev) if gws_bytes else None
+            # Kernel 2: projection GEMM that also emits the per-node score terms
+            _lib.call("gat_project_fwd", x.data_ptr(), n, f_in, x.stride(0), w_p.data_ptr(), w_p.stride(0), dp,
+                      _ptr(a_src_p), _ptr(a_tgt_p), nh, wh.data_ptr(), _ptr(s_src), _ptr(s_tgt), gemm_algo,
+                      _ptr(gws), gws_bytes, s, tag=(n, dp, f_in))
+            if not const_attention:
                 gmax = torch.full((1,), float("-inf"), **f32)
-                _lib.call("gat_edge_max", st.rowptr.data_ptr(), st.col.data_ptr(), n, s_src.data_ptr(),
-                                            s_tgt.data_ptr(), nh, gmax.data_ptr(), s)
+                _lib.call("gat_edge_max", st.rowptr.data_ptr(), st.col.data_ptr(), st.order.data_ptr(), n, s_src.data_ptr(),
+                          s_tgt.data_ptr(), nh, gmax.data_ptr(), fws.data_ptr(), fws.numel(), s)
             out_p = torch.empty((n, dp), **f32)
             alpha = torch.empty((st.n_edges, nh), **f32) if want_alpha else None
             z = torch.empty((n, nh), **f32)
@@ -73,7 +78,6 @@ class _GATFunction(torch.autograd.Function):
             seed = 0
             if p_drop > 0.0:
                 seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator: no device sync
-            fws = torch.empty(int(lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=dev)
             _lib.call("gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), n,
                                         wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax),
                                         int(const_attention), float(p_drop), seed, 0,

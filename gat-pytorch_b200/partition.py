@@ -86,6 +86,19 @@ class CudaBackend:
     def build_structure(self, edges_local, n_global):
         return build_structure(edges_local.contiguous(), n_global, False)
 
+    @staticmethod
+    def local_order(st, plan):
+        """Scheduling permutation of the OWNED target rows (relative to plan.lo), long rows first -- the same hint
+        gat_csr_build emits for a whole graph (the structure here spans all N rows, most of them empty)."""
+        cached = getattr(st, "_local_order", None)
+        if cached is None or cached[0] != (plan.lo, plan.hi):
+            deg = st.rowptr[plan.lo + 1:plan.hi + 1] - st.rowptr[plan.lo:plan.hi]
+            long_rows = deg > 256
+            order = torch.cat([long_rows.nonzero().flatten(), (~long_rows).nonzero().flatten()]).to(torch.int32)
+            st._local_order = ((plan.lo, plan.hi), order)
+            cached = st._local_order
+        return cached[1]
+
     def n_edges(self, st):
         return st.n_edges
 
@@ -98,13 +111,16 @@ class CudaBackend:
                   s_src.data_ptr(), s_tgt.data_ptr(), self._s(wh.device))
 
     def edge_max(self, st, plan, s_src_full, s_tgt_local, nh, gmax):
-        _lib.call("gat_edge_max", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), plan.rows,
-                  s_src_full.data_ptr(), s_tgt_local.data_ptr(), nh, gmax.data_ptr(), self._s(gmax.device))
+        ws = torch.empty(int(self.lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=gmax.device)
+        _lib.call("gat_edge_max", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), self.local_order(st, plan).data_ptr(),
+                  plan.rows, s_src_full.data_ptr(), s_tgt_local.data_ptr(), nh, gmax.data_ptr(), ws.data_ptr(), ws.numel(),
+                  self._s(gmax.device))
 
     def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total):
         p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
         fws = torch.empty(int(self.lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=out_p.device)
-        _lib.call("gat_edge_fwd", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(), None, plan.rows,
+        _lib.call("gat_edge_fwd", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(),
+                  self.local_order(st, plan).data_ptr(), plan.rows,
                   wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(), s_tgt_local.data_ptr(), gmax.data_ptr(),
                   0, 0.0, 0, 0, out_p.data_ptr(), None, z.data_ptr(), p(tie_dst), p(tie_src), p(tie_total),
                   fws.data_ptr(), fws.numel(), self._s(out_p.device), tag=(nh, fp))
@@ -112,13 +128,20 @@ class CudaBackend:
     def edge_bwd_dst(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z, go_p, rec, ds_tgt):
         ws_bytes = int(self.lib.gat_edge_bwd_workspace_bytes(plan.rows, st.n_edges, nh))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=go_p.device)
-        _lib.call("gat_edge_bwd_dst", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(), None, plan.rows,
+        _lib.call("gat_edge_bwd_dst", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(),
+                  self.local_order(st, plan).data_ptr(), plan.rows,
                   wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(), s_tgt_local.data_ptr(), gmax.data_ptr(), z.data_ptr(),
                   0, 0.0, 0, 0, go_p.data_ptr(), None, rec.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes,
                   self._s(go_p.device), tag=(nh, fp))
         gamma = torch.empty(1, dtype=torch.float64, device=go_p.device)
         _lib.call("gat_edge_bwd_gamma", ws.data_ptr(), ws_bytes, gamma.data_ptr(), self._s(go_p.device))
         return gamma
+
+    def scores_bwd(self, wh, n, dp, nh, ds_src, ds_tgt, da_src, da_tgt):
+        sb = int(self.lib.gat_scores_bwd_workspace_bytes(dp, nh))
+        ws = torch.empty(sb, dtype=torch.uint8, device=wh.device)
+        _lib.call("gat_scores_bwd", wh.data_ptr(), n, dp, nh, ds_src.data_ptr(), ds_tgt.data_ptr(),
+                  da_src.data_ptr(), da_tgt.data_ptr(), ws.data_ptr(), sb, self._s(wh.device))
 
     def edge_bwd_src(self, st, plan, nh, fp, rec, go_p, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
         dp = nh * fp
@@ -173,7 +196,8 @@ class _PartitionedGATFunction(torch.autograd.Function):
         rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
         go_p = go_p.contiguous()
         rec = torch.empty((max(backend.n_edges(st), 1), 2 * nh), **f32)
-        ds_tgt = torch.zeros((max(rows, 1), nh), **f32)
+        ds_tgt_full = torch.zeros((plan.n_pad + 1, nh), **f32)     # owned rows live at [lo, hi); the rest stays zero
+        ds_tgt = ds_tgt_full[plan.lo:plan.lo + max(rows, 1)]
         gamma = torch.zeros(1, dtype=torch.float64, device=dev)
         if rows:
             gamma = backend.edge_bwd_dst(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, rec, ds_tgt)
@@ -197,8 +221,7 @@ class _PartitionedGATFunction(torch.autograd.Function):
         ga_tgt = torch.zeros((nh, dp), **f32)
         if rows:
             backend.gemm(True, False, dp, f_in, rows, d_wh, dp, x_local, x_local.stride(0), gw, f_in)
-            backend.gemm(True, False, nh, dp, rows, ds_tgt, nh, wh_full[plan.lo:], dp, ga_tgt, dp)
-        backend.gemm(True, False, nh, dp, plan.n, ds_src_part, nh, wh_full, dp, ga_src, dp)
+        backend.scores_bwd(wh_full, plan.n, dp, nh, ds_src_part, ds_tgt_full, ga_src, ga_tgt)   # one pass over Wh
         flat = torch.cat([gw.reshape(-1), ga_src.reshape(-1), ga_tgt.reshape(-1)])
         dist.all_reduce(flat, group=group)                                  # the gradient all-reduce
         gw, ga_src, ga_tgt = flat[:gw.numel()].view_as(gw), flat[gw.numel():gw.numel() + ga_src.numel()].view_as(ga_src), \

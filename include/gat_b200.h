@@ -92,6 +92,15 @@ GAT_API int gat_gemm(int ta, int tb, int64_t m, int64_t n, int64_t k,
              const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
              int algo, void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
+/* The forward projection as one entry point: wh (n, dp) = x (n, f_in) * w (dp, f_in)^T  [gat_layer.py:64-65] and, when
+ * a_src/a_tgt (nh, dp) are given, s_src/s_tgt (n, nh) = wh * a_src^T / wh * a_tgt^T  [gat_layer.py:76-82].  When the
+ * tcgen05 path applies and dp <= 256 the score terms are computed in the GEMM epilogue from the accumulator tile
+ * (fp64 accumulation over the fp32-rounded wh, same arithmetic as gat_scores_fwd); otherwise gat_gemm + gat_scores_fwd.
+ * workspace: gat_gemm_workspace_bytes(0, 1, n, dp, f_in, algo). */
+GAT_API int gat_project_fwd(const float* x, int64_t n, int64_t f_in, int64_t ldx, const float* w, int64_t ldw, int dp,
+                            const float* a_src, const float* a_tgt, int nh, float* wh, float* s_src, float* s_tgt,
+                            int algo, void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
 /* s_src[i,h] = <wh[i,:], a_src[h,:]>, s_tgt[i,h] = <wh[i,:], a_tgt[h,:]>  (fp64 accumulate).
  * The decomposition of gat_layer.py:76-82: logit[e,h] = s_src[src_e,h] + s_tgt[dst_e,h]. */
 GAT_API int gat_scores_fwd(const float* wh, int64_t n, int dp, const float* a_src, const float* a_tgt, int nh,
@@ -108,9 +117,11 @@ GAT_API int gat_scores_bwd(const float* wh, int64_t n, int dp, int nh, const flo
  * ------------------------------------------------------------------------------------- */
 
 /* Kernel 3a: *gmax = max over all (e,h) of s_src[col[e],h] + s_tgt[dst(e),h]  (gat_layer.py:85).
- * gmax must hold -inf on entry (the kernel combines with an ordered atomic max). */
-GAT_API int gat_edge_max(const int32_t* rowptr, const int32_t* col, int64_t n, const float* s_src,
-                 const float* s_tgt, int nh, float* gmax, gat_stream_t stream);
+ * gmax must hold -inf on entry (the kernel combines with an order-independent atomic max).
+ * workspace: the same gat_edge_fwd_workspace_bytes() buffer that is later handed to gat_edge_fwd. */
+GAT_API int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, int64_t n,
+                 const float* s_src, const float* s_tgt, int nh, float* gmax,
+                 void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* Kernel 3: per destination row, p = exp(0.01*(l-M)) (gat_layer.py:85-96), Z = sum p (:99-103),
  * alpha = p/(Z+1e-8) (:106-109), Philox dropout on alpha (:113-115), out = sum alpha*wh[src]

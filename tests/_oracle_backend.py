@@ -69,6 +69,10 @@ class OracleBackend:
         ds_tgt[:rows].index_add_(0, dl, g)
         return g.double().sum().reshape(1)
 
+    def scores_bwd(self, wh, n, dp, nh, ds_src, ds_tgt, da_src, da_tgt):
+        da_src.copy_((ds_src[:n].double().T @ wh[:n].double()).float())
+        da_tgt.copy_((ds_tgt[:n].double().T @ wh[:n].double()).float())
+
     def edge_bwd_src(self, st, plan, nh, fp, rec, go_p, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
         e = st["src"].numel()
         g, w = rec[:e, :nh], rec[:e, nh:]
