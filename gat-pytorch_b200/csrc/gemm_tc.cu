@@ -249,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // Fused score terms: the attention halves (2*nh x N floats) are staged in the now idle pipeline memory; every
     // epilogue thread owns one full row of Wh (this CTA covers all N columns), so s = Wh A^T needs no reduction.
     const bool fuse = (!MN) && a_src != nullptr;
-    float* a_s = reinterpret_cast<float*>(smem);
+    double* a_s = reinterpret_cast<double*>(smem);   // converted once per CTA: F2F is the slow instruction here
     const int nj = 2 * nh;
     double sacc[16];
 #pragma unroll
@@ -259,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int j = i / BN, col = i - j * BN;
         float v = 0.f;
         if (col < N) v = (j < nh) ? __ldg(a_src + (int64_t)j * N + col) : __ldg(a_tgt + (int64_t)(j - nh) * N + col);
-        a_s[i] = v;
+        a_s[i] = (double)v;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kSplitThreads) : "memory");
     }
@@ -284,13 +284,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (j < nj) {
-            const float4 a0 = *reinterpret_cast<const float4*>(a_s + j * BN + c);
-            const float4 a1 = *reinterpret_cast<const float4*>(a_s + j * BN + c + 4);
+            const double2* ap = reinterpret_cast<const double2*>(a_s + j * BN + c);   // broadcast LDS.128
+            const double2 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];
             double sj = sacc[j];
-            sj = fma(dv[0], (double)a0.x, sj); sj = fma(dv[1], (double)a0.y, sj);
-            sj = fma(dv[2], (double)a0.z, sj); sj = fma(dv[3], (double)a0.w, sj);
-            sj = fma(dv[4], (double)a1.x, sj); sj = fma(dv[5], (double)a1.y, sj);
-            sj = fma(dv[6], (double)a1.z, sj); sj = fma(dv[7], (double)a1.w, sj);
+            sj = fma(dv[0], a0.x, sj); sj = fma(dv[1], a0.y, sj);
+            sj = fma(dv[2], a1.x, sj); sj = fma(dv[3], a1.y, sj);
+            sj = fma(dv[4], a2.x, sj); sj = fma(dv[5], a2.y, sj);
+            sj = fma(dv[6], a3.x, sj); sj = fma(dv[7], a3.y, sj);
             sacc[j] = sj;
           }
         }

@@ -60,4 +60,4 @@ def model_step(x, edge_index, weights, shapes):
             h = F.elu(h)
     loss = h.square().mean()
     loss.backward()
-    return float(loss)
+    return float(loss.detach())
