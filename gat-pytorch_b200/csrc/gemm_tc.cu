@@ -248,18 +248,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float* crow = C + row * ldc + n0;
     // Fused score terms: the attention halves (2*nh x N floats) are staged in the now idle pipeline memory; every
     // epilogue thread owns one full row of Wh (this CTA covers all N columns), so s = Wh A^T needs no reduction.
+    // Fused score terms s = Wh A^T in fp64 (gat_layer.py:76-82).  Vector FP64 runs at ~1/16 of the FP32 rate on this
+    // part (measured: 2.3 T DFMA/s), so the contraction goes through the FP64 tensor cores: mma.sync m8n8k4.f64,
+    // M = 8 rows, N = 8 score columns, K = 4.  The attention halves are converted to fp64 once per CTA into the now
+    // idle pipeline memory; each warp transposes its 32 rows x 8 columns of Wh through a private shared-memory
+    // tile into the A-fragment layout.
     const bool fuse = (!MN) && a_src != nullptr;
-    double* a_s = reinterpret_cast<double*>(smem);   // converted once per CTA: F2F is the slow instruction here
-    const int nj = 2 * nh;
-    double sacc[16];
+    constexpr int ASTR = BN + 4;                     // row stride (doubles) of the staged attention matrix
+    constexpr int TSTR = 36;                         // row stride (doubles) of the per-warp transpose tile
+    double* a_s = reinterpret_cast<double*>(smem);   // [16][ASTR], rows >= 2*nh are zero
+    double* tile = a_s + 16 * ASTR + (warp - 2) * (8 * TSTR);
+    const int nj = 2 * nh, nbk = nj > 8 ? 2 : 1;
+    double sacc[4][2][2];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) sacc[j] = 0.0;
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) sacc[g][nb][0] = sacc[g][nb][1] = 0.0;
     if (fuse) {
-      for (int i = t; i < nj * BN; i += kSplitThreads) {
+      for (int i = t; i < 16 * BN; i += kSplitThreads) {
         const int j = i / BN, col = i - j * BN;
         float v = 0.f;
-        if (col < N) v = (j < nh) ? __ldg(a_src + (int64_t)j * N + col) : __ldg(a_tgt + (int64_t)(j - nh) * N + col);
-        a_s[i] = (double)v;
+        if (j < nj && col < N) v = (j < nh) ? __ldg(a_src + (int64_t)j * N + col) : __ldg(a_tgt + (int64_t)(j - nh) * N + col);
+        a_s[j * ASTR + col] = (double)v;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kSplitThreads) : "memory");
     }
@@ -278,22 +288,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
       }
       if (fuse) {
-        double dv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dv[i] = (double)v[i];
+        for (int k = 0; k < 8; ++k) tile[k * TSTR + lane] = (double)v[k];      // T[col][row], conflict free
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (j < nj) {
-            const double2* ap = reinterpret_cast<const double2*>(a_s + j * BN + c);   // broadcast LDS.128
-            const double2 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];
-            double sj = sacc[j];
-            sj = fma(dv[0], a0.x, sj); sj = fma(dv[1], a0.y, sj);
-            sj = fma(dv[2], a1.x, sj); sj = fma(dv[3], a1.y, sj);
-            sj = fma(dv[4], a2.x, sj); sj = fma(dv[5], a2.y, sj);
-            sj = fma(dv[6], a3.x, sj); sj = fma(dv[7], a3.y, sj);
-            sacc[j] = sj;
+        for (int ks = 0; ks < 2; ++ks) {
+          double bf[2];
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb)
+            bf[nb] = nb < nbk ? a_s[(nb * 8 + (lane >> 2)) * ASTR + c + ks * 4 + (lane & 3)] : 0.0;   // B[k][n] = A[j=n][col=k]
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const double af = tile[(ks * 4 + (lane & 3)) * TSTR + g * 8 + (lane >> 2)];              // A[row][k]
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+              if (nb < nbk)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                             : "+d"(sacc[g][nb][0]), "+d"(sacc[g][nb][1]) : "d"(af), "d"(bf[nb]));
+            }
           }
         }
+        __syncwarp();
       }
       if (row < M) {
         if (n0 + c + 8 <= N) {
@@ -306,11 +321,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
-    if (fuse && row < M) {
+    if (fuse) {
+      // C fragment: lane holds rows g*8 + lane/4, score columns nb*8 + 2*(lane%4) + {0,1}
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j < nj) {
-          if (j < nh) s_src[row * nh + j] = (float)sacc[j]; else s_tgt[row * nh + (j - nh)] = (float)sacc[j];
+      for (int g = 0; g < 4; ++g) {
+        const int64_t srow = m0 + q * 32 + g * 8 + (lane >> 2);
+        if (srow < M) {
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = nb * 8 + 2 * (lane & 3) + e;
+              if (nb < nbk && j < nj) {
+                if (j < nh) s_src[srow * nh + j] = (float)sacc[g][nb][e]; else s_tgt[srow * nh + (j - nh)] = (float)sacc[g][nb][e];
+              }
+            }
+          }
         }
       }
     }
