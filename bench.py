@@ -179,10 +179,14 @@ def algorithmic_bytes(kernel, e, n, nh, d, d_out):
     """SURVEY.md section 8-d per-launch byte counts (fp32, int32 indices)."""
     if kernel == "gat_edge_fwd":
         return e * (4 + 4 * nh + 4 * d) + n * (8 + 8 * nh + 4 * d_out)
-    if kernel == "gat_edge_bwd_dst":
-        return e * (4 + 8 * nh + 4 * d) + n * (8 + 4 * d_out + 12 * nh)
-    if kernel == "gat_edge_bwd_src":
-        return e * (8 + 12 * nh + 4 * d_out) + n * (8 + 4 * d + 4 * nh)
+    if kernel == "gat_edge_bwd_main":
+        # per edge: col_t, s_tgt[dst], Z[dst], gather dOut[dst], write record {d_alpha, alpha}; per node: rowptr_t, Wh row,
+        # s_src, write dWh row
+        return e * (4 + 8 * nh + 4 * d_out + 8 * nh) + n * (8 + 4 * d + 4 * nh + 4 * d)
+    if kernel == "gat_edge_bwd_rowsum":
+        return e * (4 + 8 * nh) + n * (8 + 12 * nh)
+    if kernel == "gat_edge_bwd_finish":
+        return e * (4 + 8 * nh + 4 * nh) + n * (8 + 8 * d + 16 * nh)
     raise KeyError(kernel)
 
 
@@ -320,7 +324,7 @@ def run_b200(args):
     n_local = n if world == 1 else model.n_local
     e_local = e_prime if world == 1 else model.n_edges_local
     per_kernel = {}
-    for kname in ("gat_edge_fwd", "gat_edge_bwd_dst", "gat_edge_bwd_src"):
+    for kname in ("gat_edge_fwd", "gat_edge_bwd_main", "gat_edge_bwd_rowsum", "gat_edge_bwd_finish"):
         rec = kernels.get((kname, (nh, fp)))
         if rec:
             b = algorithmic_bytes(kname, e_local, n_local, nh, d, d)

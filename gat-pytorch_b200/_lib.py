@@ -26,7 +26,7 @@ SIGNATURES = {
     "gat_edges_scan": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
     "gat_csr_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "gat_csr_build": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_int64,
-                              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+                              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gat_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int64, c_int64, c_int]),
     "gat_gemm_tc_supported": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64]),
     "gat_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64,
@@ -43,10 +43,11 @@ SIGNATURES = {
     "gat_head_merge_fwd": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "gat_head_merge_bwd": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "gat_edge_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
-    "gat_edge_bwd_dst": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, c_int,
-                                 c_float, c_uint64, c_uint64, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "gat_edge_bwd_src": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, c_int,
-                                 _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_main": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, c_int,
+                                  c_float, c_uint64, c_uint64, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_rowsum": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_finish": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
+                                    _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_gamma": (c_int, [_P, c_size_t, _P, _P]),
 }
 

@@ -97,12 +97,14 @@ __global__ void gather_csr_kernel(const int32_t* __restrict__ eid, const int32_t
 // CSR by source: col_t[j] = dst[perm_t[j]]; pos_t[j] = slot_of_edge[perm_t[j]].
 __global__ void gather_csrt_kernel(const int32_t* __restrict__ perm_t, const int32_t* __restrict__ dst32,
                                    const int32_t* __restrict__ slot_of_edge, int64_t n_edges,
-                                   int32_t* __restrict__ col_t, int32_t* __restrict__ pos_t) {
+                                   int32_t* __restrict__ col_t, int32_t* __restrict__ pos_t, int32_t* __restrict__ tpos) {
   int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j < n_edges) {
     int32_t e = perm_t[j];
     col_t[j] = dst32[e];
-    pos_t[j] = slot_of_edge[e];
+    int32_t slot = slot_of_edge[e];
+    pos_t[j] = slot;
+    if (tpos) tpos[slot] = (int32_t)j;
   }
 }
 
@@ -156,7 +158,7 @@ static int plan_workspace(int64_t e_in, int64_t e_out, int64_t n_nodes, CsrWorks
 template <typename T>
 static int csr_build_impl(const T* src, const T* dst, int64_t e_in, int add_self_loops, int64_t n_idx, int64_t e_out,
                           int64_t n_nodes, int64_t* ei_out, int32_t* rowptr, int32_t* col, int32_t* eid,
-                          int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t, int32_t* row_order, int32_t* row_order_t,
+                          int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t, int32_t* tpos, int32_t* row_order, int32_t* row_order_t,
                           char* ws, const CsrWorkspace& w, cudaStream_t st) {
   int32_t* src32 = (int32_t*)(ws + w.off_src32);
   int32_t* dst32 = (int32_t*)(ws + w.off_dst32);
@@ -200,7 +202,7 @@ static int csr_build_impl(const T* src, const T* dst, int64_t e_in, int add_self
   rowptr_kernel<<<blocks(e_out + 1), T256, 0, st>>>(keys_out, e_out, n_nodes, rowptr_t);
   GAT_LAUNCH_CHECK();
   if (e_out > 0) {
-    gather_csrt_kernel<<<blocks(e_out), T256, 0, st>>>(perm, dst32, slot, e_out, col_t, pos_t);
+    gather_csrt_kernel<<<blocks(e_out), T256, 0, st>>>(perm, dst32, slot, e_out, col_t, pos_t, tpos);
     GAT_LAUNCH_CHECK();
   }
   if (n_nodes > 0) {
@@ -250,7 +252,7 @@ extern "C" size_t gat_csr_workspace_bytes(int64_t n_edges_in, int64_t n_edges_ou
 extern "C" int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t row_stride, int index_is_int64,
                              int add_self_loops, int64_t n_idx, int64_t n_edges_out, int64_t n_nodes,
                              int64_t* ei_out, int32_t* rowptr, int32_t* col, int32_t* eid,
-                             int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t,
+                             int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t, int32_t* tpos,
                              int32_t* row_order, int32_t* row_order_t,
                              void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
@@ -272,9 +274,9 @@ extern "C" int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t
   if (index_is_int64) {
     const int64_t* p = (const int64_t*)edge_index;
     return csr_build_impl<int64_t>(p, p + row_stride, n_edges_in, add_self_loops, n_idx, n_edges_out, n_nodes, ei_out,
-                                   rowptr, col, eid, rowptr_t, col_t, pos_t, row_order, row_order_t, (char*)workspace, w, st);
+                                   rowptr, col, eid, rowptr_t, col_t, pos_t, tpos, row_order, row_order_t, (char*)workspace, w, st);
   }
   const int32_t* p = (const int32_t*)edge_index;
   return csr_build_impl<int32_t>(p, p + row_stride, n_edges_in, add_self_loops, n_idx, n_edges_out, n_nodes, ei_out,
-                                 rowptr, col, eid, rowptr_t, col_t, pos_t, row_order, row_order_t, (char*)workspace, w, st);
+                                 rowptr, col, eid, rowptr_t, col_t, pos_t, tpos, row_order, row_order_t, (char*)workspace, w, st);
 }

@@ -1,0 +1,510 @@
+// Kernel 4: atomic-free deterministic backward of the edge stage (autograd of gat_layer.py:70-132; formulas in
+// SURVEY.md section 9.2) with ONE feature-row gather per edge.
+//
+// The obvious split (a dst pass that gathers Wh[src] for d_alpha, then a src pass that gathers dOut[dst] for dWh) moves
+// two rows per edge.  But d_alpha[e,h] = <dOut[dst_e,h,:], Wh[src_e,h,:]> can be formed where dOut[dst_e] is gathered
+// anyway -- in the SOURCE-major pass, whose own row Wh[src] sits in registers.  So:
+//
+//   pass 1  gat_edge_bwd_main    (CSR^T, heavy)  per source row s: recompute alpha from (s_src[s], s_tgt[d], Z[d], M),
+//                                                gather dOut[d] once, dWh[s] += m*alpha*dOut[d],
+//                                                d_alpha = m*<dOut[d],Wh[s]> + dL/dalpha, record {d_alpha, alpha} per edge
+//                                                (coalesced, CSR^T order)
+//   pass 2  gat_edge_bwd_rowsum  (CSR,  light)   per target row d: S = sum_e alpha*d_alpha (32-byte record gathers);
+//                                                ds_tgt = sum_e g = 0.01*S*eps/(Z+eps)   [closed form: sum_e alpha = Z/(Z+eps)]
+//           Gamma = sum ds_tgt (two fixed-order stages)          -> gradient through the global max()
+//   pass 3  gat_edge_bwd_finish  (CSR^T, light)  per source row s: g = 0.01*alpha*(d_alpha - S[d]), ds_src = sum g,
+//                                                arg-max corrections, dWh[s] += ds_src*A_src + ds_tgt*A_tgt
+//
+// Every sum is a fixed-order register / shuffle / shared-memory reduction; the only atomics are the integer row
+// counters of the persistent schedulers, which never influence a result.
+#include "edge_common.cuh"
+#include <cstddef>
+
+namespace gat {
+
+struct BwdHeader {          // first 256 bytes of the backward workspace
+  double gamma;             // sum over all (e,h) of g
+  float corr;               // gamma / |T|   (0 when the arg-max set is empty)
+  int n_partials;           // number of partials written by gamma_partial_kernel
+  unsigned int pad0[12];
+  unsigned int counter_a;   // row scheduler of pass 1 / pass 3 (byte offset 64)
+  unsigned int pad1[15];
+  unsigned int counter_b;   // row scheduler of pass 2          (byte offset 128)
+};
+static_assert(offsetof(BwdHeader, counter_a) == 64 && offsetof(BwdHeader, counter_b) == 128, "header layout");
+constexpr size_t kBwdHeaderBytes = 256;
+constexpr int kGammaBlocks = 592;   // 4 per SM
+
+// ------------------------------------------------------------------------------------------------------------
+// pass 1
+// ------------------------------------------------------------------------------------------------------------
+struct BwdMainParams {
+  const int32_t* rowptr_t; const int32_t* col_t; const int32_t* pos_t; const int32_t* eid; RowSched sched;
+  const float* wh; int nh; int dp; int chunks; int chunks_per_head;
+  const float* s_src; const float* s_tgt; const float* gmax; const float* z;   // s_tgt / z indexed by TARGET id
+  int const_attention; float dropout_p; uint64_t seed; uint64_t offset;
+  const float* go; const float* grad_alpha;                                    // go indexed by TARGET id
+  float* rec; float* d_wh;
+};
+
+template <int G, int SLOTS>
+struct MainShape {
+  static constexpr int TB = (G < 8) ? G : (SLOTS >= 6 ? 4 : 8);     // edges per transpose-reduce sub-batch
+  static constexpr int U = (SLOTS >= 4) ? 2 : (TB < 4 ? TB : 4);    // edges in flight
+};
+
+template <int G, int SLOTS, int NHT>
+__device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64_t row, const int tid, const int gl,
+                                             const int gbase, const unsigned gmask, const float gmax,
+                                             int* sh_dst, float* sh_w, float* sh_da, float* part) {
+  constexpr int TB = MainShape<G, SLOTS>::TB, U = MainShape<G, SLOTS>::U;
+  const int nh = P.nh;
+  const int pstride = P.chunks + 1;
+  int head[SLOTS];
+  bool ok[SLOTS];
+  float4 whr[SLOTS], acc[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    int c = s * G + gl;
+    ok[s] = c < P.chunks;
+    head[s] = ok[s] ? c / P.chunks_per_head : 0;
+    acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    whr[s] = (ok[s] && !P.const_attention) ? ldg4(P.wh + row * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int start = __ldg(P.rowptr_t + row), end = __ldg(P.rowptr_t + row + 1);
+  float ss[NHT];
+#pragma unroll
+  for (int h = 0; h < NHT; ++h) ss[h] = (!P.const_attention && h < nh) ? __ldg(P.s_src + row * nh + h) : 0.f;
+
+  for (int base = start; base < end; base += G) {
+    const int e = base + gl;
+    const bool valid = e < end;
+    float alpha[NHT], msk[NHT], ga[NHT];
+#pragma unroll
+    for (int h = 0; h < NHT; ++h) { alpha[h] = 0.f; msk[h] = 1.f; ga[h] = 0.f; }
+    if (valid) {
+      const int d = __ldg(P.col_t + e);
+      const float* zp = P.z + (int64_t)d * nh;
+      if (P.const_attention) {
+#pragma unroll
+        for (int h = 0; h < NHT; ++h) alpha[h] = h < nh ? 1.f / (__ldg(zp + h) + kSoftmaxEps) : 0.f;
+      } else {
+        const float* tp = P.s_tgt + (int64_t)d * nh;
+#pragma unroll
+        for (int h = 0; h < NHT; ++h)
+          if (h < nh) alpha[h] = attn_exp(ss[h] + __ldg(tp + h), gmax) / (__ldg(zp + h) + kSoftmaxEps);
+      }
+      if (P.dropout_p > 0.f || P.grad_alpha) {
+        const int edge_id = __ldg(P.eid + __ldg(P.pos_t + e));
+        if (P.dropout_p > 0.f) dropout_scales<NHT>(P.seed, P.offset, (uint32_t)edge_id, nh, P.dropout_p, msk);
+        if (P.grad_alpha) {
+#pragma unroll
+          for (int h = 0; h < NHT; ++h)
+            if (h < nh) ga[h] = __ldg(P.grad_alpha + (int64_t)edge_id * nh + h);
+        }
+      }
+      sh_dst[tid] = d;
+#pragma unroll
+      for (int h = 0; h < NHT; ++h) sh_w[tid * NHT + h] = msk[h] * alpha[h];
+    }
+    __syncwarp(gmask);
+    const int cnt = min(G, end - base);
+    for (int t0 = 0; t0 < cnt; t0 += TB) {
+      const int tcnt = min(TB, cnt - t0);
+#pragma unroll
+      for (int tt = 0; tt < TB; tt += U) {
+        float4 v[U][SLOTS];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool on = tt + u < tcnt;
+          const int didx = on ? sh_dst[gbase + t0 + tt + u] : 0;
+          const float* rowp = P.go + (int64_t)didx * P.dp + gl * 4;
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s)
+            v[u][s] = (on && ok[s]) ? ldg4(rowp + s * G * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (tt + u < tcnt) {
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+              const float w = sh_w[(gbase + t0 + tt + u) * NHT + head[s]];
+              acc[s].x = fmaf(w, v[u][s].x, acc[s].x);
+              acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
+              acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
+              acc[s].w = fmaf(w, v[u][s].w, acc[s].w);
+              if (ok[s] && !P.const_attention) {
+                float dd = whr[s].x * v[u][s].x;
+                dd = fmaf(whr[s].y, v[u][s].y, dd);
+                dd = fmaf(whr[s].z, v[u][s].z, dd);
+                dd = fmaf(whr[s].w, v[u][s].w, dd);
+                part[(tt + u) * pstride + s * G + gl] = dd;
+              }
+            }
+          }
+        }
+      }
+      if (!P.const_attention) {
+        __syncwarp(gmask);
+        // transpose-reduce: (edge, head) pair q sums the chunks of that head
+        for (int q = gl; q < tcnt * nh; q += G) {
+          const int t = q / nh, h = q - t * nh;
+          const float* pp = part + t * pstride + h * P.chunks_per_head;
+          float dd = 0.f;
+          for (int c = 0; c < P.chunks_per_head; ++c) dd += pp[c];
+          sh_da[(gbase + t0 + t) * NHT + h] = dd;
+        }
+        __syncwarp(gmask);
+      }
+    }
+    if (valid && !P.const_attention) {
+      float* r = P.rec + (int64_t)e * 2 * nh;
+#pragma unroll
+      for (int h = 0; h < NHT; ++h)
+        if (h < nh) { r[h] = fmaf(msk[h], sh_da[tid * NHT + h], ga[h]); r[nh + h] = alpha[h]; }
+    }
+    __syncwarp(gmask);
+  }
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s)
+    if (ok[s]) *reinterpret_cast<float4*>(P.d_wh + row * P.dp + (s * G + gl) * 4) = acc[s];
+}
+
+template <int G, int SLOTS, int NHT>
+__global__ void __launch_bounds__(kEdgeThreads, (SLOTS <= 2 ? 3 : (SLOTS <= 4 ? 2 : 1)))
+edge_bwd_main_kernel(const BwdMainParams P) {
+  constexpr int TB = MainShape<G, SLOTS>::TB;
+  extern __shared__ float dyn_smem[];
+  __shared__ int sh_dst[kEdgeThreads];
+  __shared__ float sh_w[kEdgeThreads * NHT];
+  __shared__ float sh_da[kEdgeThreads * NHT];
+  const int tid = threadIdx.x, lane = tid & 31, gl = tid & (G - 1), gbase = tid - gl;
+  const unsigned gmask = group_mask<G>(lane);
+  float* part = dyn_smem + (size_t)(tid / G) * TB * (P.chunks + 1);   // [TB][chunks+1] of my group
+  const float gmax = P.const_attention ? 0.f : __ldg(P.gmax);
+  int64_t base;
+  while (grab_rows<G>(P.sched, lane, base)) {
+#pragma unroll 1
+    for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
+      const int64_t row = sched_row<G>(P.sched, base, k, lane);
+      if (row >= 0) bwd_main_row<G, SLOTS, NHT>(P, row, tid, gl, gbase, gmask, gmax, sh_dst, sh_w, sh_da, part);
+    }
+  }
+}
+
+template <int G, int SLOTS>
+static size_t main_dyn_smem(int chunks) {
+  return (size_t)(kEdgeThreads / G) * MainShape<G, SLOTS>::TB * (chunks + 1) * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pass 2: per target row, S[h] = sum_e alpha*d_alpha; ds_tgt[h] = 0.01 * S * eps / (Z + eps)
+// ------------------------------------------------------------------------------------------------------------
+struct BwdRowsumParams {
+  const int32_t* rowptr; const int32_t* tpos; RowSched sched; int nh;
+  const float* rec; const float* z; float* s_sum; float* ds_tgt;
+};
+
+__global__ void __launch_bounds__(256)
+edge_bwd_rowsum_kernel(const BwdRowsumParams P) {
+  const int lane = threadIdx.x & 31;
+  const int nh = P.nh;
+  int64_t base;
+  while (grab_rows<32>(P.sched, lane, base)) {
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const int64_t row = sched_row<32>(P.sched, base, k, lane);
+      if (row < 0) continue;
+      const int start = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
+      float s[kMaxHeads];
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h) s[h] = 0.f;
+      for (int j = start + lane; j < end; j += 32) {
+        const float* r = P.rec + (int64_t)__ldg(P.tpos + j) * 2 * nh;
+        if (nh == 4) {
+          const float4 da = __ldg(reinterpret_cast<const float4*>(r)), al = __ldg(reinterpret_cast<const float4*>(r) + 1);
+          s[0] = fmaf(al.x, da.x, s[0]); s[1] = fmaf(al.y, da.y, s[1]); s[2] = fmaf(al.z, da.z, s[2]); s[3] = fmaf(al.w, da.w, s[3]);
+        } else {
+#pragma unroll
+          for (int h = 0; h < kMaxHeads; ++h)
+            if (h < nh) s[h] = fmaf(__ldg(r + nh + h), __ldg(r + h), s[h]);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h) {
+        if (h < nh) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h) {
+          if (h < nh) {
+            const float zz = __ldg(P.z + row * nh + h);
+            P.s_sum[row * nh + h] = s[h];
+            // sum_e g = 0.01*(S - S*sum_e alpha) with sum_e alpha = Z/(Z+eps): exact, and free of the cancellation a
+            // direct fp32 sum of g would suffer
+            P.ds_tgt[row * nh + h] = kLeakySlope * s[h] * (kSoftmaxEps / (zz + kSoftmaxEps));
+          }
+        }
+      }
+    }
+  }
+}
+
+// Gamma = sum over all (row, head) of ds_tgt, reduced in two fixed-order stages (independent of the dynamic schedule).
+__global__ void __launch_bounds__(256)
+gamma_partial_kernel(const float* __restrict__ ds_tgt, int64_t count, BwdHeader* header, double* __restrict__ partials) {
+  __shared__ double sh[256];
+  const int64_t per = (count + kGammaBlocks - 1) / kGammaBlocks;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = min(count, lo + per);
+  double t = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) t += (double)ds_tgt[i];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = sh[0];
+    if (blockIdx.x == 0) header->n_partials = kGammaBlocks;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+gamma_finalize_kernel(BwdHeader* header, const double* __restrict__ partials, const unsigned long long* __restrict__ tie_total) {
+  __shared__ double sh[1024];
+  const int n = header->n_partials;
+  double t = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) t += partials[i];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    header->gamma = sh[0];
+    unsigned long long ties = tie_total ? *tie_total : 0ull;
+    header->corr = ties ? (float)(sh[0] / (double)ties) : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pass 3
+// ------------------------------------------------------------------------------------------------------------
+struct BwdFinishParams {
+  const int32_t* rowptr_t; const int32_t* col_t; RowSched sched;
+  int nh; int dp; int chunks;
+  const float* rec; const float* s_sum;              // s_sum indexed by TARGET id
+  const float* a_src; const float* a_tgt;
+  const int32_t* tie_dst; const int32_t* tie_src; const BwdHeader* header; const float* corr_override;
+  int64_t tgt_lo; int64_t tgt_hi;   // rows this call owns as TARGETS (ds_tgt / tie_dst are indexed row - tgt_lo)
+  float* ds_src; float* ds_tgt; float* d_wh;
+};
+
+template <int G, int SLOTS, int NHT>
+__device__ __forceinline__ void bwd_finish_row(const BwdFinishParams& P, const int64_t row, const int gl,
+                                               const unsigned gmask, const float corr) {
+  const int nh = P.nh;
+  const int start = __ldg(P.rowptr_t + row), end = __ldg(P.rowptr_t + row + 1);
+  float gsum[NHT];
+#pragma unroll
+  for (int h = 0; h < NHT; ++h) gsum[h] = 0.f;
+  for (int e = start + gl; e < end; e += G) {
+    const float* r = P.rec + (int64_t)e * 2 * nh;
+    const float* sp = P.s_sum + (int64_t)__ldg(P.col_t + e) * nh;
+#pragma unroll
+    for (int h = 0; h < NHT; ++h)
+      if (h < nh) gsum[h] = fmaf(kLeakySlope * __ldg(r + nh + h), __ldg(r + h) - __ldg(sp + h), gsum[h]);   // g = 0.01*alpha*(d_alpha - S)
+  }
+  // ds_src = sum g - |T_src|*Gamma/|T|;  ds_tgt -= |T_dst|*Gamma/|T|   (gradient through max(), section 9.2)
+  const bool own_tgt = row >= P.tgt_lo && row < P.tgt_hi;   // single GPU: always; partitioned: owner rank only
+  const int64_t trow = row - P.tgt_lo;
+  float dss[NHT], dst_[NHT];
+#pragma unroll
+  for (int h = 0; h < NHT; ++h) {
+    dss[h] = 0.f; dst_[h] = 0.f;
+    if (h < nh) {
+      float g = group_sum<G>(gsum[h], gmask);
+      int ts = P.tie_src ? __ldg(P.tie_src + row * nh + h) : 0;
+      dss[h] = ts ? g - (float)ts * corr : g;
+      if (own_tgt) {
+        int td = P.tie_dst ? __ldg(P.tie_dst + trow * nh + h) : 0;
+        float t = P.ds_tgt[trow * nh + h];
+        dst_[h] = td ? t - (float)td * corr : t;
+      }
+    }
+  }
+  __syncwarp(gmask);   // every lane has read ds_tgt before lane 0 overwrites it
+  if (gl == 0) {
+#pragma unroll
+    for (int h = 0; h < NHT; ++h)
+      if (h < nh) {
+        P.ds_src[row * nh + h] = dss[h];
+        if (own_tgt) P.ds_tgt[trow * nh + h] = dst_[h];
+      }
+  }
+  // d_wh_total = d_wh + ds_src * A_src + ds_tgt * A_tgt   (in place on the row this group owns)
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int c = s * G + gl;
+    if (c < P.chunks) {
+      float4* dp4 = reinterpret_cast<float4*>(P.d_wh + row * P.dp + c * 4);
+      float4 a = *dp4;
+#pragma unroll
+      for (int h = 0; h < NHT; ++h) {
+        if (h < nh) {
+          const float4 as = ldg4(P.a_src + (int64_t)h * P.dp + c * 4);
+          const float4 at = ldg4(P.a_tgt + (int64_t)h * P.dp + c * 4);
+          a.x = fmaf(dss[h], as.x, fmaf(dst_[h], at.x, a.x));
+          a.y = fmaf(dss[h], as.y, fmaf(dst_[h], at.y, a.y));
+          a.z = fmaf(dss[h], as.z, fmaf(dst_[h], at.z, a.z));
+          a.w = fmaf(dss[h], as.w, fmaf(dst_[h], at.w, a.w));
+        }
+      }
+      *dp4 = a;
+    }
+  }
+}
+
+template <int G, int SLOTS, int NHT>
+__global__ void __launch_bounds__(kEdgeThreads)
+edge_bwd_finish_kernel(const BwdFinishParams P) {
+  const int tid = threadIdx.x, lane = tid & 31, gl = tid & (G - 1);
+  const unsigned gmask = group_mask<G>(lane);
+  const float corr = P.corr_override ? __ldg(P.corr_override) : P.header->corr;
+  int64_t base;
+  while (grab_rows<G>(P.sched, lane, base)) {
+#pragma unroll 1
+    for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
+      const int64_t row = sched_row<G>(P.sched, base, k, lane);
+      if (row >= 0) bwd_finish_row<G, SLOTS, NHT>(P, row, gl, gmask, corr);
+    }
+  }
+}
+
+static int check_common(const char* who, int nh, int fp, void* workspace, size_t workspace_bytes) {
+  if (nh < 1 || nh > kMaxHeads) { set_error("%s: num_heads %d not in [1, %d]", who, nh, kMaxHeads); return GAT_EINVAL; }
+  if (fp <= 0 || fp % 4) { set_error("%s: padded head width %d must be a positive multiple of 4", who, fp); return GAT_EINVAL; }
+  if (workspace == nullptr || workspace_bytes < gat_edge_bwd_workspace_bytes(0, 0, nh)) {
+    set_error("%s: workspace too small", who);
+    return GAT_EWORKSPACE;
+  }
+  return GAT_OK;
+}
+
+}  // namespace gat
+
+extern "C" size_t gat_edge_bwd_workspace_bytes(int64_t n, int64_t n_edges, int nh) {
+  (void)n; (void)n_edges; (void)nh;
+  return gat::kBwdHeaderBytes + (size_t)(gat::kGammaBlocks + 1) * sizeof(double);
+}
+
+extern "C" int gat_edge_bwd_main(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
+                                 const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                                 const float* s_src, const float* s_tgt, const float* gmax, const float* z,
+                                 int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
+                                 const float* go_padded, const float* grad_alpha, float* rec, float* d_wh,
+                                 void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  using namespace gat;
+  int rc = check_common("gat_edge_bwd_main", nh, fp, workspace, workspace_bytes);
+  if (rc) return rc;
+  GAT_CHECK_ARG(const_attention || (s_src && s_tgt && gmax && rec), "gat_edge_bwd_main: score buffers missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  GAT_CUDA(cudaMemsetAsync(workspace, 0, kBwdHeaderBytes, st));
+  if (n_rows == 0) return GAT_OK;
+  BwdMainParams P;
+  P.rowptr_t = rowptr_t; P.col_t = col_t; P.pos_t = pos_t; P.eid = eid;
+  P.sched.order = row_order_t; P.sched.counter = &((BwdHeader*)workspace)->counter_a; P.sched.n = n_rows;
+  P.wh = wh; P.nh = nh; P.dp = nh * fp; P.chunks = nh * fp / 4; P.chunks_per_head = fp / 4;
+  P.s_src = s_src; P.s_tgt = s_tgt; P.gmax = gmax; P.z = z; P.const_attention = const_attention;
+  P.dropout_p = dropout_p; P.seed = seed; P.offset = offset; P.go = go_padded; P.grad_alpha = grad_alpha;
+  P.rec = rec; P.d_wh = d_wh;
+  GroupShape shape = pick_group(P.chunks);
+  if (shape.slots < 0) {
+    set_error("gat_edge_bwd_main: row width %d floats exceeds the supported 1024", P.dp);
+    return GAT_EUNSUPPORTED;
+  }
+#define LAUNCH(G_, S_, N_)                                                                                   \
+  edge_bwd_main_kernel<G_, S_, N_><<<persistent_grid(edge_bwd_main_kernel<G_, S_, N_>, kEdgeThreads,                 \
+                                                     main_dyn_smem<G_, S_>(P.chunks),                                \
+                                                     (n_rows + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)),      \
+                                     kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st>>>(P)
+  GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
+#undef LAUNCH
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, const int32_t* row_order, int64_t n_rows, int nh,
+                                   const float* rec, const float* z, float* s_sum, float* ds_tgt,
+                                   void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  using namespace gat;
+  int rc = check_common("gat_edge_bwd_rowsum", nh, 4, workspace, workspace_bytes);
+  if (rc) return rc;
+  if (n_rows == 0) return GAT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdHeader* header = (BwdHeader*)workspace;
+  GAT_CUDA(cudaMemsetAsync(&header->counter_b, 0, sizeof(unsigned int), st));
+  BwdRowsumParams P;
+  P.rowptr = rowptr; P.tpos = tpos; P.sched.order = row_order; P.sched.counter = &header->counter_b; P.sched.n = n_rows;
+  P.nh = nh; P.rec = rec; P.z = z; P.s_sum = s_sum; P.ds_tgt = ds_tgt;
+  edge_bwd_rowsum_kernel<<<persistent_grid(edge_bwd_rowsum_kernel, 256, 0, (n_rows + 7) / 8), 256, 0, st>>>(P);
+  GAT_LAUNCH_CHECK();
+  gamma_partial_kernel<<<kGammaBlocks, 256, 0, st>>>(ds_tgt, n_rows * nh, header, (double*)((char*)workspace + kBwdHeaderBytes));
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_edge_bwd_gamma(void* workspace, size_t workspace_bytes, double* gamma_out, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(workspace && gamma_out && workspace_bytes >= kBwdHeaderBytes, "gat_edge_bwd_gamma: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdHeader* header = (BwdHeader*)workspace;
+  gamma_finalize_kernel<<<1, 1024, 0, st>>>(header, (const double*)((char*)workspace + kBwdHeaderBytes), nullptr);
+  GAT_LAUNCH_CHECK();
+  GAT_CUDA(cudaMemcpyAsync(gamma_out, &header->gamma, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return GAT_OK;
+}
+
+extern "C" int gat_edge_bwd_finish(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* row_order_t, int64_t n_rows,
+                                   int nh, int fp, const float* rec, const float* s_sum, const float* a_src, const float* a_tgt,
+                                   const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                                   const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
+                                   float* ds_src, float* ds_tgt, float* d_wh,
+                                   void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  using namespace gat;
+  int rc = check_common("gat_edge_bwd_finish", nh, fp, workspace, workspace_bytes);
+  if (rc) return rc;
+  GAT_CHECK_ARG(rec && s_sum && a_src && a_tgt && ds_src && ds_tgt && d_wh, "gat_edge_bwd_finish: buffers missing");
+  if (n_rows == 0) return GAT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdHeader* header = (BwdHeader*)workspace;
+  if (corr_override == nullptr) {
+    gamma_finalize_kernel<<<1, 1024, 0, st>>>(header, (const double*)((char*)workspace + kBwdHeaderBytes), tie_total);
+    GAT_LAUNCH_CHECK();
+  }
+  GAT_CUDA(cudaMemsetAsync(&header->counter_a, 0, sizeof(unsigned int), st));
+  BwdFinishParams P;
+  P.rowptr_t = rowptr_t; P.col_t = col_t; P.sched.order = row_order_t; P.sched.counter = &header->counter_a; P.sched.n = n_rows;
+  P.nh = nh; P.dp = nh * fp; P.chunks = nh * fp / 4;
+  P.rec = rec; P.s_sum = s_sum; P.a_src = a_src; P.a_tgt = a_tgt;
+  P.tie_dst = tie_dst; P.tie_src = tie_src; P.header = header; P.corr_override = corr_override;
+  P.tgt_lo = tgt_lo; P.tgt_hi = tgt_hi; P.ds_src = ds_src; P.ds_tgt = ds_tgt; P.d_wh = d_wh;
+  GroupShape shape = pick_group(P.chunks);
+  if (shape.slots < 0) {
+    set_error("gat_edge_bwd_finish: row width %d floats exceeds the supported 1024", P.dp);
+    return GAT_EUNSUPPORTED;
+  }
+#define LAUNCH(G_, S_, N_)                                                                                \
+  edge_bwd_finish_kernel<G_, S_, N_><<<persistent_grid(edge_bwd_finish_kernel<G_, S_, N_>, kEdgeThreads, 0,       \
+                                                       (n_rows + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)), \
+                                       kEdgeThreads, 0, st>>>(P)
+  GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
+#undef LAUNCH
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}

@@ -117,25 +117,27 @@ class _GATFunction(torch.autograd.Function):
                 _lib.call("gat_head_merge_bwd", grad_out.data_ptr(), n, nh, f, fp, int(concat), go_p.data_ptr(), s)
             else:
                 go_p = grad_out
-            rec = torch.empty((st.n_edges, 2 * nh), **f32)
             d_wh = torch.empty((n, dp), **f32)
-            ds_src = ds_tgt = None
+            rec = ds_src = ds_tgt = s_sum = None
             if not const_attention:
-                ds_src = torch.empty((n, nh), **f32)
-                ds_tgt = torch.empty((n, nh), **f32)
+                rec = torch.empty((st.n_edges, 2 * nh), **f32)
+                ds_src, ds_tgt, s_sum = (torch.empty((n, nh), **f32) for _ in range(3))
             ws_bytes = int(lib.gat_edge_bwd_workspace_bytes(n, st.n_edges, nh))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            _lib.call("gat_edge_bwd_dst", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), n,
-                                            wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax), z.data_ptr(),
-                                            int(const_attention), p_drop, seed, 0,
-                                            go_p.data_ptr(), _ptr(grad_alpha), rec.data_ptr(), _ptr(ds_tgt),
-                                            ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
-            _lib.call("gat_edge_bwd_src", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(),
-                                            st.order_t.data_ptr(), n,
-                                            nh, fp, rec.data_ptr(), go_p.data_ptr(), _ptr(a_src_p), _ptr(a_tgt_p),
-                                            int(const_attention), _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total),
-                                            None, 0, n, _ptr(ds_src), _ptr(ds_tgt), d_wh.data_ptr(),
-                                            ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+            # pass 1 (source-major, the only feature gather of the backward)
+            _lib.call("gat_edge_bwd_main", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
+                      st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax), z.data_ptr(),
+                      int(const_attention), p_drop, seed, 0, go_p.data_ptr(), _ptr(grad_alpha), _ptr(rec), d_wh.data_ptr(),
+                      ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+            if not const_attention:
+                # pass 2 (target-major, light): row sums S, ds_tgt, Gamma
+                _lib.call("gat_edge_bwd_rowsum", st.rowptr.data_ptr(), st.tpos.data_ptr(), st.order.data_ptr(), n, nh,
+                          rec.data_ptr(), z.data_ptr(), s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+                # pass 3 (source-major, light): ds_src, max() correction, dWh += ds_src*A_src + ds_tgt*A_tgt
+                _lib.call("gat_edge_bwd_finish", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.order_t.data_ptr(), n, nh, fp,
+                          rec.data_ptr(), s_sum.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
+                          _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), None, 0, n,
+                          ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
             gx = gw = ga_src = ga_tgt = None
             if ctx.needs_input_grad[0]:
                 gx = torch.empty((n, f_in), **f32)

@@ -30,6 +30,7 @@ class GraphStructure:
     rowptr_t: torch.Tensor      # (n+1,) int32
     col_t: torch.Tensor         # (E',) int32 target ids, grouped by source, stable
     pos_t: torch.Tensor         # (E',) int32 CSR-by-target slot of each CSR-by-source slot
+    tpos: torch.Tensor = None       # (E',) int32 CSR-by-source slot of each CSR-by-target slot (inverse of pos_t)
     order: torch.Tensor = None      # (n,) int32 scheduling permutation of the target rows (long rows first)
     order_t: torch.Tensor = None    # (n,) int32 same for the source rows
 
@@ -68,7 +69,7 @@ def build_structure(edge_index: torch.Tensor, n_nodes: int, add_self_loops: bool
         i32 = dict(dtype=torch.int32, device=dev)
         rowptr = torch.empty(n_nodes + 1, **i32)
         rowptr_t = torch.empty(n_nodes + 1, **i32)
-        col, eid, col_t, pos_t = (torch.empty(n_out, **i32) for _ in range(4))
+        col, eid, col_t, pos_t, tpos = (torch.empty(n_out, **i32) for _ in range(5))
         order, order_t = torch.empty(n_nodes, **i32), torch.empty(n_nodes, **i32)
         ei_out = torch.empty((2, n_out), dtype=torch.int64, device=dev) if add_self_loops else None
         ws_bytes = int(lib.gat_csr_workspace_bytes(n_in, n_out, n_nodes))
@@ -76,13 +77,13 @@ def build_structure(edge_index: torch.Tensor, n_nodes: int, add_self_loops: bool
         _lib.call("gat_csr_build", ei.data_ptr(), n_in, ei.stride(0), is64, int(add_self_loops), n_idx, n_out, n_nodes,
                                      ei_out.data_ptr() if ei_out is not None else None,
                                      rowptr.data_ptr(), col.data_ptr(), eid.data_ptr(),
-                                     rowptr_t.data_ptr(), col_t.data_ptr(), pos_t.data_ptr(),
+                                     rowptr_t.data_ptr(), col_t.data_ptr(), pos_t.data_ptr(), tpos.data_ptr(),
                                      order.data_ptr(), order_t.data_ptr(), ws.data_ptr(), ws_bytes, st)
     if ei_out is None:
         ei_ret = edge_index
     else:
         ei_ret = ei_out if edge_index.dtype == torch.int64 else ei_out.to(edge_index.dtype)
-    return GraphStructure(n_nodes, n_idx, n_out, ei_ret, rowptr, col, eid, rowptr_t, col_t, pos_t, order, order_t)
+    return GraphStructure(n_nodes, n_idx, n_out, ei_ret, rowptr, col, eid, rowptr_t, col_t, pos_t, tpos, order, order_t)
 
 
 class StructureCache:

@@ -125,35 +125,38 @@ class CudaBackend:
                   0, 0.0, 0, 0, out_p.data_ptr(), None, z.data_ptr(), p(tie_dst), p(tie_src), p(tie_total),
                   fws.data_ptr(), fws.numel(), self._s(out_p.device), tag=(nh, fp))
 
-    def edge_bwd_dst(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z, go_p, rec, ds_tgt):
-        ws_bytes = int(self.lib.gat_edge_bwd_workspace_bytes(plan.rows, st.n_edges, nh))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=go_p.device)
-        _lib.call("gat_edge_bwd_dst", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(),
-                  self.local_order(st, plan).data_ptr(), plan.rows,
-                  wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(), s_tgt_local.data_ptr(), gmax.data_ptr(), z.data_ptr(),
-                  0, 0.0, 0, 0, go_p.data_ptr(), None, rec.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes,
-                  self._s(go_p.device), tag=(nh, fp))
-        gamma = torch.empty(1, dtype=torch.float64, device=go_p.device)
-        _lib.call("gat_edge_bwd_gamma", ws.data_ptr(), ws_bytes, gamma.data_ptr(), self._s(go_p.device))
+    def _bwd_ws(self, dev, nh):
+        ws_bytes = int(self.lib.gat_edge_bwd_workspace_bytes(0, 0, nh))
+        return torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes
+
+    def edge_bwd_main(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh):
+        """Pass 1 over ALL source rows with this rank's edges; target-indexed arrays are local, so their base
+        pointers are shifted by plan.lo rows (col_t holds GLOBAL target ids, all in [lo, hi))."""
+        dp, lo = nh * fp, plan.lo
+        ws, ws_bytes = self._bwd_ws(go_p.device, nh)
+        _lib.call("gat_edge_bwd_main", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
+                  st.eid.data_ptr(), plan.n, wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(),
+                  s_tgt_local.data_ptr() - 4 * nh * lo, gmax.data_ptr(), z_local.data_ptr() - 4 * nh * lo,
+                  0, 0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, None, rec.data_ptr(), d_wh.data_ptr(),
+                  ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
+
+    def edge_bwd_rowsum(self, st, plan, nh, rec, z_local, s_sum, ds_tgt):
+        ws, ws_bytes = self._bwd_ws(rec.device, nh)
+        ws.zero_()   # fresh header (the rowsum call itself only resets its own row counter)
+        _lib.call("gat_edge_bwd_rowsum", st.rowptr.data_ptr() + 4 * plan.lo, st.tpos.data_ptr(), self.local_order(st, plan).data_ptr(),
+                  plan.rows, nh, rec.data_ptr(), z_local.data_ptr(), s_sum.data_ptr(), ds_tgt.data_ptr(),
+                  ws.data_ptr(), ws_bytes, self._s(rec.device), tag=(nh, 0))
+        gamma = torch.empty(1, dtype=torch.float64, device=rec.device)
+        _lib.call("gat_edge_bwd_gamma", ws.data_ptr(), ws_bytes, gamma.data_ptr(), self._s(rec.device))
         return gamma
 
-    def scores_bwd(self, wh, n, dp, nh, ds_src, ds_tgt, da_src, da_tgt):
-        sb = int(self.lib.gat_scores_bwd_workspace_bytes(dp, nh))
-        ws = torch.empty(sb, dtype=torch.uint8, device=wh.device)
-        _lib.call("gat_scores_bwd", wh.data_ptr(), n, dp, nh, ds_src.data_ptr(), ds_tgt.data_ptr(),
-                  da_src.data_ptr(), da_tgt.data_ptr(), ws.data_ptr(), sb, self._s(wh.device))
-
-    def edge_bwd_src(self, st, plan, nh, fp, rec, go_p, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
-        dp = nh * fp
-        ws_bytes = int(self.lib.gat_edge_bwd_workspace_bytes(plan.n, st.n_edges, nh))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=go_p.device)
-        go_base = go_p.data_ptr() - 4 * dp * plan.lo       # col_t holds GLOBAL target ids, all in [lo, hi)
-        _lib.call("gat_edge_bwd_src", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(),
-                  st.order_t.data_ptr(), plan.n,
-                  nh, fp, rec.data_ptr(), go_base, a_src.data_ptr(), a_tgt.data_ptr(), 0,
+    def edge_bwd_finish(self, st, plan, nh, fp, rec, s_sum_local, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
+        ws, ws_bytes = self._bwd_ws(rec.device, nh)
+        _lib.call("gat_edge_bwd_finish", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.order_t.data_ptr(), plan.n, nh, fp,
+                  rec.data_ptr(), s_sum_local.data_ptr() - 4 * nh * plan.lo, a_src.data_ptr(), a_tgt.data_ptr(),
                   tie_dst.data_ptr(), tie_src.data_ptr(), None, corr.data_ptr(), plan.lo, plan.hi,
                   ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(), ws.data_ptr(), ws_bytes,
-                  self._s(go_p.device), tag=(nh, fp))
+                  self._s(rec.device), tag=(nh, fp))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -198,15 +201,17 @@ class _PartitionedGATFunction(torch.autograd.Function):
         rec = torch.empty((max(backend.n_edges(st), 1), 2 * nh), **f32)
         ds_tgt_full = torch.zeros((plan.n_pad + 1, nh), **f32)     # owned rows live at [lo, hi); the rest stays zero
         ds_tgt = ds_tgt_full[plan.lo:plan.lo + max(rows, 1)]
+        s_sum = torch.zeros((max(rows, 1), nh), **f32)
+        d_wh_part = torch.zeros((plan.n_pad, dp), **f32)
+        ds_src_part = torch.zeros((plan.n_pad, nh), **f32)
         gamma = torch.zeros(1, dtype=torch.float64, device=dev)
+        backend.edge_bwd_main(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, rec, d_wh_part)
         if rows:
-            gamma = backend.edge_bwd_dst(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, rec, ds_tgt)
+            gamma = backend.edge_bwd_rowsum(st, plan, nh, rec, z, s_sum, ds_tgt)
         red = torch.stack([gamma[0], tie_total.view(torch.int64)[0].to(torch.float64)])
         dist.all_reduce(red, group=group)                                   # (Gamma, |T|) over ranks
         corr = torch.where(red[1] > 0, red[0] / red[1].clamp(min=1.0), torch.zeros_like(red[0])).to(torch.float32).reshape(1)
-        d_wh_part = torch.zeros((plan.n_pad, dp), **f32)
-        ds_src_part = torch.zeros((plan.n_pad, nh), **f32)
-        backend.edge_bwd_src(st, plan, nh, fp, rec, go_p, a_src_p, a_tgt_p, tie_dst, tie_src, corr, ds_src_part, ds_tgt, d_wh_part)
+        backend.edge_bwd_finish(st, plan, nh, fp, rec, s_sum, a_src_p, a_tgt_p, tie_dst, tie_src, corr, ds_src_part, ds_tgt, d_wh_part)
         d_wh = torch.empty((R, dp), **f32)
         dist.reduce_scatter_tensor(d_wh, d_wh_part, group=group)            # transpose of the all-gather
         gx = None

@@ -67,13 +67,13 @@ GAT_API size_t gat_csr_workspace_bytes(int64_t n_edges_in, int64_t n_edges_out, 
  *  rowptr   (n_nodes+1) / col / eid (n_edges_out): CSR by target, stable in edge order;
  *           rowptr diffs are the reference's degree counts (GATModel.py:196-201);
  *  rowptr_t (n_nodes+1) / col_t / pos_t: CSR by source; col_t = target ids, pos_t = slot of that
- *           edge in the target-sorted CSR;
+ *           edge in the target-sorted CSR; tpos (n_edges_out) = its inverse (CSR^T slot of each CSR slot);
  *  row_order / row_order_t (n_nodes) or NULL: scheduling permutations for the persistent edge kernels
  *           (rows with more than 256 edges first); a performance hint only, results do not depend on it. */
 GAT_API int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t row_stride, int index_is_int64,
                   int add_self_loops, int64_t n_idx, int64_t n_edges_out, int64_t n_nodes,
                   int64_t* ei_out, int32_t* rowptr, int32_t* col, int32_t* eid,
-                  int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t,
+                  int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t, int32_t* tpos,
                   int32_t* row_order, int32_t* row_order_t,
                   void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
@@ -150,41 +150,47 @@ GAT_API int gat_head_merge_bwd(const float* grad_out, int64_t n, int nh, int f, 
                        float* go_padded, gat_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
- * Kernel 4 -- atomic-free deterministic backward.  Replaces autograd of gat_layer.py:70-132.
+ * Kernel 4 -- atomic-free deterministic backward with ONE feature-row gather per edge.
+ * Replaces autograd of gat_layer.py:70-132 (formulas: SURVEY.md section 9.2).
+ * d_alpha[e,h] = m*<dOut[dst,h,:], Wh[src,h,:]> + dL/dalpha is formed in the source-major pass, where dOut[dst] is
+ * gathered anyway and Wh[src] is the pass's own row, so no second gather of Wh[src] is needed.
  * ------------------------------------------------------------------------------------- */
 
 GAT_API size_t gat_edge_bwd_workspace_bytes(int64_t n, int64_t n_edges, int nh);
 
-/* Destination pass (CSR): d_alpha = m*<go[i,h,:], wh[src,h,:]> + grad_alpha, S = sum alpha*d_alpha,
- * g = 0.01*alpha*(d_alpha - S).  Writes per-edge records rec[j] = {g[0..nh), m*alpha[0..nh)} in CSR
- * order, ds_tgt (n, nh) (before the arg-max correction) and per-block partial sums of g.
- * grad_alpha is (n_edges, nh) in rewritten edge order or NULL. */
-GAT_API int gat_edge_bwd_dst(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n,
-                     const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
-                     const float* gmax, const float* z, int const_attention,
-                     float dropout_p, uint64_t seed, uint64_t offset,
-                     const float* go_padded, const float* grad_alpha,
-                     float* rec, float* ds_tgt, void* workspace, size_t workspace_bytes,
-                     gat_stream_t stream);
+/* Pass 1 (transposed CSR, rows = SOURCE nodes 0..n_rows-1): recomputes alpha from (s_src[src], s_tgt[dst], z[dst], gmax),
+ * gathers go_padded[dst] once per edge, writes d_wh[src] = sum_e m*alpha*go[dst] (value path only) and the per-edge
+ * record rec[j] = {d_alpha[0..nh), alpha[0..nh)} in CSR^T slot order.  s_tgt, z, go_padded are indexed by TARGET id
+ * (a partitioned caller passes pointers shifted by its first owned row).  eid maps CSR slots to positions in the
+ * rewritten edge list (dropout key / row of grad_alpha).  grad_alpha is (n_edges, nh) or NULL. */
+GAT_API int gat_edge_bwd_main(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
+                              const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                              const float* s_src, const float* s_tgt, const float* gmax, const float* z,
+                              int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
+                              const float* go_padded, const float* grad_alpha, float* rec, float* d_wh,
+                              void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
-/* Source pass (transposed CSR): d_wh[j,h,:] = sum_e m*alpha*go[dst_e,h,:]; ds_src = sum g; applies the
- * arg-max correction Gamma/|T| (Gamma reduced from the dst-pass partials in `workspace`) to ds_src
- * and ds_tgt via the tie counts; then adds ds_src*A_src + ds_tgt*A_tgt so that d_wh is the total
- * gradient of Wh.  ds_src/ds_tgt (n, nh) hold the corrected values on exit.
- * Rows are SOURCE nodes 0..n-1.  [tgt_lo, tgt_hi) is the range of nodes this call also owns as targets:
- * ds_tgt and tie_dst have tgt_hi - tgt_lo rows and only those rows receive the ds_tgt*A_tgt term. */
-GAT_API int gat_edge_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t, int64_t n,
-                     int nh, int fp, const float* rec, const float* go_padded,
-                     const float* a_src, const float* a_tgt, int const_attention,
-                     const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
-                     const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
-                     float* ds_src, float* ds_tgt, float* d_wh,
-                     void* workspace, size_t workspace_bytes, gat_stream_t stream);
+/* Pass 2 (CSR by target, rows = owned TARGET nodes): s_sum[d,h] = sum_e alpha*d_alpha over the in-edges of d (records
+ * gathered through tpos = CSR^T slot of each CSR slot); ds_tgt[d,h] = sum_e g = 0.01*s_sum*eps/(z+eps) (before the arg-max
+ * correction); then reduces Gamma = sum ds_tgt in two fixed-order stages into the workspace. */
+GAT_API int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, const int32_t* row_order, int64_t n_rows, int nh,
+                                const float* rec, const float* z, float* s_sum, float* ds_tgt,
+                                void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
-/* Partitioned graphs only: *gamma_out = this rank's sum of g (fixed-order reduction of the dst-pass partials).
- * The caller all-reduces gamma and tie_total over ranks and hands Gamma/|T| to gat_edge_bwd_src as
- * `corr_override` (a device scalar).  On one GPU pass corr_override = NULL, tgt_lo = 0, tgt_hi = n. */
+/* Partitioned graphs only: *gamma_out = this rank's Gamma.  The caller all-reduces Gamma and tie_total over ranks and hands
+ * Gamma/|T| to gat_edge_bwd_finish as `corr_override` (a device scalar).  On one GPU pass corr_override = NULL. */
 GAT_API int gat_edge_bwd_gamma(void* workspace, size_t workspace_bytes, double* gamma_out, gat_stream_t stream);
+
+/* Pass 3 (transposed CSR, rows = SOURCE nodes): g = 0.01*alpha*(d_alpha - s_sum[dst]); ds_src = sum g; applies the arg-max
+ * correction Gamma/|T| to ds_src and ds_tgt via the tie counts; d_wh[src] += ds_src*A_src + ds_tgt*A_tgt, so that d_wh is the
+ * total gradient of Wh.  [tgt_lo, tgt_hi) is the range of nodes this call also owns as targets: ds_tgt and tie_dst have
+ * tgt_hi - tgt_lo rows and only those rows receive the ds_tgt*A_tgt term; s_sum is indexed by TARGET id. */
+GAT_API int gat_edge_bwd_finish(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* row_order_t, int64_t n_rows,
+                                int nh, int fp, const float* rec, const float* s_sum, const float* a_src, const float* a_tgt,
+                                const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                                const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
+                                float* ds_src, float* ds_tgt, float* d_wh,
+                                void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 #ifdef __cplusplus
 }

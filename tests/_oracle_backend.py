@@ -55,33 +55,40 @@ class OracleBackend:
         tie_src.view(-1, nh).index_add_(0, st["src"], tie)
         tie_total.view(torch.int64)[0] = int(tie.sum())
 
-    def edge_bwd_dst(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z, go_p, rec, ds_tgt):
+    def edge_bwd_main(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh):
         rows = plan.rows
         dl = st["dst"] - plan.lo
         l, p, _ = self._alpha(st, plan, s_src_full, s_tgt_local, gmax, rows, nh)
-        alpha = p / (z[:rows][dl] + EPS)
-        d_alpha = (go_p.view(-1, nh, fp)[dl] * wh_full[st["src"]].view(-1, nh, fp)).sum(-1)
-        s = torch.zeros((rows, nh)).index_add_(0, dl, alpha * d_alpha)
-        g = SLOPE * alpha * (d_alpha - s[dl])
-        rec[: g.size(0), :nh] = g
-        rec[: g.size(0), nh:] = alpha
-        ds_tgt.zero_()
-        ds_tgt[:rows].index_add_(0, dl, g)
-        return g.double().sum().reshape(1)
-
-    def scores_bwd(self, wh, n, dp, nh, ds_src, ds_tgt, da_src, da_tgt):
-        da_src.copy_((ds_src[:n].double().T @ wh[:n].double()).float())
-        da_tgt.copy_((ds_tgt[:n].double().T @ wh[:n].double()).float())
-
-    def edge_bwd_src(self, st, plan, nh, fp, rec, go_p, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
-        e = st["src"].numel()
-        g, w = rec[:e, :nh], rec[:e, nh:]
-        dl = st["dst"] - plan.lo
+        alpha = p / (z_local[:rows][dl] + EPS)
+        go_e = go_p.view(-1, nh, fp)[dl]
+        d_alpha = (go_e * wh_full[st["src"]].view(-1, nh, fp)).sum(-1)
+        e = alpha.size(0)
+        rec[:e, :nh] = d_alpha
+        rec[:e, nh:] = alpha
         d_wh.zero_()
-        d_wh.view(-1, nh, fp).index_add_(0, st["src"], w[:, :, None] * go_p.view(-1, nh, fp)[dl])
+        d_wh.view(-1, nh, fp).index_add_(0, st["src"], alpha[:, :, None] * go_e)
+
+    def edge_bwd_rowsum(self, st, plan, nh, rec, z_local, s_sum, ds_tgt):
+        e, rows = st["src"].numel(), plan.rows
+        dl = st["dst"] - plan.lo
+        s = torch.zeros((rows, nh)).index_add_(0, dl, rec[:e, nh:] * rec[:e, :nh])
+        s_sum[:rows] = s
+        ds_tgt.zero_()
+        ds_tgt[:rows] = SLOPE * s * (EPS / (z_local[:rows] + EPS))
+        return ds_tgt[:rows].double().sum().reshape(1)
+
+    def edge_bwd_finish(self, st, plan, nh, fp, rec, s_sum_local, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
+        e = st["src"].numel()
+        dl = st["dst"] - plan.lo
+        g = SLOPE * rec[:e, nh:] * (rec[:e, :nh] - s_sum_local[dl])
         ds_src.zero_()
         ds_src.index_add_(0, st["src"], g)
         ds_src -= tie_src.view(-1, nh).float() * corr
         ds_tgt[: plan.rows] -= tie_dst.view(-1, nh)[: plan.rows].float() * corr
         d_wh += ds_src @ a_src
         d_wh[plan.lo:plan.hi] += ds_tgt[: plan.rows] @ a_tgt
+
+    def scores_bwd(self, wh, n, dp, nh, ds_src, ds_tgt, da_src, da_tgt):
+        da_src.copy_((ds_src[:n].double().T @ wh[:n].double()).float())
+        da_tgt.copy_((ds_tgt[:n].double().T @ wh[:n].double()).float())
+

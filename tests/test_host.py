@@ -20,7 +20,8 @@ def declared_symbols():
 def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for must in ["gat_edges_scan", "gat_csr_build", "gat_gemm", "gat_scores_fwd", "gat_edge_max", "gat_edge_fwd",
-                 "gat_edge_bwd_dst", "gat_edge_bwd_src", "gat_last_error", "gat_version"]:
+                 "gat_edge_bwd_main", "gat_edge_bwd_rowsum", "gat_edge_bwd_finish", "gat_project_fwd", "gat_last_error",
+                 "gat_version"]:
         assert must in syms
 
 
