@@ -46,6 +46,7 @@ SIGNATURES = {
     "gat_edge_bwd_main": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, c_int,
                                   c_float, c_uint64, c_uint64, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_rowsum": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_rowdot": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_finish": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
                                     _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_gamma": (c_int, [_P, c_size_t, _P, _P]),

@@ -253,6 +253,50 @@ edge_bwd_rowsum_kernel(const BwdRowsumParams P) {
   }
 }
 
+// pass 2, common case (no upstream dL/dalpha): sum_e alpha*d_alpha = sum_e m*alpha*<dOut[d,h,:], Wh[src,h,:]>
+//   = <dOut[d,h,:], sum_e m*alpha*Wh[src,h,:]> = <dOut[d,h,:], out[d,h,:]>  -- a per-node dot product of the upstream gradient
+// with the forward output, so no per-edge record has to be gathered at all.
+struct BwdRowdotParams {
+  const float* go; const float* out; const float* z; int64_t n; int nh; int dp; int chunks; int chunks_per_head;
+  float* s_sum; float* ds_tgt;
+};
+
+__global__ void __launch_bounds__(256)
+edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  const int nh = P.nh;
+  for (int64_t row = warp; row < P.n; row += nwarps) {
+    float s[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) s[h] = 0.f;
+    for (int c = lane; c < P.chunks; c += 32) {
+      const float4 g = ldg4(P.go + row * P.dp + c * 4), o = ldg4(P.out + row * P.dp + c * 4);
+      const float d = fmaf(g.x, o.x, fmaf(g.y, o.y, fmaf(g.z, o.z, g.w * o.w)));
+      const int hh = c / P.chunks_per_head;
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h) s[h] += (h == hh) ? d : 0.f;
+    }
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) {
+      if (h < nh) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h) {
+        if (h < nh) {
+          const float zz = __ldg(P.z + row * nh + h);
+          P.s_sum[row * nh + h] = s[h];
+          P.ds_tgt[row * nh + h] = kLeakySlope * s[h] * (kSoftmaxEps / (zz + kSoftmaxEps));
+        }
+      }
+    }
+  }
+}
+
 // Gamma = sum over all (row, head) of ds_tgt, reduced in two fixed-order stages (independent of the dynamic schedule).
 __global__ void __launch_bounds__(256)
 gamma_partial_kernel(const float* __restrict__ ds_tgt, int64_t count, BwdHeader* header, double* __restrict__ partials) {
@@ -455,6 +499,24 @@ extern "C" int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, c
   edge_bwd_rowsum_kernel<<<persistent_grid(edge_bwd_rowsum_kernel, 256, 0, (n_rows + 7) / 8), 256, 0, st>>>(P);
   GAT_LAUNCH_CHECK();
   gamma_partial_kernel<<<kGammaBlocks, 256, 0, st>>>(ds_tgt, n_rows * nh, header, (double*)((char*)workspace + kBwdHeaderBytes));
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_edge_bwd_rowdot(const float* go_padded, const float* out_padded, const float* z, int64_t n_rows, int nh, int fp,
+                                   float* s_sum, float* ds_tgt, void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  using namespace gat;
+  int rc = check_common("gat_edge_bwd_rowdot", nh, fp, workspace, workspace_bytes);
+  if (rc) return rc;
+  if (n_rows == 0) return GAT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdRowdotParams P;
+  P.go = go_padded; P.out = out_padded; P.z = z; P.n = n_rows; P.nh = nh; P.dp = nh * fp; P.chunks = nh * fp / 4;
+  P.chunks_per_head = fp / 4; P.s_sum = s_sum; P.ds_tgt = ds_tgt;
+  int64_t want = (n_rows + 7) / 8;
+  edge_bwd_rowdot_kernel<<<(unsigned)(want < kNumSMs * 8 ? want : kNumSMs * 8), 256, 0, st>>>(P);
+  GAT_LAUNCH_CHECK();
+  gamma_partial_kernel<<<kGammaBlocks, 256, 0, st>>>(ds_tgt, n_rows * nh, (BwdHeader*)workspace, (double*)((char*)workspace + kBwdHeaderBytes));
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }

@@ -90,7 +90,7 @@ class _GATFunction(torch.autograd.Function):
             else:
                 out = out_p
         ctx.st, ctx.cfg = st, (nh, f, fp, concat, const_attention, float(p_drop), seed, gemm_algo)
-        ctx.save_for_backward(x, w_p, a_src_p, a_tgt_p, wh, s_src, s_tgt, gmax, z, tie_dst, tie_src, tie_total)
+        ctx.save_for_backward(x, w_p, a_src_p, a_tgt_p, wh, s_src, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p)
         if alpha is None:
             return out, None
         return out, alpha
@@ -98,7 +98,7 @@ class _GATFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, grad_alpha):
         lib = _lib.load()
-        x, w_p, a_src_p, a_tgt_p, wh, s_src, s_tgt, gmax, z, tie_dst, tie_src, tie_total = ctx.saved_tensors
+        x, w_p, a_src_p, a_tgt_p, wh, s_src, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p = ctx.saved_tensors
         st: GraphStructure = ctx.st
         nh, f, fp, concat, const_attention, p_drop, seed, gemm_algo = ctx.cfg
         dev = x.device
@@ -130,9 +130,14 @@ class _GATFunction(torch.autograd.Function):
                       int(const_attention), p_drop, seed, 0, go_p.data_ptr(), _ptr(grad_alpha), _ptr(rec), d_wh.data_ptr(),
                       ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
             if not const_attention:
-                # pass 2 (target-major, light): row sums S, ds_tgt, Gamma
-                _lib.call("gat_edge_bwd_rowsum", st.rowptr.data_ptr(), st.tpos.data_ptr(), st.order.data_ptr(), n, nh,
-                          rec.data_ptr(), z.data_ptr(), s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+                # pass 2 (per target row, light): S = sum_e alpha*d_alpha, ds_tgt, Gamma
+                if grad_alpha is None:      # S = <dOut, out>: no per-edge data needed
+                    _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), out_p.data_ptr(), z.data_ptr(), n, nh, fp,
+                              s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+                else:
+                    _lib.call("gat_edge_bwd_rowsum", st.rowptr.data_ptr(), st.tpos.data_ptr(), st.order.data_ptr(), n, nh,
+                              rec.data_ptr(), z.data_ptr(), s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s,
+                              tag=(nh, fp))
                 # pass 3 (source-major, light): ds_src, max() correction, dWh += ds_src*A_src + ds_tgt*A_tgt
                 _lib.call("gat_edge_bwd_finish", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.order_t.data_ptr(), n, nh, fp,
                           rec.data_ptr(), s_sum.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),

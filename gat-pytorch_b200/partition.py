@@ -140,14 +140,14 @@ class CudaBackend:
                   0, 0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, None, rec.data_ptr(), d_wh.data_ptr(),
                   ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
 
-    def edge_bwd_rowsum(self, st, plan, nh, rec, z_local, s_sum, ds_tgt):
-        ws, ws_bytes = self._bwd_ws(rec.device, nh)
-        ws.zero_()   # fresh header (the rowsum call itself only resets its own row counter)
-        _lib.call("gat_edge_bwd_rowsum", st.rowptr.data_ptr() + 4 * plan.lo, st.tpos.data_ptr(), self.local_order(st, plan).data_ptr(),
-                  plan.rows, nh, rec.data_ptr(), z_local.data_ptr(), s_sum.data_ptr(), ds_tgt.data_ptr(),
-                  ws.data_ptr(), ws_bytes, self._s(rec.device), tag=(nh, 0))
-        gamma = torch.empty(1, dtype=torch.float64, device=rec.device)
-        _lib.call("gat_edge_bwd_gamma", ws.data_ptr(), ws_bytes, gamma.data_ptr(), self._s(rec.device))
+    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt):
+        """Pass 2 without per-edge data: S = <dOut, out> over the owned rows; returns this rank's Gamma."""
+        ws, ws_bytes = self._bwd_ws(go_p.device, nh)
+        ws.zero_()
+        _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), out_p.data_ptr(), z_local.data_ptr(), plan.rows, nh, fp,
+                  s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
+        gamma = torch.empty(1, dtype=torch.float64, device=go_p.device)
+        _lib.call("gat_edge_bwd_gamma", ws.data_ptr(), ws_bytes, gamma.data_ptr(), self._s(go_p.device))
         return gamma
 
     def edge_bwd_finish(self, st, plan, nh, fp, rec, s_sum_local, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
@@ -188,12 +188,12 @@ class _PartitionedGATFunction(torch.autograd.Function):
         if rows:
             backend.edge_fwd(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, out_p, z, tie_dst, tie_src, tie_total)
         ctx.misc = (st, plan, nh, fp, backend, group)
-        ctx.save_for_backward(x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total)
+        ctx.save_for_backward(x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p)
         return out_p
 
     @staticmethod
     def backward(ctx, go_p):
-        x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total = ctx.saved_tensors
+        x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p = ctx.saved_tensors
         st, plan, nh, fp, backend, group = ctx.misc
         dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
         rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
@@ -207,7 +207,7 @@ class _PartitionedGATFunction(torch.autograd.Function):
         gamma = torch.zeros(1, dtype=torch.float64, device=dev)
         backend.edge_bwd_main(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, rec, d_wh_part)
         if rows:
-            gamma = backend.edge_bwd_rowsum(st, plan, nh, rec, z, s_sum, ds_tgt)
+            gamma = backend.edge_bwd_rowdot(plan, nh, fp, go_p, out_p, z, s_sum, ds_tgt)
         red = torch.stack([gamma[0], tie_total.view(torch.int64)[0].to(torch.float64)])
         dist.all_reduce(red, group=group)                                   # (Gamma, |T|) over ranks
         corr = torch.where(red[1] > 0, red[0] / red[1].clamp(min=1.0), torch.zeros_like(red[0])).to(torch.float32).reshape(1)

@@ -177,6 +177,12 @@ GAT_API int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, cons
                                 const float* rec, const float* z, float* s_sum, float* ds_tgt,
                                 void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
+/* Pass 2 when there is no upstream dL/dalpha: s_sum[d,h] = <go_padded[d,h,:], out_padded[d,h,:]> (the forward output in
+ * padded-head layout) -- identical to the record sum because out = sum_e m*alpha*Wh[src]; no per-edge gather at all.
+ * Same outputs and Gamma reduction as gat_edge_bwd_rowsum. */
+GAT_API int gat_edge_bwd_rowdot(const float* go_padded, const float* out_padded, const float* z, int64_t n_rows, int nh, int fp,
+                                float* s_sum, float* ds_tgt, void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
 /* Partitioned graphs only: *gamma_out = this rank's Gamma.  The caller all-reduces Gamma and tie_total over ranks and hands
  * Gamma/|T| to gat_edge_bwd_finish as `corr_override` (a device scalar).  On one GPU pass corr_override = NULL. */
 GAT_API int gat_edge_bwd_gamma(void* workspace, size_t workspace_bytes, double* gamma_out, gat_stream_t stream);

@@ -68,10 +68,9 @@ class OracleBackend:
         d_wh.zero_()
         d_wh.view(-1, nh, fp).index_add_(0, st["src"], alpha[:, :, None] * go_e)
 
-    def edge_bwd_rowsum(self, st, plan, nh, rec, z_local, s_sum, ds_tgt):
-        e, rows = st["src"].numel(), plan.rows
-        dl = st["dst"] - plan.lo
-        s = torch.zeros((rows, nh)).index_add_(0, dl, rec[:e, nh:] * rec[:e, :nh])
+    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt):
+        rows = plan.rows
+        s = (go_p.view(-1, nh, fp)[:rows] * out_p.view(-1, nh, fp)[:rows]).sum(-1)
         s_sum[:rows] = s
         ds_tgt.zero_()
         ds_tgt[:rows] = SLOPE * s * (EPS / (z_local[:rows] + EPS))
