@@ -263,34 +263,49 @@ struct BwdRowdotParams {
 
 __global__ void __launch_bounds__(256)
 edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
+  constexpr int R = 4;   // rows per warp iteration: 2*R*chunks/32 independent 16-byte loads in flight per lane
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
   const int nh = P.nh;
-  for (int64_t row = warp; row < P.n; row += nwarps) {
-    float s[kMaxHeads];
+  for (int64_t row0 = warp * R; row0 < P.n; row0 += nwarps * R) {
+    float s[R][kMaxHeads];
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) s[h] = 0.f;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h) s[r][h] = 0.f;
     for (int c = lane; c < P.chunks; c += 32) {
-      const float4 g = ldg4(P.go + row * P.dp + c * 4), o = ldg4(P.out + row * P.dp + c * 4);
-      const float d = fmaf(g.x, o.x, fmaf(g.y, o.y, fmaf(g.z, o.z, g.w * o.w)));
+      float4 g[R], o[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool on = row0 + r < P.n;
+        g[r] = on ? ldg4(P.go + (row0 + r) * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        o[r] = on ? ldg4(P.out + (row0 + r) * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       const int hh = c / P.chunks_per_head;
 #pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h) s[h] += (h == hh) ? d : 0.f;
-    }
+      for (int r = 0; r < R; ++r) {
+        const float d = fmaf(g[r].x, o[r].x, fmaf(g[r].y, o[r].y, fmaf(g[r].z, o[r].z, g[r].w * o[r].w)));
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) {
-      if (h < nh) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
+        for (int h = 0; h < kMaxHeads; ++h) s[r][h] += (h == hh) ? d : 0.f;
       }
     }
-    if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
 #pragma unroll
       for (int h = 0; h < kMaxHeads; ++h) {
         if (h < nh) {
-          const float zz = __ldg(P.z + row * nh + h);
-          P.s_sum[row * nh + h] = s[h];
-          P.ds_tgt[row * nh + h] = kLeakySlope * s[h] * (kSoftmaxEps / (zz + kSoftmaxEps));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s[r][h] += __shfl_xor_sync(0xffffffffu, s[r][h], o);
+        }
+      }
+      if (lane == 0 && row0 + r < P.n) {
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h) {
+          if (h < nh) {
+            const float zz = __ldg(P.z + (row0 + r) * nh + h);
+            P.s_sum[(row0 + r) * nh + h] = s[r][h];
+            P.ds_tgt[(row0 + r) * nh + h] = kLeakySlope * s[r][h] * (kSoftmaxEps / (zz + kSoftmaxEps));
+          }
         }
       }
     }
@@ -354,6 +369,12 @@ __device__ __forceinline__ void bwd_finish_row(const BwdFinishParams& P, const i
                                                const unsigned gmask, const float corr) {
   const int nh = P.nh;
   const int start = __ldg(P.rowptr_t + row), end = __ldg(P.rowptr_t + row + 1);
+  float4 own[SLOTS];   // the row to update: issued first so its latency overlaps the edge loop
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int c = s * G + gl;
+    own[s] = c < P.chunks ? *reinterpret_cast<const float4*>(P.d_wh + row * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float gsum[NHT];
 #pragma unroll
   for (int h = 0; h < NHT; ++h) gsum[h] = 0.f;
@@ -397,7 +418,7 @@ __device__ __forceinline__ void bwd_finish_row(const BwdFinishParams& P, const i
     const int c = s * G + gl;
     if (c < P.chunks) {
       float4* dp4 = reinterpret_cast<float4*>(P.d_wh + row * P.dp + c * 4);
-      float4 a = *dp4;
+      float4 a = own[s];
 #pragma unroll
       for (int h = 0; h < NHT; ++h) {
         if (h < nh) {
@@ -513,8 +534,8 @@ extern "C" int gat_edge_bwd_rowdot(const float* go_padded, const float* out_padd
   BwdRowdotParams P;
   P.go = go_padded; P.out = out_padded; P.z = z; P.n = n_rows; P.nh = nh; P.dp = nh * fp; P.chunks = nh * fp / 4;
   P.chunks_per_head = fp / 4; P.s_sum = s_sum; P.ds_tgt = ds_tgt;
-  int64_t want = (n_rows + 7) / 8;
-  edge_bwd_rowdot_kernel<<<(unsigned)(want < kNumSMs * 8 ? want : kNumSMs * 8), 256, 0, st>>>(P);
+  int64_t want = (n_rows + 31) / 32;
+  edge_bwd_rowdot_kernel<<<(unsigned)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8), 256, 0, st>>>(P);
   GAT_LAUNCH_CHECK();
   gamma_partial_kernel<<<kGammaBlocks, 256, 0, st>>>(ds_tgt, n_rows * nh, (BwdHeader*)workspace, (double*)((char*)workspace + kBwdHeaderBytes));
   GAT_LAUNCH_CHECK();
