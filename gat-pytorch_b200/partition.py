@@ -125,6 +125,12 @@ class CudaBackend:
                   0, 0.0, 0, 0, out_p.data_ptr(), None, z.data_ptr(), p(tie_dst), p(tie_src), p(tie_total),
                   fws.data_ptr(), fws.numel(), self._s(out_p.device), tag=(nh, fp))
 
+    def scores_bwd(self, wh, n, dp, nh, ds_src, ds_tgt, da_src, da_tgt):
+        sb = int(self.lib.gat_scores_bwd_workspace_bytes(dp, nh))
+        ws = torch.empty(sb, dtype=torch.uint8, device=wh.device)
+        _lib.call("gat_scores_bwd", wh.data_ptr(), n, dp, nh, ds_src.data_ptr(), ds_tgt.data_ptr(),
+                  da_src.data_ptr(), da_tgt.data_ptr(), ws.data_ptr(), sb, self._s(wh.device))
+
     def _bwd_ws(self, dev, nh):
         ws_bytes = int(self.lib.gat_edge_bwd_workspace_bytes(0, 0, nh))
         return torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes

@@ -81,3 +81,17 @@ def test_plan_covers_all_rows():
         assert plans[0].lo == 0 and plans[-1].hi == n
         assert all(a.hi == b.lo for a, b in zip(plans, plans[1:]))
         assert all(p.rows <= p.rows_per_rank and p.n_pad >= n for p in plans)
+
+
+def test_cuda_backend_implements_the_backend_interface():
+    """Every method the partitioned layer calls on its backend exists on the product (C-ABI) backend with the same
+    parameter names as on the oracle stand-in used above (guards against the two drifting apart)."""
+    import inspect
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle_backend import OracleBackend
+    from gat_pytorch_b200.partition import CudaBackend
+    for name, fn in inspect.getmembers(OracleBackend, predicate=inspect.isfunction):
+        if name.startswith("_"):
+            continue
+        assert hasattr(CudaBackend, name), name
+        assert list(inspect.signature(fn).parameters) == list(inspect.signature(getattr(CudaBackend, name)).parameters), name
