@@ -12,6 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgat_b200.so")
+LONG_ROW_EDGES = 256   # GAT_LONG_ROW_EDGES in include/gat_b200.h
 CSRC = os.path.join(_HERE, "csrc")
 
 _lock = threading.Lock()
@@ -26,7 +27,7 @@ SIGNATURES = {
     "gat_edges_scan": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
     "gat_csr_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "gat_csr_build": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_int64,
-                              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+                              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gat_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int64, c_int64, c_int]),
     "gat_gemm_tc_supported": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64]),
     "gat_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64,
@@ -36,18 +37,19 @@ SIGNATURES = {
     "gat_scores_fwd": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P]),
     "gat_scores_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gat_scores_bwd": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "gat_edge_max": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int, _P, _P, c_size_t, _P]),
+    "gat_edge_max": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, c_int, _P, _P, c_size_t, _P]),
     "gat_edge_fwd_workspace_bytes": (c_size_t, []),
-    "gat_edge_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, c_int, c_float, c_uint64, c_uint64,
+    "gat_edge_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, c_int, c_int, _P, _P, _P, c_int, c_float, c_uint64, c_uint64,
                              _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gat_head_merge_fwd": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "gat_head_merge_bwd": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "gat_edge_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
-    "gat_edge_bwd_main": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, c_int,
-                                  c_float, c_uint64, c_uint64, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "gat_edge_bwd_rowsum": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "gat_edge_bwd_rowdot": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
-    "gat_edge_bwd_finish": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
+    "gat_edge_bwd_main": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, c_int,
+                                  c_float, c_uint64, c_uint64, _P, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_head_mean_bwd_shared": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "gat_edge_bwd_rowsum": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_rowdot": (c_int, [_P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_finish": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
                                     _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_gamma": (c_int, [_P, c_size_t, _P, _P]),
 }

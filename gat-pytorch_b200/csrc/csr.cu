@@ -108,23 +108,24 @@ __global__ void gather_csrt_kernel(const int32_t* __restrict__ perm_t, const int
   }
 }
 
-// Scheduling order for the persistent edge kernels: rows longer than `thresh` first (in row order), then
-// the rest in row order.  Purely a performance hint -- results do not depend on it.
-__global__ void long_flag_kernel(const int32_t* __restrict__ rowptr, int64_t n, int thresh, int* __restrict__ flags) {
+// Scheduling order for the persistent edge kernels: rows longer than `thresh` first, LONGEST first among them (the
+// cooperative CTA-per-row phase then starts its biggest jobs at t = 0), then the rest in row order.  One stable
+// descending radix sort on key = (degree > thresh ? degree : 0).
+__global__ void order_key_kernel(const int32_t* __restrict__ rowptr, int64_t n, int thresh, int32_t* __restrict__ keys,
+                                 int32_t* __restrict__ rows, int64_t* __restrict__ n_long_out) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r < n) flags[r] = (rowptr[r + 1] - rowptr[r]) > thresh;
+  int is_long = 0;
+  if (r < n) {
+    const int deg = rowptr[r + 1] - rowptr[r];
+    is_long = deg > thresh;
+    keys[r] = is_long ? deg : 0;
+    rows[r] = (int32_t)r;
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, is_long);
+  if ((threadIdx.x & 31) == 0 && ballot && n_long_out) atomicAdd((unsigned long long*)n_long_out, (unsigned long long)__popc(ballot));
 }
 
-__global__ void order_scatter_kernel(const int* __restrict__ flags, const int* __restrict__ scan, int64_t n,
-                                     int32_t* __restrict__ order) {
-  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  const int n_long = scan[n - 1] + flags[n - 1];
-  const int before = scan[r];
-  order[flags[r] ? before : n_long + (int)r - before] = (int32_t)r;
-}
-
-constexpr int kLongRowThreshold = 256;
+constexpr int kLongRowThreshold = GAT_LONG_ROW_EDGES;
 
 static int key_bits(int64_t n_nodes) {
   int b = 1;
@@ -133,7 +134,7 @@ static int key_bits(int64_t n_nodes) {
 }
 
 struct CsrWorkspace {
-  size_t off_src32, off_dst32, off_keys_out, off_iota, off_perm, off_slot, off_flags, off_pos, off_cub, cub_bytes, total;
+  size_t off_src32, off_dst32, off_keys_out, off_iota, off_perm, off_slot, off_flags, off_pos, off_rows, off_cub, cub_bytes, total;
 };
 static inline int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
 
@@ -142,13 +143,17 @@ static int plan_workspace(int64_t e_in, int64_t e_out, int64_t n_nodes, CsrWorks
   cudaError_t e1 = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
                                                   (const int32_t*)nullptr, (int32_t*)nullptr, (int)e_out, 0, key_bits(n_nodes));
   cudaError_t e2 = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)max64(e_in, n_nodes));
-  if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
+  size_t order_bytes = 0;
+  cudaError_t e3 = cub::DeviceRadixSort::SortPairsDescending(nullptr, order_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                                            (const int32_t*)nullptr, (int32_t*)nullptr, (int)max64(n_nodes, 1), 0, 31);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
+  if (order_bytes > sort_bytes) sort_bytes = order_bytes;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
   size_t eb = (size_t)(e_out > 0 ? e_out : 1) * sizeof(int32_t);
   size_t ib = (size_t)(max64(max64(e_in, n_nodes), 1)) * sizeof(int);   // flags/pos also serve the row-order scan
   w->off_src32 = take(eb); w->off_dst32 = take(eb); w->off_keys_out = take(eb); w->off_iota = take(eb);
-  w->off_perm = take(eb); w->off_slot = take(eb); w->off_flags = take(ib); w->off_pos = take(ib);
+  w->off_perm = take(eb); w->off_slot = take(eb); w->off_flags = take(ib); w->off_pos = take(ib); w->off_rows = take(ib);
   w->cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
   w->off_cub = take(w->cub_bytes + 256);
   w->total = o;
@@ -159,7 +164,7 @@ template <typename T>
 static int csr_build_impl(const T* src, const T* dst, int64_t e_in, int add_self_loops, int64_t n_idx, int64_t e_out,
                           int64_t n_nodes, int64_t* ei_out, int32_t* rowptr, int32_t* col, int32_t* eid,
                           int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t, int32_t* tpos, int32_t* row_order, int32_t* row_order_t,
-                          char* ws, const CsrWorkspace& w, cudaStream_t st) {
+                          int64_t* n_long, char* ws, const CsrWorkspace& w, cudaStream_t st) {
   int32_t* src32 = (int32_t*)(ws + w.off_src32);
   int32_t* dst32 = (int32_t*)(ws + w.off_dst32);
   int32_t* keys_out = (int32_t*)(ws + w.off_keys_out);
@@ -168,6 +173,7 @@ static int csr_build_impl(const T* src, const T* dst, int64_t e_in, int add_self
   int32_t* slot = (int32_t*)(ws + w.off_slot);
   int* flags = (int*)(ws + w.off_flags);
   int* pos = (int*)(ws + w.off_pos);
+  int32_t* rows = (int32_t*)(ws + w.off_rows);
   void* cub_tmp = (void*)(ws + w.off_cub);
   size_t cub_bytes = w.cub_bytes;
   const int T256 = 256;
@@ -210,11 +216,10 @@ static int csr_build_impl(const T* src, const T* dst, int64_t e_in, int add_self
     int32_t* outs[2] = {row_order, row_order_t};
     for (int i = 0; i < 2; ++i) {
       if (!outs[i]) continue;
-      long_flag_kernel<<<blocks(n_nodes), T256, 0, st>>>(rps[i], n_nodes, kLongRowThreshold, flags);
+      order_key_kernel<<<blocks(n_nodes), T256, 0, st>>>(rps[i], n_nodes, kLongRowThreshold, flags, rows, n_long ? n_long + i : nullptr);
       GAT_LAUNCH_CHECK();
-      GAT_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flags, pos, (int)n_nodes, st));
-      order_scatter_kernel<<<blocks(n_nodes), T256, 0, st>>>(flags, pos, n_nodes, outs[i]);
-      GAT_LAUNCH_CHECK();
+      GAT_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp, cub_bytes, (const int32_t*)flags, (int32_t*)pos, (const int32_t*)rows,
+                                                         outs[i], (int)n_nodes, 0, 31, st));
     }
   }
   return GAT_OK;
@@ -253,7 +258,7 @@ extern "C" int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t
                              int add_self_loops, int64_t n_idx, int64_t n_edges_out, int64_t n_nodes,
                              int64_t* ei_out, int32_t* rowptr, int32_t* col, int32_t* eid,
                              int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t, int32_t* tpos,
-                             int32_t* row_order, int32_t* row_order_t,
+                             int32_t* row_order, int32_t* row_order_t, int64_t* n_long,
                              void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
   GAT_CHECK_ARG(n_edges_in >= 0 && n_edges_out >= 0 && n_nodes >= 0, "gat_csr_build: negative size");
@@ -271,12 +276,13 @@ extern "C" int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t
     return GAT_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (n_long) GAT_CUDA(cudaMemsetAsync(n_long, 0, 2 * sizeof(int64_t), st));
   if (index_is_int64) {
     const int64_t* p = (const int64_t*)edge_index;
     return csr_build_impl<int64_t>(p, p + row_stride, n_edges_in, add_self_loops, n_idx, n_edges_out, n_nodes, ei_out,
-                                   rowptr, col, eid, rowptr_t, col_t, pos_t, tpos, row_order, row_order_t, (char*)workspace, w, st);
+                                   rowptr, col, eid, rowptr_t, col_t, pos_t, tpos, row_order, row_order_t, n_long, (char*)workspace, w, st);
   }
   const int32_t* p = (const int32_t*)edge_index;
   return csr_build_impl<int32_t>(p, p + row_stride, n_edges_in, add_self_loops, n_idx, n_edges_out, n_nodes, ei_out,
-                                 rowptr, col, eid, rowptr_t, col_t, pos_t, tpos, row_order, row_order_t, (char*)workspace, w, st);
+                                 rowptr, col, eid, rowptr_t, col_t, pos_t, tpos, row_order, row_order_t, n_long, (char*)workspace, w, st);
 }

@@ -27,9 +27,11 @@ struct BwdHeader {          // first 256 bytes of the backward workspace
   float corr;               // gamma / |T|   (0 when the arg-max set is empty)
   int n_partials;           // number of partials written by gamma_partial_kernel
   unsigned int pad0[12];
-  unsigned int counter_a;   // row scheduler of pass 1 / pass 3 (byte offset 64)
-  unsigned int pad1[15];
+  unsigned int counter_a;   // row scheduler of pass 1 / pass 3 (byte offset 64): warp-level counter,
+  unsigned int counter_a_cta;   //                                                  CTA-level long-row counter
+  unsigned int pad1[14];
   unsigned int counter_b;   // row scheduler of pass 2          (byte offset 128)
+  unsigned int counter_b_cta;
 };
 static_assert(offsetof(BwdHeader, counter_a) == 64 && offsetof(BwdHeader, counter_b) == 128, "header layout");
 constexpr size_t kBwdHeaderBytes = 256;
@@ -44,6 +46,7 @@ struct BwdMainParams {
   const float* s_src; const float* s_tgt; const float* gmax; const float* z;   // s_tgt / z indexed by TARGET id
   int const_attention; float dropout_p; uint64_t seed; uint64_t offset;
   const float* go; const float* grad_alpha;                                    // go indexed by TARGET id
+  int go_ld; int go_shared;   // go row stride (floats); go_shared: one (Fp)-wide row serves every head (head-mean layers)
   float* rec; float* d_wh;
 };
 
@@ -53,14 +56,20 @@ struct MainShape {
   static constexpr int U = (SLOTS >= 4) ? 2 : (TB < 4 ? TB : 4);    // edges in flight
 };
 
-template <int G, int SLOTS, int NHT>
+// COOP (long source rows): the CTA's 256/G groups take the row's batches round-robin (each writes the records of its
+// own edges) and the dWh row is combined over the groups in group order through `coop`, which ALIASES the groups'
+// `part` tiles -- hence the CTA barrier before it is written.  Called by all threads of the CTA in that case.
+template <int G, int SLOTS, int NHT, bool COOP>
 __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64_t row, const int tid, const int gl,
                                              const int gbase, const unsigned gmask, const float gmax,
-                                             int* sh_dst, float* sh_w, float* sh_da, float* part) {
+                                             int* sh_dst, float* sh_w, float* sh_da, float* part, float* coop) {
   constexpr int TB = MainShape<G, SLOTS>::TB, U = MainShape<G, SLOTS>::U;
+  constexpr int NG = kEdgeThreads / G;
+  const int grp = tid / G;
+  const int first = COOP ? grp * G : 0, step = COOP ? NG * G : G;
   const int nh = P.nh;
   const int pstride = P.chunks + 1;
-  int head[SLOTS];
+  int head[SLOTS], goff[SLOTS];
   bool ok[SLOTS];
   float4 whr[SLOTS], acc[SLOTS];
 #pragma unroll
@@ -68,6 +77,9 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
     int c = s * G + gl;
     ok[s] = c < P.chunks;
     head[s] = ok[s] ? c / P.chunks_per_head : 0;
+    // float offset of this slot's chunk inside a gathered dOut row: the head-mean layer's upstream gradient is the same
+    // (Fp)-wide vector for every head (gat_layer.py:132), so it is stored once and every head reads the same chunk
+    goff[s] = (P.go_shared ? c - head[s] * P.chunks_per_head : c) * 4;
     acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
     whr[s] = (ok[s] && !P.const_attention) ? ldg4(P.wh + row * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -76,7 +88,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
 #pragma unroll
   for (int h = 0; h < NHT; ++h) ss[h] = (!P.const_attention && h < nh) ? __ldg(P.s_src + row * nh + h) : 0.f;
 
-  for (int base = start; base < end; base += G) {
+  for (int base = start + first; base < end; base += step) {
     const int e = base + gl;
     const bool valid = e < end;
     float alpha[NHT], msk[NHT], ga[NHT];
@@ -118,10 +130,10 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
         for (int u = 0; u < U; ++u) {
           const bool on = tt + u < tcnt;
           const int didx = on ? sh_dst[gbase + t0 + tt + u] : 0;
-          const float* rowp = P.go + (int64_t)didx * P.dp + gl * 4;
+          const float* rowp = P.go + (int64_t)didx * P.go_ld;
 #pragma unroll
           for (int s = 0; s < SLOTS; ++s)
-            v[u][s] = (on && ok[s]) ? ldg4(rowp + s * G * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[u][s] = (on && ok[s]) ? ldg4(rowp + goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -165,16 +177,33 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
     }
     __syncwarp(gmask);
   }
+  if (COOP) {
+    __syncthreads();   // every group is done with its `part` tile, which `coop` aliases
 #pragma unroll
-  for (int s = 0; s < SLOTS; ++s)
-    if (ok[s]) *reinterpret_cast<float4*>(P.d_wh + row * P.dp + (s * G + gl) * 4) = acc[s];
+    for (int s = 0; s < SLOTS; ++s)
+      if (ok[s]) *reinterpret_cast<float4*>(coop + grp * P.dp + (s * G + gl) * 4) = acc[s];
+    __syncthreads();
+    for (int c = tid; c < P.chunks; c += kEdgeThreads) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < NG; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(coop + j * P.dp + c * 4);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      *reinterpret_cast<float4*>(P.d_wh + row * P.dp + c * 4) = t;
+    }
+    // the next grab_long_row() starts with a __syncthreads()
+  } else {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+      if (ok[s]) *reinterpret_cast<float4*>(P.d_wh + row * P.dp + (s * G + gl) * 4) = acc[s];
+  }
 }
 
-template <int G, int SLOTS, int NHT>
+template <int G, int SLOTS, int NHT, bool COOP>
 __global__ void __launch_bounds__(kEdgeThreads, (SLOTS <= 2 ? 3 : (SLOTS <= 4 ? 2 : 1)))
 edge_bwd_main_kernel(const BwdMainParams P) {
   constexpr int TB = MainShape<G, SLOTS>::TB;
-  extern __shared__ float dyn_smem[];
+  extern __shared__ __align__(16) float dyn_smem[];
   __shared__ int sh_dst[kEdgeThreads];
   __shared__ float sh_w[kEdgeThreads * NHT];
   __shared__ float sh_da[kEdgeThreads * NHT];
@@ -182,19 +211,34 @@ edge_bwd_main_kernel(const BwdMainParams P) {
   const unsigned gmask = group_mask<G>(lane);
   float* part = dyn_smem + (size_t)(tid / G) * TB * (P.chunks + 1);   // [TB][chunks+1] of my group
   const float gmax = P.const_attention ? 0.f : __ldg(P.gmax);
-  int64_t base;
-  while (grab_rows<G>(P.sched, lane, base)) {
-#pragma unroll 1
-    for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
-      const int64_t row = sched_row<G>(P.sched, base, k, lane);
-      if (row >= 0) bwd_main_row<G, SLOTS, NHT>(P, row, tid, gl, gbase, gmask, gmax, sh_dst, sh_w, sh_da, part);
+  if (COOP) {   // long source rows, CTA per row (its own launch)
+    __shared__ int sh_ctl;
+    pdl_release_dependents();   // the short-row launch that follows may fill SMs as this grid drains
+    for (;;) {
+      const int64_t row = grab_long_row(P.sched, P.rowptr_t, &sh_ctl);
+      if (row < 0) break;
+      bwd_main_row<G, SLOTS, NHT, true>(P, row, tid, gl, gbase, gmask, gmax, sh_dst, sh_w, sh_da, part, dyn_smem);
     }
+  } else {
+    int64_t base;
+    while (grab_rows<G>(P.sched, lane, base)) {
+#pragma unroll 1
+      for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
+        const int64_t row = sched_row<G>(P.sched, base, k, lane);
+        if (row >= 0 && !taken_by_cta_phase(P.sched, P.rowptr_t, row))
+          bwd_main_row<G, SLOTS, NHT, false>(P, row, tid, gl, gbase, gmask, gmax, sh_dst, sh_w, sh_da, part, nullptr);
+      }
+    }
+    pdl_wait_for_primary();     // no-op unless launched behind the cooperative kernel
   }
 }
 
+// per-group transpose tiles; the cooperative path's (256/G) x dp reduction buffer aliases them
 template <int G, int SLOTS>
 static size_t main_dyn_smem(int chunks) {
-  return (size_t)(kEdgeThreads / G) * MainShape<G, SLOTS>::TB * (chunks + 1) * sizeof(float);
+  const size_t part = (size_t)(kEdgeThreads / G) * MainShape<G, SLOTS>::TB * (chunks + 1) * sizeof(float);
+  const size_t coop = (size_t)(kEdgeThreads / G) * chunks * 4 * sizeof(float);
+  return part > coop ? part : coop;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -205,50 +249,78 @@ struct BwdRowsumParams {
   const float* rec; const float* z; float* s_sum; float* ds_tgt;
 };
 
+__device__ __forceinline__ void rowsum_span(const BwdRowsumParams& P, const int start, const int end, const int first,
+                                            const int step, float (&s)[kMaxHeads]) {
+  const int nh = P.nh;
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) s[h] = 0.f;
+  for (int j = start + first; j < end; j += step) {
+    const float* r = P.rec + (int64_t)__ldg(P.tpos + j) * 2 * nh;
+    if (nh == 4) {
+      const float4 da = __ldg(reinterpret_cast<const float4*>(r)), al = __ldg(reinterpret_cast<const float4*>(r) + 1);
+      s[0] = fmaf(al.x, da.x, s[0]); s[1] = fmaf(al.y, da.y, s[1]); s[2] = fmaf(al.z, da.z, s[2]); s[3] = fmaf(al.w, da.w, s[3]);
+    } else {
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h)
+        if (h < nh) s[h] = fmaf(__ldg(r + nh + h), __ldg(r + h), s[h]);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) {
+    if (h < nh) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
+    }
+  }
+}
+
+__device__ __forceinline__ void rowsum_store(const BwdRowsumParams& P, const int64_t row, const float (&s)[kMaxHeads]) {
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) {
+    if (h < P.nh) {
+      const float zz = __ldg(P.z + row * P.nh + h);
+      P.s_sum[row * P.nh + h] = s[h];
+      // sum_e g = 0.01*(S - S*sum_e alpha) with sum_e alpha = Z/(Z+eps): exact, and free of the cancellation a
+      // direct fp32 sum of g would suffer
+      P.ds_tgt[row * P.nh + h] = kLeakySlope * s[h] * (kSoftmaxEps / (zz + kSoftmaxEps));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 edge_bwd_rowsum_kernel(const BwdRowsumParams P) {
-  const int lane = threadIdx.x & 31;
-  const int nh = P.nh;
+  __shared__ float sh_part[8][kMaxHeads];
+  __shared__ int sh_ctl;
+  const int tid = threadIdx.x, lane = tid & 31;
+  float s[kMaxHeads];
+  // long rows: the 8 warps stride over the row, warp partials are added in warp order
+  for (;;) {
+    const int64_t row = grab_long_row(P.sched, P.rowptr, &sh_ctl);
+    if (row < 0) break;
+    rowsum_span(P, __ldg(P.rowptr + row), __ldg(P.rowptr + row + 1), tid, 256, s);
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h) sh_part[tid >> 5][h] = s[h];
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += sh_part[w][h];
+        s[h] = t;
+      }
+      rowsum_store(P, row, s);
+    }
+  }
   int64_t base;
   while (grab_rows<32>(P.sched, lane, base)) {
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
       const int64_t row = sched_row<32>(P.sched, base, k, lane);
-      if (row < 0) continue;
-      const int start = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
-      float s[kMaxHeads];
-#pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h) s[h] = 0.f;
-      for (int j = start + lane; j < end; j += 32) {
-        const float* r = P.rec + (int64_t)__ldg(P.tpos + j) * 2 * nh;
-        if (nh == 4) {
-          const float4 da = __ldg(reinterpret_cast<const float4*>(r)), al = __ldg(reinterpret_cast<const float4*>(r) + 1);
-          s[0] = fmaf(al.x, da.x, s[0]); s[1] = fmaf(al.y, da.y, s[1]); s[2] = fmaf(al.z, da.z, s[2]); s[3] = fmaf(al.w, da.w, s[3]);
-        } else {
-#pragma unroll
-          for (int h = 0; h < kMaxHeads; ++h)
-            if (h < nh) s[h] = fmaf(__ldg(r + nh + h), __ldg(r + h), s[h]);
-        }
-      }
-#pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h) {
-        if (h < nh) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
-        }
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h) {
-          if (h < nh) {
-            const float zz = __ldg(P.z + row * nh + h);
-            P.s_sum[row * nh + h] = s[h];
-            // sum_e g = 0.01*(S - S*sum_e alpha) with sum_e alpha = Z/(Z+eps): exact, and free of the cancellation a
-            // direct fp32 sum of g would suffer
-            P.ds_tgt[row * nh + h] = kLeakySlope * s[h] * (kSoftmaxEps / (zz + kSoftmaxEps));
-          }
-        }
-      }
+      if (row < 0 || taken_by_cta_phase(P.sched, P.rowptr, row)) continue;
+      rowsum_span(P, __ldg(P.rowptr + row), __ldg(P.rowptr + row + 1), lane, 32, s);
+      if (lane == 0) rowsum_store(P, row, s);
     }
   }
 }
@@ -258,6 +330,7 @@ edge_bwd_rowsum_kernel(const BwdRowsumParams P) {
 // with the forward output, so no per-edge record has to be gathered at all.
 struct BwdRowdotParams {
   const float* go; const float* out; const float* z; int64_t n; int nh; int dp; int chunks; int chunks_per_head;
+  int go_ld; int go_shared;
   float* s_sum; float* ds_tgt;
 };
 
@@ -278,7 +351,7 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const bool on = row0 + r < P.n;
-        g[r] = on ? ldg4(P.go + (row0 + r) * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g[r] = on ? ldg4(P.go + (row0 + r) * P.go_ld + (P.go_shared ? c % P.chunks_per_head : c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         o[r] = on ? ldg4(P.out + (row0 + r) * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const int hh = c / P.chunks_per_head;
@@ -364,26 +437,49 @@ struct BwdFinishParams {
   float* ds_src; float* ds_tgt; float* d_wh;
 };
 
-template <int G, int SLOTS, int NHT>
+// COOP (long source rows): all 256 threads stride over the row's records; the per-head sums are combined warp by warp
+// in a fixed order through `sh_part`, then group 0 alone runs the row epilogue.  Called by all threads in that case.
+template <int G, int SLOTS, int NHT, bool COOP>
 __device__ __forceinline__ void bwd_finish_row(const BwdFinishParams& P, const int64_t row, const int gl,
-                                               const unsigned gmask, const float corr) {
+                                               const unsigned gmask, const float corr, float (*sh_part)[kMaxHeads]) {
   const int nh = P.nh;
+  const int tid = threadIdx.x;
   const int start = __ldg(P.rowptr_t + row), end = __ldg(P.rowptr_t + row + 1);
+  const bool epilogue = !COOP || tid < G;
   float4 own[SLOTS];   // the row to update: issued first so its latency overlaps the edge loop
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int c = s * G + gl;
-    own[s] = c < P.chunks ? *reinterpret_cast<const float4*>(P.d_wh + row * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    own[s] = (epilogue && c < P.chunks) ? *reinterpret_cast<const float4*>(P.d_wh + row * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float gsum[NHT];
 #pragma unroll
   for (int h = 0; h < NHT; ++h) gsum[h] = 0.f;
-  for (int e = start + gl; e < end; e += G) {
+  for (int e = start + (COOP ? tid : gl); e < end; e += (COOP ? kEdgeThreads : G)) {
     const float* r = P.rec + (int64_t)e * 2 * nh;
     const float* sp = P.s_sum + (int64_t)__ldg(P.col_t + e) * nh;
 #pragma unroll
     for (int h = 0; h < NHT; ++h)
       if (h < nh) gsum[h] = fmaf(kLeakySlope * __ldg(r + nh + h), __ldg(r + h) - __ldg(sp + h), gsum[h]);   // g = 0.01*alpha*(d_alpha - S)
+  }
+  if (COOP) {
+#pragma unroll
+    for (int h = 0; h < NHT; ++h) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gsum[h] += __shfl_xor_sync(0xffffffffu, gsum[h], o);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int h = 0; h < NHT; ++h) sh_part[tid >> 5][h] = gsum[h];
+    }
+    __syncthreads();
+    if (!epilogue) return;
+#pragma unroll
+    for (int h = 0; h < NHT; ++h) {
+      float t = 0.f;
+      for (int w = 0; w < kEdgeThreads / 32; ++w) t += sh_part[w][h];
+      gsum[h] = t;
+    }
   }
   // ds_src = sum g - |T_src|*Gamma/|T|;  ds_tgt -= |T_dst|*Gamma/|T|   (gradient through max(), section 9.2)
   const bool own_tgt = row >= P.tgt_lo && row < P.tgt_hi;   // single GPU: always; partitioned: owner rank only
@@ -393,7 +489,7 @@ __device__ __forceinline__ void bwd_finish_row(const BwdFinishParams& P, const i
   for (int h = 0; h < NHT; ++h) {
     dss[h] = 0.f; dst_[h] = 0.f;
     if (h < nh) {
-      float g = group_sum<G>(gsum[h], gmask);
+      float g = COOP ? gsum[h] : group_sum<G>(gsum[h], gmask);
       int ts = P.tie_src ? __ldg(P.tie_src + row * nh + h) : 0;
       dss[h] = ts ? g - (float)ts * corr : g;
       if (own_tgt) {
@@ -438,15 +534,23 @@ __device__ __forceinline__ void bwd_finish_row(const BwdFinishParams& P, const i
 template <int G, int SLOTS, int NHT>
 __global__ void __launch_bounds__(kEdgeThreads)
 edge_bwd_finish_kernel(const BwdFinishParams P) {
+  __shared__ float sh_part[kEdgeThreads / 32][kMaxHeads];
+  __shared__ int sh_ctl;
   const int tid = threadIdx.x, lane = tid & 31, gl = tid & (G - 1);
   const unsigned gmask = group_mask<G>(lane);
   const float corr = P.corr_override ? __ldg(P.corr_override) : P.header->corr;
+  for (;;) {
+    const int64_t row = grab_long_row(P.sched, P.rowptr_t, &sh_ctl);
+    if (row < 0) break;
+    bwd_finish_row<G, SLOTS, NHT, true>(P, row, gl, gmask, corr, sh_part);
+  }
   int64_t base;
   while (grab_rows<G>(P.sched, lane, base)) {
 #pragma unroll 1
     for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
       const int64_t row = sched_row<G>(P.sched, base, k, lane);
-      if (row >= 0) bwd_finish_row<G, SLOTS, NHT>(P, row, gl, gmask, corr);
+      if (row >= 0 && !taken_by_cta_phase(P.sched, P.rowptr_t, row))
+        bwd_finish_row<G, SLOTS, NHT, false>(P, row, gl, gmask, corr, nullptr);
     }
   }
 }
@@ -469,10 +573,10 @@ extern "C" size_t gat_edge_bwd_workspace_bytes(int64_t n, int64_t n_edges, int n
 }
 
 extern "C" int gat_edge_bwd_main(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
-                                 const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                                 int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
                                  const float* s_src, const float* s_tgt, const float* gmax, const float* z,
                                  int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
-                                 const float* go_padded, const float* grad_alpha, float* rec, float* d_wh,
+                                 const float* go_padded, int go_shared, const float* grad_alpha, float* rec, float* d_wh,
                                  void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
   int rc = check_common("gat_edge_bwd_main", nh, fp, workspace, workspace_bytes);
@@ -483,39 +587,56 @@ extern "C" int gat_edge_bwd_main(const int32_t* rowptr_t, const int32_t* col_t, 
   if (n_rows == 0) return GAT_OK;
   BwdMainParams P;
   P.rowptr_t = rowptr_t; P.col_t = col_t; P.pos_t = pos_t; P.eid = eid;
-  P.sched.order = row_order_t; P.sched.counter = &((BwdHeader*)workspace)->counter_a; P.sched.n = n_rows;
+  P.sched.order = row_order_t; P.sched.counter = &((BwdHeader*)workspace)->counter_a;
+  P.sched.cta_counter = &((BwdHeader*)workspace)->counter_a_cta; P.sched.n = n_rows;
   P.wh = wh; P.nh = nh; P.dp = nh * fp; P.chunks = nh * fp / 4; P.chunks_per_head = fp / 4;
   P.s_src = s_src; P.s_tgt = s_tgt; P.gmax = gmax; P.z = z; P.const_attention = const_attention;
   P.dropout_p = dropout_p; P.seed = seed; P.offset = offset; P.go = go_padded; P.grad_alpha = grad_alpha;
+  P.go_shared = go_shared ? 1 : 0; P.go_ld = go_shared ? fp : nh * fp;
   P.rec = rec; P.d_wh = d_wh;
   GroupShape shape = pick_group(P.chunks);
   if (shape.slots < 0) {
     set_error("gat_edge_bwd_main: row width %d floats exceeds the supported 1024", P.dp);
     return GAT_EUNSUPPORTED;
   }
-#define LAUNCH(G_, S_, N_)                                                                                   \
-  edge_bwd_main_kernel<G_, S_, N_><<<persistent_grid(edge_bwd_main_kernel<G_, S_, N_>, kEdgeThreads,                 \
-                                                     main_dyn_smem<G_, S_>(P.chunks),                                \
-                                                     (n_rows + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)),      \
-                                     kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st>>>(P)
+  const bool coop_launch = row_order_t != nullptr && n_long != 0;
+  if (coop_launch) {   // long source rows first, CTA per row; the short-row launch overlaps its tail
+    const int64_t ctas = n_long < 0 ? n_rows : n_long;
+#define LAUNCH(G_, S_, N_)                                                                                            \
+  GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, true>,                                                      \
+                         persistent_grid(edge_bwd_main_kernel<G_, S_, N_, true>, kEdgeThreads,                        \
+                                         main_dyn_smem<G_, S_>(P.chunks), ctas),                                      \
+                         kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, false))
+    GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
+#undef LAUNCH
+    GAT_LAUNCH_CHECK();
+  }
+#define LAUNCH(G_, S_, N_)                                                                                            \
+  GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, false>,                                                     \
+                         persistent_grid(edge_bwd_main_kernel<G_, S_, N_, false>, kEdgeThreads,                       \
+                                         main_dyn_smem<G_, S_>(P.chunks),                                             \
+                                         (n_rows + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)),                   \
+                         kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, coop_launch))
   GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
 #undef LAUNCH
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }
 
-extern "C" int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, const int32_t* row_order, int64_t n_rows, int nh,
+extern "C" int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, const int32_t* row_order, int64_t n_long, int64_t n_rows, int nh,
                                    const float* rec, const float* z, float* s_sum, float* ds_tgt,
                                    void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
+  (void)n_long;
   int rc = check_common("gat_edge_bwd_rowsum", nh, 4, workspace, workspace_bytes);
   if (rc) return rc;
   if (n_rows == 0) return GAT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   BwdHeader* header = (BwdHeader*)workspace;
-  GAT_CUDA(cudaMemsetAsync(&header->counter_b, 0, sizeof(unsigned int), st));
+  GAT_CUDA(cudaMemsetAsync(&header->counter_b, 0, 2 * sizeof(unsigned int), st));
   BwdRowsumParams P;
-  P.rowptr = rowptr; P.tpos = tpos; P.sched.order = row_order; P.sched.counter = &header->counter_b; P.sched.n = n_rows;
+  P.rowptr = rowptr; P.tpos = tpos; P.sched.order = row_order; P.sched.counter = &header->counter_b;
+  P.sched.cta_counter = &header->counter_b_cta; P.sched.n = n_rows;
   P.nh = nh; P.rec = rec; P.z = z; P.s_sum = s_sum; P.ds_tgt = ds_tgt;
   edge_bwd_rowsum_kernel<<<persistent_grid(edge_bwd_rowsum_kernel, 256, 0, (n_rows + 7) / 8), 256, 0, st>>>(P);
   GAT_LAUNCH_CHECK();
@@ -524,7 +645,7 @@ extern "C" int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, c
   return GAT_OK;
 }
 
-extern "C" int gat_edge_bwd_rowdot(const float* go_padded, const float* out_padded, const float* z, int64_t n_rows, int nh, int fp,
+extern "C" int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const float* out_padded, const float* z, int64_t n_rows, int nh, int fp,
                                    float* s_sum, float* ds_tgt, void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
   int rc = check_common("gat_edge_bwd_rowdot", nh, fp, workspace, workspace_bytes);
@@ -534,6 +655,7 @@ extern "C" int gat_edge_bwd_rowdot(const float* go_padded, const float* out_padd
   BwdRowdotParams P;
   P.go = go_padded; P.out = out_padded; P.z = z; P.n = n_rows; P.nh = nh; P.dp = nh * fp; P.chunks = nh * fp / 4;
   P.chunks_per_head = fp / 4; P.s_sum = s_sum; P.ds_tgt = ds_tgt;
+  P.go_shared = go_shared ? 1 : 0; P.go_ld = go_shared ? fp : nh * fp;
   int64_t want = (n_rows + 31) / 32;
   edge_bwd_rowdot_kernel<<<(unsigned)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8), 256, 0, st>>>(P);
   GAT_LAUNCH_CHECK();
@@ -553,13 +675,14 @@ extern "C" int gat_edge_bwd_gamma(void* workspace, size_t workspace_bytes, doubl
   return GAT_OK;
 }
 
-extern "C" int gat_edge_bwd_finish(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* row_order_t, int64_t n_rows,
+extern "C" int gat_edge_bwd_finish(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* row_order_t, int64_t n_long, int64_t n_rows,
                                    int nh, int fp, const float* rec, const float* s_sum, const float* a_src, const float* a_tgt,
                                    const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
                                    const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
                                    float* ds_src, float* ds_tgt, float* d_wh,
                                    void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
+  (void)n_long;
   int rc = check_common("gat_edge_bwd_finish", nh, fp, workspace, workspace_bytes);
   if (rc) return rc;
   GAT_CHECK_ARG(rec && s_sum && a_src && a_tgt && ds_src && ds_tgt && d_wh, "gat_edge_bwd_finish: buffers missing");
@@ -570,9 +693,10 @@ extern "C" int gat_edge_bwd_finish(const int32_t* rowptr_t, const int32_t* col_t
     gamma_finalize_kernel<<<1, 1024, 0, st>>>(header, (const double*)((char*)workspace + kBwdHeaderBytes), tie_total);
     GAT_LAUNCH_CHECK();
   }
-  GAT_CUDA(cudaMemsetAsync(&header->counter_a, 0, sizeof(unsigned int), st));
+  GAT_CUDA(cudaMemsetAsync(&header->counter_a, 0, 2 * sizeof(unsigned int), st));
   BwdFinishParams P;
-  P.rowptr_t = rowptr_t; P.col_t = col_t; P.sched.order = row_order_t; P.sched.counter = &header->counter_a; P.sched.n = n_rows;
+  P.rowptr_t = rowptr_t; P.col_t = col_t; P.sched.order = row_order_t; P.sched.counter = &header->counter_a;
+  P.sched.cta_counter = &header->counter_a_cta; P.sched.n = n_rows;
   P.nh = nh; P.dp = nh * fp; P.chunks = nh * fp / 4;
   P.rec = rec; P.s_sum = s_sum; P.a_src = a_src; P.a_tgt = a_tgt;
   P.tie_dst = tie_dst; P.tie_src = tie_src; P.header = header; P.corr_override = corr_override;

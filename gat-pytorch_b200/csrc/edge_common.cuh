@@ -66,11 +66,46 @@ __device__ __forceinline__ float atomic_max_float(float* addr, float value) {
 // Persistent-grid row scheduler.  Rows are handed out to WARPS from a global counter in the order given by
 // `order` (long rows first, built by gat_csr_build), so a hub row starts at t=0 and short rows fill in
 // behind it; which warp computes a row never changes the row's result, so the output stays deterministic.
+//
+// LONG rows (more than kLongRow edges) are not handed to a single warp: one hub row of 16k edges would keep one warp
+// busy for milliseconds after every other row has finished (measured on the products-shaped graph: the four longest
+// rows, 63k edges, landed on one warp and set a ~8 ms floor under the forward kernel no matter how many GPUs shared the
+// rest).  Instead every CTA first takes long rows from a second counter and processes each one COOPERATIVELY: its
+// 256/G groups split the row's batches round-robin and their partial sums are combined through shared memory in a
+// fixed order.  The path a row takes depends only on its own length, so results stay deterministic and independent of
+// the schedule and of the partition.  Contract: when `order` is given, every long row precedes every short row in it
+// (gat_csr_build emits exactly that); with order == nullptr there is no cooperative phase.
 struct RowSched {
-  const int32_t* order;      // permutation of [0, n) or nullptr for natural order
-  unsigned int* counter;     // zeroed before the launch
+  const int32_t* order;      // permutation of [0, n), long rows first, or nullptr for natural order
+  unsigned int* counter;     // warp-level row counter, zeroed before the launch
   int64_t n;
+  unsigned int* cta_counter; // CTA-level long-row counter (the word after `counter`), zeroed before the launch
 };
+
+constexpr int kLongRow = GAT_LONG_ROW_EDGES;
+
+// CTA-uniform: next long row for this CTA, or -1 when the long rows are exhausted.  Every thread must call it.
+__device__ __forceinline__ int64_t grab_long_row(const RowSched& S, const int32_t* rowptr, int* sh_ctl) {
+  __syncthreads();           // the previous row's shared-memory traffic (and reads of *sh_ctl) are done
+  if (threadIdx.x == 0) {
+    int r = -1;
+    if (S.order) {
+      const unsigned int c = atomicAdd(S.cta_counter, 1u);
+      if ((int64_t)c < S.n) {
+        const int row = __ldg(S.order + c);
+        if (__ldg(rowptr + row + 1) - __ldg(rowptr + row) > kLongRow) r = row;
+      }
+    }
+    *sh_ctl = r;
+  }
+  __syncthreads();
+  return (int64_t)*sh_ctl;
+}
+
+// Warp phase: rows the cooperative phase has taken are skipped.
+__device__ __forceinline__ bool taken_by_cta_phase(const RowSched& S, const int32_t* rowptr, int64_t row) {
+  return S.order != nullptr && (__ldg(rowptr + row + 1) - __ldg(rowptr + row)) > kLongRow;
+}
 
 template <int G>
 __device__ __forceinline__ bool grab_rows(const RowSched& S, int lane, int64_t& base) {
@@ -130,6 +165,30 @@ static inline GroupShape pick_group(int chunks) {
     if ((nh) <= 4) GAT_DISPATCH_GROUP_NHT(shape, 4, LAUNCH);                      \
     else GAT_DISPATCH_GROUP_NHT(shape, 8, LAUNCH);                                \
   } while (0)
+
+// Programmatic dependent launch, used to OVERLAP two independent launches of one entry point (the cooperative long-row
+// kernel and the short-row kernel touch disjoint rows): the first kernel releases its dependents at once
+// (pdl_release_dependents), the second is launched with programmatic stream serialisation, so its CTAs become resident
+// as soon as CTAs of the first retire, and each of its threads ends with pdl_wait_for_primary(), so the second grid --
+// and with it the stream -- completes only after the first has fully completed and flushed.
+__device__ __forceinline__ void pdl_release_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_for_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename Params>
+static inline cudaError_t launch_kernel(void (*kernel)(const Params), unsigned grid, int threads, size_t dyn_smem, cudaStream_t st,
+                                        const Params& params, bool overlap_with_previous) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = dyn_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = overlap_with_previous ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
+}
 
 // Persistent grid: enough CTAs to fill every SM at the kernel's occupancy, never more than the work.
 template <typename K>

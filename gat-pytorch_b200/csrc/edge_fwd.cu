@@ -15,33 +15,46 @@ struct EdgeMaxParams {
   const float* s_src; const float* s_tgt; int nh; float* gmax;
 };
 
+__device__ __forceinline__ float edge_max_span(const EdgeMaxParams& P, const int64_t row, const int first, const int step,
+                                               float m) {
+  const int nh = P.nh;
+  float st[kMaxHeads];
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) st[h] = h < nh ? __ldg(P.s_tgt + row * nh + h) : 0.f;
+  const int start = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
+  for (int e = start + first; e < end; e += step) {
+    const float* ss = P.s_src + (int64_t)__ldg(P.col + e) * nh;
+    if (nh == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ss));
+      m = fmaxf(m, fmaxf(fmaxf(v.x + st[0], v.y + st[1]), fmaxf(v.z + st[2], v.w + st[3])));
+    } else {
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h)
+        if (h < nh) m = fmaxf(m, __ldg(ss + h) + st[h]);
+    }
+  }
+  return m;
+}
+
 __global__ void __launch_bounds__(256)
 edge_max_kernel(const EdgeMaxParams P) {
   __shared__ float warp_max[8];
+  __shared__ int sh_ctl;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int nh = P.nh;
   float m = -INFINITY;
+  // long rows: the whole CTA strides over the row (max is exact and order independent)
+  for (;;) {
+    const int64_t row = grab_long_row(P.sched, P.rowptr, &sh_ctl);
+    if (row < 0) break;
+    m = edge_max_span(P, row, tid, 256, m);
+  }
   int64_t base;
   while (grab_rows<32>(P.sched, lane, base)) {
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
       const int64_t row = sched_row<32>(P.sched, base, k, lane);
-      if (row < 0) continue;
-      float st[kMaxHeads];
-#pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h) st[h] = h < nh ? __ldg(P.s_tgt + row * nh + h) : 0.f;
-      const int start = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
-      for (int e = start + lane; e < end; e += 32) {
-        const float* ss = P.s_src + (int64_t)__ldg(P.col + e) * nh;
-        if (nh == 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(ss));
-          m = fmaxf(m, fmaxf(fmaxf(v.x + st[0], v.y + st[1]), fmaxf(v.z + st[2], v.w + st[3])));
-        } else {
-#pragma unroll
-          for (int h = 0; h < kMaxHeads; ++h)
-            if (h < nh) m = fmaxf(m, __ldg(ss + h) + st[h]);
-        }
-      }
+      if (row < 0 || taken_by_cta_phase(P.sched, P.rowptr, row)) continue;
+      m = edge_max_span(P, row, lane, 32, m);
     }
   }
 #pragma unroll
@@ -92,11 +105,17 @@ __device__ __forceinline__ void edge_probs(const EdgeFwdParams& P, int e, bool v
   }
 }
 
-template <int G, int SLOTS, int NHT>
+// COOP = false: the group owns the whole row.  COOP = true (long rows): the CTA's NG = 256/G groups take the row's
+// batches round-robin; Z and the output row are combined over the groups through `coop` (NG*dp floats of dynamic
+// shared memory) in group order.  Called by ALL threads of the CTA in that case.
+template <int G, int SLOTS, int NHT, bool COOP>
 __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64_t row, const int tid, const int gl,
                                              const int gbase, const unsigned gmask, const float gmax,
-                                             int* sh_src, float* sh_w) {
+                                             int* sh_src, float* sh_w, float* coop) {
   constexpr int U = SLOTS >= 4 ? 2 : (SLOTS >= 2 ? 4 : 8);
+  constexpr int NG = kEdgeThreads / G;
+  const int grp = tid / G;
+  const int first = COOP ? grp * G : 0, step = COOP ? NG * G : G;
   const int nh = P.nh;
   int head[SLOTS];
   bool ok[SLOTS];
@@ -119,7 +138,7 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
   unsigned tiemask = 0;
 #pragma unroll
   for (int h = 0; h < NHT; ++h) z[h] = 0.f;
-  for (int base = start; base < end; base += G) {
+  for (int base = start + first; base < end; base += step) {
     edge_probs<NHT>(P, base + gl, base + gl < end, st, gmax, my_src, p, tiemask);
 #pragma unroll
     for (int h = 0; h < NHT; ++h) z[h] += p[h];
@@ -127,15 +146,29 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
 #pragma unroll
   for (int h = 0; h < NHT; ++h)
     if (h < nh) z[h] = group_sum<G>(z[h], gmask);
-  if (P.z_out && gl == 0) {
+  if (COOP) {
+    if (gl == 0) {
+#pragma unroll
+      for (int h = 0; h < NHT; ++h) coop[grp * NHT + h] = z[h];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < NHT; ++h) {
+      float t = 0.f;
+      for (int j = 0; j < NG; ++j) t += coop[j * NHT + h];
+      z[h] = t;
+    }
+    __syncthreads();   // coop is reused for the output row below
+  }
+  if (P.z_out && (COOP ? tid == 0 : gl == 0)) {
 #pragma unroll
     for (int h = 0; h < NHT; ++h)
       if (h < nh) P.z_out[row * nh + h] = z[h];
   }
-  const bool single = (end - start) <= G;   // p[] of the only batch is still in registers
+  const bool single = !COOP && (end - start) <= G;   // p[] of the only batch is still in registers
 
   // ---- phase B: alpha, dropout, weighted gather-accumulate  (gat_layer.py:106-127)
-  for (int base = start; base < end; base += G) {
+  for (int base = start + first; base < end; base += step) {
     const int e = base + gl;
     const bool valid = e < end;
     if (!single) edge_probs<NHT>(P, e, valid, st, gmax, my_src, p, tiemask);
@@ -201,28 +234,61 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
     }
     __syncwarp(gmask);
   }
+  if (COOP) {
 #pragma unroll
-  for (int s = 0; s < SLOTS; ++s)
-    if (ok[s]) *reinterpret_cast<float4*>(P.out + row * P.dp + (s * G + gl) * 4) = acc[s];
+    for (int s = 0; s < SLOTS; ++s)
+      if (ok[s]) *reinterpret_cast<float4*>(coop + grp * P.dp + (s * G + gl) * 4) = acc[s];
+    __syncthreads();
+    for (int c = tid; c < P.chunks; c += kEdgeThreads) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < NG; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(coop + j * P.dp + c * 4);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      *reinterpret_cast<float4*>(P.out + row * P.dp + c * 4) = t;
+    }
+    // the next grab_long_row() starts with a __syncthreads(), which also protects `coop`
+  } else {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+      if (ok[s]) *reinterpret_cast<float4*>(P.out + row * P.dp + (s * G + gl) * 4) = acc[s];
+  }
 }
 
-template <int G, int SLOTS, int NHT>
+// COOP = false: every warp takes short rows, group per row.  COOP = true: every CTA takes long rows, CTA per row (its
+// own launch, so that neither path pays for the other's registers).
+template <int G, int SLOTS, int NHT, bool COOP>
 __global__ void __launch_bounds__(kEdgeThreads, (SLOTS <= 2 ? 3 : (SLOTS <= 4 ? 2 : 1)))
 edge_fwd_kernel(const EdgeFwdParams P) {
+  extern __shared__ __align__(16) float coop[];   // COOP: (256/G) * dp floats, cross-group reduction
   __shared__ int sh_src[kEdgeThreads];
   __shared__ float sh_w[kEdgeThreads * NHT];
   const int tid = threadIdx.x, lane = tid & 31, gl = tid & (G - 1), gbase = tid - gl;
   const unsigned gmask = group_mask<G>(lane);
   const float gmax = P.const_attention ? 0.f : __ldg(P.gmax);
-  int64_t base;
-  while (grab_rows<G>(P.sched, lane, base)) {
-#pragma unroll 1
-    for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
-      const int64_t row = sched_row<G>(P.sched, base, k, lane);
-      if (row >= 0) edge_fwd_row<G, SLOTS, NHT>(P, row, tid, gl, gbase, gmask, gmax, sh_src, sh_w);
+  if (COOP) {
+    __shared__ int sh_ctl;
+    pdl_release_dependents();   // the short-row launch that follows may fill SMs as this grid drains
+    for (;;) {
+      const int64_t row = grab_long_row(P.sched, P.rowptr, &sh_ctl);
+      if (row < 0) break;
+      edge_fwd_row<G, SLOTS, NHT, true>(P, row, tid, gl, gbase, gmask, gmax, sh_src, sh_w, coop);
     }
+  } else {
+    int64_t base;
+    while (grab_rows<G>(P.sched, lane, base)) {
+#pragma unroll 1
+      for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
+        const int64_t row = sched_row<G>(P.sched, base, k, lane);
+        if (row >= 0 && !taken_by_cta_phase(P.sched, P.rowptr, row))
+          edge_fwd_row<G, SLOTS, NHT, false>(P, row, tid, gl, gbase, gmask, gmax, sh_src, sh_w, nullptr);
+      }
+    }
+    pdl_wait_for_primary();     // no-op unless launched behind the cooperative kernel
   }
 }
+
+static size_t coop_smem_bytes(int g, int dp) { return (size_t)(kEdgeThreads / g) * dp * sizeof(float); }
 
 // ------------------------------------------------------------------------------------------
 // Head merge: padded (n, NH, Fp) -> (n, NH*F) or head mean (n, F)   (gat_layer.py:129-132)
@@ -244,6 +310,16 @@ __global__ void head_merge_fwd_kernel(const float* __restrict__ o, int64_t n, in
   }
 }
 
+// Head-mean layers: the adjoint of mean(dim=1) hands every head the same vector g/NH, so it is stored ONCE as a padded
+// (n, fp) row that the backward kernels share across heads (go_shared) -- a quarter of the gather traffic at NH = 4.
+__global__ void head_mean_bwd_shared_kernel(const float* __restrict__ g, int64_t n, int nh, int f, int fp, float* __restrict__ go) {
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * fp) return;
+  const int64_t i = idx / fp;
+  const int j = (int)(idx - i * fp);
+  go[idx] = j < f ? g[i * (int64_t)f + j] / (float)nh : 0.f;
+}
+
 __global__ void head_merge_bwd_kernel(const float* __restrict__ g, int64_t n, int nh, int f, int fp, int concat,
                                       float* __restrict__ go) {
   const int dp = nh * fp;
@@ -258,7 +334,7 @@ __global__ void head_merge_bwd_kernel(const float* __restrict__ g, int64_t n, in
 
 }  // namespace gat
 
-extern "C" int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, int64_t n,
+extern "C" int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, int64_t n_long, int64_t n,
                             const float* s_src, const float* s_tgt, int nh, float* gmax,
                             void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
@@ -266,11 +342,12 @@ extern "C" int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int
   GAT_CHECK_ARG(workspace != nullptr && workspace_bytes >= 256, "gat_edge_max: workspace too small");
   if (n == 0) return GAT_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  // the row counter lives in the second word of the shared 256-byte workspace (gat_edge_fwd uses the first)
+  // the row counters (warp-level, CTA-level) live at words 16/17 of the shared 256-byte workspace (gat_edge_fwd uses 0/1)
   unsigned int* counter = (unsigned int*)workspace + 16;
-  GAT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+  GAT_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st));
   EdgeMaxParams P;
-  P.rowptr = rowptr; P.col = col; P.sched.order = row_order; P.sched.counter = counter; P.sched.n = n;
+  (void)n_long;   // one kernel serves both phases here (no register pressure to protect)
+  P.rowptr = rowptr; P.col = col; P.sched.order = row_order; P.sched.counter = counter; P.sched.cta_counter = counter + 1; P.sched.n = n;
   P.s_src = s_src; P.s_tgt = s_tgt; P.nh = nh; P.gmax = gmax;
   edge_max_kernel<<<persistent_grid(edge_max_kernel, 256, 0, (n + 7) / 8), 256, 0, st>>>(P);
   GAT_LAUNCH_CHECK();
@@ -279,8 +356,8 @@ extern "C" int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int
 
 extern "C" size_t gat_edge_fwd_workspace_bytes(void) { return 256; }
 
-extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n,
-                            const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
+extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
+                            int64_t n, const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
                             const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
                             float* out, float* alpha_out, float* z_out,
                             int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
@@ -296,7 +373,7 @@ extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int
   if (n == 0) return GAT_OK;
   EdgeFwdParams P;
   P.rowptr = rowptr; P.col = col; P.eid = eid; P.wh = wh; P.nh = nh; P.dp = nh * fp;
-  P.sched.order = row_order; P.sched.counter = (unsigned int*)workspace; P.sched.n = n;
+  P.sched.order = row_order; P.sched.counter = (unsigned int*)workspace; P.sched.cta_counter = (unsigned int*)workspace + 1; P.sched.n = n;
   P.chunks = nh * fp / 4; P.chunks_per_head = fp / 4;
   P.s_src = s_src; P.s_tgt = s_tgt; P.gmax = gmax; P.const_attention = const_attention;
   P.dropout_p = dropout_p; P.seed = seed; P.offset = offset;
@@ -309,10 +386,25 @@ extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int
     return GAT_EUNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  GAT_CUDA(cudaMemsetAsync(workspace, 0, sizeof(unsigned int), st));
-#define LAUNCH(G_, S_, N_)                                                                  \
-  edge_fwd_kernel<G_, S_, N_><<<persistent_grid(edge_fwd_kernel<G_, S_, N_>, kEdgeThreads, 0,       \
-                                                (n + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)), kEdgeThreads, 0, st>>>(P)
+  GAT_CUDA(cudaMemsetAsync(workspace, 0, 2 * sizeof(unsigned int), st));
+  // long rows first, CTA per row (skipped when the caller knows there are none; n_long < 0 = unknown); the short-row
+  // launch overlaps its tail
+  const bool coop_launch = row_order != nullptr && n_long != 0;
+  if (coop_launch) {
+    const int64_t ctas = n_long < 0 ? n : n_long;
+#define LAUNCH(G_, S_, N_)                                                                                            \
+  GAT_CUDA(launch_kernel(edge_fwd_kernel<G_, S_, N_, true>,                                                           \
+                         persistent_grid(edge_fwd_kernel<G_, S_, N_, true>, kEdgeThreads, coop_smem_bytes(G_, P.dp), ctas), \
+                         kEdgeThreads, coop_smem_bytes(G_, P.dp), st, P, false))
+    GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
+#undef LAUNCH
+    GAT_LAUNCH_CHECK();
+  }
+#define LAUNCH(G_, S_, N_)                                                                                            \
+  GAT_CUDA(launch_kernel(edge_fwd_kernel<G_, S_, N_, false>,                                                          \
+                         persistent_grid(edge_fwd_kernel<G_, S_, N_, false>, kEdgeThreads, 0,                         \
+                                         (n + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)),                        \
+                         kEdgeThreads, 0, st, P, coop_launch))
   GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
 #undef LAUNCH
   GAT_LAUNCH_CHECK();
@@ -337,6 +429,17 @@ extern "C" int gat_head_merge_bwd(const float* grad_out, int64_t n, int nh, int 
   int64_t total = n * (int64_t)nh * fp;
   if (total == 0) return GAT_OK;
   head_merge_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad_out, n, nh, f, fp, concat, go_padded);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_head_mean_bwd_shared(const float* grad_out, int64_t n, int nh, int f, int fp, float* go_shared,
+                                        gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(nh >= 1 && f >= 1 && fp >= f && fp % 4 == 0, "gat_head_mean_bwd_shared: bad shape");
+  int64_t total = n * (int64_t)fp;
+  if (total == 0) return GAT_OK;
+  head_mean_bwd_shared_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad_out, n, nh, f, fp, go_shared);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }

@@ -66,7 +66,7 @@ class _GATFunction(torch.autograd.Function):
                       _ptr(gws), gws_bytes, s, tag=(n, dp, f_in))
             if not const_attention:
                 gmax = torch.full((1,), float("-inf"), **f32)
-                _lib.call("gat_edge_max", st.rowptr.data_ptr(), st.col.data_ptr(), st.order.data_ptr(), n, s_src.data_ptr(),
+                _lib.call("gat_edge_max", st.rowptr.data_ptr(), st.col.data_ptr(), st.order.data_ptr(), st.n_long, n, s_src.data_ptr(),
                           s_tgt.data_ptr(), nh, gmax.data_ptr(), fws.data_ptr(), fws.numel(), s)
             out_p = torch.empty((n, dp), **f32)
             alpha = torch.empty((st.n_edges, nh), **f32) if want_alpha else None
@@ -78,7 +78,7 @@ class _GATFunction(torch.autograd.Function):
             seed = 0
             if p_drop > 0.0:
                 seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator: no device sync
-            _lib.call("gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), n,
+            _lib.call("gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), st.n_long, n,
                                         wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax),
                                         int(const_attention), float(p_drop), seed, 0,
                                         out_p.data_ptr(), _ptr(alpha), z.data_ptr(),
@@ -112,7 +112,13 @@ class _GATFunction(torch.autograd.Function):
             grad_out = grad_out.contiguous()
             if grad_alpha is not None:
                 grad_alpha = grad_alpha.contiguous()
-            if fp != f or not concat:
+            go_shared = 0
+            if not concat and nh > 1:
+                # head mean (gat_layer.py:132): every head receives grad_out/NH -- stored once, shared by the heads
+                go_shared = 1
+                go_p = torch.empty((n, fp), **f32)
+                _lib.call("gat_head_mean_bwd_shared", grad_out.data_ptr(), n, nh, f, fp, go_p.data_ptr(), s)
+            elif fp != f or not concat:
                 go_p = torch.empty((n, dp), **f32)
                 _lib.call("gat_head_merge_bwd", grad_out.data_ptr(), n, nh, f, fp, int(concat), go_p.data_ptr(), s)
             else:
@@ -126,20 +132,20 @@ class _GATFunction(torch.autograd.Function):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             # pass 1 (source-major, the only feature gather of the backward)
             _lib.call("gat_edge_bwd_main", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
-                      st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax), z.data_ptr(),
-                      int(const_attention), p_drop, seed, 0, go_p.data_ptr(), _ptr(grad_alpha), _ptr(rec), d_wh.data_ptr(),
+                      st.n_long_t, st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax), z.data_ptr(),
+                      int(const_attention), p_drop, seed, 0, go_p.data_ptr(), go_shared, _ptr(grad_alpha), _ptr(rec), d_wh.data_ptr(),
                       ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
             if not const_attention:
                 # pass 2 (per target row, light): S = sum_e alpha*d_alpha, ds_tgt, Gamma
                 if grad_alpha is None:      # S = <dOut, out>: no per-edge data needed
-                    _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), out_p.data_ptr(), z.data_ptr(), n, nh, fp,
+                    _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), go_shared, out_p.data_ptr(), z.data_ptr(), n, nh, fp,
                               s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
                 else:
-                    _lib.call("gat_edge_bwd_rowsum", st.rowptr.data_ptr(), st.tpos.data_ptr(), st.order.data_ptr(), n, nh,
+                    _lib.call("gat_edge_bwd_rowsum", st.rowptr.data_ptr(), st.tpos.data_ptr(), st.order.data_ptr(), st.n_long, n, nh,
                               rec.data_ptr(), z.data_ptr(), s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s,
                               tag=(nh, fp))
                 # pass 3 (source-major, light): ds_src, max() correction, dWh += ds_src*A_src + ds_tgt*A_tgt
-                _lib.call("gat_edge_bwd_finish", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.order_t.data_ptr(), n, nh, fp,
+                _lib.call("gat_edge_bwd_finish", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.order_t.data_ptr(), st.n_long_t, n, nh, fp,
                           rec.data_ptr(), s_sum.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
                           _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), None, 0, n,
                           ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))

@@ -33,6 +33,8 @@ class GraphStructure:
     tpos: torch.Tensor = None       # (E',) int32 CSR-by-source slot of each CSR-by-target slot (inverse of pos_t)
     order: torch.Tensor = None      # (n,) int32 scheduling permutation of the target rows (long rows first)
     order_t: torch.Tensor = None    # (n,) int32 same for the source rows
+    n_long: int = -1                # rows of `order` with more than GAT_LONG_ROW_EDGES edges (-1: unknown)
+    n_long_t: int = -1              # same for `order_t`
 
     def in_degrees(self) -> torch.Tensor:
         return self.rowptr[1:] - self.rowptr[:-1]
@@ -74,16 +76,19 @@ def build_structure(edge_index: torch.Tensor, n_nodes: int, add_self_loops: bool
         ei_out = torch.empty((2, n_out), dtype=torch.int64, device=dev) if add_self_loops else None
         ws_bytes = int(lib.gat_csr_workspace_bytes(n_in, n_out, n_nodes))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        n_long = torch.empty(2, dtype=torch.int64, device=dev)
         _lib.call("gat_csr_build", ei.data_ptr(), n_in, ei.stride(0), is64, int(add_self_loops), n_idx, n_out, n_nodes,
                                      ei_out.data_ptr() if ei_out is not None else None,
                                      rowptr.data_ptr(), col.data_ptr(), eid.data_ptr(),
                                      rowptr_t.data_ptr(), col_t.data_ptr(), pos_t.data_ptr(), tpos.data_ptr(),
-                                     order.data_ptr(), order_t.data_ptr(), ws.data_ptr(), ws_bytes, st)
+                                     order.data_ptr(), order_t.data_ptr(), n_long.data_ptr(), ws.data_ptr(), ws_bytes, st)
+        n_long, n_long_t = (int(v) for v in n_long.tolist())   # sizes the cooperative long-row launches
     if ei_out is None:
         ei_ret = edge_index
     else:
         ei_ret = ei_out if edge_index.dtype == torch.int64 else ei_out.to(edge_index.dtype)
-    return GraphStructure(n_nodes, n_idx, n_out, ei_ret, rowptr, col, eid, rowptr_t, col_t, pos_t, tpos, order, order_t)
+    return GraphStructure(n_nodes, n_idx, n_out, ei_ret, rowptr, col, eid, rowptr_t, col_t, pos_t, tpos, order, order_t,
+                          n_long, n_long_t)
 
 
 class StructureCache:

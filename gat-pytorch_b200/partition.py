@@ -93,11 +93,13 @@ class CudaBackend:
         cached = getattr(st, "_local_order", None)
         if cached is None or cached[0] != (plan.lo, plan.hi):
             deg = st.rowptr[plan.lo + 1:plan.hi + 1] - st.rowptr[plan.lo:plan.hi]
-            long_rows = deg > 256
-            order = torch.cat([long_rows.nonzero().flatten(), (~long_rows).nonzero().flatten()]).to(torch.int32)
-            st._local_order = ((plan.lo, plan.hi), order)
+            long_rows = deg > _lib.LONG_ROW_EDGES
+            long_ids = long_rows.nonzero().flatten()
+            long_ids = long_ids[torch.argsort(deg[long_ids], descending=True, stable=True)]     # longest first
+            order = torch.cat([long_ids, (~long_rows).nonzero().flatten()]).to(torch.int32)
+            st._local_order = ((plan.lo, plan.hi), order, int(long_rows.sum().item()))
             cached = st._local_order
-        return cached[1]
+        return cached[1], cached[2]
 
     def n_edges(self, st):
         return st.n_edges
@@ -106,21 +108,31 @@ class CudaBackend:
         from .gat_layer import gemm
         gemm(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, self.gemm_algo)
 
+    def project(self, x, rows, f_in, w_p, dp, a_src, a_tgt, nh, wh, s_src, s_tgt):
+        """Kernel 2: wh = x W^T with the score terms emitted by the GEMM epilogue (gat_project_fwd)."""
+        ws_bytes = int(self.lib.gat_gemm_workspace_bytes(0, 1, rows, dp, f_in, self.gemm_algo))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
+        _lib.call("gat_project_fwd", x.data_ptr(), rows, f_in, x.stride(0), w_p.data_ptr(), w_p.stride(0), dp,
+                  a_src.data_ptr(), a_tgt.data_ptr(), nh, wh.data_ptr(), s_src.data_ptr(), s_tgt.data_ptr(), self.gemm_algo,
+                  ws.data_ptr(), ws_bytes, self._s(x.device), tag=(rows, dp, f_in))
+
     def scores(self, wh, rows, dp, a_src, a_tgt, nh, s_src, s_tgt):
         _lib.call("gat_scores_fwd", wh.data_ptr(), rows, dp, a_src.data_ptr(), a_tgt.data_ptr(), nh,
                   s_src.data_ptr(), s_tgt.data_ptr(), self._s(wh.device))
 
     def edge_max(self, st, plan, s_src_full, s_tgt_local, nh, gmax):
         ws = torch.empty(int(self.lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=gmax.device)
-        _lib.call("gat_edge_max", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), self.local_order(st, plan).data_ptr(),
+        order, n_long = self.local_order(st, plan)
+        _lib.call("gat_edge_max", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), order.data_ptr(), n_long,
                   plan.rows, s_src_full.data_ptr(), s_tgt_local.data_ptr(), nh, gmax.data_ptr(), ws.data_ptr(), ws.numel(),
                   self._s(gmax.device))
 
     def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total):
         p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
         fws = torch.empty(int(self.lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=out_p.device)
+        order, n_long = self.local_order(st, plan)
         _lib.call("gat_edge_fwd", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(),
-                  self.local_order(st, plan).data_ptr(), plan.rows,
+                  order.data_ptr(), n_long, plan.rows,
                   wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(), s_tgt_local.data_ptr(), gmax.data_ptr(),
                   0, 0.0, 0, 0, out_p.data_ptr(), None, z.data_ptr(), p(tie_dst), p(tie_src), p(tie_total),
                   fws.data_ptr(), fws.numel(), self._s(out_p.device), tag=(nh, fp))
@@ -141,16 +153,16 @@ class CudaBackend:
         dp, lo = nh * fp, plan.lo
         ws, ws_bytes = self._bwd_ws(go_p.device, nh)
         _lib.call("gat_edge_bwd_main", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
-                  st.eid.data_ptr(), plan.n, wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(),
+                  st.n_long_t, st.eid.data_ptr(), plan.n, wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(),
                   s_tgt_local.data_ptr() - 4 * nh * lo, gmax.data_ptr(), z_local.data_ptr() - 4 * nh * lo,
-                  0, 0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, None, rec.data_ptr(), d_wh.data_ptr(),
+                  0, 0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, 0, None, rec.data_ptr(), d_wh.data_ptr(),
                   ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
 
     def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt):
         """Pass 2 without per-edge data: S = <dOut, out> over the owned rows; returns this rank's Gamma."""
         ws, ws_bytes = self._bwd_ws(go_p.device, nh)
         ws.zero_()
-        _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), out_p.data_ptr(), z_local.data_ptr(), plan.rows, nh, fp,
+        _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), 0, out_p.data_ptr(), z_local.data_ptr(), plan.rows, nh, fp,
                   s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
         gamma = torch.empty(1, dtype=torch.float64, device=go_p.device)
         _lib.call("gat_edge_bwd_gamma", ws.data_ptr(), ws_bytes, gamma.data_ptr(), self._s(go_p.device))
@@ -158,7 +170,7 @@ class CudaBackend:
 
     def edge_bwd_finish(self, st, plan, nh, fp, rec, s_sum_local, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
         ws, ws_bytes = self._bwd_ws(rec.device, nh)
-        _lib.call("gat_edge_bwd_finish", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.order_t.data_ptr(), plan.n, nh, fp,
+        _lib.call("gat_edge_bwd_finish", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.order_t.data_ptr(), st.n_long_t, plan.n, nh, fp,
                   rec.data_ptr(), s_sum_local.data_ptr() - 4 * nh * plan.lo, a_src.data_ptr(), a_tgt.data_ptr(),
                   tie_dst.data_ptr(), tie_src.data_ptr(), None, corr.data_ptr(), plan.lo, plan.hi,
                   ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(), ws.data_ptr(), ws_bytes,
@@ -177,8 +189,7 @@ class _PartitionedGATFunction(torch.autograd.Function):
         s_src_slab = torch.zeros((R, nh), **f32)
         s_tgt = torch.empty((max(rows, 1), nh), **f32)
         if rows:
-            backend.gemm(False, True, rows, dp, f_in, x_local, x_local.stride(0), w_p, w_p.stride(0), wh_slab, dp)
-            backend.scores(wh_slab, rows, dp, a_src_p, a_tgt_p, nh, s_src_slab, s_tgt)
+            backend.project(x_local, rows, f_in, w_p, dp, a_src_p, a_tgt_p, nh, wh_slab, s_src_slab, s_tgt)
         wh_full = torch.empty((plan.n_pad, dp), **f32)
         s_src_full = torch.empty((plan.n_pad, nh), **f32)
         dist.all_gather_into_tensor(wh_full, wh_slab, group=group)          # the feature exchange (NVLink)

@@ -32,6 +32,12 @@ extern "C" {
 #define GAT_EWORKSPACE (-2)  /* workspace too small */
 #define GAT_EUNSUPPORTED (-3)
 
+/* Rows (destination rows of the CSR, source rows of the transposed CSR) with more than this many edges are "long":
+ * the persistent edge kernels process them cooperatively, one CTA per row, instead of one warp per row.  A
+ * `row_order` permutation handed to an edge kernel must list every long row before every short row
+ * (gat_csr_build emits exactly that). */
+#define GAT_LONG_ROW_EDGES 256
+
 typedef void* gat_stream_t; /* cudaStream_t */
 
 #if defined(__GNUC__)
@@ -68,13 +74,15 @@ GAT_API size_t gat_csr_workspace_bytes(int64_t n_edges_in, int64_t n_edges_out, 
  *           rowptr diffs are the reference's degree counts (GATModel.py:196-201);
  *  rowptr_t (n_nodes+1) / col_t / pos_t: CSR by source; col_t = target ids, pos_t = slot of that
  *           edge in the target-sorted CSR; tpos (n_edges_out) = its inverse (CSR^T slot of each CSR slot);
- *  row_order / row_order_t (n_nodes) or NULL: scheduling permutations for the persistent edge kernels
- *           (rows with more than 256 edges first); a performance hint only, results do not depend on it. */
+ *  row_order / row_order_t (n_nodes) or NULL: scheduling permutations for the persistent edge kernels: rows with
+ *           more than GAT_LONG_ROW_EDGES edges first (in row order), then the rest in row order;
+ *  n_long   device int64[2] or NULL: number of long rows in row_order / row_order_t.  The edge kernels take it as a
+ *           HOST value `n_long` (>= 0 exact, < 0 unknown): it only sizes / skips the cooperative launch. */
 GAT_API int gat_csr_build(const void* edge_index, int64_t n_edges_in, int64_t row_stride, int index_is_int64,
                   int add_self_loops, int64_t n_idx, int64_t n_edges_out, int64_t n_nodes,
                   int64_t* ei_out, int32_t* rowptr, int32_t* col, int32_t* eid,
                   int32_t* rowptr_t, int32_t* col_t, int32_t* pos_t, int32_t* tpos,
-                  int32_t* row_order, int32_t* row_order_t,
+                  int32_t* row_order, int32_t* row_order_t, int64_t* n_long,
                   void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -119,7 +127,7 @@ GAT_API int gat_scores_bwd(const float* wh, int64_t n, int dp, int nh, const flo
 /* Kernel 3a: *gmax = max over all (e,h) of s_src[col[e],h] + s_tgt[dst(e),h]  (gat_layer.py:85).
  * gmax must hold -inf on entry (the kernel combines with an order-independent atomic max).
  * workspace: the same gat_edge_fwd_workspace_bytes() buffer that is later handed to gat_edge_fwd. */
-GAT_API int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, int64_t n,
+GAT_API int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, int64_t n_long, int64_t n,
                  const float* s_src, const float* s_tgt, int nh, float* gmax,
                  void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
@@ -132,11 +140,13 @@ GAT_API int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int32_
  *               gradient through max(), zero-initialised by the caller, or NULL;
  *  const_attention: logits are 0, gmax/s_src/s_tgt ignored (gat_layer.py:89-92);
  *  dropout_p > 0 enables the mask with (seed, offset) keyed on (edge id, head);
- *  row_order: scheduling permutation from gat_csr_build or NULL (natural order);
- *  workspace: gat_edge_fwd_workspace_bytes() bytes (the persistent grid's row counter). */
+ *  row_order: scheduling permutation from gat_csr_build (long rows first: they take the cooperative CTA-per-row path,
+ *               whose summation order differs from the warp-per-row path in the last bits) or NULL (natural order,
+ *               every row warp-per-row);
+ *  workspace: gat_edge_fwd_workspace_bytes() bytes (the persistent grid's row counters). */
 GAT_API size_t gat_edge_fwd_workspace_bytes(void);
-GAT_API int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n,
-                 const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
+GAT_API int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
+                 int64_t n, const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
                  const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
                  float* out, float* alpha_out, float* z_out,
                  int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
@@ -148,6 +158,12 @@ GAT_API int gat_head_merge_fwd(const float* o_padded, int64_t n, int nh, int f, 
 /* and its adjoint: grad (n, nh*f | f) -> padded (n, nh, fp) with zero pad lanes. */
 GAT_API int gat_head_merge_bwd(const float* grad_out, int64_t n, int nh, int f, int fp, int concat,
                        float* go_padded, gat_stream_t stream);
+
+/* Adjoint of the head mean in SHARED form: every head receives the same vector grad_out/nh, so it is stored once as
+ * go_shared (n, fp) with zero pad lanes; gat_edge_bwd_main / gat_edge_bwd_rowdot read it with go_shared = 1 (a
+ * 1/nh-th of the per-edge gather traffic of the expanded (n, nh, fp) form). */
+GAT_API int gat_head_mean_bwd_shared(const float* grad_out, int64_t n, int nh, int f, int fp, float* go_shared,
+                                     gat_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Kernel 4 -- atomic-free deterministic backward with ONE feature-row gather per edge.
@@ -162,25 +178,27 @@ GAT_API size_t gat_edge_bwd_workspace_bytes(int64_t n, int64_t n_edges, int nh);
  * gathers go_padded[dst] once per edge, writes d_wh[src] = sum_e m*alpha*go[dst] (value path only) and the per-edge
  * record rec[j] = {d_alpha[0..nh), alpha[0..nh)} in CSR^T slot order.  s_tgt, z, go_padded are indexed by TARGET id
  * (a partitioned caller passes pointers shifted by its first owned row).  eid maps CSR slots to positions in the
- * rewritten edge list (dropout key / row of grad_alpha).  grad_alpha is (n_edges, nh) or NULL. */
+ * rewritten edge list (dropout key / row of grad_alpha).  grad_alpha is (n_edges, nh) or NULL.
+ * go_shared = 0: go_padded is (n, nh, fp); go_shared = 1 (head-mean layers): go_padded is (n, fp), the same row for
+ * every head (gat_head_mean_bwd_shared). */
 GAT_API int gat_edge_bwd_main(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
-                              const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                              int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
                               const float* s_src, const float* s_tgt, const float* gmax, const float* z,
                               int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
-                              const float* go_padded, const float* grad_alpha, float* rec, float* d_wh,
+                              const float* go_padded, int go_shared, const float* grad_alpha, float* rec, float* d_wh,
                               void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* Pass 2 (CSR by target, rows = owned TARGET nodes): s_sum[d,h] = sum_e alpha*d_alpha over the in-edges of d (records
  * gathered through tpos = CSR^T slot of each CSR slot); ds_tgt[d,h] = sum_e g = 0.01*s_sum*eps/(z+eps) (before the arg-max
  * correction); then reduces Gamma = sum ds_tgt in two fixed-order stages into the workspace. */
-GAT_API int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, const int32_t* row_order, int64_t n_rows, int nh,
+GAT_API int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, const int32_t* row_order, int64_t n_long, int64_t n_rows, int nh,
                                 const float* rec, const float* z, float* s_sum, float* ds_tgt,
                                 void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* Pass 2 when there is no upstream dL/dalpha: s_sum[d,h] = <go_padded[d,h,:], out_padded[d,h,:]> (the forward output in
  * padded-head layout) -- identical to the record sum because out = sum_e m*alpha*Wh[src]; no per-edge gather at all.
  * Same outputs and Gamma reduction as gat_edge_bwd_rowsum. */
-GAT_API int gat_edge_bwd_rowdot(const float* go_padded, const float* out_padded, const float* z, int64_t n_rows, int nh, int fp,
+GAT_API int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const float* out_padded, const float* z, int64_t n_rows, int nh, int fp,
                                 float* s_sum, float* ds_tgt, void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* Partitioned graphs only: *gamma_out = this rank's Gamma.  The caller all-reduces Gamma and tie_total over ranks and hands
@@ -191,7 +209,7 @@ GAT_API int gat_edge_bwd_gamma(void* workspace, size_t workspace_bytes, double* 
  * correction Gamma/|T| to ds_src and ds_tgt via the tie counts; d_wh[src] += ds_src*A_src + ds_tgt*A_tgt, so that d_wh is the
  * total gradient of Wh.  [tgt_lo, tgt_hi) is the range of nodes this call also owns as targets: ds_tgt and tie_dst have
  * tgt_hi - tgt_lo rows and only those rows receive the ds_tgt*A_tgt term; s_sum is indexed by TARGET id. */
-GAT_API int gat_edge_bwd_finish(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* row_order_t, int64_t n_rows,
+GAT_API int gat_edge_bwd_finish(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* row_order_t, int64_t n_long, int64_t n_rows,
                                 int nh, int fp, const float* rec, const float* s_sum, const float* a_src, const float* a_tgt,
                                 const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
                                 const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,

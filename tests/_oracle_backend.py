@@ -23,6 +23,10 @@ class OracleBackend:
         B = b2[:n, :k].T if tb else b2[:k, :n]
         c.reshape(-1)[: m * ldc].view(-1, ldc)[:m, :n] = (A.double() @ B.double()).float()
 
+    def project(self, x, rows, f_in, w_p, dp, a_src, a_tgt, nh, wh, s_src, s_tgt):
+        self.gemm(False, True, rows, dp, f_in, x, x.stride(0), w_p, w_p.stride(0), wh, dp)
+        self.scores(wh, rows, dp, a_src, a_tgt, nh, s_src, s_tgt)
+
     def scores(self, wh, rows, dp, a_src, a_tgt, nh, s_src, s_tgt):
         s_src[:rows] = (wh[:rows].double() @ a_src.double().T).float()
         s_tgt[:rows] = (wh[:rows].double() @ a_tgt.double().T).float()
