@@ -183,6 +183,10 @@ def algorithmic_bytes(kernel, e, n, nh, d, d_out):
         # per edge: col_t, s_tgt[dst], Z[dst], gather dOut[dst], write record {d_alpha, alpha}; per node: rowptr_t, Wh row,
         # s_src, write dWh row
         return e * (4 + 8 * nh + 4 * d_out + 8 * nh) + n * (8 + 4 * d + 4 * nh + 4 * d)
+    if kernel == "gat_edge_bwd_fused":
+        # per edge: col_t, s_tgt[dst], Z[dst], S[dst], gather dOut[dst]; per node: rowptr_t, Wh row, s_src, tie counts,
+        # ds_tgt read+write, write ds_src, write dWh row   (no per-edge record is written)
+        return e * (4 + 12 * nh + 4 * d_out) + n * (8 + 4 * d + 4 * nh + 8 * nh + 8 * nh + 4 * nh + 4 * d)
     if kernel == "gat_edge_bwd_rowsum":
         return e * (4 + 8 * nh) + n * (8 + 12 * nh)
     if kernel == "gat_edge_bwd_finish":
@@ -324,10 +328,12 @@ def run_b200(args):
     n_local = n if world == 1 else model.n_local
     e_local = e_prime if world == 1 else model.n_edges_local
     per_kernel = {}
-    for kname in ("gat_edge_fwd", "gat_edge_bwd_main", "gat_edge_bwd_rowsum", "gat_edge_bwd_finish"):
+    for kname in ("gat_edge_fwd", "gat_edge_bwd_fused", "gat_edge_bwd_main", "gat_edge_bwd_rowsum", "gat_edge_bwd_finish"):
         rec = kernels.get((kname, (nh, fp)))
         if rec:
-            b = algorithmic_bytes(kname, e_local, n_local, nh, d, d)
+            # the source-major passes of a partitioned run walk ALL n source rows (with this rank's edges)
+            n_rows = n if kname in ("gat_edge_bwd_fused", "gat_edge_bwd_main", "gat_edge_bwd_finish") else n_local
+            b = algorithmic_bytes(kname, e_local, n_rows, nh, d, d)
             gbs = b / (rec["ms_avg"] * 1e-3) / 1e9
             per_kernel[kname] = {"ms_avg": rec["ms_avg"], "calls": rec["calls"], "algorithmic_bytes": b, "GBps": gbs, "frac": gbs / peak}
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_avg"]) if per_kernel else None

@@ -34,6 +34,8 @@ SIGNATURES = {
                          c_int, _P, c_size_t, _P]),
     "gat_project_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, _P, _P,
                                 c_int, _P, c_size_t, _P]),
+    "gat_project_fwd_allgather": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, c_int, c_int64,
+                                          _P, _P, _P]),
     "gat_scores_fwd": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P]),
     "gat_scores_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gat_scores_bwd": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
@@ -46,6 +48,9 @@ SIGNATURES = {
     "gat_edge_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "gat_edge_bwd_main": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, c_int,
                                   c_float, c_uint64, c_uint64, _P, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_fused": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P,
+                                   c_float, c_uint64, c_uint64, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
+                                   _P, _P, _P, _P, c_size_t, _P]),
     "gat_head_mean_bwd_shared": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
     "gat_edge_bwd_rowsum": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_rowdot": (c_int, [_P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),

@@ -27,7 +27,8 @@ size_t tc_workspace_bytes(int ta, int tb, int64_t m, int64_t n, int64_t k);
 bool tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc);
 bool tc_project_supported(int64_t n_rows, int64_t dp, int64_t k, int64_t ldx, int64_t ldw);
 int gemm_tc_project(int64_t n_rows, int64_t dp, int64_t k, const float* x, int64_t ldx, const float* w, int64_t ldw,
-                    float* wh, const float* a_src, const float* a_tgt, int nh, float* s_src, float* s_tgt, cudaStream_t st);
+                    float* wh, const float* a_src, const float* a_tgt, int nh, float* s_src, float* s_tgt, cudaStream_t st,
+                    float* const* wh_dests, int n_dests, int64_t row_offset);
 
 }  // namespace gat
 
@@ -84,9 +85,31 @@ extern "C" int gat_project_fwd(const float* x, int64_t n, int64_t f_in, int64_t 
   const bool fused_ok = want_scores && tc_project_supported(n, dp, f_in, ldx, ldw) &&
                         ((uintptr_t)x | (uintptr_t)w | (uintptr_t)wh | (uintptr_t)a_src | (uintptr_t)a_tgt) % 16 == 0;
   if (fused_ok && (algo == 2 || (algo == 0 && big)))
-    return gemm_tc_project(n, dp, f_in, x, ldx, w, ldw, wh, a_src, a_tgt, nh, s_src, s_tgt, st);
+    return gemm_tc_project(n, dp, f_in, x, ldx, w, ldw, wh, a_src, a_tgt, nh, s_src, s_tgt, st, nullptr, 0, 0);
   int rc = gat_gemm(0, 1, n, dp, f_in, x, ldx, w, ldw, wh, dp, algo == 2 && !tc_supported(0, 1, n, dp, f_in, ldx, ldw, dp) ? 0 : algo,
                     workspace, workspace_bytes, stream);
   if (rc != GAT_OK || !want_scores) return rc;
   return gat_scores_fwd(wh, n, dp, a_src, a_tgt, nh, s_src, s_tgt, stream);
+}
+
+// Fused projection -> all-gather over NVLink peer memory (the partitioned layer's one exchange step).
+// Every output tile of wh = x W^T is staged in shared memory once and written by TMA to row `row_offset + i` of each
+// of the n_dests gathered buffers -- this rank's own and the peers' (pointers mapped through CUDA peer / symmetric
+// memory) -- so the transfer overlaps the GEMM tile by tile and no separate collective moves the features.  The
+// score terms are computed from the same accumulator tile and stay local (n rows).
+extern "C" int gat_project_fwd_allgather(const float* x, int64_t n, int64_t f_in, int64_t ldx, const float* w, int64_t ldw, int dp,
+                                         const float* a_src, const float* a_tgt, int nh,
+                                         float* const* h_wh_dests, int n_dests, int64_t row_offset,
+                                         float* s_src, float* s_tgt, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(n >= 0 && f_in >= 1 && dp >= 4 && dp % 4 == 0 && row_offset >= 0, "gat_project_fwd_allgather: bad shape");
+  GAT_CHECK_ARG(h_wh_dests != nullptr && n_dests >= 1 && n_dests <= 8, "gat_project_fwd_allgather: 1..8 destinations");
+  GAT_CHECK_ARG(a_src != nullptr && a_tgt != nullptr && s_src != nullptr && s_tgt != nullptr, "gat_project_fwd_allgather: score buffers missing");
+  if (n == 0) return GAT_OK;
+  if (!tc_project_supported(n, dp, f_in, ldx, ldw)) {
+    set_error("gat_project_fwd_allgather: needs the tcgen05 path (dp <= 256, 16-byte aligned leading dimensions)");
+    return GAT_EUNSUPPORTED;
+  }
+  return gemm_tc_project(n, dp, f_in, x, ldx, w, ldw, nullptr, a_src, a_tgt, nh, s_src, s_tgt, (cudaStream_t)stream,
+                         h_wh_dests, n_dests, row_offset);
 }

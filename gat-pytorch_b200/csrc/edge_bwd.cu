@@ -48,6 +48,13 @@ struct BwdMainParams {
   const float* go; const float* grad_alpha;                                    // go indexed by TARGET id
   int go_ld; int go_shared;   // go row stride (floats); go_shared: one (Fp)-wide row serves every head (head-mean layers)
   float* rec; float* d_wh;
+  // FUSED mode (no upstream dL/dalpha): S = <dOut, out> and Gamma are known BEFORE this pass (gat_edge_bwd_rowdot runs
+  // first), so g, ds_src, the arg-max corrections and dWh += ds_src*A_src + ds_tgt*A_tgt are all done here; no records.
+  const float* s_sum;                      // indexed by TARGET id
+  const float* a_src; const float* a_tgt;
+  const int32_t* tie_dst; const int32_t* tie_src; const BwdHeader* header; const float* corr_override;
+  int64_t tgt_lo; int64_t tgt_hi;
+  float* ds_src; float* ds_tgt;
 };
 
 template <int G, int SLOTS>
@@ -59,9 +66,9 @@ struct MainShape {
 // COOP (long source rows): the CTA's 256/G groups take the row's batches round-robin (each writes the records of its
 // own edges) and the dWh row is combined over the groups in group order through `coop`, which ALIASES the groups'
 // `part` tiles -- hence the CTA barrier before it is written.  Called by all threads of the CTA in that case.
-template <int G, int SLOTS, int NHT, bool COOP>
+template <int G, int SLOTS, int NHT, bool COOP, bool FUSED>
 __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64_t row, const int tid, const int gl,
-                                             const int gbase, const unsigned gmask, const float gmax,
+                                             const int gbase, const unsigned gmask, const float gmax, const float corr,
                                              int* sh_dst, float* sh_w, float* sh_da, float* part, float* coop) {
   constexpr int TB = MainShape<G, SLOTS>::TB, U = MainShape<G, SLOTS>::U;
   constexpr int NG = kEdgeThreads / G;
@@ -84,9 +91,9 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
     whr[s] = (ok[s] && !P.const_attention) ? ldg4(P.wh + row * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const int start = __ldg(P.rowptr_t + row), end = __ldg(P.rowptr_t + row + 1);
-  float ss[NHT];
+  float ss[NHT], gsum[NHT];
 #pragma unroll
-  for (int h = 0; h < NHT; ++h) ss[h] = (!P.const_attention && h < nh) ? __ldg(P.s_src + row * nh + h) : 0.f;
+  for (int h = 0; h < NHT; ++h) { ss[h] = (!P.const_attention && h < nh) ? __ldg(P.s_src + row * nh + h) : 0.f; gsum[h] = 0.f; }
 
   for (int base = start + first; base < end; base += step) {
     const int e = base + gl;
@@ -170,24 +177,125 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
       }
     }
     if (valid && !P.const_attention) {
-      float* r = P.rec + (int64_t)e * 2 * nh;
+      if (FUSED) {   // g = 0.01*alpha*(d_alpha - S[dst]), summed per source row  
+        const float* sp = P.s_sum + (int64_t)sh_dst[tid] * nh;
 #pragma unroll
-      for (int h = 0; h < NHT; ++h)
-        if (h < nh) { r[h] = fmaf(msk[h], sh_da[tid * NHT + h], ga[h]); r[nh + h] = alpha[h]; }
+        for (int h = 0; h < NHT; ++h)
+          if (h < nh) gsum[h] = fmaf(kLeakySlope * alpha[h], fmaf(msk[h], sh_da[tid * NHT + h], ga[h]) - __ldg(sp + h), gsum[h]);
+      } else {
+        float* r = P.rec + (int64_t)e * 2 * nh;
+#pragma unroll
+        for (int h = 0; h < NHT; ++h)
+          if (h < nh) { r[h] = fmaf(msk[h], sh_da[tid * NHT + h], ga[h]); r[nh + h] = alpha[h]; }
+      }
     }
     __syncwarp(gmask);
+  }
+  // FUSED epilogue inputs: ds_src = sum g - |T_src|*Gamma/|T|, ds_tgt -= |T_dst|*Gamma/|T| (gradient through max())
+  const bool own_tgt = FUSED && row >= P.tgt_lo && row < P.tgt_hi;
+  const int64_t trow = row - P.tgt_lo;
+  float dss[NHT], dst_[NHT];
+#pragma unroll
+  for (int h = 0; h < NHT; ++h) { dss[h] = 0.f; dst_[h] = 0.f; }
+  if (FUSED && !COOP && !P.const_attention) {
+#pragma unroll
+    for (int h = 0; h < NHT; ++h) {
+      if (h < nh) {
+        const float g = group_sum<G>(gsum[h], gmask);
+        const int ts = P.tie_src ? __ldg(P.tie_src + row * nh + h) : 0;
+        dss[h] = ts ? g - (float)ts * corr : g;
+        if (own_tgt) {
+          const int td = P.tie_dst ? __ldg(P.tie_dst + trow * nh + h) : 0;
+          const float t = P.ds_tgt[trow * nh + h];
+          dst_[h] = td ? t - (float)td * corr : t;
+        }
+      }
+    }
+    __syncwarp(gmask);   // every lane has read ds_tgt before lane 0 overwrites it
+    if (gl == 0) {
+#pragma unroll
+      for (int h = 0; h < NHT; ++h)
+        if (h < nh) {
+          P.ds_src[row * nh + h] = dss[h];
+          if (own_tgt) P.ds_tgt[trow * nh + h] = dst_[h];
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      if (ok[s]) {
+        const int c = s * G + gl;
+#pragma unroll
+        for (int h = 0; h < NHT; ++h) {
+          if (h < nh) {
+            const float4 as = ldg4(P.a_src + (int64_t)h * P.dp + c * 4);
+            const float4 at = ldg4(P.a_tgt + (int64_t)h * P.dp + c * 4);
+            acc[s].x = fmaf(dss[h], as.x, fmaf(dst_[h], at.x, acc[s].x));
+            acc[s].y = fmaf(dss[h], as.y, fmaf(dst_[h], at.y, acc[s].y));
+            acc[s].z = fmaf(dss[h], as.z, fmaf(dst_[h], at.z, acc[s].z));
+            acc[s].w = fmaf(dss[h], as.w, fmaf(dst_[h], at.w, acc[s].w));
+          }
+        }
+      }
+    }
   }
   if (COOP) {
     __syncthreads();   // every group is done with its `part` tile, which `coop` aliases
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s)
       if (ok[s]) *reinterpret_cast<float4*>(coop + grp * P.dp + (s * G + gl) * 4) = acc[s];
+    float* coop_g = coop + NG * P.dp;   // [NG][NHT] per-group sums of g
+    if (FUSED && !P.const_attention) {
+#pragma unroll
+      for (int h = 0; h < NHT; ++h) gsum[h] = group_sum<G>(gsum[h], gmask);
+      if (gl == 0) {
+#pragma unroll
+        for (int h = 0; h < NHT; ++h) coop_g[grp * NHT + h] = gsum[h];
+      }
+    }
     __syncthreads();
+    if (FUSED && !P.const_attention) {
+#pragma unroll
+      for (int h = 0; h < NHT; ++h) {
+        if (h < nh) {
+          float g = 0.f;
+          for (int j = 0; j < NG; ++j) g += coop_g[j * NHT + h];
+          const int ts = P.tie_src ? __ldg(P.tie_src + row * nh + h) : 0;
+          dss[h] = ts ? g - (float)ts * corr : g;
+          if (own_tgt) {
+            const int td = P.tie_dst ? __ldg(P.tie_dst + trow * nh + h) : 0;
+            const float t = P.ds_tgt[trow * nh + h];
+            dst_[h] = td ? t - (float)td * corr : t;
+          }
+        }
+      }
+      __syncthreads();   // every thread has read ds_tgt before thread 0 overwrites it
+      if (tid == 0) {
+#pragma unroll
+        for (int h = 0; h < NHT; ++h)
+          if (h < nh) {
+            P.ds_src[row * nh + h] = dss[h];
+            if (own_tgt) P.ds_tgt[trow * nh + h] = dst_[h];
+          }
+      }
+    }
     for (int c = tid; c < P.chunks; c += kEdgeThreads) {
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int j = 0; j < NG; ++j) {
         const float4 v = *reinterpret_cast<const float4*>(coop + j * P.dp + c * 4);
         t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      if (FUSED && !P.const_attention) {
+#pragma unroll
+        for (int h = 0; h < NHT; ++h) {
+          if (h < nh) {
+            const float4 as = ldg4(P.a_src + (int64_t)h * P.dp + c * 4);
+            const float4 at = ldg4(P.a_tgt + (int64_t)h * P.dp + c * 4);
+            t.x = fmaf(dss[h], as.x, fmaf(dst_[h], at.x, t.x));
+            t.y = fmaf(dss[h], as.y, fmaf(dst_[h], at.y, t.y));
+            t.z = fmaf(dss[h], as.z, fmaf(dst_[h], at.z, t.z));
+            t.w = fmaf(dss[h], as.w, fmaf(dst_[h], at.w, t.w));
+          }
+        }
       }
       *reinterpret_cast<float4*>(P.d_wh + row * P.dp + c * 4) = t;
     }
@@ -199,7 +307,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
   }
 }
 
-template <int G, int SLOTS, int NHT, bool COOP>
+template <int G, int SLOTS, int NHT, bool COOP, bool FUSED>
 __global__ void __launch_bounds__(kEdgeThreads, (SLOTS <= 2 ? 3 : (SLOTS <= 4 ? 2 : 1)))
 edge_bwd_main_kernel(const BwdMainParams P) {
   constexpr int TB = MainShape<G, SLOTS>::TB;
@@ -211,13 +319,14 @@ edge_bwd_main_kernel(const BwdMainParams P) {
   const unsigned gmask = group_mask<G>(lane);
   float* part = dyn_smem + (size_t)(tid / G) * TB * (P.chunks + 1);   // [TB][chunks+1] of my group
   const float gmax = P.const_attention ? 0.f : __ldg(P.gmax);
+  const float corr = !FUSED ? 0.f : (P.corr_override ? __ldg(P.corr_override) : P.header->corr);
   if (COOP) {   // long source rows, CTA per row (its own launch)
     __shared__ int sh_ctl;
     pdl_release_dependents();   // the short-row launch that follows may fill SMs as this grid drains
     for (;;) {
       const int64_t row = grab_long_row(P.sched, P.rowptr_t, &sh_ctl);
       if (row < 0) break;
-      bwd_main_row<G, SLOTS, NHT, true>(P, row, tid, gl, gbase, gmask, gmax, sh_dst, sh_w, sh_da, part, dyn_smem);
+      bwd_main_row<G, SLOTS, NHT, true, FUSED>(P, row, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_w, sh_da, part, dyn_smem);
     }
   } else {
     int64_t base;
@@ -226,7 +335,7 @@ edge_bwd_main_kernel(const BwdMainParams P) {
       for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
         const int64_t row = sched_row<G>(P.sched, base, k, lane);
         if (row >= 0 && !taken_by_cta_phase(P.sched, P.rowptr_t, row))
-          bwd_main_row<G, SLOTS, NHT, false>(P, row, tid, gl, gbase, gmask, gmax, sh_dst, sh_w, sh_da, part, nullptr);
+          bwd_main_row<G, SLOTS, NHT, false, FUSED>(P, row, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_w, sh_da, part, nullptr);
       }
     }
     pdl_wait_for_primary();     // no-op unless launched behind the cooperative kernel
@@ -237,7 +346,7 @@ edge_bwd_main_kernel(const BwdMainParams P) {
 template <int G, int SLOTS>
 static size_t main_dyn_smem(int chunks) {
   const size_t part = (size_t)(kEdgeThreads / G) * MainShape<G, SLOTS>::TB * (chunks + 1) * sizeof(float);
-  const size_t coop = (size_t)(kEdgeThreads / G) * chunks * 4 * sizeof(float);
+  const size_t coop = (size_t)(kEdgeThreads / G) * (chunks * 4 + 8) * sizeof(float);   // + [NG][NHT] sums of g (FUSED)
   return part > coop ? part : coop;
 }
 
@@ -572,6 +681,42 @@ extern "C" size_t gat_edge_bwd_workspace_bytes(int64_t n, int64_t n_edges, int n
   return gat::kBwdHeaderBytes + (size_t)(gat::kGammaBlocks + 1) * sizeof(double);
 }
 
+namespace gat {
+
+template <bool FUSED>
+static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, int64_t n_long, int64_t n_rows, cudaStream_t st) {
+  const int nh = P.nh;
+  GroupShape shape = pick_group(P.chunks);
+  if (shape.slots < 0) {
+    set_error("gat_edge_bwd_main: row width %d floats exceeds the supported 1024", P.dp);
+    return GAT_EUNSUPPORTED;
+  }
+  const bool coop_launch = row_order_t != nullptr && n_long != 0;
+  if (coop_launch) {   // long source rows first, CTA per row; the short-row launch overlaps its tail
+    const int64_t ctas = n_long < 0 ? n_rows : n_long;
+#define LAUNCH(G_, S_, N_)                                                                                            \
+  GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, true, FUSED>,                                               \
+                         persistent_grid(edge_bwd_main_kernel<G_, S_, N_, true, FUSED>, kEdgeThreads,                 \
+                                         main_dyn_smem<G_, S_>(P.chunks), ctas),                                      \
+                         kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, false))
+    GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
+#undef LAUNCH
+    GAT_LAUNCH_CHECK();
+  }
+#define LAUNCH(G_, S_, N_)                                                                                            \
+  GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, false, FUSED>,                                              \
+                         persistent_grid(edge_bwd_main_kernel<G_, S_, N_, false, FUSED>, kEdgeThreads,                \
+                                         main_dyn_smem<G_, S_>(P.chunks),                                             \
+                                         (n_rows + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)),                   \
+                         kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, coop_launch))
+  GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
+#undef LAUNCH
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+}  // namespace gat
+
 extern "C" int gat_edge_bwd_main(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
                                  int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
                                  const float* s_src, const float* s_tgt, const float* gmax, const float* z,
@@ -585,7 +730,7 @@ extern "C" int gat_edge_bwd_main(const int32_t* rowptr_t, const int32_t* col_t, 
   cudaStream_t st = (cudaStream_t)stream;
   GAT_CUDA(cudaMemsetAsync(workspace, 0, kBwdHeaderBytes, st));
   if (n_rows == 0) return GAT_OK;
-  BwdMainParams P;
+  BwdMainParams P = {};
   P.rowptr_t = rowptr_t; P.col_t = col_t; P.pos_t = pos_t; P.eid = eid;
   P.sched.order = row_order_t; P.sched.counter = &((BwdHeader*)workspace)->counter_a;
   P.sched.cta_counter = &((BwdHeader*)workspace)->counter_a_cta; P.sched.n = n_rows;
@@ -594,33 +739,43 @@ extern "C" int gat_edge_bwd_main(const int32_t* rowptr_t, const int32_t* col_t, 
   P.dropout_p = dropout_p; P.seed = seed; P.offset = offset; P.go = go_padded; P.grad_alpha = grad_alpha;
   P.go_shared = go_shared ? 1 : 0; P.go_ld = go_shared ? fp : nh * fp;
   P.rec = rec; P.d_wh = d_wh;
-  GroupShape shape = pick_group(P.chunks);
-  if (shape.slots < 0) {
-    set_error("gat_edge_bwd_main: row width %d floats exceeds the supported 1024", P.dp);
-    return GAT_EUNSUPPORTED;
-  }
-  const bool coop_launch = row_order_t != nullptr && n_long != 0;
-  if (coop_launch) {   // long source rows first, CTA per row; the short-row launch overlaps its tail
-    const int64_t ctas = n_long < 0 ? n_rows : n_long;
-#define LAUNCH(G_, S_, N_)                                                                                            \
-  GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, true>,                                                      \
-                         persistent_grid(edge_bwd_main_kernel<G_, S_, N_, true>, kEdgeThreads,                        \
-                                         main_dyn_smem<G_, S_>(P.chunks), ctas),                                      \
-                         kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, false))
-    GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
-#undef LAUNCH
+  return launch_bwd_main<false>(P, row_order_t, n_long, n_rows, st);
+}
+
+extern "C" int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
+                                  int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                                  const float* s_src, const float* s_tgt, const float* gmax, const float* z,
+                                  float dropout_p, uint64_t seed, uint64_t offset,
+                                  const float* go_padded, int go_shared, const float* s_sum,
+                                  const float* a_src, const float* a_tgt,
+                                  const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                                  const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
+                                  float* ds_src, float* ds_tgt, float* d_wh,
+                                  void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  using namespace gat;
+  int rc = check_common("gat_edge_bwd_fused", nh, fp, workspace, workspace_bytes);
+  if (rc) return rc;
+  GAT_CHECK_ARG(s_src && s_tgt && gmax && z && s_sum && a_src && a_tgt && ds_src && ds_tgt && d_wh,
+                "gat_edge_bwd_fused: buffers missing");
+  if (n_rows == 0) return GAT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdHeader* header = (BwdHeader*)workspace;
+  if (corr_override == nullptr) {   // Gamma partials were left in the workspace by gat_edge_bwd_rowdot
+    gamma_finalize_kernel<<<1, 1024, 0, st>>>(header, (const double*)((char*)workspace + kBwdHeaderBytes), tie_total);
     GAT_LAUNCH_CHECK();
   }
-#define LAUNCH(G_, S_, N_)                                                                                            \
-  GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, false>,                                                     \
-                         persistent_grid(edge_bwd_main_kernel<G_, S_, N_, false>, kEdgeThreads,                       \
-                                         main_dyn_smem<G_, S_>(P.chunks),                                             \
-                                         (n_rows + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)),                   \
-                         kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, coop_launch))
-  GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
-#undef LAUNCH
-  GAT_LAUNCH_CHECK();
-  return GAT_OK;
+  GAT_CUDA(cudaMemsetAsync(&header->counter_a, 0, 2 * sizeof(unsigned int), st));
+  BwdMainParams P = {};
+  P.rowptr_t = rowptr_t; P.col_t = col_t; P.pos_t = pos_t; P.eid = eid;
+  P.sched.order = row_order_t; P.sched.counter = &header->counter_a; P.sched.cta_counter = &header->counter_a_cta; P.sched.n = n_rows;
+  P.wh = wh; P.nh = nh; P.dp = nh * fp; P.chunks = nh * fp / 4; P.chunks_per_head = fp / 4;
+  P.s_src = s_src; P.s_tgt = s_tgt; P.gmax = gmax; P.z = z; P.const_attention = 0;
+  P.dropout_p = dropout_p; P.seed = seed; P.offset = offset; P.go = go_padded; P.grad_alpha = nullptr;
+  P.go_shared = go_shared ? 1 : 0; P.go_ld = go_shared ? fp : nh * fp;
+  P.rec = nullptr; P.d_wh = d_wh;
+  P.s_sum = s_sum; P.a_src = a_src; P.a_tgt = a_tgt; P.tie_dst = tie_dst; P.tie_src = tie_src; P.header = header;
+  P.corr_override = corr_override; P.tgt_lo = tgt_lo; P.tgt_hi = tgt_hi; P.ds_src = ds_src; P.ds_tgt = ds_tgt;
+  return launch_bwd_main<true>(P, row_order_t, n_long, n_rows, st);
 }
 
 extern "C" int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, const int32_t* row_order, int64_t n_long, int64_t n_rows, int nh,

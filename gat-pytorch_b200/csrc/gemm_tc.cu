@@ -58,6 +58,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA store of one swizzled shared-memory box; rows / columns beyond the tensor map's extent are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -114,12 +124,23 @@ struct Smem {
   static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
 };
 
+// Destinations of an NT output tile.  The tile is staged in shared memory and written by TMA to `count` row-major
+// matrices with the same geometry: the caller's C and, for the fused projection -> all-gather, the same slab of every
+// peer GPU's gathered buffer (NVLink peer memory: the stores leave over the switch while the next CTAs compute).  The
+// tile's rows land at row_offset + m0; each map's row extent is row_offset + M, so tail rows are clipped.
+constexpr int kMaxDests = 8;
+struct CStoreMaps {
+  CUtensorMap maps[kMaxDests];
+  int count;
+  int row_offset;
+};
+
 // MN = false: NT product, one CTA per output tile, whole K.   MN = true: TN product, blockIdx.z = K split, the CTA
 // writes its partial tile to C + blockIdx.z * split_stride (reduced in a fixed order by splitk_reduce_kernel).
 template <int BN, bool MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, int kb_per_split, int64_t split_stride,
+               const __grid_constant__ CStoreMaps cmaps, float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, int kb_per_split, int64_t split_stride,
                uint32_t mn_lbo, uint32_t mn_sbo,
                // fused score epilogue (NT only, one N tile): s_src = C A_src^T, s_tgt = C A_tgt^T in fp64, or nullptr
                const float* __restrict__ a_src, const float* __restrict__ a_tgt, int nh,
@@ -254,11 +275,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // idle pipeline memory; each warp transposes its 32 rows x 8 columns of Wh through a private shared-memory
     // tile into the A-fragment layout.
     const bool fuse = (!MN) && a_src != nullptr;
+    // NT: the tile is staged in the (now idle) pipeline memory as BN/32 boxes of 128 rows x 128 B in the SWIZZLE_128B
+    // pattern the C tensor maps expect (16-byte chunk j of row r sits at chunk j ^ (r % 8)), then one thread writes
+    // it with TMA to every destination.  TN (split-K partials) keeps plain 32-byte row-segment stores.
+    constexpr int kBoxes = BN / 32;
+    constexpr int kBoxBytes = BM * 128;
+    uint8_t* stage_c = smem;
     constexpr int ASTR = BN + 4;                     // row stride (doubles) of the staged attention matrix
     constexpr int TSTR = 36;                         // row stride (doubles) of the per-warp transpose tile
-    double* a_s = reinterpret_cast<double*>(smem);   // [16][ASTR], rows >= 2*nh are zero
+    double* a_s = reinterpret_cast<double*>(smem + (MN ? 0 : kBoxes * kBoxBytes));   // [16][ASTR], rows >= 2*nh are zero
     double* tile = a_s + 16 * ASTR + (warp - 2) * (8 * TSTR);
     const int nj = 2 * nh, nbk = nj > 8 ? 2 : 1;
+    const int rl = q * 32 + lane;                    // row inside the tile
     double sacc[4][2][2];
 #pragma unroll
     for (int g = 0; g < 4; ++g)
@@ -310,7 +338,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         __syncwarp();
       }
-      if (row < M) {
+      if (!MN) {
+        uint8_t* bx = stage_c + (c >> 5) * kBoxBytes + rl * 128;
+        const int j0 = (c & 31) >> 2, sw = rl & 7;
+        *reinterpret_cast<float4*>(bx + (((j0) ^ sw) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(bx + (((j0 + 1) ^ sw) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
+      } else if (row < M) {
         if (n0 + c + 8 <= N) {
           *reinterpret_cast<float4*>(crow + c) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(crow + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -319,6 +352,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 0; j < 8; ++j)
             if (n0 + c + j < N) crow[c + j] = v[j];
         }
+      }
+    }
+    if (!MN) {
+      fence_proxy_async();                           // generic-proxy writes of the staged tile -> visible to TMA
+      asm volatile("bar.sync 1, %0;" ::"n"(kSplitThreads) : "memory");
+      if (t == 0) {
+        for (int d = 0; d < cmaps.count; ++d) {
+#pragma unroll 1
+          for (int b = 0; b < kBoxes; ++b)
+            if (n0 + 32 * b < N) tma_store_2d(&cmaps.maps[d], stage_c + b * kBoxBytes, (int)n0 + 32 * b, cmaps.row_offset + (int)m0);
+        }
+        tma_store_commit_and_wait();
       }
     }
     if (fuse) {
@@ -404,14 +449,29 @@ void splitk_reduce_launch(const float* partial, int splits, int64_t m, int64_t n
 
 struct ScoreFuse { const float* a_src; const float* a_tgt; int nh; float* s_src; float* s_tgt; };
 
+// Extra destinations of the output (fused projection -> all-gather): `count` base pointers of (row_offset + m, n)
+// matrices with leading dimension ldc; the tile rows are written at row_offset.  count == 0: only `c`.
+struct Dests { float* const* ptrs; int count; int64_t row_offset; };
+
 template <int BN, bool MN>
 static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb, float* c,
-                  int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st, ScoreFuse f = ScoreFuse{nullptr, nullptr, 0, nullptr, nullptr}) {
+                  int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st, ScoreFuse f = ScoreFuse{nullptr, nullptr, 0, nullptr, nullptr},
+                  Dests dests = Dests{nullptr, 0, 0}) {
   CUtensorMap map_a, map_b;
+  CStoreMaps cm;          // only .count/.row_offset and the first `count` maps are meaningful; copied by value at launch
+  cm.count = 0; cm.row_offset = 0;
   int rc;
   if (!MN) {
     rc = make_map(&map_a, a, m, k, lda, BM);
     if (!rc) rc = make_map(&map_b, b, n, k, ldb, BN);
+    if (dests.count > kMaxDests || dests.row_offset + m >= ((int64_t)1 << 31)) { set_error("gat_gemm: too many destinations"); return GAT_EINVAL; }
+    if (dests.count == 0) {
+      if (!rc) rc = make_map(&cm.maps[0], c, m, n, ldc, BM);
+      cm.count = 1;
+    } else {
+      for (int d = 0; d < dests.count && !rc; ++d) rc = make_map(&cm.maps[d], dests.ptrs[d], dests.row_offset + m, n, ldc, BM);
+      cm.count = dests.count; cm.row_offset = (int)dests.row_offset;
+    }
   } else {   // stored (K, M) and (K, N): boxes of 32 MN-elements x BK k-rows
     rc = make_map(&map_a, a, k, m, lda, BK, true);
     if (!rc) rc = make_map(&map_b, b, k, n, ldb, BK, true);
@@ -424,7 +484,7 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
   }
   if (!MN) {
     dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), 1);
-    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, 0, 0, 0, 0, f.a_src, f.a_tgt, f.nh, f.s_src, f.s_tgt);
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, c, ldc, m, n, k, 0, 0, 0, 0, f.a_src, f.a_tgt, f.nh, f.s_src, f.s_tgt);
     GAT_LAUNCH_CHECK();
     return GAT_OK;
   }
@@ -432,7 +492,7 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
   const uint32_t mn_lbo = BK * 128, mn_sbo = 512;   // measured on B200: the swapped assignment gives wrong products
   dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), (unsigned)p.splits);
   if (p.splits == 1) {
-    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, c, ldc, m, n, k, p.kb_per_split, 0, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr);
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, c, ldc, m, n, k, p.kb_per_split, 0, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr);
     GAT_LAUNCH_CHECK();
     return GAT_OK;
   }
@@ -441,7 +501,7 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
     set_error("gat_gemm: workspace too small (%zu < %zu)", workspace_bytes, need);
     return GAT_EWORKSPACE;
   }
-  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, (float*)workspace, n, m, n, k, p.kb_per_split, m * n, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr);
+  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, (float*)workspace, n, m, n, k, p.kb_per_split, m * n, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr);
   GAT_LAUNCH_CHECK();
   splitk_reduce_launch((const float*)workspace, p.splits, m, n, c, ldc, st);
   GAT_LAUNCH_CHECK();
@@ -474,16 +534,20 @@ bool tc_project_supported(int64_t n_rows, int64_t dp, int64_t k, int64_t ldx, in
 }
 
 int gemm_tc_project(int64_t n_rows, int64_t dp, int64_t k, const float* x, int64_t ldx, const float* w, int64_t ldw,
-                    float* wh, const float* a_src, const float* a_tgt, int nh, float* s_src, float* s_tgt, cudaStream_t st) {
-  if (!tc_project_supported(n_rows, dp, k, ldx, ldw) || ((uintptr_t)x | (uintptr_t)w | (uintptr_t)wh | (uintptr_t)a_src | (uintptr_t)a_tgt) % 16) {
+                    float* wh, const float* a_src, const float* a_tgt, int nh, float* s_src, float* s_tgt, cudaStream_t st,
+                    float* const* wh_dests, int n_dests, int64_t row_offset) {
+  uintptr_t bits = (uintptr_t)x | (uintptr_t)w | (uintptr_t)a_src | (uintptr_t)a_tgt | (n_dests ? 0 : (uintptr_t)wh);
+  for (int d = 0; d < n_dests; ++d) bits |= (uintptr_t)wh_dests[d];
+  if (!tc_project_supported(n_rows, dp, k, ldx, ldw) || bits % 16) {
     set_error("gat_project_fwd: fused tcgen05 path unsupported for this shape/alignment");
     return GAT_EUNSUPPORTED;
   }
   tc::ScoreFuse f{a_src, a_tgt, nh, s_src, s_tgt};
+  tc::Dests dd{wh_dests, n_dests, row_offset};
   const int bn = tc::bn_for(dp);
-  if (bn == 256) return tc::launch<256, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f);
-  if (bn == 128) return tc::launch<128, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f);
-  return tc::launch<64, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f);
+  if (bn == 256) return tc::launch<256, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd);
+  if (bn == 128) return tc::launch<128, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd);
+  return tc::launch<64, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd);
 }
 
 int gemm_tc(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb,

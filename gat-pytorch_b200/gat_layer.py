@@ -124,31 +124,38 @@ class _GATFunction(torch.autograd.Function):
             else:
                 go_p = grad_out
             d_wh = torch.empty((n, dp), **f32)
-            rec = ds_src = ds_tgt = s_sum = None
+            ds_src = ds_tgt = s_sum = None
             if not const_attention:
-                rec = torch.empty((st.n_edges, 2 * nh), **f32)
                 ds_src, ds_tgt, s_sum = (torch.empty((n, nh), **f32) for _ in range(3))
             ws_bytes = int(lib.gat_edge_bwd_workspace_bytes(n, st.n_edges, nh))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            # pass 1 (source-major, the only feature gather of the backward)
-            _lib.call("gat_edge_bwd_main", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
-                      st.n_long_t, st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax), z.data_ptr(),
-                      int(const_attention), p_drop, seed, 0, go_p.data_ptr(), go_shared, _ptr(grad_alpha), _ptr(rec), d_wh.data_ptr(),
-                      ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
-            if not const_attention:
-                # pass 2 (per target row, light): S = sum_e alpha*d_alpha, ds_tgt, Gamma
-                if grad_alpha is None:      # S = <dOut, out>: no per-edge data needed
-                    _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), go_shared, out_p.data_ptr(), z.data_ptr(), n, nh, fp,
-                              s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
-                else:
+            if not const_attention and grad_alpha is None:
+                # common case (nothing consumed the returned attention): S = <dOut, out> needs no per-edge data, so it
+                # goes FIRST and ONE source-major pass does the rest (no records, no finish pass)
+                _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), go_shared, out_p.data_ptr(), z.data_ptr(), n, nh, fp,
+                          s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+                _lib.call("gat_edge_bwd_fused", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
+                          st.n_long_t, st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, s_src.data_ptr(), s_tgt.data_ptr(), gmax.data_ptr(),
+                          z.data_ptr(), p_drop, seed, 0, go_p.data_ptr(), go_shared, s_sum.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
+                          _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), None, 0, n, ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(),
+                          ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+            else:
+                rec = torch.empty((st.n_edges, 2 * nh), **f32) if not const_attention else None
+                # pass 1 (source-major, the only feature gather of the backward)
+                _lib.call("gat_edge_bwd_main", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
+                          st.n_long_t, st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax), z.data_ptr(),
+                          int(const_attention), p_drop, seed, 0, go_p.data_ptr(), go_shared, _ptr(grad_alpha), _ptr(rec), d_wh.data_ptr(),
+                          ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+                if not const_attention:
+                    # pass 2 (per target row, light): S = sum_e alpha*d_alpha from the records, ds_tgt, Gamma
                     _lib.call("gat_edge_bwd_rowsum", st.rowptr.data_ptr(), st.tpos.data_ptr(), st.order.data_ptr(), st.n_long, n, nh,
                               rec.data_ptr(), z.data_ptr(), s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s,
                               tag=(nh, fp))
-                # pass 3 (source-major, light): ds_src, max() correction, dWh += ds_src*A_src + ds_tgt*A_tgt
-                _lib.call("gat_edge_bwd_finish", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.order_t.data_ptr(), st.n_long_t, n, nh, fp,
-                          rec.data_ptr(), s_sum.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
-                          _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), None, 0, n,
-                          ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+                    # pass 3 (source-major, light): ds_src, max() correction, dWh += ds_src*A_src + ds_tgt*A_tgt
+                    _lib.call("gat_edge_bwd_finish", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.order_t.data_ptr(), st.n_long_t, n, nh, fp,
+                              rec.data_ptr(), s_sum.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
+                              _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), None, 0, n,
+                              ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
             gx = gw = ga_src = ga_tgt = None
             if ctx.needs_input_grad[0]:
                 gx = torch.empty((n, f_in), **f32)

@@ -75,9 +75,48 @@ def local_edge_list(edge_index: torch.Tensor, n_idx: int, lo: int, hi: int, add_
 class CudaBackend:
     """One method per entry point of include/gat_b200.h; tensors in, tensors out."""
 
-    def __init__(self, gemm_algo: int = 0):
+    def __init__(self, gemm_algo: int = 0, fused_allgather=None):
         self.gemm_algo = gemm_algo
         self.lib = _lib.load()
+        # GAT_B200_FUSED_ALLGATHER=0 selects the NCCL all-gather (the baseline the fused kernel is checked against)
+        import os
+        self.fused_allgather = (os.environ.get("GAT_B200_FUSED_ALLGATHER", "1") != "0") if fused_allgather is None else fused_allgather
+        self._symm_warned = False
+
+    def gathered_buffer(self, n_pad, dp, group):
+        """(n_pad, dp) buffer for the gathered features of one layer plus the addresses of the same buffer on every
+        rank, mapped into this process through torch's symmetric memory (CUDA VMM handles exchanged over the process
+        group; NVLink peer access).  Returns (tensor, None) when peer mapping is unavailable -> NCCL all-gather."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if self.fused_allgather and dist.get_world_size(group) <= 8:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                g = group if group is not None else dist.group.WORLD
+                if hasattr(symm_mem, "enable_symm_mem_for_group"):
+                    try:
+                        symm_mem.enable_symm_mem_for_group(g.group_name)
+                    except Exception:
+                        pass
+                buf = symm_mem.empty((n_pad, dp), dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(buf, g)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                assert len(ptrs) == dist.get_world_size(group) and ptrs[dist.get_rank(group)] == buf.data_ptr()
+                buf._gat_symm_handle = hdl        # keep the mapping alive as long as the buffer
+                return buf, ptrs
+            except Exception as exc:   # peer mapping refused (no P2P / VMM export): fall back to the NCCL exchange
+                if not self._symm_warned:
+                    print(f"[gat_b200] symmetric memory unavailable ({type(exc).__name__}: {exc}); using the NCCL all-gather", flush=True)
+                    self._symm_warned = True
+                self.fused_allgather = False
+        return torch.empty((n_pad, dp), dtype=torch.float32, device=dev), None
+
+    def project_allgather(self, x, rows, f_in, w_p, dp, a_src, a_tgt, nh, peer_ptrs, row_offset, s_src, s_tgt):
+        """Kernel 2 fused with the feature exchange: every tile of wh goes by TMA into all ranks' gathered buffers."""
+        import ctypes
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        _lib.call("gat_project_fwd_allgather", x.data_ptr(), rows, f_in, x.stride(0), w_p.data_ptr(), w_p.stride(0), dp,
+                  a_src.data_ptr(), a_tgt.data_ptr(), nh, arr, len(peer_ptrs), row_offset,
+                  s_src.data_ptr(), s_tgt.data_ptr(), self._s(x.device), tag=(rows, dp, f_in))
 
     @staticmethod
     def _s(dev):
@@ -158,6 +197,20 @@ class CudaBackend:
                   0, 0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, 0, None, rec.data_ptr(), d_wh.data_ptr(),
                   ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
 
+    def edge_bwd_fused(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, s_sum_local,
+                       a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
+        """The backward's one heavy pass (gat_edge_bwd_fused) over ALL source rows with this rank's edges; target-indexed
+        arrays are local, so their base pointers are shifted by plan.lo rows (col_t holds GLOBAL target ids in [lo, hi))."""
+        dp, lo = nh * fp, plan.lo
+        ws, ws_bytes = self._bwd_ws(go_p.device, nh)
+        _lib.call("gat_edge_bwd_fused", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
+                  st.n_long_t, st.eid.data_ptr(), plan.n, wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(),
+                  s_tgt_local.data_ptr() - 4 * nh * lo, gmax.data_ptr(), z_local.data_ptr() - 4 * nh * lo,
+                  0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, 0, s_sum_local.data_ptr() - 4 * nh * lo,
+                  a_src.data_ptr(), a_tgt.data_ptr(), tie_dst.data_ptr(), tie_src.data_ptr(), None, corr.data_ptr(),
+                  plan.lo, plan.hi, ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(), ws.data_ptr(), ws_bytes,
+                  self._s(go_p.device), tag=(nh, fp))
+
     def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt):
         """Pass 2 without per-edge data: S = <dOut, out> over the owned rows; returns this rank's Gamma."""
         ws, ws_bytes = self._bwd_ws(go_p.device, nh)
@@ -182,23 +235,34 @@ class CudaBackend:
 # ----------------------------------------------------------------------------------------------
 class _PartitionedGATFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_local, w_p, a_src_p, a_tgt_p, st, plan: Plan, nh, fp, backend, group):
+    def forward(ctx, x_local, w_p, a_src_p, a_tgt_p, st, plan: Plan, nh, fp, backend, group, gathered):
         dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
         rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
-        wh_slab = torch.zeros((R, dp), **f32)
         s_src_slab = torch.zeros((R, nh), **f32)
         s_tgt = torch.empty((max(rows, 1), nh), **f32)
-        if rows:
-            backend.project(x_local, rows, f_in, w_p, dp, a_src_p, a_tgt_p, nh, wh_slab, s_src_slab, s_tgt)
-        wh_full = torch.empty((plan.n_pad, dp), **f32)
         s_src_full = torch.empty((plan.n_pad, nh), **f32)
-        dist.all_gather_into_tensor(wh_full, wh_slab, group=group)          # the feature exchange (NVLink)
-        dist.all_gather_into_tensor(s_src_full, s_src_slab, group=group)
+        wh_full, peer_ptrs = gathered if gathered is not None else (None, None)
+        fused = peer_ptrs is not None and (rows == 0 or _lib.load().gat_gemm_tc_supported(0, 1, rows, dp, f_in, x_local.stride(0), w_p.stride(0), dp)) and dp <= 256
+        if fused:
+            # ONE kernel: GEMM tiles -> shared memory -> TMA stores into every rank's gathered buffer over NVLink
+            if rows:
+                backend.project_allgather(x_local, rows, f_in, w_p, dp, a_src_p, a_tgt_p, nh, peer_ptrs, plan.lo, s_src_slab, s_tgt)
+            dist.all_gather_into_tensor(s_src_full, s_src_slab, group=group)    # tiny; doubles as the cross-rank barrier for wh_full
+        else:
+            wh_slab = torch.empty((R, dp), **f32)
+            if rows < R:
+                wh_slab[rows:].zero_()
+            if rows:
+                backend.project(x_local, rows, f_in, w_p, dp, a_src_p, a_tgt_p, nh, wh_slab, s_src_slab, s_tgt)
+            if wh_full is None:
+                wh_full = torch.empty((plan.n_pad, dp), **f32)
+            dist.all_gather_into_tensor(wh_full, wh_slab, group=group)          # the feature exchange (NCCL over NVLink)
+            dist.all_gather_into_tensor(s_src_full, s_src_slab, group=group)
         gmax = torch.full((1,), float("-inf"), **f32)
         if rows:
             backend.edge_max(st, plan, s_src_full, s_tgt, nh, gmax)
         dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)            # ONE global max, gat_layer.py:85
-        out_p = torch.zeros((max(rows, 1), dp), **f32)[:rows]
+        out_p = torch.empty((max(rows, 1), dp), **f32)[:rows]       # every owned row is written by the edge kernel
         z = torch.zeros((max(rows, 1), nh), **f32)
         ties = torch.zeros(2 + max(rows, 1) * nh + plan.n_pad * nh, dtype=torch.int32, device=dev)
         tie_total, tie_dst, tie_src = ties[:2], ties[2:2 + max(rows, 1) * nh], ties[2 + max(rows, 1) * nh:]
@@ -215,20 +279,21 @@ class _PartitionedGATFunction(torch.autograd.Function):
         dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
         rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
         go_p = go_p.contiguous()
-        rec = torch.empty((max(backend.n_edges(st), 1), 2 * nh), **f32)
         ds_tgt_full = torch.zeros((plan.n_pad + 1, nh), **f32)     # owned rows live at [lo, hi); the rest stays zero
         ds_tgt = ds_tgt_full[plan.lo:plan.lo + max(rows, 1)]
         s_sum = torch.zeros((max(rows, 1), nh), **f32)
-        d_wh_part = torch.zeros((plan.n_pad, dp), **f32)
+        d_wh_part = torch.empty((plan.n_pad, dp), **f32)            # rows [0, n) are all written by the source-major pass
+        if plan.n_pad > plan.n:
+            d_wh_part[plan.n:].zero_()
         ds_src_part = torch.zeros((plan.n_pad, nh), **f32)
         gamma = torch.zeros(1, dtype=torch.float64, device=dev)
-        backend.edge_bwd_main(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, rec, d_wh_part)
-        if rows:
+        if rows:    # S = <dOut, out> over the owned rows first: no per-edge data needed
             gamma = backend.edge_bwd_rowdot(plan, nh, fp, go_p, out_p, z, s_sum, ds_tgt)
         red = torch.stack([gamma[0], tie_total.view(torch.int64)[0].to(torch.float64)])
         dist.all_reduce(red, group=group)                                   # (Gamma, |T|) over ranks
         corr = torch.where(red[1] > 0, red[0] / red[1].clamp(min=1.0), torch.zeros_like(red[0])).to(torch.float32).reshape(1)
-        backend.edge_bwd_finish(st, plan, nh, fp, rec, s_sum, a_src_p, a_tgt_p, tie_dst, tie_src, corr, ds_src_part, ds_tgt, d_wh_part)
+        backend.edge_bwd_fused(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, s_sum, a_src_p, a_tgt_p,
+                               tie_dst, tie_src, corr, ds_src_part, ds_tgt, d_wh_part)
         d_wh = torch.empty((R, dp), **f32)
         dist.reduce_scatter_tensor(d_wh, d_wh_part, group=group)            # transpose of the all-gather
         gx = None
@@ -248,7 +313,7 @@ class _PartitionedGATFunction(torch.autograd.Function):
         dist.all_reduce(flat, group=group)                                  # the gradient all-reduce
         gw, ga_src, ga_tgt = flat[:gw.numel()].view_as(gw), flat[gw.numel():gw.numel() + ga_src.numel()].view_as(ga_src), \
             flat[gw.numel() + ga_src.numel():].view_as(ga_tgt)
-        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None
+        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None
 
 
 class PartitionedGATLayer(torch.nn.Module):
@@ -263,6 +328,7 @@ class PartitionedGATLayer(torch.nn.Module):
         torch.nn.init.xavier_uniform_(self.W.weight)
         torch.nn.init.xavier_uniform_(self.a.weight)
         self.backend, self.group = backend, group
+        self._gathered = None       # (wh_full, peer pointers) of this layer, allocated once (symmetric memory)
 
     def _padded_operands(self):
         nh, f = self.num_heads, self.out_features
@@ -281,7 +347,11 @@ class PartitionedGATLayer(torch.nn.Module):
             self.backend = CudaBackend()
         w_p, a_src, a_tgt, fp = self._padded_operands()
         nh, f = self.num_heads, self.out_features
-        out_p = _PartitionedGATFunction.apply(x_local.contiguous(), w_p, a_src, a_tgt, st, plan, nh, fp, self.backend, self.group)
+        if hasattr(self.backend, "gathered_buffer"):
+            if self._gathered is None or self._gathered[0].shape != (plan.n_pad, nh * fp) or self._gathered[0].device != x_local.device:
+                self._gathered = self.backend.gathered_buffer(plan.n_pad, nh * fp, self.group)
+        out_p = _PartitionedGATFunction.apply(x_local.contiguous(), w_p, a_src, a_tgt, st, plan, nh, fp, self.backend, self.group,
+                                              self._gathered)
         o = out_p.view(-1, nh, fp)[:, :, :f]
         return o.reshape(-1, nh * f) if self.concat else o.mean(dim=1)      # gat_layer.py:129-132
 

@@ -109,6 +109,18 @@ GAT_API int gat_project_fwd(const float* x, int64_t n, int64_t f_in, int64_t ldx
                             const float* a_src, const float* a_tgt, int nh, float* wh, float* s_src, float* s_tgt,
                             int algo, void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
+/* Fused projection -> all-gather for the destination-range partitioned layer (one process per GPU).  Computes this
+ * rank's slab wh[row_offset .. row_offset+n) = x W^T exactly like gat_project_fwd (tcgen05 path only: dp <= 256,
+ * 16-byte aligned leading dimensions) and writes every output tile, from shared memory by TMA, into row
+ * row_offset + i of EACH of the n_dests (1..8) gathered (>= row_offset + n, dp) buffers in h_wh_dests -- a HOST array of
+ * device pointers: this rank's own buffer and the peers' buffers mapped into this process (CUDA peer / symmetric
+ * memory over NVLink).  No separate collective moves the features; the caller only needs a cross-rank barrier (any
+ * small collective) before reading its gathered buffer.  s_src / s_tgt (n, nh) are this rank's rows only. */
+GAT_API int gat_project_fwd_allgather(const float* x, int64_t n, int64_t f_in, int64_t ldx, const float* w, int64_t ldw, int dp,
+                                      const float* a_src, const float* a_tgt, int nh,
+                                      float* const* h_wh_dests, int n_dests, int64_t row_offset,
+                                      float* s_src, float* s_tgt, gat_stream_t stream);
+
 /* s_src[i,h] = <wh[i,:], a_src[h,:]>, s_tgt[i,h] = <wh[i,:], a_tgt[h,:]>  (fp64 accumulate).
  * The decomposition of gat_layer.py:76-82: logit[e,h] = s_src[src_e,h] + s_tgt[dst_e,h]. */
 GAT_API int gat_scores_fwd(const float* wh, int64_t n, int dp, const float* a_src, const float* a_tgt, int nh,
@@ -187,6 +199,25 @@ GAT_API int gat_edge_bwd_main(const int32_t* rowptr_t, const int32_t* col_t, con
                               int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
                               const float* go_padded, int go_shared, const float* grad_alpha, float* rec, float* d_wh,
                               void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
+/* The backward in TWO passes, for the common case without an upstream dL/dalpha (nothing consumed the returned
+ * attention): run gat_edge_bwd_rowdot FIRST -- S = <dOut, out>, ds_tgt and the Gamma partials need no per-edge data --
+ * then this source-major pass, which does everything gat_edge_bwd_main + gat_edge_bwd_finish do, without records:
+ * alpha recomputed, dOut[dst] gathered once, g = 0.01*alpha*(d_alpha - S[dst]) summed into ds_src, the arg-max
+ * correction Gamma/|T| applied to ds_src / ds_tgt through the tie counts, and
+ * d_wh[src] = sum_e m*alpha*dOut[dst] + ds_src*A_src + ds_tgt*A_tgt written once.  Arguments as in gat_edge_bwd_main /
+ * gat_edge_bwd_finish (s_sum indexed by TARGET id; corr_override NULL on one GPU: Gamma is then finalised here from the
+ * partials gat_edge_bwd_rowdot left in `workspace`, which must be the same buffer). */
+GAT_API int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
+                               int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                               const float* s_src, const float* s_tgt, const float* gmax, const float* z,
+                               float dropout_p, uint64_t seed, uint64_t offset,
+                               const float* go_padded, int go_shared, const float* s_sum,
+                               const float* a_src, const float* a_tgt,
+                               const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                               const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
+                               float* ds_src, float* ds_tgt, float* d_wh,
+                               void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* Pass 2 (CSR by target, rows = owned TARGET nodes): s_sum[d,h] = sum_e alpha*d_alpha over the in-edges of d (records
  * gathered through tpos = CSR^T slot of each CSR slot); ds_tgt[d,h] = sum_e g = 0.01*s_sum*eps/(z+eps) (before the arg-max

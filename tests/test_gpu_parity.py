@@ -261,3 +261,57 @@ def test_gemm_tcgen05_3xtf32():
         err = ((c.double() - want).abs().max() / want.abs().max()).item()
         assert err < 4e-6, ("TN", m, n, k, err)
     assert not lib.gat_gemm_tc_supported(0, 1, 100, 64, 1433, 1433, 1433, 64)     # Cora: K*4 bytes is not a 16-byte multiple
+
+
+def test_project_allgather_multi_destination():
+    """Fused projection -> all-gather kernel, exercised on ONE GPU: the destinations are two local buffers standing in
+    for the ranks' gathered buffers (a peer pointer is an ordinary global address to the kernel).  Every destination
+    must receive exactly gat_project_fwd's slab at row_offset, and no row outside the slab may be touched."""
+    import ctypes
+    from gat_pytorch_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(3)
+    for (rows, f_in, nh, fp, lo) in [(1000, 100, 4, 64, 0), (777, 256, 4, 48, 1300), (130, 64, 8, 8, 5)]:
+        dp = nh * fp
+        x = torch.randn(rows, f_in, device="cuda")
+        w = torch.randn(dp, f_in, device="cuda") * 0.1
+        a_src, a_tgt = torch.randn(nh, dp, device="cuda"), torch.randn(nh, dp, device="cuda")
+        want_wh = torch.empty(rows, dp, device="cuda")
+        want_s, want_t = torch.empty(rows, nh, device="cuda"), torch.empty(rows, nh, device="cuda")
+        _lib.call("gat_project_fwd", x.data_ptr(), rows, f_in, f_in, w.data_ptr(), f_in, dp, a_src.data_ptr(), a_tgt.data_ptr(), nh,
+                  want_wh.data_ptr(), want_s.data_ptr(), want_t.data_ptr(), 2, None, 0, torch.cuda.current_stream().cuda_stream)
+        total = lo + rows + 37
+        dests = [torch.full((total, dp), float("nan"), device="cuda") for _ in range(2)]
+        s_src, s_tgt = torch.empty(rows, nh, device="cuda"), torch.empty(rows, nh, device="cuda")
+        arr = (ctypes.c_void_p * 2)(*[d.data_ptr() for d in dests])
+        _lib.call("gat_project_fwd_allgather", x.data_ptr(), rows, f_in, f_in, w.data_ptr(), f_in, dp, a_src.data_ptr(), a_tgt.data_ptr(),
+                  nh, arr, 2, lo, s_src.data_ptr(), s_tgt.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        ref = (x.double() @ w.double().T)
+        assert ((want_wh.double() - ref).abs().max() / ref.abs().max()).item() < 3e-6
+        for d in dests:
+            assert torch.equal(d[lo:lo + rows], want_wh)
+            assert torch.isnan(d[:lo]).all() and torch.isnan(d[lo + rows:]).all()
+        assert torch.equal(s_src, want_s) and torch.equal(s_tgt, want_t)
+
+
+@pytest.mark.parametrize("name", ["adv_concat", "adv_mean_oddF", "adv_1x1", "adv_wide", "adv_ties", "adv_eps_dominated", "adv_bias",
+                                  "cora_L0", "cora_L1", "pubmed_L1", "ppi_L2", "pattern_L0", "pattern_L2",
+                                  "products_L0", "products_L1", "products_L2"])
+def test_backward_without_attention_gradient(name, small_cases):
+    """Nothing consumes the returned attention (GATModel.forward, PATTERN training, inference): the backward then runs
+    as rowdot + ONE fused source-major pass (gat_edge_bwd_fused) instead of main + rowsum + finish.  Same bar."""
+    case = small_cases[name]
+    layer = make_layer(case)
+    x = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+    ei = torch.from_numpy(case["edge_index"]).cuda()
+    out = layer(x, ei)
+    fw = O.forward(case["x"], case["edge_index"].astype(np.int64), case["W"], case["a"], case["nh"], case["f"], case["concat"],
+                   case["add_self_loops"], case["bias"], case["const_attention"])
+    go, _ = cases.upstream_grads(case, fw["out"].shape[0], fw["out"].shape[1], fw["alpha"].shape[0])
+    (out * torch.from_numpy(go).cuda()).sum().backward()
+    gr = O.backward(fw, go, None)
+    tol = TOL_OVERRIDE.get(name, TOL)
+    errs = {"out": O.rel_err(out.detach().cpu().numpy(), fw["out"]), "gx": O.rel_err(x.grad.cpu().numpy(), gr["x"]),
+            "gW": O.rel_err(layer.W.weight.grad.cpu().numpy(), gr["W"]), "ga": O.rel_err(layer.a.weight.grad.cpu().numpy(), gr["a"])}
+    assert all(e <= tol for e in errs.values()), errs
