@@ -19,6 +19,7 @@
 // counters of the persistent schedulers, which never influence a result.
 #include "edge_common.cuh"
 #include <cstddef>
+#include <cstdlib>
 
 namespace gat {
 
@@ -55,45 +56,74 @@ struct BwdMainParams {
   const int32_t* tie_dst; const int32_t* tie_src; const BwdHeader* header; const float* corr_override;
   int64_t tgt_lo; int64_t tgt_hi;
   float* ds_src; float* ds_tgt;
+  // PUSH mode (partitioned graphs, fused reduce-scatter): the finished dWh row of source `row` is stored straight into
+  // its OWNER's receive buffer -- slab `my_rank`, row `row - owner*rows_per_rank` -- through the peer-mapped pointers
+  // push_dst[owner] (this rank's own buffer included), so the exchange rides NVLink while the pass is still running.
+  float* push_dst[8]; int push; int my_rank; int64_t rows_per_rank;
 };
+
+__device__ __forceinline__ float* dwh_row_ptr(const BwdMainParams& P, const int64_t row) {
+  if (!P.push) return P.d_wh + row * P.dp;
+  const int64_t owner = row / P.rows_per_rank;
+  return P.push_dst[owner] + ((int64_t)P.my_rank * P.rows_per_rank + (row - owner * P.rows_per_rank)) * P.dp;
+}
 
 template <int G, int SLOTS>
 struct MainShape {
   static constexpr int TB = (G < 8) ? G : (SLOTS >= 6 ? 4 : 8);     // edges per transpose-reduce sub-batch
   static constexpr int U = (SLOTS >= 4) ? 2 : (TB < 4 ? TB : 4);    // edges in flight
+  static constexpr int PSTRIDE = SLOTS * G + 1;                      // floats per row of the transpose tile (odd: conflict free)
 };
 
 // COOP (long source rows): the CTA's 256/G groups take the row's batches round-robin (each writes the records of its
 // own edges) and the dWh row is combined over the groups in group order through `coop`, which ALIASES the groups'
 // `part` tiles -- hence the CTA barrier before it is written.  Called by all threads of the CTA in that case.
+// What a lane owns of a padded row: fixed for the whole kernel, so it is computed once per thread, not once per row.
+template <int SLOTS>
+struct LaneShape {
+  int head[SLOTS];   // head of the lane's chunk in slot s
+  int goff[SLOTS];   // float offset of that chunk inside a gathered dOut row
+  bool ok[SLOTS];    // chunk exists (row narrower than SLOTS*G chunks)
+};
+
+template <int G, int SLOTS>
+__device__ __forceinline__ LaneShape<SLOTS> make_lane_shape(const BwdMainParams& P, const int gl) {
+  LaneShape<SLOTS> L;
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int c = s * G + gl;
+    L.ok[s] = c < P.chunks;
+    L.head[s] = L.ok[s] ? c / P.chunks_per_head : 0;
+    // the head-mean layer's upstream gradient is the same (Fp)-wide vector for every head (gat_layer.py:132), so it is
+    // stored once and every head reads the same chunk
+    L.goff[s] = (P.go_shared ? c - L.head[s] * P.chunks_per_head : c) * 4;
+  }
+  return L;
+}
+
 template <int G, int SLOTS, int NHT, bool COOP, bool FUSED>
-__device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64_t row, const int tid, const int gl,
-                                             const int gbase, const unsigned gmask, const float gmax, const float corr,
-                                             int* sh_dst, float* sh_w, float* sh_da, float* part, float* coop) {
+__device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneShape<SLOTS>& L, const int64_t row, const int tid,
+                                             const int gl, const int gbase, const unsigned gmask, const float gmax, const float corr,
+                                             int* sh_dst, const float** sh_gp, float* sh_w, float* sh_da, float* part, float* coop) {
   constexpr int TB = MainShape<G, SLOTS>::TB, U = MainShape<G, SLOTS>::U;
+  constexpr int PSTRIDE = MainShape<G, SLOTS>::PSTRIDE;   // compile-time stride of the transpose tile rows
   constexpr int NG = kEdgeThreads / G;
   const int grp = tid / G;
   const int first = COOP ? grp * G : 0, step = COOP ? NG * G : G;
   const int nh = P.nh;
-  const int pstride = P.chunks + 1;
-  int head[SLOTS], goff[SLOTS];
-  bool ok[SLOTS];
   float4 whr[SLOTS], acc[SLOTS];
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
-    int c = s * G + gl;
-    ok[s] = c < P.chunks;
-    head[s] = ok[s] ? c / P.chunks_per_head : 0;
-    // float offset of this slot's chunk inside a gathered dOut row: the head-mean layer's upstream gradient is the same
-    // (Fp)-wide vector for every head (gat_layer.py:132), so it is stored once and every head reads the same chunk
-    goff[s] = (P.go_shared ? c - head[s] * P.chunks_per_head : c) * 4;
     acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-    whr[s] = (ok[s] && !P.const_attention) ? ldg4(P.wh + row * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    whr[s] = (L.ok[s] && !P.const_attention) ? ldg4(P.wh + row * P.dp + (s * G + gl) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const int start = __ldg(P.rowptr_t + row), end = __ldg(P.rowptr_t + row + 1);
   float ss[NHT], gsum[NHT];
 #pragma unroll
   for (int h = 0; h < NHT; ++h) { ss[h] = (!P.const_attention && h < nh) ? __ldg(P.s_src + row * nh + h) : 0.f; gsum[h] = 0.f; }
+  const float* wbase[SLOTS];   // this lane's weight of edge k in slot s: wbase[s][k * NHT]
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) wbase[s] = sh_w + gbase * NHT + L.head[s];
 
   for (int base = start + first; base < end; base += step) {
     const int e = base + gl;
@@ -123,6 +153,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
         }
       }
       sh_dst[tid] = d;
+      sh_gp[tid] = P.go + (int64_t)d * P.go_ld;   // the 64-bit row address is formed once, by the lane that owns the edge
 #pragma unroll
       for (int h = 0; h < NHT; ++h) sh_w[tid * NHT + h] = msk[h] * alpha[h];
     }
@@ -130,34 +161,46 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
     const int cnt = min(G, end - base);
     for (int t0 = 0; t0 < cnt; t0 += TB) {
       const int tcnt = min(TB, cnt - t0);
-#pragma unroll
-      for (int tt = 0; tt < TB; tt += U) {
+      // groups of U edges: all loads of a group are issued before its first use; only the groups that exist are executed
+#pragma unroll 1
+      for (int tt = 0; tt < tcnt; tt += U) {
+        const int k0 = t0 + tt;
         float4 v[U][SLOTS];
+        if (tt + U <= tcnt) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const bool on = tt + u < tcnt;
-          const int didx = on ? sh_dst[gbase + t0 + tt + u] : 0;
-          const float* rowp = P.go + (int64_t)didx * P.go_ld;
+          for (int u = 0; u < U; ++u) {
+            const float* rowp = sh_gp[gbase + k0 + u];
 #pragma unroll
-          for (int s = 0; s < SLOTS; ++s)
-            v[u][s] = (on && ok[s]) ? ldg4(rowp + goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < SLOTS; ++s)
+              v[u][s] = L.ok[s] ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool on = tt + u < tcnt;
+            const float* rowp = sh_gp[gbase + (on ? k0 + u : k0)];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s)
+              v[u][s] = (on && L.ok[s]) ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
+        float* prow = part + tt * PSTRIDE + gl;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (tt + u < tcnt) {
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
-              const float w = sh_w[(gbase + t0 + tt + u) * NHT + head[s]];
+              const float w = wbase[s][(k0 + u) * NHT];
               acc[s].x = fmaf(w, v[u][s].x, acc[s].x);
               acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
               acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
               acc[s].w = fmaf(w, v[u][s].w, acc[s].w);
-              if (ok[s] && !P.const_attention) {
+              if (L.ok[s] && !P.const_attention) {
                 float dd = whr[s].x * v[u][s].x;
                 dd = fmaf(whr[s].y, v[u][s].y, dd);
                 dd = fmaf(whr[s].z, v[u][s].z, dd);
                 dd = fmaf(whr[s].w, v[u][s].w, dd);
-                part[(tt + u) * pstride + s * G + gl] = dd;
+                prow[u * PSTRIDE + s * G] = dd;
               }
             }
           }
@@ -165,13 +208,16 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
       }
       if (!P.const_attention) {
         __syncwarp(gmask);
-        // transpose-reduce: (edge, head) pair q sums the chunks of that head
+        // transpose-reduce: (edge, head) pair q sums the chunks of that head (four independent partial sums)
         for (int q = gl; q < tcnt * nh; q += G) {
-          const int t = q / nh, h = q - t * nh;
-          const float* pp = part + t * pstride + h * P.chunks_per_head;
-          float dd = 0.f;
-          for (int c = 0; c < P.chunks_per_head; ++c) dd += pp[c];
-          sh_da[(gbase + t0 + t) * NHT + h] = dd;
+          int t, h;
+          if (nh == NHT) { t = q / NHT; h = q - t * NHT; } else { t = q / nh; h = q - t * nh; }
+          const float* pp = part + t * PSTRIDE + h * P.chunks_per_head;
+          float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+          int c = 0;
+          for (; c + 4 <= P.chunks_per_head; c += 4) { d0 += pp[c]; d1 += pp[c + 1]; d2 += pp[c + 2]; d3 += pp[c + 3]; }
+          for (; c < P.chunks_per_head; ++c) d0 += pp[c];
+          sh_da[(gbase + t0 + t) * NHT + h] = (d0 + d1) + (d2 + d3);
         }
         __syncwarp(gmask);
       }
@@ -191,6 +237,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
     }
     __syncwarp(gmask);
   }
+  float* const drow = dwh_row_ptr(P, row);
   // FUSED epilogue inputs: ds_src = sum g - |T_src|*Gamma/|T|, ds_tgt -= |T_dst|*Gamma/|T| (gradient through max())
   const bool own_tgt = FUSED && row >= P.tgt_lo && row < P.tgt_hi;
   const int64_t trow = row - P.tgt_lo;
@@ -222,7 +269,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
     }
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
-      if (ok[s]) {
+      if (L.ok[s]) {
         const int c = s * G + gl;
 #pragma unroll
         for (int h = 0; h < NHT; ++h) {
@@ -242,7 +289,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
     __syncthreads();   // every group is done with its `part` tile, which `coop` aliases
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s)
-      if (ok[s]) *reinterpret_cast<float4*>(coop + grp * P.dp + (s * G + gl) * 4) = acc[s];
+      if (L.ok[s]) *reinterpret_cast<float4*>(coop + grp * P.dp + (s * G + gl) * 4) = acc[s];
     float* coop_g = coop + NG * P.dp;   // [NG][NHT] per-group sums of g
     if (FUSED && !P.const_attention) {
 #pragma unroll
@@ -297,13 +344,13 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const int64
           }
         }
       }
-      *reinterpret_cast<float4*>(P.d_wh + row * P.dp + c * 4) = t;
+      *reinterpret_cast<float4*>(drow + c * 4) = t;
     }
     // the next grab_long_row() starts with a __syncthreads()
   } else {
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s)
-      if (ok[s]) *reinterpret_cast<float4*>(P.d_wh + row * P.dp + (s * G + gl) * 4) = acc[s];
+      if (L.ok[s]) *reinterpret_cast<float4*>(drow + (s * G + gl) * 4) = acc[s];
   }
 }
 
@@ -315,9 +362,11 @@ edge_bwd_main_kernel(const BwdMainParams P) {
   __shared__ int sh_dst[kEdgeThreads];
   __shared__ float sh_w[kEdgeThreads * NHT];
   __shared__ float sh_da[kEdgeThreads * NHT];
+  __shared__ const float* sh_gp[kEdgeThreads];
   const int tid = threadIdx.x, lane = tid & 31, gl = tid & (G - 1), gbase = tid - gl;
   const unsigned gmask = group_mask<G>(lane);
-  float* part = dyn_smem + (size_t)(tid / G) * TB * (P.chunks + 1);   // [TB][chunks+1] of my group
+  const LaneShape<SLOTS> L = make_lane_shape<G, SLOTS>(P, gl);
+  float* part = dyn_smem + (size_t)(tid / G) * TB * MainShape<G, SLOTS>::PSTRIDE;   // [TB][PSTRIDE] of my group
   const float gmax = P.const_attention ? 0.f : __ldg(P.gmax);
   const float corr = !FUSED ? 0.f : (P.corr_override ? __ldg(P.corr_override) : P.header->corr);
   if (COOP) {   // long source rows, CTA per row (its own launch)
@@ -326,7 +375,7 @@ edge_bwd_main_kernel(const BwdMainParams P) {
     for (;;) {
       const int64_t row = grab_long_row(P.sched, P.rowptr_t, &sh_ctl);
       if (row < 0) break;
-      bwd_main_row<G, SLOTS, NHT, true, FUSED>(P, row, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_w, sh_da, part, dyn_smem);
+      bwd_main_row<G, SLOTS, NHT, true, FUSED>(P, L, row, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, part, dyn_smem);
     }
   } else {
     int64_t base;
@@ -335,7 +384,7 @@ edge_bwd_main_kernel(const BwdMainParams P) {
       for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
         const int64_t row = sched_row<G>(P.sched, base, k, lane);
         if (row >= 0 && !taken_by_cta_phase(P.sched, P.rowptr_t, row))
-          bwd_main_row<G, SLOTS, NHT, false, FUSED>(P, row, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_w, sh_da, part, nullptr);
+          bwd_main_row<G, SLOTS, NHT, false, FUSED>(P, L, row, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, part, nullptr);
       }
     }
     pdl_wait_for_primary();     // no-op unless launched behind the cooperative kernel
@@ -345,7 +394,7 @@ edge_bwd_main_kernel(const BwdMainParams P) {
 // per-group transpose tiles; the cooperative path's (256/G) x dp reduction buffer aliases them
 template <int G, int SLOTS>
 static size_t main_dyn_smem(int chunks) {
-  const size_t part = (size_t)(kEdgeThreads / G) * MainShape<G, SLOTS>::TB * (chunks + 1) * sizeof(float);
+  const size_t part = (size_t)(kEdgeThreads / G) * MainShape<G, SLOTS>::TB * MainShape<G, SLOTS>::PSTRIDE * sizeof(float);
   const size_t coop = (size_t)(kEdgeThreads / G) * (chunks * 4 + 8) * sizeof(float);   // + [NG][NHT] sums of g (FUSED)
   return part > coop ? part : coop;
 }
@@ -664,6 +713,19 @@ edge_bwd_finish_kernel(const BwdFinishParams P) {
   }
 }
 
+// Owner-side half of the fused reduce-scatter: out[r] = sum over slabs q (ranks, fixed order) of recv[q][r].
+__global__ void __launch_bounds__(256)
+slab_sum_kernel(const float* __restrict__ recv, int n_slabs, int64_t slab_floats, int64_t count4, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(recv) + i);
+    for (int q = 1; q < n_slabs; ++q) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(recv + q * slab_floats) + i);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = t;
+  }
+}
+
 static int check_common(const char* who, int nh, int fp, void* workspace, size_t workspace_bytes) {
   if (nh < 1 || nh > kMaxHeads) { set_error("%s: num_heads %d not in [1, %d]", who, nh, kMaxHeads); return GAT_EINVAL; }
   if (fp <= 0 || fp % 4) { set_error("%s: padded head width %d must be a positive multiple of 4", who, fp); return GAT_EINVAL; }
@@ -751,12 +813,16 @@ extern "C" int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t,
                                   const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
                                   const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
                                   float* ds_src, float* ds_tgt, float* d_wh,
+                                  float* const* h_push_dst, int n_push, int my_rank, int64_t rows_per_rank,
                                   void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
   int rc = check_common("gat_edge_bwd_fused", nh, fp, workspace, workspace_bytes);
   if (rc) return rc;
-  GAT_CHECK_ARG(s_src && s_tgt && gmax && z && s_sum && a_src && a_tgt && ds_src && ds_tgt && d_wh,
+  GAT_CHECK_ARG(s_src && s_tgt && gmax && z && s_sum && a_src && a_tgt && ds_src && ds_tgt && (d_wh || n_push > 0),
                 "gat_edge_bwd_fused: buffers missing");
+  GAT_CHECK_ARG(n_push == 0 || (h_push_dst && n_push >= 1 && n_push <= 8 && my_rank >= 0 && my_rank < n_push && rows_per_rank >= 1 &&
+                                rows_per_rank * n_push >= n_rows),
+                "gat_edge_bwd_fused: bad push configuration");
   if (n_rows == 0) return GAT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   BwdHeader* header = (BwdHeader*)workspace;
@@ -775,6 +841,8 @@ extern "C" int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t,
   P.rec = nullptr; P.d_wh = d_wh;
   P.s_sum = s_sum; P.a_src = a_src; P.a_tgt = a_tgt; P.tie_dst = tie_dst; P.tie_src = tie_src; P.header = header;
   P.corr_override = corr_override; P.tgt_lo = tgt_lo; P.tgt_hi = tgt_hi; P.ds_src = ds_src; P.ds_tgt = ds_tgt;
+  P.push = n_push > 0; P.my_rank = my_rank; P.rows_per_rank = rows_per_rank > 0 ? rows_per_rank : 1;
+  for (int q = 0; q < n_push; ++q) P.push_dst[q] = h_push_dst[q];
   return launch_bwd_main<true>(P, row_order_t, n_long, n_rows, st);
 }
 
@@ -867,6 +935,18 @@ extern "C" int gat_edge_bwd_finish(const int32_t* rowptr_t, const int32_t* col_t
                                        kEdgeThreads, 0, st>>>(P)
   GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
 #undef LAUNCH
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_slab_sum(const float* recv, int n_slabs, int64_t slab_rows, int dp, float* out, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(recv && out && n_slabs >= 1 && slab_rows >= 0 && dp > 0 && dp % 4 == 0, "gat_slab_sum: bad arguments");
+  const int64_t count4 = slab_rows * dp / 4;
+  if (count4 == 0) return GAT_OK;
+  const int64_t want = (count4 + 255) / 256;
+  slab_sum_kernel<<<(unsigned)(want < kNumSMs * 16 ? want : kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
+      recv, n_slabs, slab_rows * dp, count4, out);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }

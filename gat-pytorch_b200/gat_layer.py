@@ -138,7 +138,7 @@ class _GATFunction(torch.autograd.Function):
                           st.n_long_t, st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, s_src.data_ptr(), s_tgt.data_ptr(), gmax.data_ptr(),
                           z.data_ptr(), p_drop, seed, 0, go_p.data_ptr(), go_shared, s_sum.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
                           _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), None, 0, n, ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(),
-                          ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+                          None, 0, 0, 0, ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
             else:
                 rec = torch.empty((st.n_edges, 2 * nh), **f32) if not const_attention else None
                 # pass 1 (source-major, the only feature gather of the backward)

@@ -197,18 +197,36 @@ class CudaBackend:
                   0, 0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, 0, None, rec.data_ptr(), d_wh.data_ptr(),
                   ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
 
+    def recv_buffer(self, plan, dp, group):
+        """(P, rows_per_rank, dp) receive buffer of the fused reduce-scatter (one per model: a layer's slabs are summed
+        before the next layer's backward may write -- the (Gamma, |T|) all-reduce in between orders the ranks) plus its
+        address on every rank, or (None, None) when peer mapping is unavailable -> NCCL reduce-scatter."""
+        need = plan.n_pad * dp
+        cur = getattr(self, "_recv", None)
+        if cur is None or cur[0].numel() < need:
+            buf, ptrs = self.gathered_buffer(plan.n_pad, dp, group)
+            self._recv = (buf.view(-1), ptrs)
+        return self._recv
+
+    def slab_sum(self, recv, n_slabs, slab_rows, dp, out):
+        _lib.call("gat_slab_sum", recv.data_ptr(), n_slabs, slab_rows, dp, out.data_ptr(), self._s(out.device), tag=(n_slabs, dp))
+
     def edge_bwd_fused(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, s_sum_local,
-                       a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
+                       a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh, push_ptrs=None):
         """The backward's one heavy pass (gat_edge_bwd_fused) over ALL source rows with this rank's edges; target-indexed
-        arrays are local, so their base pointers are shifted by plan.lo rows (col_t holds GLOBAL target ids in [lo, hi))."""
+        arrays are local, so their base pointers are shifted by plan.lo rows (col_t holds GLOBAL target ids in [lo, hi)).
+        With push_ptrs (the ranks' receive buffers) every finished dWh row goes straight to its owner over NVLink."""
+        import ctypes
         dp, lo = nh * fp, plan.lo
         ws, ws_bytes = self._bwd_ws(go_p.device, nh)
+        arr = (ctypes.c_void_p * len(push_ptrs))(*push_ptrs) if push_ptrs else None
         _lib.call("gat_edge_bwd_fused", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
                   st.n_long_t, st.eid.data_ptr(), plan.n, wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(),
                   s_tgt_local.data_ptr() - 4 * nh * lo, gmax.data_ptr(), z_local.data_ptr() - 4 * nh * lo,
                   0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, 0, s_sum_local.data_ptr() - 4 * nh * lo,
                   a_src.data_ptr(), a_tgt.data_ptr(), tie_dst.data_ptr(), tie_src.data_ptr(), None, corr.data_ptr(),
-                  plan.lo, plan.hi, ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(), ws.data_ptr(), ws_bytes,
+                  plan.lo, plan.hi, ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr() if d_wh is not None else None,
+                  arr, len(push_ptrs) if push_ptrs else 0, plan.rank, plan.rows_per_rank, ws.data_ptr(), ws_bytes,
                   self._s(go_p.device), tag=(nh, fp))
 
     def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt):
@@ -282,9 +300,7 @@ class _PartitionedGATFunction(torch.autograd.Function):
         ds_tgt_full = torch.zeros((plan.n_pad + 1, nh), **f32)     # owned rows live at [lo, hi); the rest stays zero
         ds_tgt = ds_tgt_full[plan.lo:plan.lo + max(rows, 1)]
         s_sum = torch.zeros((max(rows, 1), nh), **f32)
-        d_wh_part = torch.empty((plan.n_pad, dp), **f32)            # rows [0, n) are all written by the source-major pass
-        if plan.n_pad > plan.n:
-            d_wh_part[plan.n:].zero_()
+        recv, push_ptrs = backend.recv_buffer(plan, dp, group) if hasattr(backend, "recv_buffer") else (None, None)
         ds_src_part = torch.zeros((plan.n_pad, nh), **f32)
         gamma = torch.zeros(1, dtype=torch.float64, device=dev)
         if rows:    # S = <dOut, out> over the owned rows first: no per-edge data needed
@@ -292,10 +308,21 @@ class _PartitionedGATFunction(torch.autograd.Function):
         red = torch.stack([gamma[0], tie_total.view(torch.int64)[0].to(torch.float64)])
         dist.all_reduce(red, group=group)                                   # (Gamma, |T|) over ranks
         corr = torch.where(red[1] > 0, red[0] / red[1].clamp(min=1.0), torch.zeros_like(red[0])).to(torch.float32).reshape(1)
-        backend.edge_bwd_fused(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, s_sum, a_src_p, a_tgt_p,
-                               tie_dst, tie_src, corr, ds_src_part, ds_tgt, d_wh_part)
         d_wh = torch.empty((R, dp), **f32)
-        dist.reduce_scatter_tensor(d_wh, d_wh_part, group=group)            # transpose of the all-gather
+        if push_ptrs is not None:
+            # fused reduce-scatter: the pass stores every finished dWh row into its owner's receive slab over NVLink;
+            # a tiny collective is the barrier, then the owner adds its P slabs in rank order
+            backend.edge_bwd_fused(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, s_sum, a_src_p, a_tgt_p,
+                                   tie_dst, tie_src, corr, ds_src_part, ds_tgt, None, push_ptrs=push_ptrs)
+            dist.all_reduce(torch.zeros(1, **f32), group=group)            # barrier: every rank's pushes have landed
+            backend.slab_sum(recv, plan.world, R, dp, d_wh)
+        else:
+            d_wh_part = torch.empty((plan.n_pad, dp), **f32)        # rows [0, n) are all written by the source-major pass
+            if plan.n_pad > plan.n:
+                d_wh_part[plan.n:].zero_()
+            backend.edge_bwd_fused(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, s_sum, a_src_p, a_tgt_p,
+                                   tie_dst, tie_src, corr, ds_src_part, ds_tgt, d_wh_part)
+            dist.reduce_scatter_tensor(d_wh, d_wh_part, group=group)        # transpose of the all-gather (NCCL)
         gx = None
         if ctx.needs_input_grad[0] and rows:
             gx = torch.empty((rows, f_in), **f32)

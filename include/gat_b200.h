@@ -217,7 +217,14 @@ GAT_API int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t, co
                                const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
                                const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
                                float* ds_src, float* ds_tgt, float* d_wh,
+                               float* const* h_push_dst, int n_push, int my_rank, int64_t rows_per_rank,
                                void* workspace, size_t workspace_bytes, gat_stream_t stream);
+/* PUSH mode of gat_edge_bwd_fused (partitioned graphs: the reduce-scatter of dWh fused into the pass).  With n_push = P > 0,
+ * h_push_dst is a HOST array of the P ranks' receive buffers, each (P, rows_per_rank, dp) floats and mapped into this
+ * process (peer / symmetric memory); the finished dWh row of source `row` is stored into slab `my_rank`, row
+ * row - owner*rows_per_rank of its owner's buffer (owner = row / rows_per_rank) instead of d_wh.  After a cross-rank barrier
+ * the owner adds its P slabs in rank order with gat_slab_sum.  n_push = 0: plain d_wh (n_rows, dp). */
+GAT_API int gat_slab_sum(const float* recv, int n_slabs, int64_t slab_rows, int dp, float* out, gat_stream_t stream);
 
 /* Pass 2 (CSR by target, rows = owned TARGET nodes): s_sum[d,h] = sum_e alpha*d_alpha over the in-edges of d (records
  * gathered through tpos = CSR^T slot of each CSR slot); ds_tgt[d,h] = sum_e g = 0.01*s_sum*eps/(z+eps) (before the arg-max

@@ -73,7 +73,8 @@ class OracleBackend:
         d_wh.view(-1, nh, fp).index_add_(0, st["src"], alpha[:, :, None] * go_e)
 
     def edge_bwd_fused(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, s_sum_local,
-                       a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh):
+                       a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh, push_ptrs=None):
+        assert push_ptrs is None   # peer-memory push is a CUDA-only path (the oracle backend has no recv_buffer)
         rec = torch.zeros((max(self.n_edges(st), 1), 2 * nh))
         self.edge_bwd_main(st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh)
         self.edge_bwd_finish(st, plan, nh, fp, rec, s_sum_local, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh)
