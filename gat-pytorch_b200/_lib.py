@@ -32,9 +32,11 @@ SIGNATURES = {
     "gat_gemm_tc_supported": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64]),
     "gat_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64,
                          c_int, _P, c_size_t, _P]),
-    "gat_project_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, _P, _P,
+    "gat_gemm_ex": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64,
+                            c_int, c_int, _P, c_int64, c_int, _P, c_size_t, _P]),
+    "gat_project_fwd": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, _P, c_int, _P, _P, _P,
                                 c_int, _P, c_size_t, _P]),
-    "gat_project_fwd_allgather": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, c_int, c_int64,
+    "gat_project_fwd_allgather": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, _P, c_int, _P, c_int, c_int64,
                                           _P, _P, _P]),
     "gat_scores_fwd": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P]),
     "gat_scores_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -42,7 +44,7 @@ SIGNATURES = {
     "gat_edge_max": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, c_int, _P, _P, c_size_t, _P]),
     "gat_edge_fwd_workspace_bytes": (c_size_t, []),
     "gat_edge_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, c_int, c_int, _P, _P, _P, c_int, c_float, c_uint64, c_uint64,
-                             _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+                             _P, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gat_head_merge_fwd": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "gat_head_merge_bwd": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "gat_edge_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
@@ -51,10 +53,13 @@ SIGNATURES = {
     "gat_edge_bwd_fused": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P,
                                    c_float, c_uint64, c_uint64, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
                                    _P, _P, _P, _P, c_int, c_int, c_int64, _P, c_size_t, _P]),
+    "gat_attention_norm_workspace_bytes": (c_size_t, []),
+    "gat_attention_norm_fwd": (c_int, [_P, c_int, _P, _P, c_int64, c_int, _P, _P, c_size_t, _P]),
+    "gat_attention_norm_bwd": (c_int, [_P, c_int, _P, _P, c_int64, c_int, _P, _P, _P]),
     "gat_slab_sum": (c_int, [_P, c_int, c_int64, c_int, _P, _P]),
     "gat_head_mean_bwd_shared": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
     "gat_edge_bwd_rowsum": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "gat_edge_bwd_rowdot": (c_int, [_P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_rowdot": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_finish": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
                                     _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_gamma": (c_int, [_P, c_size_t, _P, _P]),

@@ -101,10 +101,12 @@ __device__ __forceinline__ LaneShape<SLOTS> make_lane_shape(const BwdMainParams&
   return L;
 }
 
-template <int G, int SLOTS, int NHT, bool COOP, bool FUSED>
-__device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneShape<SLOTS>& L, const int64_t row, const int tid,
-                                             const int gl, const int gbase, const unsigned gmask, const float gmax, const float corr,
-                                             int* sh_dst, const float** sh_gp, float* sh_w, float* sh_da, float* part, float* coop) {
+// FULL: the row has exactly SLOTS*G chunks (e.g. products' 256 floats), so every slot of every lane exists and the
+// per-slot predicates fold away at compile time.
+template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL>
+__device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneShape<SLOTS>& L, const int64_t row, const int start,
+                                             const int end, const int tid, const int gl, const int gbase, const unsigned gmask, const float gmax, const float corr,
+                                             int* sh_dst, const float** sh_gp, float* sh_w, float* sh_da, float* sh_s, float* part, float* coop) {
   constexpr int TB = MainShape<G, SLOTS>::TB, U = MainShape<G, SLOTS>::U;
   constexpr int PSTRIDE = MainShape<G, SLOTS>::PSTRIDE;   // compile-time stride of the transpose tile rows
   constexpr int NG = kEdgeThreads / G;
@@ -115,12 +117,23 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-    whr[s] = (L.ok[s] && !P.const_attention) ? ldg4(P.wh + row * P.dp + (s * G + gl) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    whr[s] = ((FULL || L.ok[s]) && (FUSED || !P.const_attention)) ? ldg4(P.wh + row * P.dp + (s * G + gl) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const int start = __ldg(P.rowptr_t + row), end = __ldg(P.rowptr_t + row + 1);
   float ss[NHT], gsum[NHT];
 #pragma unroll
-  for (int h = 0; h < NHT; ++h) { ss[h] = (!P.const_attention && h < nh) ? __ldg(P.s_src + row * nh + h) : 0.f; gsum[h] = 0.f; }
+  for (int h = 0; h < NHT; ++h) { ss[h] = ((FUSED || !P.const_attention) && h < nh) ? __ldg(P.s_src + row * nh + h) : 0.f; gsum[h] = 0.f; }
+  // FUSED, group per row: lane h < nh prefetches the row's tie counts / ds_tgt now, so the epilogue needs no extra round trip
+  const bool own_tgt = FUSED && row >= P.tgt_lo && row < P.tgt_hi;
+  const int64_t trow = row - P.tgt_lo;
+  int p_ts = 0, p_td = 0;
+  float p_t = 0.f;
+  if (FUSED && !COOP && gl < nh) {
+    if (P.tie_src) p_ts = __ldg(P.tie_src + row * nh + gl);
+    if (own_tgt) {
+      if (P.tie_dst) p_td = __ldg(P.tie_dst + trow * nh + gl);
+      p_t = P.ds_tgt[trow * nh + gl];
+    }
+  }
   const float* wbase[SLOTS];   // this lane's weight of edge k in slot s: wbase[s][k * NHT]
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) wbase[s] = sh_w + gbase * NHT + L.head[s];
@@ -134,14 +147,24 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
     if (valid) {
       const int d = __ldg(P.col_t + e);
       const float* zp = P.z + (int64_t)d * nh;
-      if (P.const_attention) {
+      if (!FUSED && P.const_attention) {
 #pragma unroll
         for (int h = 0; h < NHT; ++h) alpha[h] = h < nh ? 1.f / (__ldg(zp + h) + kSoftmaxEps) : 0.f;
       } else {
         const float* tp = P.s_tgt + (int64_t)d * nh;
+        float sv[NHT];
+        if (FUSED) {   // S[dst] travels with s_tgt[dst] / Z[dst] (same round trip) and waits in shared memory
+          const float* sp = P.s_sum + (int64_t)d * nh;
+#pragma unroll
+          for (int h = 0; h < NHT; ++h) sv[h] = h < nh ? __ldg(sp + h) : 0.f;
+        }
 #pragma unroll
         for (int h = 0; h < NHT; ++h)
           if (h < nh) alpha[h] = attn_exp(ss[h] + __ldg(tp + h), gmax) / (__ldg(zp + h) + kSoftmaxEps);
+        if (FUSED) {
+#pragma unroll
+          for (int h = 0; h < NHT; ++h) sh_s[tid * NHT + h] = sv[h];
+        }
       }
       if (P.dropout_p > 0.f || P.grad_alpha) {
         const int edge_id = __ldg(P.eid + __ldg(P.pos_t + e));
@@ -172,7 +195,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
             const float* rowp = sh_gp[gbase + k0 + u];
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s)
-              v[u][s] = L.ok[s] ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[u][s] = (FULL || L.ok[s]) ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         } else {
 #pragma unroll
@@ -181,7 +204,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
             const float* rowp = sh_gp[gbase + (on ? k0 + u : k0)];
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s)
-              v[u][s] = (on && L.ok[s]) ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[u][s] = (on && (FULL || L.ok[s])) ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         float* prow = part + tt * PSTRIDE + gl;
@@ -195,7 +218,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
               acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
               acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
               acc[s].w = fmaf(w, v[u][s].w, acc[s].w);
-              if (L.ok[s] && !P.const_attention) {
+              if ((FULL || L.ok[s]) && (FUSED || !P.const_attention)) {
                 float dd = whr[s].x * v[u][s].x;
                 dd = fmaf(whr[s].y, v[u][s].y, dd);
                 dd = fmaf(whr[s].z, v[u][s].z, dd);
@@ -206,7 +229,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
           }
         }
       }
-      if (!P.const_attention) {
+      if ((FUSED || !P.const_attention)) {
         __syncwarp(gmask);
         // transpose-reduce: (edge, head) pair q sums the chunks of that head (four independent partial sums)
         for (int q = gl; q < tcnt * nh; q += G) {
@@ -222,12 +245,11 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
         __syncwarp(gmask);
       }
     }
-    if (valid && !P.const_attention) {
+    if (valid && (FUSED || !P.const_attention)) {
       if (FUSED) {   // g = 0.01*alpha*(d_alpha - S[dst]), summed per source row  
-        const float* sp = P.s_sum + (int64_t)sh_dst[tid] * nh;
 #pragma unroll
         for (int h = 0; h < NHT; ++h)
-          if (h < nh) gsum[h] = fmaf(kLeakySlope * alpha[h], fmaf(msk[h], sh_da[tid * NHT + h], ga[h]) - __ldg(sp + h), gsum[h]);
+          if (h < nh) gsum[h] = fmaf(kLeakySlope * alpha[h], fmaf(msk[h], sh_da[tid * NHT + h], ga[h]) - sh_s[tid * NHT + h], gsum[h]);
       } else {
         float* r = P.rec + (int64_t)e * 2 * nh;
 #pragma unroll
@@ -239,26 +261,22 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
   }
   float* const drow = dwh_row_ptr(P, row);
   // FUSED epilogue inputs: ds_src = sum g - |T_src|*Gamma/|T|, ds_tgt -= |T_dst|*Gamma/|T| (gradient through max())
-  const bool own_tgt = FUSED && row >= P.tgt_lo && row < P.tgt_hi;
-  const int64_t trow = row - P.tgt_lo;
   float dss[NHT], dst_[NHT];
 #pragma unroll
   for (int h = 0; h < NHT; ++h) { dss[h] = 0.f; dst_[h] = 0.f; }
-  if (FUSED && !COOP && !P.const_attention) {
+  if (FUSED && !COOP && (FUSED || !P.const_attention)) {
 #pragma unroll
     for (int h = 0; h < NHT; ++h) {
       if (h < nh) {
         const float g = group_sum<G>(gsum[h], gmask);
-        const int ts = P.tie_src ? __ldg(P.tie_src + row * nh + h) : 0;
+        const int src_lane = (tid & 31 & ~(G - 1)) + h;     // lane h of this group holds head h's prefetched values
+        const int ts = __shfl_sync(gmask, p_ts, src_lane);
+        const int td = __shfl_sync(gmask, p_td, src_lane);
+        const float t = __shfl_sync(gmask, p_t, src_lane);
         dss[h] = ts ? g - (float)ts * corr : g;
-        if (own_tgt) {
-          const int td = P.tie_dst ? __ldg(P.tie_dst + trow * nh + h) : 0;
-          const float t = P.ds_tgt[trow * nh + h];
-          dst_[h] = td ? t - (float)td * corr : t;
-        }
+        if (own_tgt) dst_[h] = td ? t - (float)td * corr : t;
       }
     }
-    __syncwarp(gmask);   // every lane has read ds_tgt before lane 0 overwrites it
     if (gl == 0) {
 #pragma unroll
       for (int h = 0; h < NHT; ++h)
@@ -269,7 +287,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
     }
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
-      if (L.ok[s]) {
+      if ((FULL || L.ok[s])) {
         const int c = s * G + gl;
 #pragma unroll
         for (int h = 0; h < NHT; ++h) {
@@ -289,9 +307,9 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
     __syncthreads();   // every group is done with its `part` tile, which `coop` aliases
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s)
-      if (L.ok[s]) *reinterpret_cast<float4*>(coop + grp * P.dp + (s * G + gl) * 4) = acc[s];
+      if ((FULL || L.ok[s])) *reinterpret_cast<float4*>(coop + grp * P.dp + (s * G + gl) * 4) = acc[s];
     float* coop_g = coop + NG * P.dp;   // [NG][NHT] per-group sums of g
-    if (FUSED && !P.const_attention) {
+    if (FUSED && (FUSED || !P.const_attention)) {
 #pragma unroll
       for (int h = 0; h < NHT; ++h) gsum[h] = group_sum<G>(gsum[h], gmask);
       if (gl == 0) {
@@ -300,7 +318,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
       }
     }
     __syncthreads();
-    if (FUSED && !P.const_attention) {
+    if (FUSED && (FUSED || !P.const_attention)) {
 #pragma unroll
       for (int h = 0; h < NHT; ++h) {
         if (h < nh) {
@@ -331,7 +349,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
         const float4 v = *reinterpret_cast<const float4*>(coop + j * P.dp + c * 4);
         t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
       }
-      if (FUSED && !P.const_attention) {
+      if (FUSED && (FUSED || !P.const_attention)) {
 #pragma unroll
         for (int h = 0; h < NHT; ++h) {
           if (h < nh) {
@@ -350,11 +368,11 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
   } else {
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s)
-      if (L.ok[s]) *reinterpret_cast<float4*>(drow + (s * G + gl) * 4) = acc[s];
+      if ((FULL || L.ok[s])) *reinterpret_cast<float4*>(drow + (s * G + gl) * 4) = acc[s];
   }
 }
 
-template <int G, int SLOTS, int NHT, bool COOP, bool FUSED>
+template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL>
 __global__ void __launch_bounds__(kEdgeThreads, (SLOTS <= 2 ? 3 : (SLOTS <= 4 ? 2 : 1)))
 edge_bwd_main_kernel(const BwdMainParams P) {
   constexpr int TB = MainShape<G, SLOTS>::TB;
@@ -363,6 +381,7 @@ edge_bwd_main_kernel(const BwdMainParams P) {
   __shared__ float sh_w[kEdgeThreads * NHT];
   __shared__ float sh_da[kEdgeThreads * NHT];
   __shared__ const float* sh_gp[kEdgeThreads];
+  __shared__ float sh_s[FUSED ? kEdgeThreads * NHT : 1];
   const int tid = threadIdx.x, lane = tid & 31, gl = tid & (G - 1), gbase = tid - gl;
   const unsigned gmask = group_mask<G>(lane);
   const LaneShape<SLOTS> L = make_lane_shape<G, SLOTS>(P, gl);
@@ -375,16 +394,20 @@ edge_bwd_main_kernel(const BwdMainParams P) {
     for (;;) {
       const int64_t row = grab_long_row(P.sched, P.rowptr_t, &sh_ctl);
       if (row < 0) break;
-      bwd_main_row<G, SLOTS, NHT, true, FUSED>(P, L, row, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, part, dyn_smem);
+      bwd_main_row<G, SLOTS, NHT, true, FUSED, FULL>(P, L, row, __ldg(P.rowptr_t + row), __ldg(P.rowptr_t + row + 1), tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, sh_s, part, dyn_smem);
     }
   } else {
     int64_t base;
     while (grab_rows<G>(P.sched, lane, base)) {
+      int pr, ps, pe;
+      prefetch_rows<G>(P.sched, P.rowptr_t, base, lane, pr, ps, pe);
 #pragma unroll 1
-      for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
-        const int64_t row = sched_row<G>(P.sched, base, k, lane);
-        if (row >= 0 && !taken_by_cta_phase(P.sched, P.rowptr_t, row))
-          bwd_main_row<G, SLOTS, NHT, false, FUSED>(P, L, row, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, part, nullptr);
+      for (int k = 0; k < kGrabIters<G>; ++k) {
+        int64_t row;
+        int start, end;
+        if (prefetched_row<G>(P.sched, k, lane, pr, ps, pe, row, start, end))
+          bwd_main_row<G, SLOTS, NHT, false, FUSED, FULL>(P, L, row, start, end, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da,
+                                                          sh_s, part, nullptr);
       }
     }
     pdl_wait_for_primary();     // no-op unless launched behind the cooperative kernel
@@ -489,9 +512,20 @@ edge_bwd_rowsum_kernel(const BwdRowsumParams P) {
 struct BwdRowdotParams {
   const float* go; const float* out; const float* z; int64_t n; int nh; int dp; int chunks; int chunks_per_head;
   int go_ld; int go_shared;
+  // out_is_act: `out` holds ELU(out) (gat_edge_fwd out_act) and `go` is the gradient w.r.t. that activated output; the pass
+  // then recovers out = h > 0 ? h : log1p(h) and ELU'(out) = h > 0 ? 1 : h + 1, forms the gradient w.r.t. the pre-activation
+  // output go*ELU', writes it to go_out (what the source-major pass gathers) and uses it in S -- the ELU backward fused.
+  int out_is_act; float* go_out;
   float* s_sum; float* ds_tgt;
 };
 
+// out = log1p(h) for h in (-1, 0], cheaply: the series where 1 + h would round away h's low bits, the fast log elsewhere
+// (|error| <= ~1e-7 absolute; the term it enters, go*ELU'*out, is scaled by ELU' = h + 1 wherever out is large).
+__device__ __forceinline__ float log1p_neg_fast(float h) {
+  return h > -1e-3f ? h * fmaf(h, fmaf(h, 0.33333334f, -0.5f), 1.0f) : __logf(1.0f + h);
+}
+
+template <int NHT>
 __global__ void __launch_bounds__(256)
 edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
   constexpr int R = 4;   // rows per warp iteration: 2*R*chunks/32 independent 16-byte loads in flight per lane
@@ -499,11 +533,11 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
   const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
   const int nh = P.nh;
   for (int64_t row0 = warp * R; row0 < P.n; row0 += nwarps * R) {
-    float s[R][kMaxHeads];
+    float s[R][NHT];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h) s[r][h] = 0.f;
+      for (int h = 0; h < NHT; ++h) s[r][h] = 0.f;
     for (int c = lane; c < P.chunks; c += 32) {
       float4 g[R], o[R];
 #pragma unroll
@@ -513,17 +547,32 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
         o[r] = on ? ldg4(P.out + (row0 + r) * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const int hh = c / P.chunks_per_head;
+      if (P.out_is_act) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float* gv = reinterpret_cast<float*>(&g[r]);
+          float* ov = reinterpret_cast<float*>(&o[r]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float h = ov[j];
+            const bool neg = h <= 0.f;
+            gv[j] = neg ? gv[j] * (h + 1.0f) : gv[j];      // dL/dout = dL/dh * ELU'(out)
+            ov[j] = neg ? log1p_neg_fast(h) : h;           // out recovered from h = ELU(out)
+          }
+          if (row0 + r < P.n) *reinterpret_cast<float4*>(P.go_out + (row0 + r) * P.dp + c * 4) = g[r];
+        }
+      }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const float d = fmaf(g[r].x, o[r].x, fmaf(g[r].y, o[r].y, fmaf(g[r].z, o[r].z, g[r].w * o[r].w)));
 #pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h) s[r][h] += (h == hh) ? d : 0.f;
+        for (int h = 0; h < NHT; ++h) s[r][h] += (h == hh) ? d : 0.f;
       }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
 #pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h) {
+      for (int h = 0; h < NHT; ++h) {
         if (h < nh) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) s[r][h] += __shfl_xor_sync(0xffffffffu, s[r][h], o);
@@ -531,7 +580,7 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
       }
       if (lane == 0 && row0 + r < P.n) {
 #pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h) {
+        for (int h = 0; h < NHT; ++h) {
           if (h < nh) {
             const float zz = __ldg(P.z + (row0 + r) * nh + h);
             P.s_sum[(row0 + r) * nh + h] = s[r][h];
@@ -705,7 +754,7 @@ edge_bwd_finish_kernel(const BwdFinishParams P) {
   int64_t base;
   while (grab_rows<G>(P.sched, lane, base)) {
 #pragma unroll 1
-    for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
+    for (int k = 0; k < kGrabIters<G>; ++k) {
       const int64_t row = sched_row<G>(P.sched, base, k, lane);
       if (row >= 0 && !taken_by_cta_phase(P.sched, P.rowptr_t, row))
         bwd_finish_row<G, SLOTS, NHT, false>(P, row, gl, gmask, corr, nullptr);
@@ -754,26 +803,40 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
     return GAT_EUNSUPPORTED;
   }
   const bool coop_launch = row_order_t != nullptr && n_long != 0;
-  if (coop_launch) {   // long source rows first, CTA per row; the short-row launch overlaps its tail
-    const int64_t ctas = n_long < 0 ? n_rows : n_long;
-#define LAUNCH(G_, S_, N_)                                                                                            \
-  GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, true, FUSED>,                                               \
-                         persistent_grid(edge_bwd_main_kernel<G_, S_, N_, true, FUSED>, kEdgeThreads,                 \
-                                         main_dyn_smem<G_, S_>(P.chunks), ctas),                                      \
-                         kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, false))
-    GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
-#undef LAUNCH
-    GAT_LAUNCH_CHECK();
-  }
-#define LAUNCH(G_, S_, N_)                                                                                            \
-  GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, false, FUSED>,                                              \
-                         persistent_grid(edge_bwd_main_kernel<G_, S_, N_, false, FUSED>, kEdgeThreads,                \
-                                         main_dyn_smem<G_, S_>(P.chunks),                                             \
-                                         (n_rows + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)),                   \
-                         kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, coop_launch))
+  const bool full = FUSED && P.chunks == shape.g * shape.slots && !P.go_shared;   // predicate-free instantiation
+#define LAUNCH_BOTH(G_, S_, N_, FULL_)                                                                                 \
+  do {                                                                                                                 \
+    /* static + dynamic shared memory can exceed the 48 KB default (wide rows, 8 heads): opt in once per size */       \
+    static size_t optin_ = 0;                                                                                          \
+    if (main_dyn_smem<G_, S_>(P.chunks) > optin_) {                                                                    \
+      optin_ = main_dyn_smem<G_, S_>(P.chunks);                                                                        \
+      GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<G_, S_, N_, true, FUSED, FULL_>,                              \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin_));                        \
+      GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<G_, S_, N_, false, FUSED, FULL_>,                             \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin_));                        \
+    }                                                                                                                  \
+    if (coop_launch) {   /* long source rows first, CTA per row; the short-row launch overlaps its tail */             \
+      GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, true, FUSED, FULL_>,                                     \
+                             persistent_grid(edge_bwd_main_kernel<G_, S_, N_, true, FUSED, FULL_>, kEdgeThreads,       \
+                                             main_dyn_smem<G_, S_>(P.chunks), n_long < 0 ? n_rows : n_long),           \
+                             kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, false));                            \
+      GAT_LAUNCH_CHECK();                                                                                              \
+    }                                                                                                                  \
+    GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, false, FUSED, FULL_>,                                      \
+                           persistent_grid(edge_bwd_main_kernel<G_, S_, N_, false, FUSED, FULL_>, kEdgeThreads,        \
+                                           main_dyn_smem<G_, S_>(P.chunks),                                            \
+                                           (n_rows + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)),                  \
+                           kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, coop_launch));                        \
+    GAT_LAUNCH_CHECK();                                                                                                \
+  } while (0)
+#define LAUNCH(G_, S_, N_)                                                                                             \
+  do {                                                                                                                 \
+    if (FUSED && full) LAUNCH_BOTH(G_, S_, N_, FUSED);                                                                 \
+    else LAUNCH_BOTH(G_, S_, N_, false);                                                                               \
+  } while (0)
   GAT_DISPATCH_GROUP(shape, nh, LAUNCH);
 #undef LAUNCH
-  GAT_LAUNCH_CHECK();
+#undef LAUNCH_BOTH
   return GAT_OK;
 }
 
@@ -868,19 +931,24 @@ extern "C" int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, c
   return GAT_OK;
 }
 
-extern "C" int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const float* out_padded, const float* z, int64_t n_rows, int nh, int fp,
+extern "C" int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const float* out_padded, int out_is_act, float* go_out,
+                                   const float* z, int64_t n_rows, int nh, int fp,
                                    float* s_sum, float* ds_tgt, void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
   int rc = check_common("gat_edge_bwd_rowdot", nh, fp, workspace, workspace_bytes);
   if (rc) return rc;
+  GAT_CHECK_ARG(!out_is_act || (go_out != nullptr && !go_shared), "gat_edge_bwd_rowdot: out_is_act needs go_out and an unshared gradient");
   if (n_rows == 0) return GAT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   BwdRowdotParams P;
   P.go = go_padded; P.out = out_padded; P.z = z; P.n = n_rows; P.nh = nh; P.dp = nh * fp; P.chunks = nh * fp / 4;
   P.chunks_per_head = fp / 4; P.s_sum = s_sum; P.ds_tgt = ds_tgt;
   P.go_shared = go_shared ? 1 : 0; P.go_ld = go_shared ? fp : nh * fp;
+  P.out_is_act = out_is_act ? 1 : 0; P.go_out = go_out;
   int64_t want = (n_rows + 31) / 32;
-  edge_bwd_rowdot_kernel<<<(unsigned)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8), 256, 0, st>>>(P);
+  const unsigned grid = (unsigned)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8);
+  if (nh <= 4) edge_bwd_rowdot_kernel<4><<<grid, 256, 0, st>>>(P);
+  else edge_bwd_rowdot_kernel<8><<<grid, 256, 0, st>>>(P);
   GAT_LAUNCH_CHECK();
   gamma_partial_kernel<<<kGammaBlocks, 256, 0, st>>>(ds_tgt, n_rows * nh, (BwdHeader*)workspace, (double*)((char*)workspace + kBwdHeaderBytes));
   GAT_LAUNCH_CHECK();

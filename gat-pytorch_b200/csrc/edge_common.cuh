@@ -107,9 +107,12 @@ __device__ __forceinline__ bool taken_by_cta_phase(const RowSched& S, const int3
   return S.order != nullptr && (__ldg(rowptr + row + 1) - __ldg(rowptr + row)) > kLongRow;
 }
 
+// A warp takes kGrabIters<G> rounds of 32/G rows per grab (never more than 32 rows: one prefetched entry per lane).
+template <int G> constexpr int kGrabIters = G == 32 ? 4 : (G == 1 ? 1 : 2);
+
 template <int G>
 __device__ __forceinline__ bool grab_rows(const RowSched& S, int lane, int64_t& base) {
-  constexpr int kRowsPerGrab = (32 / G) * (G == 32 ? 4 : 2);
+  constexpr int kRowsPerGrab = (32 / G) * kGrabIters<G>;
   __syncwarp();
   unsigned int b = 0;
   if (lane == 0) b = atomicAdd(S.counter, (unsigned int)kRowsPerGrab);
@@ -123,6 +126,33 @@ __device__ __forceinline__ int64_t sched_row(const RowSched& S, int64_t base, in
   const int64_t idx = base + (int64_t)k * (32 / G) + lane / G;
   if (idx >= S.n) return -1;
   return S.order ? (int64_t)__ldg(S.order + idx) : idx;
+}
+
+// Row metadata of a whole grab, fetched by the first lanes in ONE round trip (order[idx] -> rowptr[row], rowptr[row+1]) instead
+// of two dependent loads per row on the critical path of every row; iteration k reads its entry with shuffles.
+template <int G>
+__device__ __forceinline__ void prefetch_rows(const RowSched& S, const int32_t* rowptr, const int64_t base, const int lane,
+                                              int& pr, int& ps, int& pe) {
+  constexpr int kRowsPerGrab = (32 / G) * kGrabIters<G>;
+  static_assert(kRowsPerGrab <= 32, "one prefetched row per lane");
+  pr = -1; ps = 0; pe = 0;
+  const int64_t idx = base + lane;
+  if (lane < kRowsPerGrab && idx < S.n) {
+    pr = S.order ? __ldg(S.order + idx) : (int)idx;
+    ps = __ldg(rowptr + pr);
+    pe = __ldg(rowptr + pr + 1);
+  }
+}
+
+// Entry of iteration k for this lane's group; returns false when there is no row (or the cooperative phase owns it).
+template <int G>
+__device__ __forceinline__ bool prefetched_row(const RowSched& S, const int k, const int lane, const int pr, const int ps, const int pe,
+                                               int64_t& row, int& start, int& end) {
+  const int j = k * (32 / G) + lane / G;
+  row = (int64_t)__shfl_sync(0xffffffffu, pr, j);
+  start = __shfl_sync(0xffffffffu, ps, j);
+  end = __shfl_sync(0xffffffffu, pe, j);
+  return row >= 0 && !(S.order != nullptr && end - start > kLongRow);
 }
 
 // Host-side choice of (G, SLOTS) for a padded row of `chunks` float4s.

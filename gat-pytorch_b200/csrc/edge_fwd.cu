@@ -77,8 +77,14 @@ struct EdgeFwdParams {
   const float* s_src; const float* s_tgt; const float* gmax;
   int const_attention; float dropout_p; uint64_t seed; uint64_t offset;
   float* out; float* alpha_out; float* z_out;
+  int out_act;   // 1: the stored row is ELU(out) -- the F.elu that follows a hidden layer (GATModel.py:148-149), fused
   int32_t* tie_dst; int32_t* tie_src; unsigned long long* tie_total;
 };
+
+__device__ __forceinline__ float4 elu_f4(float4 v) {
+  return make_float4(v.x > 0.f ? v.x : expm1f(v.x), v.y > 0.f ? v.y : expm1f(v.y), v.z > 0.f ? v.z : expm1f(v.z),
+                     v.w > 0.f ? v.w : expm1f(v.w));
+}
 
 template <int NHT>
 __device__ __forceinline__ void edge_probs(const EdgeFwdParams& P, int e, bool valid, const float (&st)[NHT],
@@ -109,7 +115,7 @@ __device__ __forceinline__ void edge_probs(const EdgeFwdParams& P, int e, bool v
 // batches round-robin; Z and the output row are combined over the groups through `coop` (NG*dp floats of dynamic
 // shared memory) in group order.  Called by ALL threads of the CTA in that case.
 template <int G, int SLOTS, int NHT, bool COOP>
-__device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64_t row, const int tid, const int gl,
+__device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64_t row, const int start, const int end, const int tid, const int gl,
                                              const int gbase, const unsigned gmask, const float gmax,
                                              int* sh_src, float* sh_w, float* coop) {
   constexpr int U = SLOTS >= 4 ? 2 : (SLOTS >= 2 ? 4 : 8);
@@ -127,7 +133,6 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
     head[s] = ok[s] ? c / P.chunks_per_head : 0;
     acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const int start = __ldg(P.rowptr + row), end = __ldg(P.rowptr + row + 1);
   float st[NHT];
 #pragma unroll
   for (int h = 0; h < NHT; ++h) st[h] = (!P.const_attention && h < nh) ? __ldg(P.s_tgt + row * nh + h) : 0.f;
@@ -245,13 +250,14 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
         const float4 v = *reinterpret_cast<const float4*>(coop + j * P.dp + c * 4);
         t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
       }
+      if (P.out_act) t = elu_f4(t);
       *reinterpret_cast<float4*>(P.out + row * P.dp + c * 4) = t;
     }
     // the next grab_long_row() starts with a __syncthreads(), which also protects `coop`
   } else {
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s)
-      if (ok[s]) *reinterpret_cast<float4*>(P.out + row * P.dp + (s * G + gl) * 4) = acc[s];
+      if (ok[s]) *reinterpret_cast<float4*>(P.out + row * P.dp + (s * G + gl) * 4) = P.out_act ? elu_f4(acc[s]) : acc[s];
   }
 }
 
@@ -272,16 +278,19 @@ edge_fwd_kernel(const EdgeFwdParams P) {
     for (;;) {
       const int64_t row = grab_long_row(P.sched, P.rowptr, &sh_ctl);
       if (row < 0) break;
-      edge_fwd_row<G, SLOTS, NHT, true>(P, row, tid, gl, gbase, gmask, gmax, sh_src, sh_w, coop);
+      edge_fwd_row<G, SLOTS, NHT, true>(P, row, __ldg(P.rowptr + row), __ldg(P.rowptr + row + 1), tid, gl, gbase, gmask, gmax, sh_src, sh_w, coop);
     }
   } else {
     int64_t base;
     while (grab_rows<G>(P.sched, lane, base)) {
+      int pr, ps, pe;
+      prefetch_rows<G>(P.sched, P.rowptr, base, lane, pr, ps, pe);
 #pragma unroll 1
-      for (int k = 0; k < (G == 32 ? 4 : 2); ++k) {
-        const int64_t row = sched_row<G>(P.sched, base, k, lane);
-        if (row >= 0 && !taken_by_cta_phase(P.sched, P.rowptr, row))
-          edge_fwd_row<G, SLOTS, NHT, false>(P, row, tid, gl, gbase, gmask, gmax, sh_src, sh_w, nullptr);
+      for (int k = 0; k < kGrabIters<G>; ++k) {
+        int64_t row;
+        int start, end;
+        if (prefetched_row<G>(P.sched, k, lane, pr, ps, pe, row, start, end))
+          edge_fwd_row<G, SLOTS, NHT, false>(P, row, start, end, tid, gl, gbase, gmask, gmax, sh_src, sh_w, nullptr);
       }
     }
     pdl_wait_for_primary();     // no-op unless launched behind the cooperative kernel
@@ -359,7 +368,7 @@ extern "C" size_t gat_edge_fwd_workspace_bytes(void) { return 256; }
 extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
                             int64_t n, const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
                             const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
-                            float* out, float* alpha_out, float* z_out,
+                            float* out, int out_act, float* alpha_out, float* z_out,
                             int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
                             void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
@@ -377,7 +386,7 @@ extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int
   P.chunks = nh * fp / 4; P.chunks_per_head = fp / 4;
   P.s_src = s_src; P.s_tgt = s_tgt; P.gmax = gmax; P.const_attention = const_attention;
   P.dropout_p = dropout_p; P.seed = seed; P.offset = offset;
-  P.out = out; P.alpha_out = alpha_out; P.z_out = z_out;
+  P.out = out; P.alpha_out = alpha_out; P.z_out = z_out; P.out_act = out_act ? 1 : 0;
   P.tie_dst = const_attention ? nullptr : tie_dst; P.tie_src = const_attention ? nullptr : tie_src;
   P.tie_total = const_attention ? nullptr : tie_total;
   GroupShape shape = pick_group(P.chunks);

@@ -12,7 +12,7 @@ template <int BM, int BN, bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda,
                  const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
-                 int64_t k_chunk, int64_t c_split_stride) {
+                 int64_t k_chunk, int64_t c_split_stride, int act_a, int act_b, const float* __restrict__ mul_src, int64_t mul_ld) {
   constexpr int TM = BM / 16, TN = BN / 16;
   __shared__ __align__(16) float As[kBK][BM + 4];
   __shared__ __align__(16) float Bs[kBK][BN + 4];
@@ -36,6 +36,7 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, i
       int64_t gm = m0 + m, gk = k0 + k;
       float v = 0.f;
       if (gm < M && gk < k_end) v = TA ? A[gk * lda + gm] : A[gm * lda + gk];
+      if (act_a) v = v > 0.f ? v : expm1f(v);        // fused glue: ELU on the operand
       As[k][m] = v;
     }
 #pragma unroll
@@ -46,6 +47,7 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, i
       int64_t gn = n0 + n, gk = k0 + k;
       float v = 0.f;
       if (gn < N && gk < k_end) v = TB ? B[gn * ldb + gk] : B[gk * ldb + gn];
+      if (act_b) v = v > 0.f ? v : expm1f(v);
       Bs[k][n] = v;
     }
     __syncthreads();
@@ -77,24 +79,30 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, i
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int64_t gn = n0 + tx * 4 + (j / 4) * 64 + (j % 4);
-      if (gn < N) Cz[gm * ldc + gn] = acc[i][j];
+      if (gn < N) {
+        float v = acc[i][j];
+        if (mul_src != nullptr) { const float x = mul_src[gm * mul_ld + gn]; v *= x > 0.f ? 1.f : expf(x); }   // ELU'(x)
+        Cz[gm * ldc + gn] = v;
+      }
     }
   }
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ P, int splits, int64_t M, int64_t N,
-                                     float* __restrict__ C, int64_t ldc) {
+                                     float* __restrict__ C, int64_t ldc, const float* __restrict__ mul_src, int64_t mul_ld) {
   int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= M * N) return;
   double s = 0.0;
   for (int z = 0; z < splits; ++z) s += (double)P[(int64_t)z * M * N + idx];
-  C[(idx / N) * ldc + (idx % N)] = (float)s;
+  float v = (float)s;
+  if (mul_src != nullptr) { const float x = mul_src[(idx / N) * mul_ld + (idx % N)]; v *= x > 0.f ? 1.f : expf(x); }
+  C[(idx / N) * ldc + (idx % N)] = v;
 }
 
 namespace tc {
 void splitk_reduce_launch(const float* partial, int splits, int64_t m, int64_t n, float* c, int64_t ldc, cudaStream_t st) {
   const int64_t total = m * n;
-  splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, m, n, c, ldc);
+  splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, m, n, c, ldc, nullptr, 0);
 }
 }  // namespace tc
 
@@ -129,15 +137,17 @@ size_t simt_workspace_bytes(int64_t m, int64_t n, int64_t k) {
 
 template <int BM, int BN>
 static void launch_simt(bool ta, bool tb, dim3 grid, cudaStream_t st, int64_t M, int64_t N, int64_t K, const float* A,
-                        int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t kc, int64_t cs) {
-  if (!ta && !tb) gemm_simt_kernel<BM, BN, false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, kc, cs);
-  else if (!ta && tb) gemm_simt_kernel<BM, BN, false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, kc, cs);
-  else if (ta && !tb) gemm_simt_kernel<BM, BN, true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, kc, cs);
-  else gemm_simt_kernel<BM, BN, true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, kc, cs);
+                        int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t kc, int64_t cs,
+                        int aa, int ab, const float* ms, int64_t ml) {
+  if (!ta && !tb) gemm_simt_kernel<BM, BN, false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, kc, cs, aa, ab, ms, ml);
+  else if (!ta && tb) gemm_simt_kernel<BM, BN, false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, kc, cs, aa, ab, ms, ml);
+  else if (ta && !tb) gemm_simt_kernel<BM, BN, true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, kc, cs, aa, ab, ms, ml);
+  else gemm_simt_kernel<BM, BN, true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, kc, cs, aa, ab, ms, ml);
 }
 
 int gemm_simt(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b,
-              int64_t ldb, float* c, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+              int64_t ldb, float* c, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st,
+              int act_a, int act_b, const float* mul_src, int64_t mul_ld) {
   if (m == 0 || n == 0) return GAT_OK;
   SimtPlan p = simt_plan(m, n, k);
   size_t need = p.splits > 1 ? (size_t)p.splits * m * n * sizeof(float) : 0;
@@ -149,14 +159,15 @@ int gemm_simt(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, i
   float* out = p.splits > 1 ? (float*)workspace : c;
   int64_t out_ld = p.splits > 1 ? n : ldc;
   int64_t cs = p.splits > 1 ? m * n : 0;
-  if (p.bm == 128 && p.bn == 128) launch_simt<128, 128>(ta, tb, grid, st, m, n, k, a, lda, b, ldb, out, out_ld, p.k_chunk, cs);
-  else if (p.bm == 128 && p.bn == 64) launch_simt<128, 64>(ta, tb, grid, st, m, n, k, a, lda, b, ldb, out, out_ld, p.k_chunk, cs);
-  else if (p.bm == 64 && p.bn == 128) launch_simt<64, 128>(ta, tb, grid, st, m, n, k, a, lda, b, ldb, out, out_ld, p.k_chunk, cs);
-  else launch_simt<64, 64>(ta, tb, grid, st, m, n, k, a, lda, b, ldb, out, out_ld, p.k_chunk, cs);
+  const float* ms = p.splits > 1 ? nullptr : mul_src;    // with split-K the multiplier is applied after the reduction
+  if (p.bm == 128 && p.bn == 128) launch_simt<128, 128>(ta, tb, grid, st, m, n, k, a, lda, b, ldb, out, out_ld, p.k_chunk, cs, act_a, act_b, ms, mul_ld);
+  else if (p.bm == 128 && p.bn == 64) launch_simt<128, 64>(ta, tb, grid, st, m, n, k, a, lda, b, ldb, out, out_ld, p.k_chunk, cs, act_a, act_b, ms, mul_ld);
+  else if (p.bm == 64 && p.bn == 128) launch_simt<64, 128>(ta, tb, grid, st, m, n, k, a, lda, b, ldb, out, out_ld, p.k_chunk, cs, act_a, act_b, ms, mul_ld);
+  else launch_simt<64, 64>(ta, tb, grid, st, m, n, k, a, lda, b, ldb, out, out_ld, p.k_chunk, cs, act_a, act_b, ms, mul_ld);
   GAT_LAUNCH_CHECK();
   if (p.splits > 1) {
     int64_t total = m * n;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, p.splits, m, n, c, ldc);
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, p.splits, m, n, c, ldc, mul_src, mul_ld);
     GAT_LAUNCH_CHECK();
   }
   return GAT_OK;

@@ -109,6 +109,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Inter-layer glue fused into the GEMM (GATModel.py:148-149 applies F.elu between layers):
+//   ELU(x)  on an operand tile while it is split in shared memory (the activated tensor is never written to HBM);
+//   ELU'(x) as a multiplier of the output tile (the adjoint, for dX).
+// (fast exp: the 4 splitter warps touch every operand element, so the activation must cost a handful of instructions;
+// |error| <= 2e-7 absolute, far inside the 1e-5 parity bar)
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+__device__ __forceinline__ float elu_grad1(float x) { return x > 0.f ? 1.f : __expf(x); }
+__device__ __forceinline__ float4 elu4(float4 v) { return make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w)); }
+
 __device__ __forceinline__ float tf32_round(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -144,7 +153,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                uint32_t mn_lbo, uint32_t mn_sbo,
                // fused score epilogue (NT only, one N tile): s_src = C A_src^T, s_tgt = C A_tgt^T in fp64, or nullptr
                const float* __restrict__ a_src, const float* __restrict__ a_tgt, int nh,
-               float* __restrict__ s_src, float* __restrict__ s_tgt) {
+               float* __restrict__ s_src, float* __restrict__ s_tgt,
+               // fused glue: ELU on the A / B operand tiles; output multiplied by ELU'(mul_src[row, col]) (NT only)
+               int act_a, int act_b, const float* __restrict__ mul_src, int64_t mul_ld) {
   using S = Smem<BN>;
   constexpr int kStages = S::kStages;
   // two accumulators: [0, BN) leading term hi*hi, [BN, 2BN) cross terms hi*lo + lo*hi.  The tensor core rounds its
@@ -245,6 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 4
       for (int i = t; i < S::kABytes / 16; i += kSplitThreads) {
         float4 v = a_hi[i], h, l;
+        if (act_a) v = elu4(v);
         h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
         // lo is rounded too: the tensor core would otherwise TRUNCATE its low 13 bits, a one-sided error that
         // accumulates linearly over K
@@ -254,6 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 4
       for (int i = t; i < S::kBBytes / 16; i += kSplitThreads) {
         float4 v = b_hi[i], h, l;
+        if (act_b) v = elu4(v);
         h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
         l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
         b_hi[i] = h; b_lo[i] = l;
@@ -337,6 +350,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
         __syncwarp();
+      }
+      if (!MN && mul_src != nullptr && row < M) {
+        const float* mp = mul_src + row * mul_ld + n0 + c;
+        if (n0 + c + 8 <= N && (mul_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(mul_src) & 15) == 0) {
+          const float4 m0v = __ldg(reinterpret_cast<const float4*>(mp)), m1v = __ldg(reinterpret_cast<const float4*>(mp) + 1);
+          v[0] *= elu_grad1(m0v.x); v[1] *= elu_grad1(m0v.y); v[2] *= elu_grad1(m0v.z); v[3] *= elu_grad1(m0v.w);
+          v[4] *= elu_grad1(m1v.x); v[5] *= elu_grad1(m1v.y); v[6] *= elu_grad1(m1v.z); v[7] *= elu_grad1(m1v.w);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (n0 + c + j < N) v[j] *= elu_grad1(__ldg(mp + j));
+        }
       }
       if (!MN) {
         uint8_t* bx = stage_c + (c >> 5) * kBoxBytes + rl * 128;
@@ -452,11 +477,12 @@ struct ScoreFuse { const float* a_src; const float* a_tgt; int nh; float* s_src;
 // Extra destinations of the output (fused projection -> all-gather): `count` base pointers of (row_offset + m, n)
 // matrices with leading dimension ldc; the tile rows are written at row_offset.  count == 0: only `c`.
 struct Dests { float* const* ptrs; int count; int64_t row_offset; };
+struct Glue { int act_a; int act_b; const float* mul_src; int64_t mul_ld; };
 
 template <int BN, bool MN>
 static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb, float* c,
                   int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st, ScoreFuse f = ScoreFuse{nullptr, nullptr, 0, nullptr, nullptr},
-                  Dests dests = Dests{nullptr, 0, 0}) {
+                  Dests dests = Dests{nullptr, 0, 0}, Glue g = Glue{0, 0, nullptr, 0}) {
   CUtensorMap map_a, map_b;
   CStoreMaps cm;          // only .count/.row_offset and the first `count` maps are meaningful; copied by value at launch
   cm.count = 0; cm.row_offset = 0;
@@ -484,7 +510,8 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
   }
   if (!MN) {
     dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), 1);
-    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, c, ldc, m, n, k, 0, 0, 0, 0, f.a_src, f.a_tgt, f.nh, f.s_src, f.s_tgt);
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, c, ldc, m, n, k, 0, 0, 0, 0, f.a_src, f.a_tgt, f.nh, f.s_src, f.s_tgt,
+                                                                     g.act_a, g.act_b, g.mul_src, g.mul_ld);
     GAT_LAUNCH_CHECK();
     return GAT_OK;
   }
@@ -492,7 +519,8 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
   const uint32_t mn_lbo = BK * 128, mn_sbo = 512;   // measured on B200: the swapped assignment gives wrong products
   dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), (unsigned)p.splits);
   if (p.splits == 1) {
-    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, c, ldc, m, n, k, p.kb_per_split, 0, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr);
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, c, ldc, m, n, k, p.kb_per_split, 0, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr,
+                                                                     g.act_a, g.act_b, nullptr, 0);
     GAT_LAUNCH_CHECK();
     return GAT_OK;
   }
@@ -501,7 +529,8 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
     set_error("gat_gemm: workspace too small (%zu < %zu)", workspace_bytes, need);
     return GAT_EWORKSPACE;
   }
-  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, (float*)workspace, n, m, n, k, p.kb_per_split, m * n, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr);
+  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, (float*)workspace, n, m, n, k, p.kb_per_split, m * n, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr,
+                                                                   g.act_a, g.act_b, nullptr, 0);
   GAT_LAUNCH_CHECK();
   splitk_reduce_launch((const float*)workspace, p.splits, m, n, c, ldc, st);
   GAT_LAUNCH_CHECK();
@@ -535,7 +564,7 @@ bool tc_project_supported(int64_t n_rows, int64_t dp, int64_t k, int64_t ldx, in
 
 int gemm_tc_project(int64_t n_rows, int64_t dp, int64_t k, const float* x, int64_t ldx, const float* w, int64_t ldw,
                     float* wh, const float* a_src, const float* a_tgt, int nh, float* s_src, float* s_tgt, cudaStream_t st,
-                    float* const* wh_dests, int n_dests, int64_t row_offset) {
+                    float* const* wh_dests, int n_dests, int64_t row_offset, int x_act) {
   uintptr_t bits = (uintptr_t)x | (uintptr_t)w | (uintptr_t)a_src | (uintptr_t)a_tgt | (n_dests ? 0 : (uintptr_t)wh);
   for (int d = 0; d < n_dests; ++d) bits |= (uintptr_t)wh_dests[d];
   if (!tc_project_supported(n_rows, dp, k, ldx, ldw) || bits % 16) {
@@ -544,27 +573,33 @@ int gemm_tc_project(int64_t n_rows, int64_t dp, int64_t k, const float* x, int64
   }
   tc::ScoreFuse f{a_src, a_tgt, nh, s_src, s_tgt};
   tc::Dests dd{wh_dests, n_dests, row_offset};
+  tc::Glue g{x_act, 0, nullptr, 0};
   const int bn = tc::bn_for(dp);
-  if (bn == 256) return tc::launch<256, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd);
-  if (bn == 128) return tc::launch<128, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd);
-  return tc::launch<64, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd);
+  if (bn == 256) return tc::launch<256, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd, g);
+  if (bn == 128) return tc::launch<128, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd, g);
+  return tc::launch<64, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd, g);
 }
 
 int gemm_tc(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb,
-            float* c, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+            float* c, int64_t ldc, void* workspace, size_t workspace_bytes, cudaStream_t st,
+            int act_a, int act_b, const float* mul_src, int64_t mul_ld) {
   if (!tc_supported(ta, tb, m, n, k, lda, ldb, ldc) || ((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) % 16) {
     set_error("gat_gemm: tcgen05 path needs (ta,tb) = (0,1) or (1,0) and 16-byte aligned pointers / leading dimensions");
     return GAT_EUNSUPPORTED;
   }
   const int bn = tc::bn_for(n);
+  const tc::ScoreFuse nf{nullptr, nullptr, 0, nullptr, nullptr};
+  const tc::Dests nd{nullptr, 0, 0};
+  const tc::Glue g{act_a, act_b, mul_src, mul_ld};
   if (ta == 0) {
-    if (bn == 256) return tc::launch<256, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
-    if (bn == 128) return tc::launch<128, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
-    return tc::launch<64, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
+    if (bn == 256) return tc::launch<256, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
+    if (bn == 128) return tc::launch<128, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
+    return tc::launch<64, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
   }
-  if (bn == 256) return tc::launch<256, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
-  if (bn == 128) return tc::launch<128, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
-  return tc::launch<64, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st);
+  if (mul_src != nullptr) { set_error("gat_gemm: the ELU' output multiplier is only implemented for ta = 0"); return GAT_EUNSUPPORTED; }
+  if (bn == 256) return tc::launch<256, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
+  if (bn == 128) return tc::launch<128, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
+  return tc::launch<64, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
 }
 
 }  // namespace gat

@@ -1,0 +1,102 @@
+// Caller-side glue next to the layer: the attention-norm regulariser of
+// GATModel.calc_attention_norm (GATModel.py:189-234) on the structure Kernel 1 already built.
+//
+//   norm_l = sum_{e,h} | alpha_l[e,h] * deg(dst_e) - 1 | / E'          (GATModel.py:207-224, one layer)
+//   d norm_l / d alpha_l[e,h] = sign(alpha*deg - 1) * deg(dst_e) / E'
+//
+// The reference builds deg per edge with a scatter_add of ones and an index_select (GATModel.py:196-201), multiplies,
+// subtracts and takes torch.norm(p=1): five (E', NH) passes plus their autograd.  Here deg(dst) is a rowptr difference
+// (GATModel.py:196-201 == rowptr[d+1]-rowptr[d]), the forward is one pass over alpha and the backward
+// one pass that writes dL/dalpha directly.  The sum is reduced in two fixed-order stages in fp64 (deterministic).
+#include "common.cuh"
+
+namespace gat {
+
+constexpr int kNormBlocks = 592;   // 4 per SM
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_norm_partial_kernel(const T* __restrict__ dst, const int32_t* __restrict__ rowptr, const float* __restrict__ alpha,
+                         int64_t n_edges, int nh, double* __restrict__ partials) {
+  __shared__ double sh[256];
+  const int64_t per = (n_edges + kNormBlocks - 1) / kNormBlocks;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n_edges, lo + per);
+  double t = 0.0;
+  for (int64_t e = lo + threadIdx.x; e < hi; e += 256) {
+    const int64_t d = (int64_t)dst[e];
+    const float deg = (float)(__ldg(rowptr + d + 1) - __ldg(rowptr + d));
+    const float* a = alpha + e * nh;
+    float s = 0.f;
+    for (int h = 0; h < nh; ++h) s += fabsf(a[h] * deg - 1.0f);
+    t += (double)s;
+  }
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(1024)
+attn_norm_finalize_kernel(const double* __restrict__ partials, double inv_edges, float* __restrict__ out) {
+  __shared__ double sh[1024];
+  double t = 0.0;
+  for (int i = threadIdx.x; i < kNormBlocks; i += 1024) t += partials[i];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)(sh[0] * inv_edges);
+}
+
+template <typename T>
+__global__ void attn_norm_bwd_kernel(const T* __restrict__ dst, const int32_t* __restrict__ rowptr, const float* __restrict__ alpha,
+                                     int64_t n_edges, int nh, const float* __restrict__ upstream, float inv_edges,
+                                     float* __restrict__ grad_alpha) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n_edges * nh) return;
+  const int64_t e = idx / nh;
+  const int64_t d = (int64_t)dst[e];
+  const float deg = (float)(__ldg(rowptr + d + 1) - __ldg(rowptr + d));
+  const float v = alpha[idx] * deg - 1.0f;
+  const float sgn = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);       // torch's sign(): 0 at 0
+  grad_alpha[idx] = __ldg(upstream) * sgn * deg * inv_edges;
+}
+
+}  // namespace gat
+
+extern "C" size_t gat_attention_norm_workspace_bytes(void) { return (size_t)gat::kNormBlocks * sizeof(double); }
+
+extern "C" int gat_attention_norm_fwd(const void* edge_dst, int index_is_int64, const int32_t* rowptr, const float* alpha,
+                                      int64_t n_edges, int nh, float* norm_out, void* workspace, size_t workspace_bytes,
+                                      gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(edge_dst && rowptr && alpha && norm_out && n_edges >= 1 && nh >= 1, "gat_attention_norm_fwd: bad arguments");
+  GAT_CHECK_ARG(workspace && workspace_bytes >= gat_attention_norm_workspace_bytes(), "gat_attention_norm_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* partials = (double*)workspace;
+  if (index_is_int64) attn_norm_partial_kernel<int64_t><<<kNormBlocks, 256, 0, st>>>((const int64_t*)edge_dst, rowptr, alpha, n_edges, nh, partials);
+  else attn_norm_partial_kernel<int32_t><<<kNormBlocks, 256, 0, st>>>((const int32_t*)edge_dst, rowptr, alpha, n_edges, nh, partials);
+  GAT_LAUNCH_CHECK();
+  attn_norm_finalize_kernel<<<1, 1024, 0, st>>>(partials, 1.0 / (double)n_edges, norm_out);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_attention_norm_bwd(const void* edge_dst, int index_is_int64, const int32_t* rowptr, const float* alpha,
+                                      int64_t n_edges, int nh, const float* upstream, float* grad_alpha, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(edge_dst && rowptr && alpha && upstream && grad_alpha && n_edges >= 1 && nh >= 1, "gat_attention_norm_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = n_edges * nh;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  const float inv = (float)(1.0 / (double)n_edges);
+  if (index_is_int64) attn_norm_bwd_kernel<int64_t><<<blocks, 256, 0, st>>>((const int64_t*)edge_dst, rowptr, alpha, n_edges, nh, upstream, inv, grad_alpha);
+  else attn_norm_bwd_kernel<int32_t><<<blocks, 256, 0, st>>>((const int32_t*)edge_dst, rowptr, alpha, n_edges, nh, upstream, inv, grad_alpha);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}

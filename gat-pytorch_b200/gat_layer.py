@@ -28,13 +28,16 @@ def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-def gemm(ta: bool, tb: bool, m: int, n: int, k: int, a, lda, b, ldb, c, ldc, algo: int = 0):
-    """C[m,n] = op(A) op(B) through gat_gemm (include/gat_b200.h)."""
+def gemm(ta: bool, tb: bool, m: int, n: int, k: int, a, lda, b, ldb, c, ldc, algo: int = 0, act_a: bool = False,
+         act_b: bool = False, mul_elu_grad=None):
+    """C[m,n] = op(A) op(B) through gat_gemm_ex (include/gat_b200.h); act_a/act_b: the operand is ELU(stored values);
+    mul_elu_grad: C *= ELU'(that tensor), the adjoint of the fused activation."""
     lib = _lib.load()
     dev = c.device
     ws_bytes = int(lib.gat_gemm_workspace_bytes(int(ta), int(tb), m, n, k, algo))
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev) if ws_bytes else None
-    _lib.call("gat_gemm", int(ta), int(tb), m, n, k, a.data_ptr(), lda, b.data_ptr(), ldb, c.data_ptr(), ldc,
+    _lib.call("gat_gemm_ex", int(ta), int(tb), m, n, k, a.data_ptr(), lda, b.data_ptr(), ldb, c.data_ptr(), ldc,
+              int(act_a), int(act_b), _ptr(mul_elu_grad), mul_elu_grad.stride(0) if mul_elu_grad is not None else 0,
               algo, _ptr(ws), ws_bytes, _stream(dev), tag=(int(ta), int(tb), m, n, k))
 
 
@@ -44,7 +47,7 @@ class _GATFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_p, a_src_p, a_tgt_p, st: GraphStructure, nh, f, fp, concat, const_attention,
-                p_drop, want_alpha, gemm_algo):
+                p_drop, want_alpha, gemm_algo, x_act=False, out_act=False):
         lib = _lib.load()
         dev = x.device
         n, f_in, dp = x.size(0), x.size(1), nh * fp
@@ -61,7 +64,7 @@ class _GATFunction(torch.autograd.Function):
             gws_bytes = int(lib.gat_gemm_workspace_bytes(0, 1, n, dp, f_in, gemm_algo))
             gws = torch.empty(gws_bytes, dtype=torch.uint8, device=dev) if gws_bytes else None
             # Kernel 2: projection GEMM that also emits the per-node score terms
-            _lib.call("gat_project_fwd", x.data_ptr(), n, f_in, x.stride(0), w_p.data_ptr(), w_p.stride(0), dp,
+            _lib.call("gat_project_fwd", x.data_ptr(), n, f_in, x.stride(0), int(x_act), w_p.data_ptr(), w_p.stride(0), dp,
                       _ptr(a_src_p), _ptr(a_tgt_p), nh, wh.data_ptr(), _ptr(s_src), _ptr(s_tgt), gemm_algo,
                       _ptr(gws), gws_bytes, s, tag=(n, dp, f_in))
             if not const_attention:
@@ -81,7 +84,7 @@ class _GATFunction(torch.autograd.Function):
             _lib.call("gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), st.n_long, n,
                                         wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax),
                                         int(const_attention), float(p_drop), seed, 0,
-                                        out_p.data_ptr(), _ptr(alpha), z.data_ptr(),
+                                        out_p.data_ptr(), int(out_act), _ptr(alpha), z.data_ptr(),
                                         _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), fws.data_ptr(), fws.numel(), s,
                                         tag=(nh, fp))
             if fp != f or not concat:
@@ -89,7 +92,7 @@ class _GATFunction(torch.autograd.Function):
                 _lib.call("gat_head_merge_fwd", out_p.data_ptr(), n, nh, f, fp, int(concat), out.data_ptr(), s)
             else:
                 out = out_p
-        ctx.st, ctx.cfg = st, (nh, f, fp, concat, const_attention, float(p_drop), seed, gemm_algo)
+        ctx.st, ctx.cfg = st, (nh, f, fp, concat, const_attention, float(p_drop), seed, gemm_algo, bool(x_act), bool(out_act))
         ctx.save_for_backward(x, w_p, a_src_p, a_tgt_p, wh, s_src, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p)
         if alpha is None:
             return out, None
@@ -100,7 +103,7 @@ class _GATFunction(torch.autograd.Function):
         lib = _lib.load()
         x, w_p, a_src_p, a_tgt_p, wh, s_src, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p = ctx.saved_tensors
         st: GraphStructure = ctx.st
-        nh, f, fp, concat, const_attention, p_drop, seed, gemm_algo = ctx.cfg
+        nh, f, fp, concat, const_attention, p_drop, seed, gemm_algo, x_act, out_act = ctx.cfg
         dev = x.device
         n, f_in, dp = x.size(0), x.size(1), nh * fp
         with torch.cuda.device(dev):
@@ -129,11 +132,19 @@ class _GATFunction(torch.autograd.Function):
                 ds_src, ds_tgt, s_sum = (torch.empty((n, nh), **f32) for _ in range(3))
             ws_bytes = int(lib.gat_edge_bwd_workspace_bytes(n, st.n_edges, nh))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            if not const_attention and grad_alpha is None:
+            fused = not const_attention and grad_alpha is None
+            if out_act and not fused:
+                # the forward stored h = ELU(out): dL/dout = dL/dh * ELU'(out), ELU' = 1 (h > 0) or h + 1
+                go_p = go_p * torch.where(out_p > 0, torch.ones_like(out_p), out_p + 1.0)
+            if fused:
                 # common case (nothing consumed the returned attention): S = <dOut, out> needs no per-edge data, so it
-                # goes FIRST and ONE source-major pass does the rest (no records, no finish pass)
-                _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), go_shared, out_p.data_ptr(), z.data_ptr(), n, nh, fp,
-                          s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+                # goes FIRST (applying the fused ELU's adjoint on the way when the forward stored ELU(out)) and ONE
+                # source-major pass does the rest (no records, no finish pass)
+                go_pre = torch.empty((n, dp), **f32) if out_act else None
+                _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), go_shared, out_p.data_ptr(), int(out_act), _ptr(go_pre),
+                          z.data_ptr(), n, nh, fp, s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+                if out_act:
+                    go_p = go_pre
                 _lib.call("gat_edge_bwd_fused", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
                           st.n_long_t, st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, s_src.data_ptr(), s_tgt.data_ptr(), gmax.data_ptr(),
                           z.data_ptr(), p_drop, seed, 0, go_p.data_ptr(), go_shared, s_sum.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
@@ -160,10 +171,11 @@ class _GATFunction(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty((n, f_in), **f32)
                 w_t = w_p.t().contiguous()      # (f_in, dp): makes dX = dWh * W a K-major x K-major product (tcgen05 path)
-                gemm(False, True, n, f_in, dp, d_wh, dp, w_t, dp, gx, f_in, gemm_algo)
+                # with a fused input activation the layer saw ELU(x): dL/dx = (dWh W) * ELU'(x), applied in the epilogue
+                gemm(False, True, n, f_in, dp, d_wh, dp, w_t, dp, gx, f_in, gemm_algo, mul_elu_grad=x if x_act else None)
             if ctx.needs_input_grad[1]:
                 gw = torch.empty((dp, f_in), **f32)
-                gemm(True, False, dp, f_in, n, d_wh, dp, x, x.stride(0), gw, f_in, gemm_algo)
+                gemm(True, False, dp, f_in, n, d_wh, dp, x, x.stride(0), gw, f_in, gemm_algo, act_b=x_act)
             if not const_attention and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
                 ga_src = torch.empty((nh, dp), **f32)
                 ga_tgt = torch.empty((nh, dp), **f32)
@@ -171,7 +183,7 @@ class _GATFunction(torch.autograd.Function):
                 sws = torch.empty(sb, dtype=torch.uint8, device=dev)
                 _lib.call("gat_scores_bwd", wh.data_ptr(), n, dp, nh, ds_src.data_ptr(), ds_tgt.data_ptr(),
                           ga_src.data_ptr(), ga_tgt.data_ptr(), sws.data_ptr(), sb, s)
-        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None
+        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None, None, None
 
 
 class GATLayer(nn.Module):
@@ -211,6 +223,15 @@ class GATLayer(nn.Module):
 
         self.normalised_attention_coeffs = None
         self.gemm_algo = 0          # 0 auto, 1 fp32 FFMA, 2 tcgen05 3xTF32
+        # Opt-in glue fusion: "elu" makes forward(x, ...) compute the layer on ELU(x) -- the F.elu that
+        # GATModel.forward applies between layers (GATModel.py:148-149) -- inside the projection GEMM (the activated
+        # tensor is never written) and its adjoint inside the dX GEMM.  None (default) = the reference's semantics.
+        self.input_activation = None
+        # "elu" on the OUTPUT side: forward returns ELU(out), computed in the edge kernel's epilogue, and the backward
+        # applies the adjoint inside its per-node pass -- no separate activation kernels in either direction.  This is
+        # the cheaper of the two fusions (measured, profiles/README.md); concat layers without bias only (ELU does not
+        # commute with the head mean).
+        self.output_activation = None
         self.structure_cache = GLOBAL_CACHE
         self.reset_parameters()
 
@@ -237,6 +258,22 @@ class GATLayer(nn.Module):
             a_src, a_tgt = a_src.reshape(nh, nh * fp).contiguous(), a_tgt.reshape(nh, nh * fp).contiguous()
         return w, a_src, a_tgt, fp
 
+    def _x_act(self) -> bool:
+        if self.input_activation in (None, "none"):
+            return False
+        if self.input_activation != "elu":
+            raise ValueError(f"input_activation must be None or 'elu', got {self.input_activation!r}")
+        return True
+
+    def _out_act(self) -> bool:
+        if self.output_activation in (None, "none"):
+            return False
+        if self.output_activation != "elu":
+            raise ValueError(f"output_activation must be None or 'elu', got {self.output_activation!r}")
+        if not self.concat or self.bias:
+            raise ValueError("output_activation='elu' is fused only for concat layers without bias (apply F.elu outside otherwise)")
+        return True
+
     def forward(self, x, edge_index, return_attention_weights=False):
         if not x.is_cuda:
             raise RuntimeError("gat_b200.GATLayer runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -257,7 +294,7 @@ class GATLayer(nn.Module):
         p_drop = float(self.dropout) if (self.training and self.dropout > 0) else 0.0
         out, alpha = _GATFunction.apply(x, w_p, a_src, a_tgt, st, self.num_heads, self.out_features, fp,
                                         bool(self.concat), bool(self.const_attention), p_drop,
-                                        bool(return_attention_weights), int(self.gemm_algo))
+                                        bool(return_attention_weights), int(self.gemm_algo), self._x_act(), self._out_act())
         self.normalised_attention_coeffs = alpha
         if self.bias:
             out = out + self.bias_param          # gat_layer.py:134-135 (same broadcast rules, same latent shape error)

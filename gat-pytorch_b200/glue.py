@@ -1,0 +1,70 @@
+"""Caller-side glue of the reference model stack, on the structures the layer already built.
+
+`attention_norm(edge_index, attention_list)` mirrors `GATModel.calc_attention_norm(edge_index, attention_list)`
+(models/GATModel.py:189-234): the mean over layers of  sum_{e,h} |alpha_l[e,h] * deg(dst_e) - 1| / E'.  The reference
+rebuilds the per-edge degrees with a scatter_add and an index_select and runs five (E', NH) torch passes per layer; here
+the degree is a `rowptr` difference of the cached CSR (the rewritten `edge_index` a layer returns is registered in the
+structure cache, graph.py), the forward is one pass over alpha and the backward writes dL/dalpha in one pass
+(include/gat_b200.h: gat_attention_norm_fwd / _bwd).  CUDA only, like the layer.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .graph import GLOBAL_CACHE
+
+
+class _AttentionNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha, edge_dst, rowptr):
+        lib = _lib.load()
+        dev = alpha.device
+        alpha = alpha.contiguous()
+        e, nh = alpha.shape
+        with torch.cuda.device(dev):
+            s = torch.cuda.current_stream(dev).cuda_stream
+            out = torch.empty((), dtype=torch.float32, device=dev)
+            ws_bytes = int(lib.gat_attention_norm_workspace_bytes())
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.call("gat_attention_norm_fwd", edge_dst.data_ptr(), int(edge_dst.dtype == torch.int64), rowptr.data_ptr(),
+                      alpha.data_ptr(), e, nh, out.data_ptr(), ws.data_ptr(), ws_bytes, s)
+        ctx.save_for_backward(alpha, edge_dst, rowptr)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        alpha, edge_dst, rowptr = ctx.saved_tensors
+        dev = alpha.device
+        e, nh = alpha.shape
+        with torch.cuda.device(dev):
+            s = torch.cuda.current_stream(dev).cuda_stream
+            g = grad.to(torch.float32).contiguous()
+            ga = torch.empty_like(alpha)
+            _lib.call("gat_attention_norm_bwd", edge_dst.data_ptr(), int(edge_dst.dtype == torch.int64), rowptr.data_ptr(),
+                      alpha.data_ptr(), e, nh, g.data_ptr(), ga.data_ptr(), s)
+        return ga, None, None
+
+
+def attention_norm(edge_index: torch.Tensor, attention_list, n_nodes: int | None = None) -> torch.Tensor:
+    """`GATModel.calc_attention_norm` (GATModel.py:189-234) for the rewritten `edge_index` and the per-layer attention a
+    stack of `GATLayer`s returned.  Differentiable w.r.t. every attention tensor."""
+    if not edge_index.is_cuda:
+        raise RuntimeError("gat_b200.attention_norm runs on CUDA only; there is no CPU fallback")
+    if len(attention_list) == 0:
+        raise ValueError("attention_list is empty")
+    n = int(n_nodes) if n_nodes is not None else None
+    st = GLOBAL_CACHE.find(edge_index) if n is None else GLOBAL_CACHE.get(edge_index, n, False)
+    if st is None:
+        raise RuntimeError("attention_norm: edge_index is not a rewritten edge list returned by a GATLayer on this graph; "
+                           "pass n_nodes to build its structure")
+    dst = edge_index[1]
+    if dst.stride(0) != 1:
+        dst = dst.contiguous()
+    total = None
+    for alpha in attention_list:
+        if alpha.size(0) != st.n_edges:
+            raise ValueError(f"attention has {alpha.size(0)} rows, the edge list {st.n_edges}")
+        norm_l = _AttentionNorm.apply(alpha, dst, st.rowptr)
+        total = norm_l if total is None else total + norm_l
+    return total / len(attention_list)

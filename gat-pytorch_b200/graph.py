@@ -118,6 +118,14 @@ class StructureCache:
             self._put(self._key(s.edge_index, n_nodes, True), s.edge_index, s)
         return s
 
+    def find(self, edge_index):
+        """Structure of an edge list some layer has already seen (any N / self-loop flag), or None."""
+        probe = self._key(edge_index, 0, False)[:6]
+        for key, (_, s) in reversed(self._items.items()):
+            if key[:6] == probe and s.edge_index.data_ptr() == edge_index.data_ptr():
+                return s
+        return None
+
     def _put(self, key, tensor, s):
         self._items[key] = (tensor, s)   # holding `tensor` keeps its storage (and data_ptr) alive
         while len(self._items) > self.capacity:

@@ -110,11 +110,11 @@ class CudaBackend:
                 self.fused_allgather = False
         return torch.empty((n_pad, dp), dtype=torch.float32, device=dev), None
 
-    def project_allgather(self, x, rows, f_in, w_p, dp, a_src, a_tgt, nh, peer_ptrs, row_offset, s_src, s_tgt):
+    def project_allgather(self, x, rows, f_in, w_p, dp, a_src, a_tgt, nh, peer_ptrs, row_offset, s_src, s_tgt, x_act=False):
         """Kernel 2 fused with the feature exchange: every tile of wh goes by TMA into all ranks' gathered buffers."""
         import ctypes
         arr = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs)
-        _lib.call("gat_project_fwd_allgather", x.data_ptr(), rows, f_in, x.stride(0), w_p.data_ptr(), w_p.stride(0), dp,
+        _lib.call("gat_project_fwd_allgather", x.data_ptr(), rows, f_in, x.stride(0), int(x_act), w_p.data_ptr(), w_p.stride(0), dp,
                   a_src.data_ptr(), a_tgt.data_ptr(), nh, arr, len(peer_ptrs), row_offset,
                   s_src.data_ptr(), s_tgt.data_ptr(), self._s(x.device), tag=(rows, dp, f_in))
 
@@ -143,15 +143,15 @@ class CudaBackend:
     def n_edges(self, st):
         return st.n_edges
 
-    def gemm(self, ta, tb, m, n, k, a, lda, b, ldb, c, ldc):
+    def gemm(self, ta, tb, m, n, k, a, lda, b, ldb, c, ldc, act_b=False, mul_elu_grad=None):
         from .gat_layer import gemm
-        gemm(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, self.gemm_algo)
+        gemm(ta, tb, m, n, k, a, lda, b, ldb, c, ldc, self.gemm_algo, act_b=act_b, mul_elu_grad=mul_elu_grad)
 
-    def project(self, x, rows, f_in, w_p, dp, a_src, a_tgt, nh, wh, s_src, s_tgt):
-        """Kernel 2: wh = x W^T with the score terms emitted by the GEMM epilogue (gat_project_fwd)."""
+    def project(self, x, rows, f_in, w_p, dp, a_src, a_tgt, nh, wh, s_src, s_tgt, x_act=False):
+        """Kernel 2: wh = [ELU](x) W^T with the score terms emitted by the GEMM epilogue (gat_project_fwd)."""
         ws_bytes = int(self.lib.gat_gemm_workspace_bytes(0, 1, rows, dp, f_in, self.gemm_algo))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
-        _lib.call("gat_project_fwd", x.data_ptr(), rows, f_in, x.stride(0), w_p.data_ptr(), w_p.stride(0), dp,
+        _lib.call("gat_project_fwd", x.data_ptr(), rows, f_in, x.stride(0), int(x_act), w_p.data_ptr(), w_p.stride(0), dp,
                   a_src.data_ptr(), a_tgt.data_ptr(), nh, wh.data_ptr(), s_src.data_ptr(), s_tgt.data_ptr(), self.gemm_algo,
                   ws.data_ptr(), ws_bytes, self._s(x.device), tag=(rows, dp, f_in))
 
@@ -166,14 +166,14 @@ class CudaBackend:
                   plan.rows, s_src_full.data_ptr(), s_tgt_local.data_ptr(), nh, gmax.data_ptr(), ws.data_ptr(), ws.numel(),
                   self._s(gmax.device))
 
-    def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total):
+    def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act=False):
         p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
         fws = torch.empty(int(self.lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=out_p.device)
         order, n_long = self.local_order(st, plan)
         _lib.call("gat_edge_fwd", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(),
                   order.data_ptr(), n_long, plan.rows,
                   wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(), s_tgt_local.data_ptr(), gmax.data_ptr(),
-                  0, 0.0, 0, 0, out_p.data_ptr(), None, z.data_ptr(), p(tie_dst), p(tie_src), p(tie_total),
+                  0, 0.0, 0, 0, out_p.data_ptr(), int(out_act), None, z.data_ptr(), p(tie_dst), p(tie_src), p(tie_total),
                   fws.data_ptr(), fws.numel(), self._s(out_p.device), tag=(nh, fp))
 
     def scores_bwd(self, wh, n, dp, nh, ds_src, ds_tgt, da_src, da_tgt):
@@ -229,11 +229,13 @@ class CudaBackend:
                   arr, len(push_ptrs) if push_ptrs else 0, plan.rank, plan.rows_per_rank, ws.data_ptr(), ws_bytes,
                   self._s(go_p.device), tag=(nh, fp))
 
-    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt):
-        """Pass 2 without per-edge data: S = <dOut, out> over the owned rows; returns this rank's Gamma."""
+    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt, go_pre=None):
+        """Pass 2 without per-edge data: S = <dOut, out> over the owned rows; returns this rank's Gamma.  With go_pre
+        (the forward stored ELU(out)) the ELU adjoint is applied on the way and dL/dout is written to go_pre."""
         ws, ws_bytes = self._bwd_ws(go_p.device, nh)
         ws.zero_()
-        _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), 0, out_p.data_ptr(), z_local.data_ptr(), plan.rows, nh, fp,
+        _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), 0, out_p.data_ptr(), int(go_pre is not None),
+                  go_pre.data_ptr() if go_pre is not None else None, z_local.data_ptr(), plan.rows, nh, fp,
                   s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
         gamma = torch.empty(1, dtype=torch.float64, device=go_p.device)
         _lib.call("gat_edge_bwd_gamma", ws.data_ptr(), ws_bytes, gamma.data_ptr(), self._s(go_p.device))
@@ -253,7 +255,7 @@ class CudaBackend:
 # ----------------------------------------------------------------------------------------------
 class _PartitionedGATFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_local, w_p, a_src_p, a_tgt_p, st, plan: Plan, nh, fp, backend, group, gathered):
+    def forward(ctx, x_local, w_p, a_src_p, a_tgt_p, st, plan: Plan, nh, fp, backend, group, gathered, x_act=False, out_act=False):
         dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
         rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
         s_src_slab = torch.zeros((R, nh), **f32)
@@ -264,14 +266,14 @@ class _PartitionedGATFunction(torch.autograd.Function):
         if fused:
             # ONE kernel: GEMM tiles -> shared memory -> TMA stores into every rank's gathered buffer over NVLink
             if rows:
-                backend.project_allgather(x_local, rows, f_in, w_p, dp, a_src_p, a_tgt_p, nh, peer_ptrs, plan.lo, s_src_slab, s_tgt)
+                backend.project_allgather(x_local, rows, f_in, w_p, dp, a_src_p, a_tgt_p, nh, peer_ptrs, plan.lo, s_src_slab, s_tgt, x_act)
             dist.all_gather_into_tensor(s_src_full, s_src_slab, group=group)    # tiny; doubles as the cross-rank barrier for wh_full
         else:
             wh_slab = torch.empty((R, dp), **f32)
             if rows < R:
                 wh_slab[rows:].zero_()
             if rows:
-                backend.project(x_local, rows, f_in, w_p, dp, a_src_p, a_tgt_p, nh, wh_slab, s_src_slab, s_tgt)
+                backend.project(x_local, rows, f_in, w_p, dp, a_src_p, a_tgt_p, nh, wh_slab, s_src_slab, s_tgt, x_act)
             if wh_full is None:
                 wh_full = torch.empty((plan.n_pad, dp), **f32)
             dist.all_gather_into_tensor(wh_full, wh_slab, group=group)          # the feature exchange (NCCL over NVLink)
@@ -285,15 +287,15 @@ class _PartitionedGATFunction(torch.autograd.Function):
         ties = torch.zeros(2 + max(rows, 1) * nh + plan.n_pad * nh, dtype=torch.int32, device=dev)
         tie_total, tie_dst, tie_src = ties[:2], ties[2:2 + max(rows, 1) * nh], ties[2 + max(rows, 1) * nh:]
         if rows:
-            backend.edge_fwd(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, out_p, z, tie_dst, tie_src, tie_total)
-        ctx.misc = (st, plan, nh, fp, backend, group)
+            backend.edge_fwd(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act)
+        ctx.misc = (st, plan, nh, fp, backend, group, bool(x_act), bool(out_act))
         ctx.save_for_backward(x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p)
         return out_p
 
     @staticmethod
     def backward(ctx, go_p):
         x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p = ctx.saved_tensors
-        st, plan, nh, fp, backend, group = ctx.misc
+        st, plan, nh, fp, backend, group, x_act, out_act = ctx.misc
         dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
         rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
         go_p = go_p.contiguous()
@@ -304,7 +306,10 @@ class _PartitionedGATFunction(torch.autograd.Function):
         ds_src_part = torch.zeros((plan.n_pad, nh), **f32)
         gamma = torch.zeros(1, dtype=torch.float64, device=dev)
         if rows:    # S = <dOut, out> over the owned rows first: no per-edge data needed
-            gamma = backend.edge_bwd_rowdot(plan, nh, fp, go_p, out_p, z, s_sum, ds_tgt)
+            go_pre = torch.empty_like(go_p) if out_act else None     # dL/dout when the forward stored ELU(out)
+            gamma = backend.edge_bwd_rowdot(plan, nh, fp, go_p, out_p, z, s_sum, ds_tgt, go_pre)
+            if out_act:
+                go_p = go_pre
         red = torch.stack([gamma[0], tie_total.view(torch.int64)[0].to(torch.float64)])
         dist.all_reduce(red, group=group)                                   # (Gamma, |T|) over ranks
         corr = torch.where(red[1] > 0, red[0] / red[1].clamp(min=1.0), torch.zeros_like(red[0])).to(torch.float32).reshape(1)
@@ -327,20 +332,20 @@ class _PartitionedGATFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0] and rows:
             gx = torch.empty((rows, f_in), **f32)
             w_t = w_p.t().contiguous()
-            backend.gemm(False, True, rows, f_in, dp, d_wh, dp, w_t, dp, gx, f_in)
+            backend.gemm(False, True, rows, f_in, dp, d_wh, dp, w_t, dp, gx, f_in, mul_elu_grad=x_local if x_act else None)
         elif ctx.needs_input_grad[0]:
             gx = torch.zeros((0, f_in), **f32)
         gw = torch.zeros((dp, f_in), **f32)
         ga_src = torch.zeros((nh, dp), **f32)
         ga_tgt = torch.zeros((nh, dp), **f32)
         if rows:
-            backend.gemm(True, False, dp, f_in, rows, d_wh, dp, x_local, x_local.stride(0), gw, f_in)
+            backend.gemm(True, False, dp, f_in, rows, d_wh, dp, x_local, x_local.stride(0), gw, f_in, act_b=x_act)
         backend.scores_bwd(wh_full, plan.n, dp, nh, ds_src_part, ds_tgt_full, ga_src, ga_tgt)   # one pass over Wh
         flat = torch.cat([gw.reshape(-1), ga_src.reshape(-1), ga_tgt.reshape(-1)])
         dist.all_reduce(flat, group=group)                                  # the gradient all-reduce
         gw, ga_src, ga_tgt = flat[:gw.numel()].view_as(gw), flat[gw.numel():gw.numel() + ga_src.numel()].view_as(ga_src), \
             flat[gw.numel() + ga_src.numel():].view_as(ga_tgt)
-        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None
+        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None
 
 
 class PartitionedGATLayer(torch.nn.Module):
@@ -356,6 +361,8 @@ class PartitionedGATLayer(torch.nn.Module):
         torch.nn.init.xavier_uniform_(self.a.weight)
         self.backend, self.group = backend, group
         self._gathered = None       # (wh_full, peer pointers) of this layer, allocated once (symmetric memory)
+        self.input_activation = None    # "elu": the layer runs on ELU(x), fused into the GEMMs (see GATLayer)
+        self.output_activation = None   # "elu": the layer returns ELU(out), fused into the edge kernel's epilogue (concat only)
 
     def _padded_operands(self):
         nh, f = self.num_heads, self.out_features
@@ -378,7 +385,8 @@ class PartitionedGATLayer(torch.nn.Module):
             if self._gathered is None or self._gathered[0].shape != (plan.n_pad, nh * fp) or self._gathered[0].device != x_local.device:
                 self._gathered = self.backend.gathered_buffer(plan.n_pad, nh * fp, self.group)
         out_p = _PartitionedGATFunction.apply(x_local.contiguous(), w_p, a_src, a_tgt, st, plan, nh, fp, self.backend, self.group,
-                                              self._gathered)
+                                              self._gathered, self.input_activation == "elu",
+                                              self.output_activation == "elu" and bool(self.concat))
         o = out_p.view(-1, nh, fp)[:, :, :f]
         return o.reshape(-1, nh * f) if self.concat else o.mean(dim=1)      # gat_layer.py:129-132
 
@@ -386,8 +394,9 @@ class PartitionedGATLayer(torch.nn.Module):
 class PartitionedGAT:
     """bench.py's multi-GPU model: the stacked layers of one config over a partitioned graph."""
 
-    def __init__(self, shapes, weights, x_host, ei_host, dev, backend=None):
+    def __init__(self, shapes, weights, x_host, ei_host, dev, backend=None, fuse_glue=False):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.fuse_glue = fuse_glue      # the inter-layer ELU rides in the next layer's GEMMs (SURVEY.md 8-f1)
         self.dev, self.x_host, self.ei_host = dev, x_host, ei_host
         self.plan = make_plan(x_host.size(0), self.world, self.rank)
         self.backend = backend or CudaBackend()
@@ -398,6 +407,9 @@ class PartitionedGAT:
                 layer.W.weight.copy_(torch.as_tensor(w))
                 layer.a.weight.copy_(torch.as_tensor(a))
             self.layers.append(layer)
+        if fuse_glue:   # F.elu after every layer but the last (GATModel.py:148-149), in the edge kernel's epilogue
+            for layer in self.layers[:-1]:
+                layer.output_activation = "elu" if layer.concat else None
         self.x_local_host = x_host[self.plan.lo:self.plan.hi].contiguous()
         if x_host.is_pinned():
             self.x_local_host = self.x_local_host.pin_memory()
@@ -418,7 +430,7 @@ class PartitionedGAT:
         for i, layer in enumerate(self.layers):
             layer.W.weight.grad = layer.a.weight.grad = None
             h = layer(h, st, self.plan)
-            if i != len(self.layers) - 1:
+            if i != len(self.layers) - 1 and layer.output_activation != "elu":
                 h = F.elu(h)
         loss = h.square().sum() / (self.plan.n * h.size(1))     # this rank's share of the global mean
         loss.backward()

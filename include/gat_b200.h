@@ -99,13 +99,22 @@ GAT_API int gat_gemm_tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t 
 GAT_API int gat_gemm(int ta, int tb, int64_t m, int64_t n, int64_t k,
              const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
              int algo, void* workspace, size_t workspace_bytes, gat_stream_t stream);
+/* gat_gemm with the reference's inter-layer glue fused in (GATModel.py:148-149 applies F.elu between layers; SURVEY.md
+ * 8-f1).  act_a / act_b != 0: the A / B operand is ELU(stored values), applied to the tile on its way to the tensor
+ * cores, so the activated tensor is never written.  mul_elu_grad_src != NULL (ta = 0 only): C[i,j] *= ELU'(src[i*mul_ld+j])
+ * -- the adjoint of that activation, applied to dX in the epilogue. */
+GAT_API int gat_gemm_ex(int ta, int tb, int64_t m, int64_t n, int64_t k,
+                const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
+                int act_a, int act_b, const float* mul_elu_grad_src, int64_t mul_ld,
+                int algo, void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* The forward projection as one entry point: wh (n, dp) = x (n, f_in) * w (dp, f_in)^T  [gat_layer.py:64-65] and, when
  * a_src/a_tgt (nh, dp) are given, s_src/s_tgt (n, nh) = wh * a_src^T / wh * a_tgt^T  [gat_layer.py:76-82].  When the
  * tcgen05 path applies and dp <= 256 the score terms are computed in the GEMM epilogue from the accumulator tile
  * (fp64 accumulation over the fp32-rounded wh, same arithmetic as gat_scores_fwd); otherwise gat_gemm + gat_scores_fwd.
+ * x_act != 0: the layer input is ELU(x) (fused glue, see gat_gemm_ex).
  * workspace: gat_gemm_workspace_bytes(0, 1, n, dp, f_in, algo). */
-GAT_API int gat_project_fwd(const float* x, int64_t n, int64_t f_in, int64_t ldx, const float* w, int64_t ldw, int dp,
+GAT_API int gat_project_fwd(const float* x, int64_t n, int64_t f_in, int64_t ldx, int x_act, const float* w, int64_t ldw, int dp,
                             const float* a_src, const float* a_tgt, int nh, float* wh, float* s_src, float* s_tgt,
                             int algo, void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
@@ -116,7 +125,7 @@ GAT_API int gat_project_fwd(const float* x, int64_t n, int64_t f_in, int64_t ldx
  * device pointers: this rank's own buffer and the peers' buffers mapped into this process (CUDA peer / symmetric
  * memory over NVLink).  No separate collective moves the features; the caller only needs a cross-rank barrier (any
  * small collective) before reading its gathered buffer.  s_src / s_tgt (n, nh) are this rank's rows only. */
-GAT_API int gat_project_fwd_allgather(const float* x, int64_t n, int64_t f_in, int64_t ldx, const float* w, int64_t ldw, int dp,
+GAT_API int gat_project_fwd_allgather(const float* x, int64_t n, int64_t f_in, int64_t ldx, int x_act, const float* w, int64_t ldw, int dp,
                                       const float* a_src, const float* a_tgt, int nh,
                                       float* const* h_wh_dests, int n_dests, int64_t row_offset,
                                       float* s_src, float* s_tgt, gat_stream_t stream);
@@ -146,6 +155,8 @@ GAT_API int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int32_
 /* Kernel 3: per destination row, p = exp(0.01*(l-M)) (gat_layer.py:85-96), Z = sum p (:99-103),
  * alpha = p/(Z+1e-8) (:106-109), Philox dropout on alpha (:113-115), out = sum alpha*wh[src]
  * (:119-127), written in padded-head concat layout (n, dp).
+ *  out_act     1: store ELU(out) -- the F.elu GATModel.forward applies to a hidden layer's output (GATModel.py:148-149) fused
+ *               into this kernel's epilogue (opt-in); 0: the reference layer's pre-activation output;
  *  alpha_out   (n_edges, nh) in REWRITTEN EDGE ORDER (row eid[j]), pre-dropout, or NULL;
  *  z_out       (n, nh) saved for backward, or NULL;
  *  tie_dst/tie_src (n, nh) int32 + tie_total (1) uint64: arg-max-set bookkeeping for the
@@ -160,7 +171,7 @@ GAT_API size_t gat_edge_fwd_workspace_bytes(void);
 GAT_API int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
                  int64_t n, const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
                  const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
-                 float* out, float* alpha_out, float* z_out,
+                 float* out, int out_act, float* alpha_out, float* z_out,
                  int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
                  void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
@@ -235,8 +246,12 @@ GAT_API int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, cons
 
 /* Pass 2 when there is no upstream dL/dalpha: s_sum[d,h] = <go_padded[d,h,:], out_padded[d,h,:]> (the forward output in
  * padded-head layout) -- identical to the record sum because out = sum_e m*alpha*Wh[src]; no per-edge gather at all.
- * Same outputs and Gamma reduction as gat_edge_bwd_rowsum. */
-GAT_API int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const float* out_padded, const float* z, int64_t n_rows, int nh, int fp,
+ * Same outputs and Gamma reduction as gat_edge_bwd_rowsum.
+ * out_is_act = 1 (the forward ran with out_act): out_padded holds h = ELU(out) and go_padded is dL/dh; the pass recovers
+ * out = h > 0 ? h : log1p(h) and ELU'(out) = h > 0 ? 1 : h + 1, writes dL/dout = go*ELU' to go_out (n_rows, nh*fp) -- the buffer
+ * the source-major pass must then gather -- and uses it in S: the ELU backward costs no pass of its own. */
+GAT_API int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const float* out_padded, int out_is_act, float* go_out,
+                                const float* z, int64_t n_rows, int nh, int fp,
                                 float* s_sum, float* ds_tgt, void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* Partitioned graphs only: *gamma_out = this rank's Gamma.  The caller all-reduces Gamma and tie_total over ranks and hands
@@ -253,6 +268,20 @@ GAT_API int gat_edge_bwd_finish(const int32_t* rowptr_t, const int32_t* col_t, c
                                 const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
                                 float* ds_src, float* ds_tgt, float* d_wh,
                                 void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Caller-side glue: the attention-norm regulariser of GATModel.calc_attention_norm
+ * (GATModel.py:189-234) for ONE layer:  *norm_out = sum_{e,h} |alpha[e,h]*deg(dst_e) - 1| / n_edges, with deg(dst) the
+ * rowptr difference of gat_csr_build (== the scatter_add/index_select degrees of GATModel.py:196-201).  edge_dst is row 1 of
+ * the rewritten edge list (n_edges entries, int64 or int32); alpha is (n_edges, nh) in that edge order.  The backward
+ * writes grad_alpha = *upstream * sign(alpha*deg - 1) * deg / n_edges.  Deterministic (fixed-order fp64 reduction).
+ * ------------------------------------------------------------------------------------- */
+GAT_API size_t gat_attention_norm_workspace_bytes(void);
+GAT_API int gat_attention_norm_fwd(const void* edge_dst, int index_is_int64, const int32_t* rowptr, const float* alpha,
+                                   int64_t n_edges, int nh, float* norm_out, void* workspace, size_t workspace_bytes,
+                                   gat_stream_t stream);
+GAT_API int gat_attention_norm_bwd(const void* edge_dst, int index_is_int64, const int32_t* rowptr, const float* alpha,
+                                   int64_t n_edges, int nh, const float* upstream, float* grad_alpha, gat_stream_t stream);
 
 #ifdef __cplusplus
 }

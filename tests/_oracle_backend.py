@@ -16,14 +16,22 @@ class OracleBackend:
     def n_edges(self, st):
         return int(st["src"].numel())
 
-    def gemm(self, ta, tb, m, n, k, a, lda, b, ldb, c, ldc):
+    def gemm(self, ta, tb, m, n, k, a, lda, b, ldb, c, ldc, act_b=False, mul_elu_grad=None):
         a2 = a.reshape(-1)[: (k if ta else m) * lda].view(-1, lda)
         b2 = b.reshape(-1)[: (n if tb else k) * ldb].view(-1, ldb)
         A = a2[:k, :m].T if ta else a2[:m, :k]
         B = b2[:n, :k].T if tb else b2[:k, :n]
-        c.reshape(-1)[: m * ldc].view(-1, ldc)[:m, :n] = (A.double() @ B.double()).float()
+        if act_b:
+            B = torch.nn.functional.elu(B)
+        out = A.double() @ B.double()
+        if mul_elu_grad is not None:
+            xs = mul_elu_grad[:m, :n].double()
+            out = out * torch.where(xs > 0, torch.ones_like(xs), torch.exp(xs))
+        c.reshape(-1)[: m * ldc].view(-1, ldc)[:m, :n] = out.float()
 
-    def project(self, x, rows, f_in, w_p, dp, a_src, a_tgt, nh, wh, s_src, s_tgt):
+    def project(self, x, rows, f_in, w_p, dp, a_src, a_tgt, nh, wh, s_src, s_tgt, x_act=False):
+        if x_act:
+            x = torch.nn.functional.elu(x)
         self.gemm(False, True, rows, dp, f_in, x, x.stride(0), w_p, w_p.stride(0), wh, dp)
         self.scores(wh, rows, dp, a_src, a_tgt, nh, s_src, s_tgt)
 
@@ -46,7 +54,7 @@ class OracleBackend:
         z = torch.zeros((rows, nh)).index_add_(0, st["dst"] - plan.lo, p)
         return l, p, z
 
-    def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total):
+    def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act=False):
         rows = plan.rows
         l, p, zz = self._alpha(st, plan, s_src_full, s_tgt_local, gmax, rows, nh)
         z[:rows] = zz
@@ -58,6 +66,8 @@ class OracleBackend:
         tie_dst.view(-1, nh).index_add_(0, st["dst"] - plan.lo, tie)
         tie_src.view(-1, nh).index_add_(0, st["src"], tie)
         tie_total.view(torch.int64)[0] = int(tie.sum())
+        if out_act:
+            out_p.copy_(torch.nn.functional.elu(out_p))
 
     def edge_bwd_main(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh):
         rows = plan.rows
@@ -79,8 +89,12 @@ class OracleBackend:
         self.edge_bwd_main(st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh)
         self.edge_bwd_finish(st, plan, nh, fp, rec, s_sum_local, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh)
 
-    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt):
+    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt, go_pre=None):
         rows = plan.rows
+        if go_pre is not None:     # out_p holds h = ELU(out): recover out and apply ELU'
+            h = out_p
+            go_pre.copy_(go_p * torch.where(h > 0, torch.ones_like(h), h + 1.0))
+            go_p, out_p = go_pre, torch.where(h > 0, h, torch.log1p(h.clamp(min=-1 + 1e-30)))
         s = (go_p.view(-1, nh, fp)[:rows] * out_p.view(-1, nh, fp)[:rows]).sum(-1)
         s_sum[:rows] = s
         ds_tgt.zero_()

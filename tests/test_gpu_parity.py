@@ -278,13 +278,13 @@ def test_project_allgather_multi_destination():
         a_src, a_tgt = torch.randn(nh, dp, device="cuda"), torch.randn(nh, dp, device="cuda")
         want_wh = torch.empty(rows, dp, device="cuda")
         want_s, want_t = torch.empty(rows, nh, device="cuda"), torch.empty(rows, nh, device="cuda")
-        _lib.call("gat_project_fwd", x.data_ptr(), rows, f_in, f_in, w.data_ptr(), f_in, dp, a_src.data_ptr(), a_tgt.data_ptr(), nh,
+        _lib.call("gat_project_fwd", x.data_ptr(), rows, f_in, f_in, 0, w.data_ptr(), f_in, dp, a_src.data_ptr(), a_tgt.data_ptr(), nh,
                   want_wh.data_ptr(), want_s.data_ptr(), want_t.data_ptr(), 2, None, 0, torch.cuda.current_stream().cuda_stream)
         total = lo + rows + 37
         dests = [torch.full((total, dp), float("nan"), device="cuda") for _ in range(2)]
         s_src, s_tgt = torch.empty(rows, nh, device="cuda"), torch.empty(rows, nh, device="cuda")
         arr = (ctypes.c_void_p * 2)(*[d.data_ptr() for d in dests])
-        _lib.call("gat_project_fwd_allgather", x.data_ptr(), rows, f_in, f_in, w.data_ptr(), f_in, dp, a_src.data_ptr(), a_tgt.data_ptr(),
+        _lib.call("gat_project_fwd_allgather", x.data_ptr(), rows, f_in, f_in, 0, w.data_ptr(), f_in, dp, a_src.data_ptr(), a_tgt.data_ptr(),
                   nh, arr, 2, lo, s_src.data_ptr(), s_tgt.data_ptr(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         ref = (x.double() @ w.double().T)
@@ -315,3 +315,87 @@ def test_backward_without_attention_gradient(name, small_cases):
     errs = {"out": O.rel_err(out.detach().cpu().numpy(), fw["out"]), "gx": O.rel_err(x.grad.cpu().numpy(), gr["x"]),
             "gW": O.rel_err(layer.W.weight.grad.cpu().numpy(), gr["W"]), "ga": O.rel_err(layer.a.weight.grad.cpu().numpy(), gr["a"])}
     assert all(e <= tol for e in errs.values()), errs
+
+
+@pytest.mark.parametrize("name", ["products_L1", "cora_L1", "pattern_L1", "ppi_L1"])
+def test_fused_input_elu_matches_explicit_elu(name, small_cases):
+    """Opt-in glue fusion: layer.input_activation = "elu" must equal layer(F.elu(x)) -- the F.elu
+    GATModel.forward applies between layers (GATModel.py:148-149) -- in the output and in every gradient, on both GEMM
+    paths (tcgen05 for the aligned shapes, FFMA otherwise)."""
+    import torch.nn.functional as F
+    case = small_cases[name]
+    rng = np.random.default_rng(11)
+    x_np = (rng.standard_normal(case["x"].shape) * 1.5).astype(np.float32)     # both signs, so ELU matters
+    ei = torch.from_numpy(case["edge_index"]).cuda()
+    res = []
+    for fused in (False, True):
+        layer = make_layer(case)
+        layer.input_activation = "elu" if fused else None
+        x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+        out = layer(x if fused else F.elu(x), ei)
+        go, _ = cases.upstream_grads(case, out.shape[0], out.shape[1], 1)
+        (out * torch.from_numpy(go).cuda()).sum().backward()
+        res.append({"out": out.detach(), "gx": x.grad, "gW": layer.W.weight.grad, "ga": layer.a.weight.grad})
+    for k in res[0]:
+        a, b = res[0][k].double(), res[1][k].double()
+        err = ((a - b).abs().max() / a.abs().max().clamp(min=1e-30)).item()
+        assert err <= 2e-6, (k, err)
+
+
+@pytest.mark.parametrize("name", ["products_L1", "cora_L0", "pattern_L1", "ppi_L1", "adv_concat_oddF", "adv_wide"])
+def test_fused_output_elu_matches_explicit_elu(name, small_cases):
+    """Opt-in glue fusion on the output side (the north star's "...then ELU"): layer.output_activation =
+    "elu" must equal F.elu(layer(x)) in the output and every gradient -- ELU in the edge kernel's epilogue, its adjoint in
+    the backward's per-node pass (out recovered as log1p(h))."""
+    import torch.nn.functional as F
+    case = small_cases[name]
+    ei = torch.from_numpy(case["edge_index"]).cuda()
+    for with_alpha in (False, True):
+        res = []
+        for fused in (False, True):
+            layer = make_layer(case)
+            layer.output_activation = "elu" if fused else None
+            x = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+            if with_alpha:
+                out, (_, alpha) = layer(x, ei, return_attention_weights=True)
+            else:
+                out, alpha = layer(x, ei), None
+            if not fused:
+                out = F.elu(out)
+            go, ga = cases.upstream_grads(case, out.shape[0], out.shape[1], alpha.shape[0] if with_alpha else 1)
+            loss = (out * torch.from_numpy(go).cuda()).sum()
+            if with_alpha:
+                loss = loss + (alpha * torch.from_numpy(ga).cuda()).sum()
+            loss.backward()
+            res.append({"out": out.detach(), "gx": x.grad, "gW": layer.W.weight.grad, "ga": layer.a.weight.grad})
+        for k in res[0]:
+            a, b = res[0][k].double(), res[1][k].double()
+            err = ((a - b).abs().max() / a.abs().max().clamp(min=1e-30)).item()
+            assert err <= 5e-6, (name, with_alpha, k, err)
+
+
+def test_attention_norm_matches_reference_formula(small_cases):
+    """gat_pytorch_b200.attention_norm == GATModel.calc_attention_norm (GATModel.py:189-234), restated
+    here with the reference's own torch ops (scatter_add degrees, broadcast back, |alpha*deg - 1|_1 / E', mean over
+    layers), value and gradient w.r.t. every attention tensor."""
+    from gat_pytorch_b200 import attention_norm
+    for name in ("adv_concat", "cora_L0", "products_L1"):
+        case = small_cases[name]
+        layer = make_layer(case)
+        x = torch.from_numpy(case["x"]).cuda()
+        ei = torch.from_numpy(case["edge_index"]).cuda()
+        _, (ei2, alpha) = layer(x, ei, return_attention_weights=True)
+        att = [alpha.detach().clone().requires_grad_(True), (alpha.detach() * 0.5 + 0.01).requires_grad_(True)]
+        got = attention_norm(ei2, att)
+        got.backward()
+        # the reference formulation
+        ref_att = [a.detach().clone().double().requires_grad_(True) for a in att]
+        dst = ei2[1]
+        ones = torch.ones(dst.numel(), dtype=torch.float64, device="cuda")
+        deg = torch.zeros(dst.numel(), dtype=torch.float64, device="cuda").scatter_add_(0, dst, ones).index_select(0, dst)
+        want = sum(torch.norm(a * deg[:, None] - 1.0, p=1) / dst.numel() for a in ref_att) / len(ref_att)
+        want.backward()
+        assert abs(got.item() - want.item()) <= 1e-6 * max(abs(want.item()), 1e-30), (name, got.item(), want.item())
+        for a, r in zip(att, ref_att):
+            err = ((a.grad.double() - r.grad).abs().max() / r.grad.abs().max()).item()
+            assert err <= 1e-6, (name, err)
