@@ -113,14 +113,22 @@ scores_bwd_partial_kernel(const float* __restrict__ wh, int64_t n, int dp, int n
   }
 }
 
-__global__ void scores_bwd_reduce_kernel(const float* __restrict__ partial, int slabs, int nh, int dp,
-                                         float* __restrict__ da_src, float* __restrict__ da_tgt) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 2*nh*dp
+// One WARP per output element: lane l sums slabs l, l+32, ... in fp64, then a fixed xor tree -- deterministic, and the
+// serial chain is slabs/32 long instead of slabs (which cost milliseconds on the small graphs).
+__global__ void __launch_bounds__(256)
+scores_bwd_reduce_kernel(const float* __restrict__ partial, int slabs, int nh, int dp,
+                         float* __restrict__ da_src, float* __restrict__ da_tgt) {
+  const int idx = blockIdx.x * 8 + (threadIdx.x >> 5);   // over 2*nh*dp
+  const int lane = threadIdx.x & 31;
   if (idx >= 2 * nh * dp) return;
   double s = 0.0;
-  for (int b = 0; b < slabs; ++b) s += (double)partial[(int64_t)b * 2 * nh * dp + idx];
-  const int j = idx / dp, d = idx - j * dp;
-  if (j < nh) da_src[(int64_t)j * dp + d] = (float)s; else da_tgt[(int64_t)(j - nh) * dp + d] = (float)s;
+  for (int b = lane; b < slabs; b += 32) s += (double)partial[(int64_t)b * 2 * nh * dp + idx];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const int j = idx / dp, d = idx - j * dp;
+    if (j < nh) da_src[(int64_t)j * dp + d] = (float)s; else da_tgt[(int64_t)(j - nh) * dp + d] = (float)s;
+  }
 }
 
 static int cp_log2_for(int chunks) {
@@ -161,11 +169,14 @@ extern "C" int gat_scores_bwd(const float* wh, int64_t n, int dp, int nh, const 
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int l2 = cp_log2_for(dp / 4), rs = 256 >> l2;
-  if (nh <= 4) scores_bwd_partial_kernel<4><<<kScoreBwdBlocks, 256, 0, st>>>(wh, n, dp, nh, l2, ds_src, ds_tgt, (float*)workspace);
-  else scores_bwd_partial_kernel<8><<<kScoreBwdBlocks, 256, 0, st>>>(wh, n, dp, nh, l2, ds_src, ds_tgt, (float*)workspace);
+  // every (CTA, row sub-group) should own at least ~8 rows: small graphs get few CTAs (and few partial slabs to reduce)
+  int64_t want = n / ((int64_t)rs * 8);
+  const int blocks = (int)(want < 1 ? 1 : (want > kScoreBwdBlocks ? kScoreBwdBlocks : want));
+  if (nh <= 4) scores_bwd_partial_kernel<4><<<blocks, 256, 0, st>>>(wh, n, dp, nh, l2, ds_src, ds_tgt, (float*)workspace);
+  else scores_bwd_partial_kernel<8><<<blocks, 256, 0, st>>>(wh, n, dp, nh, l2, ds_src, ds_tgt, (float*)workspace);
   GAT_LAUNCH_CHECK();
   const int total = 2 * nh * dp;
-  scores_bwd_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, kScoreBwdBlocks * rs, nh, dp, da_src, da_tgt);
+  scores_bwd_reduce_kernel<<<(total + 7) / 8, 256, 0, st>>>((const float*)workspace, blocks * rs, nh, dp, da_src, da_tgt);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }
