@@ -114,9 +114,11 @@ SimtPlan simt_plan(int64_t m, int64_t n, int64_t k) {
   p.bn = n <= 64 ? 64 : 128;
   int64_t tiles = ((m + p.bm - 1) / p.bm) * ((n + p.bn - 1) / p.bn);
   p.splits = 1;
-  if (tiles < kNumSMs && k >= 4096) {
+  // few tiles and a long contraction (dW of the small graphs: 64 x 1433 over K = 2708 nodes; Cora's projection: 22 tiles over
+  // K = 1433): split K so the grid covers the SMs; a split never gets fewer than 128 k-steps
+  if (tiles < kNumSMs && k >= 512) {
     int64_t want = (2 * kNumSMs + tiles - 1) / tiles;
-    int64_t cap = k / 1024;
+    int64_t cap = k / 128;
     p.splits = (int)(want < cap ? want : cap);
     if (p.splits < 1) p.splits = 1;
     if (p.splits > 1024) p.splits = 1024;

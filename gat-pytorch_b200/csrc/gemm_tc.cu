@@ -23,7 +23,8 @@ namespace gat {
 namespace tc {
 
 constexpr int BM = 128;          // UMMA M (cta_group::1)
-constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int BK = 16;           // fp32 elements per k-block = one 64-byte swizzle row (NT) / 16 k-rows of a 128-byte atom column (TN)
+constexpr int CBOX = 32;         // columns per TMA box of the staged output tile (one 128-byte swizzle row)
 constexpr int UMMA_K = 8;        // tf32
 constexpr int kThreads = 192;
 constexpr int kSplitThreads = 128;
@@ -72,11 +73,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
-// LBO unused (1), SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO unused (1), SBO = 512 B (8 rows x 64 B) >> 4, version 1 (Blackwell), layout type 4 (SWIZZLE_64B).  A k-block is
+// 16 fp32 = 64 B per row (not 128): a stage is half as large, so the pipeline is twice as deep in the same memory --
+// load, split and MMA are three phases and need more than two stages to overlap.
+__device__ __forceinline__ uint64_t make_desc_k_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 // MN-major tf32: the only layout the tensor core accepts is SWIZZLE_128B_BASE32B (layout type 1; TMA mode
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): an atom is 32 MN-elements (128 B) x 4 K-rows (512 B, 32-byte chunks XORed with
@@ -118,19 +121,30 @@ __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) 
 __device__ __forceinline__ float elu_grad1(float x) { return x > 0.f ? 1.f : __expf(x); }
 __device__ __forceinline__ float4 elu4(float4 v) { return make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w)); }
 
+// Round to tf32 precision (11 significant bits).  sm_100a has no hardware cvt.rna.tf32.f32: ptxas expands it into
+// VIADD + LOP3 + FSETP + SEL on the half-rate integer pipe, which made the 4 splitter warps -- not the tensor core -- the
+// limiter of the main loop (1400 clk per 16-wide k-block against 786 clk of MMA).  Veltkamp's splitting does the same
+// rounding (to nearest, ties to even) in three full-rate FP32 operations and propagates NaN; |v| > 4e34 overflows to
+// NaN, which no feature matrix reaches.  __fmul_rn / __fadd_rn keep the compiler from contracting the sequence into FMAs.
 __device__ __forceinline__ float tf32_round(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
+  const float g = __fmul_rn(v, 8193.0f);      // 2^13 + 1
+  return __fadd_rn(g, __fsub_rn(v, g));
 }
 
-template <int BN>
+// NT tiles are at most 128 columns wide and sized so that TWO CTAs are resident per SM (<= 113 KB of shared memory and
+// 256 TMEM columns each): a non-persistent CTA spends ~10 us per tile outside its main loop (launch, TMEM allocation,
+// pipeline fill, TMEM drain, output store) -- measured as the K-independent part of the tile time -- and with a second
+// CTA on the SM that time is covered by the other CTA's main loop.  TN (split-K, long K, tiny epilogue) keeps one CTA
+// per SM with 256-wide tiles and a deeper pipeline.
+template <int BN, bool MN>
 struct Smem {
-  static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
-  static constexpr int kABytes = BM * BK * 4;     // 16 KB
+  static constexpr int kABytes = BM * BK * 4;     // 8 KB
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // raw/hi + lo for both operands
+  static constexpr int kCtasPerSm = (!MN && BN <= 128) ? 2 : 1;
+  static constexpr int kStages = MN ? (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8)) : (BN >= 256 ? 4 : (BN >= 128 ? 3 : 4));
   static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+  static_assert(kTotal * kCtasPerSm <= 227 * 1024, "shared memory budget");
 };
 
 // Destinations of an NT output tile.  The tile is staged in shared memory and written by TMA to `count` row-major
@@ -147,7 +161,7 @@ struct CStoreMaps {
 // MN = false: NT product, one CTA per output tile, whole K.   MN = true: TN product, blockIdx.z = K split, the CTA
 // writes its partial tile to C + blockIdx.z * split_stride (reduced in a fixed order by splitk_reduce_kernel).
 template <int BN, bool MN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (Smem<BN, MN>::kCtasPerSm))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CStoreMaps cmaps, float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, int kb_per_split, int64_t split_stride,
                uint32_t mn_lbo, uint32_t mn_sbo,
@@ -156,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                float* __restrict__ s_src, float* __restrict__ s_tgt,
                // fused glue: ELU on the A / B operand tiles; output multiplied by ELU'(mul_src[row, col]) (NT only)
                int act_a, int act_b, const float* __restrict__ mul_src, int64_t mul_ld) {
-  using S = Smem<BN>;
+  using S = Smem<BN, MN>;
   constexpr int kStages = S::kStages;
   // two accumulators: [0, BN) leading term hi*hi, [BN, 2BN) cross terms hi*lo + lo*hi.  The tensor core rounds its
   // fp32 accumulator toward zero at every step, a one-sided error proportional to the accumulator's magnitude; keeping
@@ -172,7 +186,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_ptr = (uint32_t*)(bars + 3 * kStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  // NT: 1-D grid, the N tiles of one M tile are adjacent (they share the A tile: the second read hits L2)
+  const int n_tiles = (int)((N + BN - 1) / BN);
+  const int64_t m0 = (MN ? (int64_t)blockIdx.x : (int64_t)(blockIdx.x / n_tiles)) * BM;
+  const int64_t n0 = (MN ? (int64_t)blockIdx.y : (int64_t)(blockIdx.x % n_tiles)) * BN;
   const int total_kb = (int)((K + BK - 1) / BK);
   const int kb_begin = MN ? (int)blockIdx.z * kb_per_split : 0;
   const int num_kb = MN ? max(0, min(kb_per_split, total_kb - kb_begin)) : total_kb;
@@ -228,10 +245,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint32_t first = (kb | k) != 0;
           if (!MN) {
-            const uint32_t off = k * UMMA_K * 4;   // bytes along the 128-byte swizzled row
-            umma_tf32(tmem_cross, make_desc_k_sw128(a_hi + off), make_desc_k_sw128(b_lo + off), idesc, first);
-            umma_tf32(tmem_cross, make_desc_k_sw128(a_lo + off), make_desc_k_sw128(b_hi + off), idesc, 1);
-            umma_tf32(tmem_main, make_desc_k_sw128(a_hi + off), make_desc_k_sw128(b_hi + off), idesc, first);
+            const uint32_t off = k * UMMA_K * 4;   // bytes along the 64-byte swizzled row
+            umma_tf32(tmem_cross, make_desc_k_sw64(a_hi + off), make_desc_k_sw64(b_lo + off), idesc, first);
+            umma_tf32(tmem_cross, make_desc_k_sw64(a_lo + off), make_desc_k_sw64(b_hi + off), idesc, 1);
+            umma_tf32(tmem_main, make_desc_k_sw64(a_hi + off), make_desc_k_sw64(b_hi + off), idesc, first);
           } else {
             const uint32_t off = k * 1024;         // one 8-row swizzle atom per UMMA_K
             umma_tf32(tmem_cross, make_desc_mn_sw128(a_hi + off, mn_lbo, mn_sbo), make_desc_mn_sw128(b_lo + off, mn_lbo, mn_sbo), idesc, first);
@@ -298,6 +315,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int TSTR = 36;                         // row stride (doubles) of the per-warp transpose tile
     double* a_s = reinterpret_cast<double*>(smem + (MN ? 0 : kBoxes * kBoxBytes));   // [16][ASTR], rows >= 2*nh are zero
     double* tile = a_s + 16 * ASTR + (warp - 2) * (8 * TSTR);
+    static_assert(MN || kBoxes * kBoxBytes + (16 * ASTR + 4 * 8 * TSTR) * 8 <= S::kStages * S::kStageBytes,
+                  "the epilogue's staging buffers alias the pipeline memory and must fit inside it");
     const int nj = 2 * nh, nbk = nj > 8 ? 2 : 1;
     const int rl = q * 32 + lane;                    // row inside the tile
     double sacc[4][2][2];
@@ -309,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int i = t; i < 16 * BN; i += kSplitThreads) {
         const int j = i / BN, col = i - j * BN;
         float v = 0.f;
-        if (j < nj && col < N) v = (j < nh) ? __ldg(a_src + (int64_t)j * N + col) : __ldg(a_tgt + (int64_t)(j - nh) * N + col);
+        if (j < nj && n0 + col < N) v = (j < nh) ? __ldg(a_src + (int64_t)j * N + n0 + col) : __ldg(a_tgt + (int64_t)(j - nh) * N + n0 + col);
         a_s[j * ASTR + col] = (double)v;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kSplitThreads) : "memory");
@@ -403,7 +422,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int e = 0; e < 2; ++e) {
               const int j = nb * 8 + 2 * (lane & 3) + e;
               if (nb < nbk && j < nj) {
-                if (j < nh) s_src[srow * nh + j] = (float)sacc[g][nb][e]; else s_tgt[srow * nh + (j - nh)] = (float)sacc[g][nb][e];
+                float* sp = j < nh ? s_src + srow * nh + j : s_tgt + srow * nh + (j - nh);
+                // two N tiles: each adds its half of the dot product to the zero-initialised score (at most two addends per
+                // element, and a + b == b + a, so the result does not depend on which CTA arrives first)
+                if (n_tiles > 1) atomicAdd(sp, (float)sacc[g][nb][e]); else *sp = (float)sacc[g][nb][e];
               }
             }
           }
@@ -436,16 +458,18 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D fp32 row-major (rows x cols, leading dimension ld elements); box = box_rows x 32 columns, SWIZZLE_128B,
 // out-of-bounds elements read as zero (so M, N and K tails need no special casing).
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                    bool atom32 = false) {
+enum MapKind { kMapK64, kMapC128, kMapMN };   // K-major operand (64-byte rows), output tile (128-byte rows), MN-major operand
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, MapKind kind) {
+  const int box_cols = kind == kMapK64 ? BK : 32;
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("gat_gemm: cuTensorMapEncodeTiled is unavailable"); return GAT_EUNSUPPORTED; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  kind == kMapMN ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (kind == kMapK64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("gat_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r); return GAT_EINVAL; }
   return GAT_OK;
@@ -463,7 +487,7 @@ static TnPlan tn_plan(int64_t m, int64_t n, int64_t k, int bn) {
   // The tensor core rounds its fp32 accumulator toward zero at every MMA, so the error of one accumulator grows
   // linearly with the number of k-steps (measured: 7e-5 after 4136 steps, ~1e-6 after 128).  Cap the steps per
   // split; the partials are then summed in fp64 by splitk_reduce_kernel.
-  constexpr int kMaxKbPerSplit = 64;
+  constexpr int kMaxKbPerSplit = 2048 / BK;
   if (p.kb_per_split > kMaxKbPerSplit) p.kb_per_split = kMaxKbPerSplit;
   p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (p.splits < 1) p.splits = 1;
@@ -488,29 +512,36 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
   cm.count = 0; cm.row_offset = 0;
   int rc;
   if (!MN) {
-    rc = make_map(&map_a, a, m, k, lda, BM);
-    if (!rc) rc = make_map(&map_b, b, n, k, ldb, BN);
+    rc = make_map(&map_a, a, m, k, lda, BM, kMapK64);
+    if (!rc) rc = make_map(&map_b, b, n, k, ldb, BN, kMapK64);
     if (dests.count > kMaxDests || dests.row_offset + m >= ((int64_t)1 << 31)) { set_error("gat_gemm: too many destinations"); return GAT_EINVAL; }
     if (dests.count == 0) {
-      if (!rc) rc = make_map(&cm.maps[0], c, m, n, ldc, BM);
+      if (!rc) rc = make_map(&cm.maps[0], c, m, n, ldc, BM, kMapC128);
       cm.count = 1;
     } else {
-      for (int d = 0; d < dests.count && !rc; ++d) rc = make_map(&cm.maps[d], dests.ptrs[d], dests.row_offset + m, n, ldc, BM);
+      for (int d = 0; d < dests.count && !rc; ++d) rc = make_map(&cm.maps[d], dests.ptrs[d], dests.row_offset + m, n, ldc, BM, kMapC128);
       cm.count = dests.count; cm.row_offset = (int)dests.row_offset;
     }
   } else {   // stored (K, M) and (K, N): boxes of 32 MN-elements x BK k-rows
-    rc = make_map(&map_a, a, k, m, lda, BK, true);
-    if (!rc) rc = make_map(&map_b, b, k, n, ldb, BK, true);
+    rc = make_map(&map_a, a, k, m, lda, BK, kMapMN);
+    if (!rc) rc = make_map(&map_b, b, k, n, ldb, BK, kMapMN);
   }
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    GAT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal));
+    GAT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, MN>::kTotal));
     attr_set = true;
   }
   if (!MN) {
-    dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), 1);
-    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, c, ldc, m, n, k, 0, 0, 0, 0, f.a_src, f.a_tgt, f.nh, f.s_src, f.s_tgt,
+    const int64_t tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
+    if (tiles >= ((int64_t)1 << 31)) { set_error("gat_gemm: too many tiles"); return GAT_EINVAL; }
+    if (f.a_src != nullptr && n > BN) {   // partial dot products of the N tiles are added into the scores
+      if (n > 2 * BN) { set_error("gat_project_fwd: fused scores support at most two N tiles"); return GAT_EUNSUPPORTED; }
+      GAT_CUDA(cudaMemsetAsync(f.s_src, 0, (size_t)m * f.nh * sizeof(float), st));
+      GAT_CUDA(cudaMemsetAsync(f.s_tgt, 0, (size_t)m * f.nh * sizeof(float), st));
+    }
+    dim3 grid((unsigned)tiles, 1, 1);
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN, MN>::kTotal, st>>>(map_a, map_b, cm, c, ldc, m, n, k, 0, 0, 0, 0, f.a_src, f.a_tgt, f.nh, f.s_src, f.s_tgt,
                                                                      g.act_a, g.act_b, g.mul_src, g.mul_ld);
     GAT_LAUNCH_CHECK();
     return GAT_OK;
@@ -519,7 +550,7 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
   const uint32_t mn_lbo = BK * 128, mn_sbo = 512;   // measured on B200: the swapped assignment gives wrong products
   dim3 grid((unsigned)((m + BM - 1) / BM), (unsigned)((n + BN - 1) / BN), (unsigned)p.splits);
   if (p.splits == 1) {
-    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, c, ldc, m, n, k, p.kb_per_split, 0, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr,
+    gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN, MN>::kTotal, st>>>(map_a, map_b, cm, c, ldc, m, n, k, p.kb_per_split, 0, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr,
                                                                      g.act_a, g.act_b, nullptr, 0);
     GAT_LAUNCH_CHECK();
     return GAT_OK;
@@ -529,7 +560,7 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
     set_error("gat_gemm: workspace too small (%zu < %zu)", workspace_bytes, need);
     return GAT_EWORKSPACE;
   }
-  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(map_a, map_b, cm, (float*)workspace, n, m, n, k, p.kb_per_split, m * n, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr,
+  gemm_tc_kernel<BN, MN><<<grid, kThreads, Smem<BN, MN>::kTotal, st>>>(map_a, map_b, cm, (float*)workspace, n, m, n, k, p.kb_per_split, m * n, mn_lbo, mn_sbo, nullptr, nullptr, 0, nullptr, nullptr,
                                                                    g.act_a, g.act_b, nullptr, 0);
   GAT_LAUNCH_CHECK();
   splitk_reduce_launch((const float*)workspace, p.splits, m, n, c, ldc, st);
@@ -537,7 +568,8 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
   return GAT_OK;
 }
 
-static int bn_for(int64_t n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
+static int bn_for(int64_t n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }      // TN
+static int bn_for_nt(int64_t n) { return n > 64 ? 128 : 64; }                      // NT: two CTAs per SM
 
 }  // namespace tc
 
@@ -574,8 +606,7 @@ int gemm_tc_project(int64_t n_rows, int64_t dp, int64_t k, const float* x, int64
   tc::ScoreFuse f{a_src, a_tgt, nh, s_src, s_tgt};
   tc::Dests dd{wh_dests, n_dests, row_offset};
   tc::Glue g{x_act, 0, nullptr, 0};
-  const int bn = tc::bn_for(dp);
-  if (bn == 256) return tc::launch<256, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd, g);
+  const int bn = tc::bn_for_nt(dp);
   if (bn == 128) return tc::launch<128, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd, g);
   return tc::launch<64, false>(n_rows, dp, k, x, ldx, w, ldw, wh, dp, nullptr, 0, st, f, dd, g);
 }
@@ -587,12 +618,11 @@ int gemm_tc(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int
     set_error("gat_gemm: tcgen05 path needs (ta,tb) = (0,1) or (1,0) and 16-byte aligned pointers / leading dimensions");
     return GAT_EUNSUPPORTED;
   }
-  const int bn = tc::bn_for(n);
+  const int bn = ta == 0 ? tc::bn_for_nt(n) : tc::bn_for(n);
   const tc::ScoreFuse nf{nullptr, nullptr, 0, nullptr, nullptr};
   const tc::Dests nd{nullptr, 0, 0};
   const tc::Glue g{act_a, act_b, mul_src, mul_ld};
   if (ta == 0) {
-    if (bn == 256) return tc::launch<256, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
     if (bn == 128) return tc::launch<128, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
     return tc::launch<64, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
   }

@@ -340,7 +340,12 @@ class _PartitionedGATFunction(torch.autograd.Function):
         ga_tgt = torch.zeros((nh, dp), **f32)
         if rows:
             backend.gemm(True, False, dp, f_in, rows, d_wh, dp, x_local, x_local.stride(0), gw, f_in, act_b=x_act)
-        backend.scores_bwd(wh_full, plan.n, dp, nh, ds_src_part, ds_tgt_full, ga_src, ga_tgt)   # one pass over Wh
+        # dA = ds^T Wh over the OWNED rows only: this rank's edges gave partial ds_src for every source, so the small
+        # (N, NH) array is reduce-scattered to the owners first (was: every rank streamed all N rows of Wh)
+        ds_src_local = torch.empty((R, nh), **f32)
+        dist.reduce_scatter_tensor(ds_src_local, ds_src_part, group=group)
+        if rows:
+            backend.scores_bwd(wh_full[plan.lo:plan.lo + rows], rows, dp, nh, ds_src_local, ds_tgt, ga_src, ga_tgt)
         flat = torch.cat([gw.reshape(-1), ga_src.reshape(-1), ga_tgt.reshape(-1)])
         dist.all_reduce(flat, group=group)                                  # the gradient all-reduce
         gw, ga_src, ga_tgt = flat[:gw.numel()].view_as(gw), flat[gw.numel():gw.numel() + ga_src.numel()].view_as(ga_src), \
