@@ -51,15 +51,18 @@ SIGNATURES = {
     "gat_edge_bwd_main": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, c_int,
                                   c_float, c_uint64, c_uint64, _P, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_fused": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P,
-                                   c_float, c_uint64, c_uint64, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
+                                   c_float, c_uint64, c_uint64, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
                                    _P, _P, _P, _P, c_int, c_int, c_int64, _P, c_size_t, _P]),
     "gat_attention_norm_workspace_bytes": (c_size_t, []),
     "gat_attention_norm_fwd": (c_int, [_P, c_int, _P, _P, c_int64, c_int, _P, _P, c_size_t, _P]),
     "gat_attention_norm_bwd": (c_int, [_P, c_int, _P, _P, c_int64, c_int, _P, _P, _P]),
+    "gat_attention_entropy": (c_int, [_P, _P, c_int64, _P, c_int, _P, _P, _P]),
+    "gat_attention_degree_scaled": (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
     "gat_slab_sum": (c_int, [_P, c_int, c_int64, c_int, _P, _P]),
     "gat_head_mean_bwd_shared": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
     "gat_edge_bwd_rowsum": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "gat_edge_bwd_rowdot": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "gat_tgt_pack_stride": (c_int, [c_int]),
+    "gat_edge_bwd_rowdot": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_finish": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
                                     _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_gamma": (c_int, [_P, c_size_t, _P, _P]),

@@ -52,6 +52,11 @@ struct BwdMainParams {
   // FUSED mode (no upstream dL/dalpha): S = <dOut, out> and Gamma are known BEFORE this pass (gat_edge_bwd_rowdot runs
   // first), so g, ds_src, the arg-max corrections and dWh += ds_src*A_src + ds_tgt*A_tgt are all done here; no records.
   const float* s_sum;                      // indexed by TARGET id
+  // per-target record {s_tgt[NHT] | Z[NHT] | S[NHT] | pad} written by gat_edge_bwd_rowdot (stride 4*NHT floats = one 64 B
+  // DRAM atom for NH <= 4): the three per-edge gathers of a target's scalars become ONE.  ncu: the fused pass moved
+  // 84 GB for 74.5 GB of algorithmic bytes on the products graph because each of the three 16-byte gathers (three
+  // 39 MB arrays, not L2 resident under the streaming traffic) cost its own 64-byte DRAM atom.
+  const float* tpack;
   const float* a_src; const float* a_tgt;
   const int32_t* tie_dst; const int32_t* tie_src; const BwdHeader* header; const float* corr_override;
   int64_t tgt_lo; int64_t tgt_hi;
@@ -153,17 +158,33 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
       } else {
         const float* tp = P.s_tgt + (int64_t)d * nh;
         float sv[NHT];
-        if (FUSED) {   // S[dst] travels with s_tgt[dst] / Z[dst] (same round trip) and waits in shared memory
-          const float* sp = P.s_sum + (int64_t)d * nh;
+        if (FUSED && P.tpack != nullptr) {   // one 16-byte-aligned record per target: s_tgt | Z | S
+          const float* pk = P.tpack + (int64_t)d * (4 * NHT);
+          float tv[NHT], zv[NHT];
 #pragma unroll
-          for (int h = 0; h < NHT; ++h) sv[h] = h < nh ? __ldg(sp + h) : 0.f;
+          for (int q = 0; q < NHT / 4; ++q) {
+            const float4 t4 = ldg4(pk + 4 * q), z4 = ldg4(pk + NHT + 4 * q), s4 = ldg4(pk + 2 * NHT + 4 * q);
+            tv[4 * q] = t4.x; tv[4 * q + 1] = t4.y; tv[4 * q + 2] = t4.z; tv[4 * q + 3] = t4.w;
+            zv[4 * q] = z4.x; zv[4 * q + 1] = z4.y; zv[4 * q + 2] = z4.z; zv[4 * q + 3] = z4.w;
+            sv[4 * q] = s4.x; sv[4 * q + 1] = s4.y; sv[4 * q + 2] = s4.z; sv[4 * q + 3] = s4.w;
+          }
+#pragma unroll
+          for (int h = 0; h < NHT; ++h)
+            if (h < nh) alpha[h] = attn_exp(ss[h] + tv[h], gmax) / (zv[h] + kSoftmaxEps);
+        } else {
+          if (FUSED) {   // S[dst] travels with s_tgt[dst] / Z[dst] (same round trip) and waits in shared memory
+            const float* sp = P.s_sum + (int64_t)d * nh;
+#pragma unroll
+            for (int h = 0; h < NHT; ++h) sv[h] = h < nh ? __ldg(sp + h) : 0.f;
+          }
+#pragma unroll
+          for (int h = 0; h < NHT; ++h)
+            if (h < nh) alpha[h] = attn_exp(ss[h] + __ldg(tp + h), gmax) / (__ldg(zp + h) + kSoftmaxEps);
         }
+        if (FUSED) {   // alpha * S[dst]: all the epilogue of this batch needs besides m*alpha (sh_w), so that no per-edge
+                       // register array stays live across the gather loop (the loop needs them for its loads in flight)
 #pragma unroll
-        for (int h = 0; h < NHT; ++h)
-          if (h < nh) alpha[h] = attn_exp(ss[h] + __ldg(tp + h), gmax) / (__ldg(zp + h) + kSoftmaxEps);
-        if (FUSED) {
-#pragma unroll
-          for (int h = 0; h < NHT; ++h) sh_s[tid * NHT + h] = sv[h];
+          for (int h = 0; h < NHT; ++h) sh_s[tid * NHT + h] = alpha[h] * sv[h];
         }
       }
       if (P.dropout_p > 0.f || P.grad_alpha) {
@@ -184,36 +205,32 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
     const int cnt = min(G, end - base);
     for (int t0 = 0; t0 < cnt; t0 += TB) {
       const int tcnt = min(TB, cnt - t0);
-      // groups of U edges: all loads of a group are issued before its first use; only the groups that exist are executed
+      // groups of U edges: all loads of a group are issued before its first use; only the groups that exist are executed.
+      // A FULL group (the common case) is one branch-free block whose shared-memory addresses are a base formed once per
+      // group plus compile-time offsets; with per-edge `exists` branches inside it the compiler re-derived every address
+      // from %tid for every edge (ncu source page: ~22 of the ~55 instructions per edge).
 #pragma unroll 1
       for (int tt = 0; tt < tcnt; tt += U) {
         const int k0 = t0 + tt;
+        const float* const* gp = sh_gp + gbase + k0;       // row address of edge k0 + u: gp[u]
+        const float* wp[SLOTS];                            // weight of edge k0 + u in slot s: wp[s][u * NHT]
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) wp[s] = wbase[s] + k0 * NHT;
+        float* prow = part + tt * PSTRIDE + gl;
         float4 v[U][SLOTS];
         if (tt + U <= tcnt) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const float* rowp = sh_gp[gbase + k0 + u];
+            const float* rowp = gp[u];
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s)
               v[u][s] = (FULL || L.ok[s]) ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-        } else {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const bool on = tt + u < tcnt;
-            const float* rowp = sh_gp[gbase + (on ? k0 + u : k0)];
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s)
-              v[u][s] = (on && (FULL || L.ok[s])) ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        float* prow = part + tt * PSTRIDE + gl;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (tt + u < tcnt) {
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
-              const float w = wbase[s][(k0 + u) * NHT];
+              const float w = wp[s][u * NHT];
               acc[s].x = fmaf(w, v[u][s].x, acc[s].x);
               acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
               acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
@@ -224,6 +241,35 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
                 dd = fmaf(whr[s].z, v[u][s].z, dd);
                 dd = fmaf(whr[s].w, v[u][s].w, dd);
                 prow[u * PSTRIDE + s * G] = dd;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool on = tt + u < tcnt;
+            const float* rowp = gp[on ? u : 0];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s)
+              v[u][s] = (on && (FULL || L.ok[s])) ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (tt + u < tcnt) {
+#pragma unroll
+              for (int s = 0; s < SLOTS; ++s) {
+                const float w = wp[s][u * NHT];
+                acc[s].x = fmaf(w, v[u][s].x, acc[s].x);
+                acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
+                acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
+                acc[s].w = fmaf(w, v[u][s].w, acc[s].w);
+                if ((FULL || L.ok[s]) && (FUSED || !P.const_attention)) {
+                  float dd = whr[s].x * v[u][s].x;
+                  dd = fmaf(whr[s].y, v[u][s].y, dd);
+                  dd = fmaf(whr[s].z, v[u][s].z, dd);
+                  dd = fmaf(whr[s].w, v[u][s].w, dd);
+                  prow[u * PSTRIDE + s * G] = dd;
+                }
               }
             }
           }
@@ -246,10 +292,10 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
       }
     }
     if (valid && (FUSED || !P.const_attention)) {
-      if (FUSED) {   // g = 0.01*alpha*(d_alpha - S[dst]), summed per source row  
+      if (FUSED) {   // g = 0.01*alpha*(d_alpha - S[dst]) = 0.01*((m*alpha)*<dOut,Wh> - alpha*S[dst]), summed per source row  
 #pragma unroll
         for (int h = 0; h < NHT; ++h)
-          if (h < nh) gsum[h] = fmaf(kLeakySlope * alpha[h], fmaf(msk[h], sh_da[tid * NHT + h], ga[h]) - sh_s[tid * NHT + h], gsum[h]);
+          if (h < nh) gsum[h] = fmaf(kLeakySlope, fmaf(sh_w[tid * NHT + h], sh_da[tid * NHT + h], -sh_s[tid * NHT + h]), gsum[h]);
       } else {
         float* r = P.rec + (int64_t)e * 2 * nh;
 #pragma unroll
@@ -517,6 +563,7 @@ struct BwdRowdotParams {
   // output go*ELU', writes it to go_out (what the source-major pass gathers) and uses it in S -- the ELU backward fused.
   int out_is_act; float* go_out;
   float* s_sum; float* ds_tgt;
+  const float* s_tgt; float* tpack;   // optional: write the per-target record {s_tgt | Z | S} for gat_edge_bwd_fused
 };
 
 // out = log1p(h) for h in (-1, 0], cheaply: the series where 1 + h would round away h's low bits, the fast log elsewhere
@@ -532,21 +579,27 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
   const int nh = P.nh;
+  // head / in-head chunk of this lane's chunk c = lane + 32k, advanced without a division per chunk (the two runtime
+  // divisions per chunk made this streaming pass instruction-bound: 52 % issue slots busy at 23-54 % of the DRAM rate)
+  const int cph = P.chunks_per_head;
+  const int hh0 = lane / cph, gc0 = lane - hh0 * cph, q32 = 32 / cph, r32 = 32 - q32 * cph;
   for (int64_t row0 = warp * R; row0 < P.n; row0 += nwarps * R) {
     float s[R][NHT];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int h = 0; h < NHT; ++h) s[r][h] = 0.f;
+    int hh = hh0 - q32, gc = gc0 - r32;
     for (int c = lane; c < P.chunks; c += 32) {
+      hh += q32; gc += r32;
+      if (gc >= cph) { gc -= cph; ++hh; }
       float4 g[R], o[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const bool on = row0 + r < P.n;
-        g[r] = on ? ldg4(P.go + (row0 + r) * P.go_ld + (P.go_shared ? c % P.chunks_per_head : c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g[r] = on ? ldg4(P.go + (row0 + r) * P.go_ld + (P.go_shared ? gc : c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         o[r] = on ? ldg4(P.out + (row0 + r) * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const int hh = c / P.chunks_per_head;
       if (P.out_is_act) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -579,12 +632,25 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
         }
       }
       if (lane == 0 && row0 + r < P.n) {
+        float zrow[NHT], trow[NHT], srow[NHT];
 #pragma unroll
         for (int h = 0; h < NHT; ++h) {
+          zrow[h] = 0.f; trow[h] = 0.f; srow[h] = 0.f;
           if (h < nh) {
             const float zz = __ldg(P.z + (row0 + r) * nh + h);
             P.s_sum[(row0 + r) * nh + h] = s[r][h];
             P.ds_tgt[(row0 + r) * nh + h] = kLeakySlope * s[r][h] * (kSoftmaxEps / (zz + kSoftmaxEps));
+            zrow[h] = zz; srow[h] = s[r][h];
+            if (P.tpack) trow[h] = __ldg(P.s_tgt + (row0 + r) * nh + h);
+          }
+        }
+        if (P.tpack) {
+          float* pk = P.tpack + (row0 + r) * (4 * NHT);
+#pragma unroll
+          for (int q = 0; q < NHT / 4; ++q) {
+            *reinterpret_cast<float4*>(pk + 4 * q) = make_float4(trow[4 * q], trow[4 * q + 1], trow[4 * q + 2], trow[4 * q + 3]);
+            *reinterpret_cast<float4*>(pk + NHT + 4 * q) = make_float4(zrow[4 * q], zrow[4 * q + 1], zrow[4 * q + 2], zrow[4 * q + 3]);
+            *reinterpret_cast<float4*>(pk + 2 * NHT + 4 * q) = make_float4(srow[4 * q], srow[4 * q + 1], srow[4 * q + 2], srow[4 * q + 3]);
           }
         }
       }
@@ -871,7 +937,7 @@ extern "C" int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t,
                                   int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
                                   const float* s_src, const float* s_tgt, const float* gmax, const float* z,
                                   float dropout_p, uint64_t seed, uint64_t offset,
-                                  const float* go_padded, int go_shared, const float* s_sum,
+                                  const float* go_padded, int go_shared, const float* s_sum, const float* tgt_pack,
                                   const float* a_src, const float* a_tgt,
                                   const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
                                   const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
@@ -881,7 +947,7 @@ extern "C" int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t,
   using namespace gat;
   int rc = check_common("gat_edge_bwd_fused", nh, fp, workspace, workspace_bytes);
   if (rc) return rc;
-  GAT_CHECK_ARG(s_src && s_tgt && gmax && z && s_sum && a_src && a_tgt && ds_src && ds_tgt && (d_wh || n_push > 0),
+  GAT_CHECK_ARG(s_src && gmax && (tgt_pack || (s_tgt && z && s_sum)) && a_src && a_tgt && ds_src && ds_tgt && (d_wh || n_push > 0),
                 "gat_edge_bwd_fused: buffers missing");
   GAT_CHECK_ARG(n_push == 0 || (h_push_dst && n_push >= 1 && n_push <= 8 && my_rank >= 0 && my_rank < n_push && rows_per_rank >= 1 &&
                                 rows_per_rank * n_push >= n_rows),
@@ -902,7 +968,7 @@ extern "C" int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t,
   P.dropout_p = dropout_p; P.seed = seed; P.offset = offset; P.go = go_padded; P.grad_alpha = nullptr;
   P.go_shared = go_shared ? 1 : 0; P.go_ld = go_shared ? fp : nh * fp;
   P.rec = nullptr; P.d_wh = d_wh;
-  P.s_sum = s_sum; P.a_src = a_src; P.a_tgt = a_tgt; P.tie_dst = tie_dst; P.tie_src = tie_src; P.header = header;
+  P.s_sum = s_sum; P.tpack = tgt_pack; P.a_src = a_src; P.a_tgt = a_tgt; P.tie_dst = tie_dst; P.tie_src = tie_src; P.header = header;
   P.corr_override = corr_override; P.tgt_lo = tgt_lo; P.tgt_hi = tgt_hi; P.ds_src = ds_src; P.ds_tgt = ds_tgt;
   P.push = n_push > 0; P.my_rank = my_rank; P.rows_per_rank = rows_per_rank > 0 ? rows_per_rank : 1;
   for (int q = 0; q < n_push; ++q) P.push_dst[q] = h_push_dst[q];
@@ -931,13 +997,17 @@ extern "C" int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, c
   return GAT_OK;
 }
 
+extern "C" int gat_tgt_pack_stride(int nh) { return nh <= 4 ? 16 : 32; }
+
 extern "C" int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const float* out_padded, int out_is_act, float* go_out,
                                    const float* z, int64_t n_rows, int nh, int fp,
-                                   float* s_sum, float* ds_tgt, void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+                                   float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
+                                   void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
   int rc = check_common("gat_edge_bwd_rowdot", nh, fp, workspace, workspace_bytes);
   if (rc) return rc;
   GAT_CHECK_ARG(!out_is_act || (go_out != nullptr && !go_shared), "gat_edge_bwd_rowdot: out_is_act needs go_out and an unshared gradient");
+  GAT_CHECK_ARG(tgt_pack == nullptr || (s_tgt != nullptr && ((uintptr_t)tgt_pack & 15) == 0), "gat_edge_bwd_rowdot: tgt_pack needs s_tgt and 16-byte alignment");
   if (n_rows == 0) return GAT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   BwdRowdotParams P;
@@ -945,6 +1015,7 @@ extern "C" int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const 
   P.chunks_per_head = fp / 4; P.s_sum = s_sum; P.ds_tgt = ds_tgt;
   P.go_shared = go_shared ? 1 : 0; P.go_ld = go_shared ? fp : nh * fp;
   P.out_is_act = out_is_act ? 1 : 0; P.go_out = go_out;
+  P.s_tgt = s_tgt; P.tpack = tgt_pack;
   int64_t want = (n_rows + 31) / 32;
   const unsigned grid = (unsigned)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8);
   if (nh <= 4) edge_bwd_rowdot_kernel<4><<<grid, 256, 0, st>>>(P);

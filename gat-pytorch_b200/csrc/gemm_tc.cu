@@ -4,8 +4,8 @@
 //   TN:  C[M,N] = A[K,M]^T * B[K,N]    A, B row-major fp32, both MN-major  (gat_gemm ta=1, tb=0: dW = dWh^T x), split-K
 //
 // tcgen05 has no fp32 MMA kind, and plain TF32 (~5e-4) cannot meet the 1e-5 parity bar, so
-// every operand tile is split IN SHARED MEMORY into hi = tf32(v) and lo = v - hi, and three MMAs accumulate
-// hi*lo + lo*hi + hi*hi into the same fp32 TMEM accumulator.  The global operands are read exactly once, as
+// every operand tile gets a companion lo = v - tf32(v) tile IN SHARED MEMORY, and three MMAs accumulate
+// hi*lo + lo*hi + hi*hi into fp32 TMEM accumulators.  The global operands are read exactly once, as
 // fp32, by TMA (no pre-split pass, no extra HBM traffic).
 //
 // CTA = one 128 x BN output tile, 192 threads, warp-specialised:
@@ -136,6 +136,15 @@ __device__ __forceinline__ float tf32_round(float v) {
 // pipeline fill, TMEM drain, output store) -- measured as the K-independent part of the tile time -- and with a second
 // CTA on the SM that time is covered by the other CTA's main loop.  TN (split-K, long K, tiny epilogue) keeps one CTA
 // per SM with 256-wide tiles and a deeper pipeline.
+// The "hi" operand is the fp32 value itself, left where TMA put it: the tensor core reads only the top 19 bits of an
+// fp32 word for kind::tf32, i.e. it sees hi = trunc_tf32(v).  The splitters therefore write only
+// lo = round_tf32(v - trunc_tf32(v)) (the subtraction is exact; lo is rounded because the tensor core would otherwise
+// truncate its low bits too, a one-sided error).  Dropped term lo_a*lo_b <= 2^-20 |a b|.  One shared-memory write per
+// element instead of two: the main loop is bound by shared-memory traffic (TMA fill + split + MMA operand reads).
+// Used by the NT products (K <= a few thousand); the TN product (K = number of nodes) keeps the round-to-nearest split.
+__device__ __forceinline__ float lo1(float v) { return tf32_round(v - __uint_as_float(__float_as_uint(v) & 0xffffe000u)); }
+__device__ __forceinline__ float4 lo4(float4 v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
+
 template <int BN, bool MN>
 struct Smem {
   static constexpr int kABytes = BM * BK * 4;     // 8 KB
@@ -272,21 +281,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       float4* b_lo = (float4*)(smem + s * S::kStageBytes + 2 * S::kABytes + S::kBBytes);
 #pragma unroll 4
       for (int i = t; i < S::kABytes / 16; i += kSplitThreads) {
-        float4 v = a_hi[i], h, l;
-        if (act_a) v = elu4(v);
-        h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
-        // lo is rounded too: the tensor core would otherwise TRUNCATE its low 13 bits, a one-sided error that
-        // accumulates linearly over K
-        l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
-        a_hi[i] = h; a_lo[i] = l;
+        float4 v = a_hi[i];
+        if (MN) {   // long-K products (dW): round-to-nearest hi, written back -- 4x smaller representation error
+          if (act_a) v = elu4(v);
+          const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+          a_hi[i] = h;
+          a_lo[i] = make_float4(tf32_round(v.x - h.x), tf32_round(v.y - h.y), tf32_round(v.z - h.z), tf32_round(v.w - h.w));
+        } else {
+          if (act_a) { v = elu4(v); a_hi[i] = v; }
+          a_lo[i] = lo4(v);
+        }
       }
 #pragma unroll 4
       for (int i = t; i < S::kBBytes / 16; i += kSplitThreads) {
-        float4 v = b_hi[i], h, l;
-        if (act_b) v = elu4(v);
-        h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
-        l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
-        b_hi[i] = h; b_lo[i] = l;
+        float4 v = b_hi[i];
+        if (MN) {
+          if (act_b) v = elu4(v);
+          const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+          b_hi[i] = h;
+          b_lo[i] = make_float4(tf32_round(v.x - h.x), tf32_round(v.y - h.y), tf32_round(v.z - h.z), tf32_round(v.w - h.w));
+        } else {
+          if (act_b) { v = elu4(v); b_hi[i] = v; }
+          b_lo[i] = lo4(v);
+        }
       }
       fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&ready[s]);

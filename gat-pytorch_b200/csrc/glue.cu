@@ -67,7 +67,101 @@ __global__ void attn_norm_bwd_kernel(const T* __restrict__ dst, const int32_t* _
   grad_alpha[idx] = __ldg(upstream) * sgn * deg * inv_edges;
 }
 
+// ---- visualisation feed -----------------------------------------------------------------------------
+// visualisation/entropy_histograms.py:103-115 loops over every node, masks the whole edge list with
+// `target_nodes == node_id` (O(N * E')) and calls scipy.stats.entropy(weights, base=2) on the node's incoming attention;
+// visualisation/weight_histograms.py:74-87 does the same masking and multiplies the weights by the neighbourhood size.
+// On the CSR of Kernel 1 a node's incoming edges are one contiguous segment (in the reference's edge order), so both are
+// one pass: a warp per (node) row, lanes over the row's slots, heads in registers.
+//   entropy[i,h]  = -sum_e p log2 p,  p = alpha[e,h] / sum_e alpha[e,h]   (scipy normalises pk; terms with p == 0 are 0)
+//   uniform[i]    = log2(deg_i)                                            (entropy of ones(deg)/deg, :115)
+//   scaled[j,h]   = alpha[eid[j],h] * deg(row of j)                        (CSR order == the reference's node-major order)
+// Rows without incoming edges get entropy 0 and uniform 0 (the reference would divide 0/0 there; it never visits such a
+// node because every node has a self-loop after the rewrite).
+__global__ void __launch_bounds__(256)
+attn_entropy_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ eid, int64_t n, const float* __restrict__ alpha,
+                    int nh, float* __restrict__ entropy, float* __restrict__ uniform) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t row = warp; row < n; row += nwarps) {
+    const int start = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    float sum[8], ent[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) { sum[h] = 0.f; ent[h] = 0.f; }
+    for (int j = start + lane; j < end; j += 32) {
+      const float* a = alpha + (int64_t)__ldg(eid + j) * nh;
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        if (h < nh) sum[h] += __ldg(a + h);
+    }
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+      if (h < nh) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], o);
+      }
+    for (int j = start + lane; j < end; j += 32) {
+      const float* a = alpha + (int64_t)__ldg(eid + j) * nh;
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        if (h < nh) {
+          const float p = __ldg(a + h) / sum[h];
+          if (p > 0.f) ent[h] -= p * log2f(p);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+      if (h < nh) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ent[h] += __shfl_xor_sync(0xffffffffu, ent[h], o);
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        if (h < nh) entropy[row * nh + h] = end > start ? ent[h] : 0.f;
+      uniform[row] = end > start ? log2f((float)(end - start)) : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+attn_degree_scaled_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ eid, int64_t n, const float* __restrict__ alpha,
+                          int nh, float* __restrict__ scaled) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t row = warp; row < n; row += nwarps) {
+    const int start = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    const float deg = (float)(end - start);
+    for (int j = start + lane; j < end; j += 32) {
+      const float* a = alpha + (int64_t)__ldg(eid + j) * nh;
+      for (int h = 0; h < nh; ++h) scaled[(int64_t)j * nh + h] = __ldg(a + h) * deg;
+    }
+  }
+}
+
 }  // namespace gat
+
+extern "C" int gat_attention_entropy(const int32_t* rowptr, const int32_t* eid, int64_t n, const float* alpha, int nh,
+                                     float* entropy, float* uniform, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(rowptr && eid && alpha && entropy && uniform && n >= 0 && nh >= 1 && nh <= 8, "gat_attention_entropy: bad arguments");
+  if (n == 0) return GAT_OK;
+  const int64_t want = (n + 7) / 8;
+  attn_entropy_kernel<<<(unsigned)(want < kNumSMs * 8 ? want : kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(rowptr, eid, n, alpha, nh, entropy, uniform);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_attention_degree_scaled(const int32_t* rowptr, const int32_t* eid, int64_t n, const float* alpha, int nh,
+                                           float* scaled, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(rowptr && eid && alpha && scaled && n >= 0 && nh >= 1, "gat_attention_degree_scaled: bad arguments");
+  if (n == 0) return GAT_OK;
+  const int64_t want = (n + 7) / 8;
+  attn_degree_scaled_kernel<<<(unsigned)(want < kNumSMs * 8 ? want : kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(rowptr, eid, n, alpha, nh, scaled);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
 
 extern "C" size_t gat_attention_norm_workspace_bytes(void) { return (size_t)gat::kNormBlocks * sizeof(double); }
 

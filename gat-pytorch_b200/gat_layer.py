@@ -141,13 +141,16 @@ class _GATFunction(torch.autograd.Function):
                 # goes FIRST (applying the fused ELU's adjoint on the way when the forward stored ELU(out)) and ONE
                 # source-major pass does the rest (no records, no finish pass)
                 go_pre = torch.empty((n, dp), **f32) if out_act else None
+                # one {s_tgt | Z | S} record per target, so the source-major pass gathers a target's scalars in ONE transaction
+                tpack = torch.empty((n, int(lib.gat_tgt_pack_stride(nh))), **f32)
                 _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), go_shared, out_p.data_ptr(), int(out_act), _ptr(go_pre),
-                          z.data_ptr(), n, nh, fp, s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
+                          z.data_ptr(), n, nh, fp, s_sum.data_ptr(), ds_tgt.data_ptr(), s_tgt.data_ptr(), tpack.data_ptr(),
+                          ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
                 if out_act:
                     go_p = go_pre
                 _lib.call("gat_edge_bwd_fused", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
                           st.n_long_t, st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, s_src.data_ptr(), s_tgt.data_ptr(), gmax.data_ptr(),
-                          z.data_ptr(), p_drop, seed, 0, go_p.data_ptr(), go_shared, s_sum.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
+                          z.data_ptr(), p_drop, seed, 0, go_p.data_ptr(), go_shared, s_sum.data_ptr(), tpack.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
                           _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), None, 0, n, ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(),
                           None, 0, 0, 0, ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
             else:

@@ -68,3 +68,48 @@ def attention_norm(edge_index: torch.Tensor, attention_list, n_nodes: int | None
         norm_l = _AttentionNorm.apply(alpha, dst, st.rowptr)
         total = norm_l if total is None else total + norm_l
     return total / len(attention_list)
+
+
+def _structure_for(edge_index: torch.Tensor, n_nodes: int | None, who: str):
+    if not edge_index.is_cuda:
+        raise RuntimeError(f"gat_b200.{who} runs on CUDA only; there is no CPU fallback")
+    st = GLOBAL_CACHE.find(edge_index) if n_nodes is None else GLOBAL_CACHE.get(edge_index, int(n_nodes), False)
+    if st is None:
+        raise RuntimeError(f"{who}: edge_index is not a rewritten edge list returned by a GATLayer on this graph; "
+                           "pass n_nodes to build its structure")
+    return st
+
+
+def neighbourhood_entropy(edge_index: torch.Tensor, attention: torch.Tensor, n_nodes: int | None = None):
+    """Visualisation feed.  For the rewritten `edge_index` and one layer's attention (E', NH) as returned by
+    `GATLayer`, returns `(entropy (N, NH), uniform_entropy (N,))`:
+    `entropy[i, h] == scipy.stats.entropy(attention[edge_index[1] == i, h], base=2)` and `uniform_entropy[i] ==
+    scipy.stats.entropy(ones(deg_i) / deg_i, base=2)` -- the two lists `visualisation/entropy_histograms.py:103-115` builds
+    with one full-edge-list mask per node, here one pass over the CSR segments."""
+    st = _structure_for(edge_index, n_nodes, "neighbourhood_entropy")
+    alpha = attention.detach().to(torch.float32).contiguous()
+    if alpha.dim() != 2 or alpha.size(0) != st.n_edges:
+        raise ValueError(f"attention must be (E', NH) with E' = {st.n_edges}")
+    dev, nh = alpha.device, alpha.size(1)
+    with torch.cuda.device(dev):
+        ent = torch.empty((st.n, nh), dtype=torch.float32, device=dev)
+        uni = torch.empty((st.n,), dtype=torch.float32, device=dev)
+        _lib.call("gat_attention_entropy", st.rowptr.data_ptr(), st.eid.data_ptr(), st.n, alpha.data_ptr(), nh,
+                  ent.data_ptr(), uni.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    return ent, uni
+
+
+def degree_scaled_attention(edge_index: torch.Tensor, attention: torch.Tensor, n_nodes: int | None = None) -> torch.Tensor:
+    """Visualisation feed: `attention[e, h] * in_degree(dst_e)` for every edge, ordered node by node and,
+    inside a node, in edge-list order -- the concatenation `visualisation/weight_histograms.py:74-87` builds (before its
+    `weight < 5` filter) with one full-edge-list mask per node.  Shape (E', NH)."""
+    st = _structure_for(edge_index, n_nodes, "degree_scaled_attention")
+    alpha = attention.detach().to(torch.float32).contiguous()
+    if alpha.dim() != 2 or alpha.size(0) != st.n_edges:
+        raise ValueError(f"attention must be (E', NH) with E' = {st.n_edges}")
+    dev, nh = alpha.device, alpha.size(1)
+    with torch.cuda.device(dev):
+        out = torch.empty((st.n_edges, nh), dtype=torch.float32, device=dev)
+        _lib.call("gat_attention_degree_scaled", st.rowptr.data_ptr(), st.eid.data_ptr(), st.n, alpha.data_ptr(), nh,
+                  out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    return out

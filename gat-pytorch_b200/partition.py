@@ -220,23 +220,31 @@ class CudaBackend:
         dp, lo = nh * fp, plan.lo
         ws, ws_bytes = self._bwd_ws(go_p.device, nh)
         arr = (ctypes.c_void_p * len(push_ptrs))(*push_ptrs) if push_ptrs else None
+        tpack, self._tpack = getattr(self, "_tpack", None), None    # the records edge_bwd_rowdot just wrote for these rows
         _lib.call("gat_edge_bwd_fused", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
                   st.n_long_t, st.eid.data_ptr(), plan.n, wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(),
                   s_tgt_local.data_ptr() - 4 * nh * lo, gmax.data_ptr(), z_local.data_ptr() - 4 * nh * lo,
                   0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, 0, s_sum_local.data_ptr() - 4 * nh * lo,
+                  (tpack.data_ptr() - 4 * tpack.size(1) * lo) if tpack is not None else None,
                   a_src.data_ptr(), a_tgt.data_ptr(), tie_dst.data_ptr(), tie_src.data_ptr(), None, corr.data_ptr(),
                   plan.lo, plan.hi, ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr() if d_wh is not None else None,
                   arr, len(push_ptrs) if push_ptrs else 0, plan.rank, plan.rows_per_rank, ws.data_ptr(), ws_bytes,
                   self._s(go_p.device), tag=(nh, fp))
 
-    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt, go_pre=None):
+    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt, go_pre=None, s_tgt_local=None):
         """Pass 2 without per-edge data: S = <dOut, out> over the owned rows; returns this rank's Gamma.  With go_pre
-        (the forward stored ELU(out)) the ELU adjoint is applied on the way and dL/dout is written to go_pre."""
+        (the forward stored ELU(out)) the ELU adjoint is applied on the way and dL/dout is written to go_pre.  With
+        s_tgt_local the pass also writes the per-target records {s_tgt | Z | S} that the next edge_bwd_fused call gathers."""
         ws, ws_bytes = self._bwd_ws(go_p.device, nh)
         ws.zero_()
+        tpack = None
+        if s_tgt_local is not None:
+            tpack = torch.empty((max(plan.rows, 1), int(self.lib.gat_tgt_pack_stride(nh))), dtype=torch.float32, device=go_p.device)
+        self._tpack = tpack
         _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), 0, out_p.data_ptr(), int(go_pre is not None),
                   go_pre.data_ptr() if go_pre is not None else None, z_local.data_ptr(), plan.rows, nh, fp,
-                  s_sum.data_ptr(), ds_tgt.data_ptr(), ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
+                  s_sum.data_ptr(), ds_tgt.data_ptr(), s_tgt_local.data_ptr() if tpack is not None else None,
+                  tpack.data_ptr() if tpack is not None else None, ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
         gamma = torch.empty(1, dtype=torch.float64, device=go_p.device)
         _lib.call("gat_edge_bwd_gamma", ws.data_ptr(), ws_bytes, gamma.data_ptr(), self._s(go_p.device))
         return gamma
@@ -307,7 +315,7 @@ class _PartitionedGATFunction(torch.autograd.Function):
         gamma = torch.zeros(1, dtype=torch.float64, device=dev)
         if rows:    # S = <dOut, out> over the owned rows first: no per-edge data needed
             go_pre = torch.empty_like(go_p) if out_act else None     # dL/dout when the forward stored ELU(out)
-            gamma = backend.edge_bwd_rowdot(plan, nh, fp, go_p, out_p, z, s_sum, ds_tgt, go_pre)
+            gamma = backend.edge_bwd_rowdot(plan, nh, fp, go_p, out_p, z, s_sum, ds_tgt, go_pre, s_tgt)
             if out_act:
                 go_p = go_pre
         red = torch.stack([gamma[0], tie_total.view(torch.int64)[0].to(torch.float64)])

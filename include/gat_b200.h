@@ -223,14 +223,15 @@ GAT_API int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t, co
                                int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
                                const float* s_src, const float* s_tgt, const float* gmax, const float* z,
                                float dropout_p, uint64_t seed, uint64_t offset,
-                               const float* go_padded, int go_shared, const float* s_sum,
+                               const float* go_padded, int go_shared, const float* s_sum, const float* tgt_pack,
                                const float* a_src, const float* a_tgt,
                                const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
                                const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
                                float* ds_src, float* ds_tgt, float* d_wh,
                                float* const* h_push_dst, int n_push, int my_rank, int64_t rows_per_rank,
                                void* workspace, size_t workspace_bytes, gat_stream_t stream);
-/* PUSH mode of gat_edge_bwd_fused (partitioned graphs: the reduce-scatter of dWh fused into the pass).  With n_push = P > 0,
+/* tgt_pack (optional): the per-target records written by gat_edge_bwd_rowdot; when given, s_tgt / z / s_sum are not read.
+ * PUSH mode of gat_edge_bwd_fused (partitioned graphs: the reduce-scatter of dWh fused into the pass).  With n_push = P > 0,
  * h_push_dst is a HOST array of the P ranks' receive buffers, each (P, rows_per_rank, dp) floats and mapped into this
  * process (peer / symmetric memory); the finished dWh row of source `row` is stored into slab `my_rank`, row
  * row - owner*rows_per_rank of its owner's buffer (owner = row / rows_per_rank) instead of d_wh.  After a cross-rank barrier
@@ -249,10 +250,15 @@ GAT_API int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, cons
  * Same outputs and Gamma reduction as gat_edge_bwd_rowsum.
  * out_is_act = 1 (the forward ran with out_act): out_padded holds h = ELU(out) and go_padded is dL/dh; the pass recovers
  * out = h > 0 ? h : log1p(h) and ELU'(out) = h > 0 ? 1 : h + 1, writes dL/dout = go*ELU' to go_out (n_rows, nh*fp) -- the buffer
- * the source-major pass must then gather -- and uses it in S: the ELU backward costs no pass of its own. */
+ * the source-major pass must then gather -- and uses it in S: the ELU backward costs no pass of its own.
+ * tgt_pack (optional, with s_tgt): the pass also writes one record per target, {s_tgt[d,:] | z[d,:] | s_sum[d,:]} in three
+ * groups of (nh <= 4 ? 4 : 8) floats at a stride of gat_tgt_pack_stride(nh) floats (16-byte aligned), which gat_edge_bwd_fused
+ * then gathers with ONE memory transaction per edge instead of three. */
+GAT_API int gat_tgt_pack_stride(int nh);
 GAT_API int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const float* out_padded, int out_is_act, float* go_out,
                                 const float* z, int64_t n_rows, int nh, int fp,
-                                float* s_sum, float* ds_tgt, void* workspace, size_t workspace_bytes, gat_stream_t stream);
+                                float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
+                                void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* Partitioned graphs only: *gamma_out = this rank's Gamma.  The caller all-reduces Gamma and tie_total over ranks and hands
  * Gamma/|T| to gat_edge_bwd_finish as `corr_override` (a device scalar).  On one GPU pass corr_override = NULL. */
@@ -282,6 +288,21 @@ GAT_API int gat_attention_norm_fwd(const void* edge_dst, int index_is_int64, con
                                    gat_stream_t stream);
 GAT_API int gat_attention_norm_bwd(const void* edge_dst, int index_is_int64, const int32_t* rowptr, const float* alpha,
                                    int64_t n_edges, int nh, const float* upstream, float* grad_alpha, gat_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Visualisation feed.  Replaces the per-node `target_nodes == node_id` masks of
+ * visualisation/entropy_histograms.py:103-115 and visualisation/weight_histograms.py:74-87 by one pass over the CSR of
+ * gat_csr_build (a node's incoming edges are one segment, in the reference's edge order).  alpha is (n_edges, nh) in
+ * edge-list order (what GATLayer returns); eid maps a CSR slot to its edge.
+ *   gat_attention_entropy:        entropy[i,h] = scipy.stats.entropy(alpha[dst==i, h], base=2)   (n, nh)
+ *                                 uniform[i]   = log2(in-degree of i)                             (n)
+ *   gat_attention_degree_scaled:  scaled[j,h]  = alpha[eid[j],h] * in-degree(row of slot j)      (n_edges, nh), CSR order
+ *                                 (== the concatenation over node_id of weight_histograms.py:81 before its `< 5` filter)
+ * ------------------------------------------------------------------------------------- */
+GAT_API int gat_attention_entropy(const int32_t* rowptr, const int32_t* eid, int64_t n, const float* alpha, int nh,
+                                  float* entropy, float* uniform, gat_stream_t stream);
+GAT_API int gat_attention_degree_scaled(const int32_t* rowptr, const int32_t* eid, int64_t n, const float* alpha, int nh,
+                                        float* scaled, gat_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -187,6 +187,39 @@ def attention_norm(edge_index, alphas, n):
     return total / len(alphas)
 
 
+def neighbourhood_entropy(edge_index, alpha, n):
+    """visualisation/entropy_histograms.py:103-115, restated loop for loop: for every node, mask the edge list with
+    `target_nodes == node_id` and take scipy.stats.entropy(weights, base=2) of the node's incoming attention (one head at a
+    time, :95-97), next to the entropy of the uniform distribution over the same neighbourhood (:115).
+    Returns (entropy (n, NH), uniform (n,)).  Nodes without incoming edges (never visited with self-loops) give 0."""
+    from scipy.stats import entropy
+    alpha = np.asarray(alpha, np.float64)
+    target_nodes = np.asarray(edge_index[1])
+    ent = np.zeros((n, alpha.shape[1]))
+    uni = np.zeros(n)
+    for node_id in range(n):
+        sel = target_nodes == node_id
+        k = int(sel.sum())
+        if k == 0:
+            continue
+        for head in range(alpha.shape[1]):
+            ent[node_id, head] = entropy(alpha[sel, head], base=2)
+        uni[node_id] = entropy(np.ones(k) / k, base=2)
+    return ent, uni
+
+
+def degree_scaled_attention(edge_index, alpha, n):
+    """visualisation/weight_histograms.py:74-87: per node, the incoming attention weights times the neighbourhood size,
+    concatenated node by node (edge-list order inside a node); the reference's `weight < 5` filter is the consumer's."""
+    alpha = np.asarray(alpha, np.float64)
+    target_nodes = np.asarray(edge_index[1])
+    out = []
+    for node_id in range(n):
+        sel = target_nodes == node_id
+        out.append(alpha[sel] * int(sel.sum()))
+    return np.concatenate(out, axis=0) if out else np.zeros((0, alpha.shape[1]))
+
+
 def rel_err(got, want) -> float:
     """Tensor-relative error used by every parity test: max|got-want| / max(|want|, tiny)."""
     got = np.asarray(got, dtype=np.float64)

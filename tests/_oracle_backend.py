@@ -89,7 +89,7 @@ class OracleBackend:
         self.edge_bwd_main(st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh)
         self.edge_bwd_finish(st, plan, nh, fp, rec, s_sum_local, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh)
 
-    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt, go_pre=None):
+    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt, go_pre=None, s_tgt_local=None):
         rows = plan.rows
         if go_pre is not None:     # out_p holds h = ELU(out): recover out and apply ELU'
             h = out_p

@@ -9,11 +9,11 @@ mkdir -p gpurun_out
 $CMD > gpurun_out/plain_${tag}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_${tag}.csv $CMD > gpurun_out/ncu_launch_${tag}.log 2>&1 &&
 ncu --set full --clock-control none --import-source on \
-    -k 'regex:edge_bwd_main_kernel|edge_fwd_kernel|gemm_tc_kernel|edge_bwd_rowdot_kernel|edge_max_kernel|scores_bwd_partial' -s 75 -c 26 \
+    -k 'regex:edge_bwd_main_kernel|edge_fwd_kernel|gemm_tc_kernel|edge_bwd_rowdot_kernel|edge_max_kernel|scores_bwd_partial' -s 90 -c 32 \
     -f -o /tmp/prof_${tag} $CMD > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "profile exit $?"
 python tools/ncu_summary.py /tmp/prof_${tag}.ncu-rep gpurun_out/ncu_${tag}_kernels.csv > /dev/null
 # per-instruction page of the dominant kernel (fused source-major backward pass, hidden-layer shape)
-ncu -i /tmp/prof_${tag}.ncu-rep --page source --csv -k 'regex:edge_bwd_main_kernel' -c 1 > gpurun_out/ncu_${tag}_top_source.csv 2>/dev/null
+ncu -i /tmp/prof_${tag}.ncu-rep --page source --csv -k 'regex:edge_bwd_main_kernel.*bool.0, .bool.1, .bool.1' -c 1 > gpurun_out/ncu_${tag}_top_source.csv 2>/dev/null
 ls -la /tmp/prof_${tag}.ncu-rep gpurun_out | tail -12
 tail -2 gpurun_out/ncu_full_${tag}.log | cut -c1-300
