@@ -65,6 +65,7 @@ struct BwdMainParams {
   // its OWNER's receive buffer -- slab `my_rank`, row `row - owner*rows_per_rank` -- through the peer-mapped pointers
   // push_dst[owner] (this rank's own buffer included), so the exchange rides NVLink while the pass is still running.
   float* push_dst[8]; int push; int my_rank; int64_t rows_per_rank;
+  int stage_offset_floats;   // GS: where the staging area starts inside the dynamic shared memory
 };
 
 __device__ __forceinline__ float* dwh_row_ptr(const BwdMainParams& P, const int64_t row) {
@@ -101,17 +102,32 @@ __device__ __forceinline__ LaneShape<SLOTS> make_lane_shape(const BwdMainParams&
     L.head[s] = L.ok[s] ? c / P.chunks_per_head : 0;
     // the head-mean layer's upstream gradient is the same (Fp)-wide vector for every head (gat_layer.py:132), so it is
     // stored once and every head reads the same chunk
-    L.goff[s] = (P.go_shared ? c - L.head[s] * P.chunks_per_head : c) * 4;
+    // a slot that does not exist (row narrower than SLOTS*G chunks) points at chunk 0: the gather loop treats every slot
+    // alike (no per-lane predicates, no divergence); what such a slot accumulates is never stored or read
+    L.goff[s] = L.ok[s] ? (P.go_shared ? c - L.head[s] * P.chunks_per_head : c) * 4 : 0;
   }
   return L;
 }
 
 // FULL: the row has exactly SLOTS*G chunks (e.g. products' 256 floats), so every slot of every lane exists and the
 // per-slot predicates fold away at compile time.
-template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL>
+// GS ("gathered rows staged"): head-mean layers hand every head the SAME (Fp)-wide upstream-gradient row, so the row an edge
+// gathers is narrow (products' last layer: 192 B) and four edges in flight per warp are only 768 B -- the pass was
+// latency-bound at a third of the DRAM rate (ncu: 33 % DRAM, 10.3 ms for 26 GB).  With GS the warp copies the rows of 16
+// edges at a time into shared memory with cp.async (no registers held: 3 KB in flight per warp) and the gather loop reads
+// its chunks from there.
+constexpr int kStageEdges = 16;
+constexpr int kStageMaxChunks = 16;     // widest staged row: 16 float4 = 64 floats per head
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL, bool GS = false>
 __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneShape<SLOTS>& L, const int64_t row, const int start,
                                              const int end, const int tid, const int gl, const int gbase, const unsigned gmask, const float gmax, const float corr,
-                                             int* sh_dst, const float** sh_gp, float* sh_w, float* sh_da, float* sh_s, float* part, float* coop) {
+                                             int* sh_dst, const float** sh_gp, float* sh_w, float* sh_da, float* sh_s, float* part, float* coop,
+                                             float4* stage = nullptr) {
   constexpr int TB = MainShape<G, SLOTS>::TB, U = MainShape<G, SLOTS>::U;
   constexpr int PSTRIDE = MainShape<G, SLOTS>::PSTRIDE;   // compile-time stride of the transpose tile rows
   constexpr int NG = kEdgeThreads / G;
@@ -205,6 +221,20 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
     const int cnt = min(G, end - base);
     for (int t0 = 0; t0 < cnt; t0 += TB) {
       const int tcnt = min(TB, cnt - t0);
+      if (GS && (t0 % kStageEdges) == 0) {   // stage the gathered rows of edges t0 .. t0+15 of this batch (G == 32)
+        const int gch = P.chunks_per_head;
+        const int total = min(kStageEdges, cnt - t0) * gch;
+        const int q32 = 32 / gch, r32 = 32 - q32 * gch;
+        int k = gl / gch, j = gl - k * gch;
+        __syncwarp(gmask);                   // the previous 16 edges have been consumed by every lane
+        for (int i = gl; i < total; i += 32) {
+          cp_async16(stage + i, sh_gp[gbase + t0 + k] + j * 4);
+          k += q32; j += r32;
+          if (j >= gch) { j -= gch; ++k; }
+        }
+        cp_async_wait_all();
+        __syncwarp(gmask);
+      }
       // groups of U edges: all loads of a group are issued before its first use; only the groups that exist are executed.
       // A FULL group (the common case) is one branch-free block whose shared-memory addresses are a base formed once per
       // group plus compile-time offsets; with per-edge `exists` branches inside it the compiler re-derived every address
@@ -221,10 +251,17 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
         if (tt + U <= tcnt) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const float* rowp = gp[u];
+            if (GS) {
+              const float4* srow = stage + ((k0 + u) % kStageEdges) * P.chunks_per_head;
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s)
-              v[u][s] = (FULL || L.ok[s]) ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int s = 0; s < SLOTS; ++s)
+                v[u][s] = srow[L.goff[s] >> 2];
+            } else {
+              const float* rowp = gp[u];
+#pragma unroll
+              for (int s = 0; s < SLOTS; ++s)
+                v[u][s] = ldg4(rowp + L.goff[s]);
+            }
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -235,7 +272,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
               acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
               acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
               acc[s].w = fmaf(w, v[u][s].w, acc[s].w);
-              if ((FULL || L.ok[s]) && (FUSED || !P.const_attention)) {
+              if (FUSED || !P.const_attention) {
                 float dd = whr[s].x * v[u][s].x;
                 dd = fmaf(whr[s].y, v[u][s].y, dd);
                 dd = fmaf(whr[s].z, v[u][s].z, dd);
@@ -248,10 +285,17 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const bool on = tt + u < tcnt;
-            const float* rowp = gp[on ? u : 0];
+            if (GS) {
+              const float4* srow = stage + ((k0 + (on ? u : 0)) % kStageEdges) * P.chunks_per_head;
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s)
-              v[u][s] = (on && (FULL || L.ok[s])) ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int s = 0; s < SLOTS; ++s)
+                v[u][s] = on ? srow[L.goff[s] >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+              const float* rowp = gp[on ? u : 0];
+#pragma unroll
+              for (int s = 0; s < SLOTS; ++s)
+                v[u][s] = on ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -263,7 +307,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
                 acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
                 acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
                 acc[s].w = fmaf(w, v[u][s].w, acc[s].w);
-                if ((FULL || L.ok[s]) && (FUSED || !P.const_attention)) {
+                if (FUSED || !P.const_attention) {
                   float dd = whr[s].x * v[u][s].x;
                   dd = fmaf(whr[s].y, v[u][s].y, dd);
                   dd = fmaf(whr[s].z, v[u][s].z, dd);
@@ -418,7 +462,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
   }
 }
 
-template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL>
+template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL, bool GS = false>
 __global__ void __launch_bounds__(kEdgeThreads, (SLOTS <= 2 ? 3 : (SLOTS <= 4 ? 2 : 1)))
 edge_bwd_main_kernel(const BwdMainParams P) {
   constexpr int TB = MainShape<G, SLOTS>::TB;
@@ -432,6 +476,8 @@ edge_bwd_main_kernel(const BwdMainParams P) {
   const unsigned gmask = group_mask<G>(lane);
   const LaneShape<SLOTS> L = make_lane_shape<G, SLOTS>(P, gl);
   float* part = dyn_smem + (size_t)(tid / G) * TB * MainShape<G, SLOTS>::PSTRIDE;   // [TB][PSTRIDE] of my group
+  // GS: per-group staging area behind the part / coop region (main_dyn_smem(), 16-byte aligned)
+  float4* stage = GS ? reinterpret_cast<float4*>(dyn_smem + P.stage_offset_floats) + (size_t)(tid / G) * kStageEdges * kStageMaxChunks : nullptr;
   const float gmax = P.const_attention ? 0.f : __ldg(P.gmax);
   const float corr = !FUSED ? 0.f : (P.corr_override ? __ldg(P.corr_override) : P.header->corr);
   if (COOP) {   // long source rows, CTA per row (its own launch)
@@ -440,7 +486,7 @@ edge_bwd_main_kernel(const BwdMainParams P) {
     for (;;) {
       const int64_t row = grab_long_row(P.sched, P.rowptr_t, &sh_ctl);
       if (row < 0) break;
-      bwd_main_row<G, SLOTS, NHT, true, FUSED, FULL>(P, L, row, __ldg(P.rowptr_t + row), __ldg(P.rowptr_t + row + 1), tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, sh_s, part, dyn_smem);
+      bwd_main_row<G, SLOTS, NHT, true, FUSED, FULL, GS>(P, L, row, __ldg(P.rowptr_t + row), __ldg(P.rowptr_t + row + 1), tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, sh_s, part, dyn_smem, stage);
     }
   } else {
     int64_t base;
@@ -452,8 +498,8 @@ edge_bwd_main_kernel(const BwdMainParams P) {
         int64_t row;
         int start, end;
         if (prefetched_row<G>(P.sched, k, lane, pr, ps, pe, row, start, end))
-          bwd_main_row<G, SLOTS, NHT, false, FUSED, FULL>(P, L, row, start, end, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da,
-                                                          sh_s, part, nullptr);
+          bwd_main_row<G, SLOTS, NHT, false, FUSED, FULL, GS>(P, L, row, start, end, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da,
+                                                              sh_s, part, nullptr, stage);
       }
     }
     pdl_wait_for_primary();     // no-op unless launched behind the cooperative kernel
@@ -870,6 +916,39 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
   }
   const bool coop_launch = row_order_t != nullptr && n_long != 0;
   const bool full = FUSED && P.chunks == shape.g * shape.slots && !P.go_shared;   // predicate-free instantiation
+  // GS: narrow shared upstream-gradient rows are staged through shared memory (see bwd_main_row)
+  if (FUSED && P.go_shared && shape.g == 32 && shape.slots <= 2 && nh <= 4 && P.chunks_per_head <= kStageMaxChunks) {
+    BwdMainParams Q = P;
+#define LAUNCH_GS(S_)                                                                                                  \
+    do {                                                                                                               \
+      const size_t base_ = (main_dyn_smem<32, S_>(P.chunks) + 15) / 16 * 16;                                           \
+      const size_t smem_ = base_ + (size_t)(kEdgeThreads / 32) * kStageEdges * kStageMaxChunks * sizeof(float4);       \
+      Q.stage_offset_floats = (int)(base_ / sizeof(float));                                                            \
+      static bool optin_gs_ = false;                                                                                   \
+      if (!optin_gs_) {                                                                                                \
+        GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<32, S_, 4, true, FUSED, false, true>,                       \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024)));                 \
+        GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<32, S_, 4, false, FUSED, false, true>,                      \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024)));                 \
+        optin_gs_ = true;                                                                                              \
+      }                                                                                                                \
+      if (coop_launch) {                                                                                               \
+        GAT_CUDA(launch_kernel(edge_bwd_main_kernel<32, S_, 4, true, FUSED, false, true>,                              \
+                               persistent_grid(edge_bwd_main_kernel<32, S_, 4, true, FUSED, false, true>, kEdgeThreads, smem_, \
+                                               n_long < 0 ? n_rows : n_long),                                          \
+                               kEdgeThreads, smem_, st, Q, false));                                                    \
+        GAT_LAUNCH_CHECK();                                                                                            \
+      }                                                                                                                \
+      GAT_CUDA(launch_kernel(edge_bwd_main_kernel<32, S_, 4, false, FUSED, false, true>,                               \
+                             persistent_grid(edge_bwd_main_kernel<32, S_, 4, false, FUSED, false, true>, kEdgeThreads, smem_, \
+                                             (n_rows + 7) / 8),                                                        \
+                             kEdgeThreads, smem_, st, Q, coop_launch));                                                \
+      GAT_LAUNCH_CHECK();                                                                                              \
+    } while (0)
+    if (shape.slots == 1) LAUNCH_GS(1); else LAUNCH_GS(2);
+#undef LAUNCH_GS
+    return GAT_OK;
+  }
 #define LAUNCH_BOTH(G_, S_, N_, FULL_)                                                                                 \
   do {                                                                                                                 \
     /* static + dynamic shared memory can exceed the 48 KB default (wide rows, 8 heads): opt in once per size */       \
