@@ -12,8 +12,9 @@ inter-layer glue (layer -> ELU, GATModel.py:120-151).  metric = layer-edges/s = 
   value    device-resident inputs, graph structure cached (steady-state training step)
   e2e      same step through the public GATLayer API starting from PINNED HOST buffers: H2D of x and
            edge_index, CSR/CSR^T build for the freshly uploaded graph, fwd+bwd, D2H of the loss
-  roofline dominant kernel (edge backward, destination pass) timed live with CUDA events inside the
-           timed region; algorithmic bytes per SURVEY.md section 8-d / DESIGN.md
+  roofline dominant kernel (the fused source-major backward pass gat_edge_bwd_fused on the hidden-layer
+           shape) timed live with CUDA events inside the timed region; algorithmic bytes per SURVEY.md
+           section 8-d / DESIGN.md section 4; traffic = ncu dram bytes of the same launch (profiles/traffic.json)
   cpu_baseline / --impl reference: the torch CPU port of the reference layer (oracle/torch_port.py; the
            reference is Python and cannot travel to the GPU box) on all host cores, on a 1/128-scale
            products-shaped graph (the reference formulation cannot allocate full scale)

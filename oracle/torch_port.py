@@ -18,7 +18,7 @@ def rewrite_edges(edge_index: torch.Tensor) -> torch.Tensor:
     """utils.py:47-72: drop every loop, keep order, append loops 0..max."""
     n_idx = int(edge_index.max()) + 1
     keep = edge_index[0] != edge_index[1]
-    loops = torch.arange(n_idx, dtype=edge_index.dtype)
+    loops = torch.arange(n_idx, dtype=edge_index.dtype, device=edge_index.device)
     return torch.cat([edge_index[:, keep], torch.stack([loops, loops])], dim=1)
 
 
