@@ -123,7 +123,7 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
   const int grp = tid / G;
   const int first = COOP ? grp * G : 0, step = COOP ? NG * G : G;
   const int nh = P.nh;
-  int head[SLOTS];
+  int head[SLOTS], coff[SLOTS];
   bool ok[SLOTS];
   float4 acc[SLOTS];
 #pragma unroll
@@ -131,6 +131,7 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
     int c = s * G + gl;
     ok[s] = c < P.chunks;
     head[s] = ok[s] ? c / P.chunks_per_head : 0;
+    coff[s] = ok[s] ? c * 4 : 0;      // float offset of the lane's chunk in a gathered row
     acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float st[NHT];
@@ -212,27 +213,54 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
     }
     __syncwarp(gmask);
     const int cnt = min(G, end - base);
+    // A full group of U edges is one branch-free block (all loads, then all FMAs); a slot that does not exist (row
+    // narrower than SLOTS*G chunks) reads chunk 0 of the row instead of being predicated per lane -- what it accumulates
+    // is never stored -- so narrow rows (192 floats on a 256-float lane grid) run the same code as full ones.
+#pragma unroll 1
     for (int t = 0; t < cnt; t += U) {
       float4 v[U][SLOTS];
+      const int* sp = sh_src + gbase + t;
+      const float* wp[SLOTS];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool on = t + u < cnt;
-        const int sidx = on ? sh_src[gbase + t + u] : 0;
-        const float* rowp = P.wh + (int64_t)sidx * P.dp + gl * 4;
+      for (int s = 0; s < SLOTS; ++s) wp[s] = sh_w + (gbase + t) * NHT + head[s];
+      if (t + U <= cnt) {
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s)
-          v[u][s] = (on && ok[s]) ? ldg4(rowp + s * G * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int u = 0; u < U; ++u) {
+          const float* rowp = P.wh + (int64_t)sp[u] * P.dp;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (t + u < cnt) {
+          for (int s = 0; s < SLOTS; ++s) v[u][s] = ldg4(rowp + coff[s]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
 #pragma unroll
           for (int s = 0; s < SLOTS; ++s) {
-            const float w = sh_w[(gbase + t + u) * NHT + head[s]];
+            const float w = wp[s][u * NHT];
             acc[s].x = fmaf(w, v[u][s].x, acc[s].x);
             acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
             acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
             acc[s].w = fmaf(w, v[u][s].w, acc[s].w);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool on = t + u < cnt;
+          const float* rowp = P.wh + (int64_t)(on ? sp[u] : 0) * P.dp;
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s)
+            v[u][s] = on ? ldg4(rowp + coff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (t + u < cnt) {
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+              const float w = wp[s][u * NHT];
+              acc[s].x = fmaf(w, v[u][s].x, acc[s].x);
+              acc[s].y = fmaf(w, v[u][s].y, acc[s].y);
+              acc[s].z = fmaf(w, v[u][s].z, acc[s].z);
+              acc[s].w = fmaf(w, v[u][s].w, acc[s].w);
+            }
           }
         }
       }
