@@ -135,6 +135,26 @@ class KernelTimer:
 _timer = None
 
 
+class timed:
+    """Bracket an arbitrary region of the current stream (a collective, a torch op) with the active KernelTimer's events,
+    so that bench.py's per-step breakdown also shows the time between our kernels; free when no timer is active."""
+
+    def __init__(self, name, tag=None):
+        self.name, self.tag = name, tag
+
+    def __enter__(self):
+        if _timer is not None:
+            import torch
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timer is not None and hasattr(self, "e0"):
+            self.e1.record()
+            _timer.records.append((self.name, self.tag, self.e0, self.e1))
+
+
 def call(name: str, *args, tag=None):
     """Invoke C-ABI entry point `name`; raise on a non-zero status."""
     fn = getattr(load(), name)

@@ -66,6 +66,15 @@ struct BwdMainParams {
   // push_dst[owner] (this rank's own buffer included), so the exchange rides NVLink while the pass is still running.
   float* push_dst[8]; int push; int my_rank; int64_t rows_per_rank;
   int stage_offset_floats;   // GS: where the staging area starts inside the dynamic shared memory
+  // PUSH with G == 32: a finished row is staged in shared memory (two dp-float buffers per warp) and leaves as ONE bulk
+  // copy (cp.async.bulk, the TMA engine).  Per-thread 16-byte stores to peer memory reached ~280 GB/s over NVLink (the
+  // kernel "finished" and the barrier behind it then waited 2.4 ms per layer for the posted writes to drain at 4 GPUs);
+  // the projection's TMA stores reach 700 GB/s on the same links.
+  int rowbuf_offset_floats;  // < 0: per-thread stores
+  // PUSH: every rank walks the source rows in the same order, so without a rotation all P ranks push into the SAME owner's
+  // slab at the same time (its NVLink ingress serialises them: measured as a 2.4 ms wait per layer at 4 GPUs behind a
+  // 4.4 ms pass); rank r starts at the slab of owner r+1 instead.
+  int64_t sched_rot;
 };
 
 __device__ __forceinline__ float* dwh_row_ptr(const BwdMainParams& P, const int64_t row) {
@@ -122,12 +131,20 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// at most one bulk store of this thread may still be READING its shared-memory source (the other buffer)
+__device__ __forceinline__ void bulk_wait_read_keep1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL, bool GS = false>
 __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneShape<SLOTS>& L, const int64_t row, const int start,
                                              const int end, const int tid, const int gl, const int gbase, const unsigned gmask, const float gmax, const float corr,
                                              int* sh_dst, const float** sh_gp, float* sh_w, float* sh_da, float* sh_s, float* part, float* coop,
-                                             float4* stage = nullptr) {
+                                             float4* stage, int* sh_flip) {
   constexpr int TB = MainShape<G, SLOTS>::TB, U = MainShape<G, SLOTS>::U;
   constexpr int PSTRIDE = MainShape<G, SLOTS>::PSTRIDE;   // compile-time stride of the transpose tile rows
   constexpr int NG = kEdgeThreads / G;
@@ -455,6 +472,20 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
       *reinterpret_cast<float4*>(drow + c * 4) = t;
     }
     // the next grab_long_row() starts with a __syncthreads()
+  } else if (G == 32 && P.rowbuf_offset_floats >= 0) {
+    // bulk-copy push: lane 0 owns the bulk-async group of this warp; which of the warp's two row buffers is next lives in
+    // shared memory (nothing about the push stays in registers across the row)
+    extern __shared__ __align__(16) float dyn_smem_rb[];
+    const int flip = sh_flip[tid >> 5];
+    float* rb = dyn_smem_rb + P.rowbuf_offset_floats + ((tid >> 5) * 2 + flip) * P.dp;
+    if (gl == 0) bulk_wait_read_keep1();          // the copy issued from this buffer two rows ago has read it
+    __syncwarp(gmask);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+      if ((FULL || L.ok[s])) *reinterpret_cast<float4*>(rb + (s * G + gl) * 4) = acc[s];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk copy
+    __syncwarp(gmask);
+    if (gl == 0) { bulk_store(drow, rb, (unsigned)(P.dp * sizeof(float))); sh_flip[tid >> 5] = flip ^ 1; }
   } else {
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s)
@@ -478,6 +509,9 @@ edge_bwd_main_kernel(const BwdMainParams P) {
   float* part = dyn_smem + (size_t)(tid / G) * TB * MainShape<G, SLOTS>::PSTRIDE;   // [TB][PSTRIDE] of my group
   // GS: per-group staging area behind the part / coop region (main_dyn_smem(), 16-byte aligned)
   float4* stage = GS ? reinterpret_cast<float4*>(dyn_smem + P.stage_offset_floats) + (size_t)(tid / G) * kStageEdges * kStageMaxChunks : nullptr;
+  __shared__ int sh_flip[kEdgeThreads / 32];
+  if (lane == 0) sh_flip[tid >> 5] = 0;
+  __syncwarp();
   const float gmax = P.const_attention ? 0.f : __ldg(P.gmax);
   const float corr = !FUSED ? 0.f : (P.corr_override ? __ldg(P.corr_override) : P.header->corr);
   if (COOP) {   // long source rows, CTA per row (its own launch)
@@ -486,22 +520,23 @@ edge_bwd_main_kernel(const BwdMainParams P) {
     for (;;) {
       const int64_t row = grab_long_row(P.sched, P.rowptr_t, &sh_ctl);
       if (row < 0) break;
-      bwd_main_row<G, SLOTS, NHT, true, FUSED, FULL, GS>(P, L, row, __ldg(P.rowptr_t + row), __ldg(P.rowptr_t + row + 1), tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, sh_s, part, dyn_smem, stage);
+      bwd_main_row<G, SLOTS, NHT, true, FUSED, FULL, GS>(P, L, row, __ldg(P.rowptr_t + row), __ldg(P.rowptr_t + row + 1), tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, sh_s, part, dyn_smem, stage, sh_flip);
     }
   } else {
     int64_t base;
     while (grab_rows<G>(P.sched, lane, base)) {
       int pr, ps, pe;
-      prefetch_rows<G>(P.sched, P.rowptr_t, base, lane, pr, ps, pe);
+      prefetch_rows<G>(P.sched, P.rowptr_t, base, lane, pr, ps, pe, P.sched_rot);
 #pragma unroll 1
       for (int k = 0; k < kGrabIters<G>; ++k) {
         int64_t row;
         int start, end;
         if (prefetched_row<G>(P.sched, k, lane, pr, ps, pe, row, start, end))
           bwd_main_row<G, SLOTS, NHT, false, FUSED, FULL, GS>(P, L, row, start, end, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da,
-                                                              sh_s, part, nullptr, stage);
+                                                              sh_s, part, nullptr, stage, sh_flip);
       }
     }
+    if (G == 32 && P.rowbuf_offset_floats >= 0 && lane == 0) bulk_wait_all();   // every pushed row has left before the grid may complete
     pdl_wait_for_primary();     // no-op unless launched behind the cooperative kernel
   }
 }
@@ -916,14 +951,20 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
   }
   const bool coop_launch = row_order_t != nullptr && n_long != 0;
   const bool full = FUSED && P.chunks == shape.g * shape.slots && !P.go_shared;   // predicate-free instantiation
+  BwdMainParams Q = P;
+  // bulk-copy push (see BwdMainParams::rowbuf_offset_floats): two row buffers per warp behind everything else
+  const size_t push_bytes = (P.push && shape.g == 32) ? (size_t)(kEdgeThreads / 32) * 2 * P.dp * sizeof(float) : 0;
+  Q.rowbuf_offset_floats = -1;
+  Q.sched_rot = P.push ? (((int64_t)P.my_rank + 1) * P.rows_per_rank) % (n_rows > 0 ? n_rows : 1) : 0;
   // GS: narrow shared upstream-gradient rows are staged through shared memory (see bwd_main_row)
   if (FUSED && P.go_shared && shape.g == 32 && shape.slots <= 2 && nh <= 4 && P.chunks_per_head <= kStageMaxChunks) {
-    BwdMainParams Q = P;
 #define LAUNCH_GS(S_)                                                                                                  \
     do {                                                                                                               \
       const size_t base_ = (main_dyn_smem<32, S_>(P.chunks) + 15) / 16 * 16;                                           \
-      const size_t smem_ = base_ + (size_t)(kEdgeThreads / 32) * kStageEdges * kStageMaxChunks * sizeof(float4);       \
+      const size_t stage_ = (size_t)(kEdgeThreads / 32) * kStageEdges * kStageMaxChunks * sizeof(float4);              \
+      const size_t smem_ = base_ + stage_ + push_bytes;                                                                \
       Q.stage_offset_floats = (int)(base_ / sizeof(float));                                                            \
+      if (push_bytes) Q.rowbuf_offset_floats = (int)((base_ + stage_) / sizeof(float));                                \
       static bool optin_gs_ = false;                                                                                   \
       if (!optin_gs_) {                                                                                                \
         GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<32, S_, 4, true, FUSED, false, true>,                       \
@@ -953,8 +994,11 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
   do {                                                                                                                 \
     /* static + dynamic shared memory can exceed the 48 KB default (wide rows, 8 heads): opt in once per size */       \
     static size_t optin_ = 0;                                                                                          \
-    if (main_dyn_smem<G_, S_>(P.chunks) > optin_) {                                                                    \
-      optin_ = main_dyn_smem<G_, S_>(P.chunks);                                                                        \
+    const size_t base_ = (main_dyn_smem<G_, S_>(P.chunks) + 15) / 16 * 16;                                             \
+    const size_t smem_ = base_ + push_bytes;                                                                           \
+    if (push_bytes) Q.rowbuf_offset_floats = (int)(base_ / sizeof(float));                                             \
+    if (smem_ > optin_) {                                                                                              \
+      optin_ = smem_;                                                                                                  \
       GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<G_, S_, N_, true, FUSED, FULL_>,                              \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin_));                        \
       GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<G_, S_, N_, false, FUSED, FULL_>,                             \
@@ -963,15 +1007,15 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
     if (coop_launch) {   /* long source rows first, CTA per row; the short-row launch overlaps its tail */             \
       GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, true, FUSED, FULL_>,                                     \
                              persistent_grid(edge_bwd_main_kernel<G_, S_, N_, true, FUSED, FULL_>, kEdgeThreads,       \
-                                             main_dyn_smem<G_, S_>(P.chunks), n_long < 0 ? n_rows : n_long),           \
-                             kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, false));                            \
+                                             smem_, n_long < 0 ? n_rows : n_long),                                     \
+                             kEdgeThreads, smem_, st, Q, false));                                                      \
       GAT_LAUNCH_CHECK();                                                                                              \
     }                                                                                                                  \
     GAT_CUDA(launch_kernel(edge_bwd_main_kernel<G_, S_, N_, false, FUSED, FULL_>,                                      \
                            persistent_grid(edge_bwd_main_kernel<G_, S_, N_, false, FUSED, FULL_>, kEdgeThreads,        \
-                                           main_dyn_smem<G_, S_>(P.chunks),                                            \
+                                           smem_,                                                                      \
                                            (n_rows + (kEdgeThreads / G_) - 1) / (kEdgeThreads / G_)),                  \
-                           kEdgeThreads, main_dyn_smem<G_, S_>(P.chunks), st, P, coop_launch));                        \
+                           kEdgeThreads, smem_, st, Q, coop_launch));                                                  \
     GAT_LAUNCH_CHECK();                                                                                                \
   } while (0)
 #define LAUNCH(G_, S_, N_)                                                                                             \

@@ -130,14 +130,18 @@ __device__ __forceinline__ int64_t sched_row(const RowSched& S, int64_t base, in
 
 // Row metadata of a whole grab, fetched by the first lanes in ONE round trip (order[idx] -> rowptr[row], rowptr[row+1]) instead
 // of two dependent loads per row on the critical path of every row; iteration k reads its entry with shuffles.
+// `rot` rotates the schedule (position idx -> idx + rot mod n): ranks of a partitioned run start their walk over the source
+// rows at different owners' slabs, so that at any time they push to DIFFERENT peers (see BwdMainParams::sched_rot).
 template <int G>
 __device__ __forceinline__ void prefetch_rows(const RowSched& S, const int32_t* rowptr, const int64_t base, const int lane,
-                                              int& pr, int& ps, int& pe) {
+                                              int& pr, int& ps, int& pe, const int64_t rot = 0) {
   constexpr int kRowsPerGrab = (32 / G) * kGrabIters<G>;
   static_assert(kRowsPerGrab <= 32, "one prefetched row per lane");
   pr = -1; ps = 0; pe = 0;
-  const int64_t idx = base + lane;
+  int64_t idx = base + lane;
   if (lane < kRowsPerGrab && idx < S.n) {
+    idx += rot;
+    if (idx >= S.n) idx -= S.n;
     pr = S.order ? __ldg(S.order + idx) : (int)idx;
     ps = __ldg(rowptr + pr);
     pe = __ldg(rowptr + pr + 1);

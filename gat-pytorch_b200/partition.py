@@ -275,7 +275,8 @@ class _PartitionedGATFunction(torch.autograd.Function):
             # ONE kernel: GEMM tiles -> shared memory -> TMA stores into every rank's gathered buffer over NVLink
             if rows:
                 backend.project_allgather(x_local, rows, f_in, w_p, dp, a_src_p, a_tgt_p, nh, peer_ptrs, plan.lo, s_src_slab, s_tgt, x_act)
-            dist.all_gather_into_tensor(s_src_full, s_src_slab, group=group)    # tiny; doubles as the cross-rank barrier for wh_full
+            with _lib.timed("nccl:all_gather(s_src)+barrier"):
+                dist.all_gather_into_tensor(s_src_full, s_src_slab, group=group)    # tiny; doubles as the cross-rank barrier for wh_full
         else:
             wh_slab = torch.empty((R, dp), **f32)
             if rows < R:
@@ -289,7 +290,8 @@ class _PartitionedGATFunction(torch.autograd.Function):
         gmax = torch.full((1,), float("-inf"), **f32)
         if rows:
             backend.edge_max(st, plan, s_src_full, s_tgt, nh, gmax)
-        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)            # ONE global max, gat_layer.py:85
+        with _lib.timed("nccl:all_reduce(max)"):
+            dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)            # ONE global max, gat_layer.py:85
         out_p = torch.empty((max(rows, 1), dp), **f32)[:rows]       # every owned row is written by the edge kernel
         z = torch.zeros((max(rows, 1), nh), **f32)
         ties = torch.zeros(2 + max(rows, 1) * nh + plan.n_pad * nh, dtype=torch.int32, device=dev)
@@ -319,7 +321,8 @@ class _PartitionedGATFunction(torch.autograd.Function):
             if out_act:
                 go_p = go_pre
         red = torch.stack([gamma[0], tie_total.view(torch.int64)[0].to(torch.float64)])
-        dist.all_reduce(red, group=group)                                   # (Gamma, |T|) over ranks
+        with _lib.timed("nccl:all_reduce(gamma,ties)"):
+            dist.all_reduce(red, group=group)                                   # (Gamma, |T|) over ranks
         corr = torch.where(red[1] > 0, red[0] / red[1].clamp(min=1.0), torch.zeros_like(red[0])).to(torch.float32).reshape(1)
         d_wh = torch.empty((R, dp), **f32)
         if push_ptrs is not None:
@@ -327,7 +330,8 @@ class _PartitionedGATFunction(torch.autograd.Function):
             # a tiny collective is the barrier, then the owner adds its P slabs in rank order
             backend.edge_bwd_fused(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, s_sum, a_src_p, a_tgt_p,
                                    tie_dst, tie_src, corr, ds_src_part, ds_tgt, None, push_ptrs=push_ptrs)
-            dist.all_reduce(torch.zeros(1, **f32), group=group)            # barrier: every rank's pushes have landed
+            with _lib.timed("nccl:barrier(push)"):
+                dist.all_reduce(torch.zeros(1, **f32), group=group)            # barrier: every rank's pushes have landed
             backend.slab_sum(recv, plan.world, R, dp, d_wh)
         else:
             d_wh_part = torch.empty((plan.n_pad, dp), **f32)        # rows [0, n) are all written by the source-major pass
@@ -351,11 +355,13 @@ class _PartitionedGATFunction(torch.autograd.Function):
         # dA = ds^T Wh over the OWNED rows only: this rank's edges gave partial ds_src for every source, so the small
         # (N, NH) array is reduce-scattered to the owners first (was: every rank streamed all N rows of Wh)
         ds_src_local = torch.empty((R, nh), **f32)
-        dist.reduce_scatter_tensor(ds_src_local, ds_src_part, group=group)
+        with _lib.timed("nccl:reduce_scatter(ds_src)"):
+            dist.reduce_scatter_tensor(ds_src_local, ds_src_part, group=group)
         if rows:
             backend.scores_bwd(wh_full[plan.lo:plan.lo + rows], rows, dp, nh, ds_src_local, ds_tgt, ga_src, ga_tgt)
         flat = torch.cat([gw.reshape(-1), ga_src.reshape(-1), ga_tgt.reshape(-1)])
-        dist.all_reduce(flat, group=group)                                  # the gradient all-reduce
+        with _lib.timed("nccl:all_reduce(grads)"):
+            dist.all_reduce(flat, group=group)                                  # the gradient all-reduce
         gw, ga_src, ga_tgt = flat[:gw.numel()].view_as(gw), flat[gw.numel():gw.numel() + ga_src.numel()].view_as(ga_src), \
             flat[gw.numel() + ga_src.numel():].view_as(ga_tgt)
         return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None
