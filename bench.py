@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--unfused-glue", action="store_true", help="run the inter-layer ELU as separate torch kernels")
+    ap.add_argument("--feature-dtype", default="f32", choices=["f32", "bf16"],
+                    help="bf16: the opt-in variant whose per-edge gathers read bfloat16 copies (stated separately from the fp32 headline)")
     return ap.parse_args()
 
 
@@ -232,6 +234,7 @@ def run_b200(args):
         fused_glue = [not args.unfused_glue and i != len(layers) - 1 and bool(layer.concat) for i, layer in enumerate(layers)]
         for layer, fz in zip(layers, fused_glue):
             layer.output_activation = "elu" if fz else None
+            layer.feature_dtype = None if args.feature_dtype == "f32" else args.feature_dtype
 
         def fwd_bwd(x, ei):
             h = x
@@ -383,7 +386,8 @@ def run_b200(args):
                                   f"oracle/torch_port.py on {torch.get_num_threads()} threads"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if args.feature_dtype == "f32" else "f32 accumulate, bf16 gathered features (variant; parity bar 2e-2)",
             "data": "synthetic", "config": dict(workload_config(args.workload, world), n_nodes=n, n_edges_rewritten=e_prime,
                                                  scale=args.scale, layers=[list(s) for s in shapes]),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,

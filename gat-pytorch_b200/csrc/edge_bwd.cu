@@ -75,6 +75,7 @@ struct BwdMainParams {
   // slab at the same time (its NVLink ingress serialises them: measured as a 2.4 ms wait per layer at 4 GPUs behind a
   // 4.4 ms pass); rank r starts at the slab of owner r+1 instead.
   int64_t sched_rot;
+  int go_bf16;               // host-side switch: launch the BF16 instantiation (go is a bfloat16 matrix)
 };
 
 __device__ __forceinline__ float* dwh_row_ptr(const BwdMainParams& P, const int64_t row) {
@@ -140,7 +141,19 @@ __device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src,
 __device__ __forceinline__ void bulk_wait_read_keep1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL, bool GS = false>
+// BF16 (opt-in bf16 variant): the gathered upstream-gradient matrix is a bfloat16 copy (half the bytes per
+// edge); a chunk is 8 bytes, widened to fp32 in registers; the row's own Wh, every accumulation and every output stay fp32.
+template <bool BF16>
+__device__ __forceinline__ float4 gathered_chunk(const float* rowp, const int off) {
+  if (BF16) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(rowp) + off));
+    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                       __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+  }
+  return ldg4(rowp + off);
+}
+
+template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL, bool GS = false, bool BF16 = false>
 __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneShape<SLOTS>& L, const int64_t row, const int start,
                                              const int end, const int tid, const int gl, const int gbase, const unsigned gmask, const float gmax, const float corr,
                                              int* sh_dst, const float** sh_gp, float* sh_w, float* sh_da, float* sh_s, float* part, float* coop,
@@ -230,7 +243,9 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
         }
       }
       sh_dst[tid] = d;
-      sh_gp[tid] = P.go + (int64_t)d * P.go_ld;   // the 64-bit row address is formed once, by the lane that owns the edge
+      // the 64-bit row address is formed once, by the lane that owns the edge (BF16: rows of 2-byte elements)
+      sh_gp[tid] = BF16 ? reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(P.go) + (int64_t)d * P.go_ld)
+                        : P.go + (int64_t)d * P.go_ld;
 #pragma unroll
       for (int h = 0; h < NHT; ++h) sh_w[tid * NHT + h] = msk[h] * alpha[h];
     }
@@ -277,7 +292,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
               const float* rowp = gp[u];
 #pragma unroll
               for (int s = 0; s < SLOTS; ++s)
-                v[u][s] = ldg4(rowp + L.goff[s]);
+                v[u][s] = gathered_chunk<BF16>(rowp, L.goff[s]);
             }
           }
 #pragma unroll
@@ -311,7 +326,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
               const float* rowp = gp[on ? u : 0];
 #pragma unroll
               for (int s = 0; s < SLOTS; ++s)
-                v[u][s] = on ? ldg4(rowp + L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u][s] = on ? gathered_chunk<BF16>(rowp, L.goff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
 #pragma unroll
@@ -493,7 +508,7 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
   }
 }
 
-template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL, bool GS = false>
+template <int G, int SLOTS, int NHT, bool COOP, bool FUSED, bool FULL, bool GS = false, bool BF16 = false>
 __global__ void __launch_bounds__(kEdgeThreads, (SLOTS <= 2 ? 3 : (SLOTS <= 4 ? 2 : 1)))
 edge_bwd_main_kernel(const BwdMainParams P) {
   constexpr int TB = MainShape<G, SLOTS>::TB;
@@ -520,7 +535,7 @@ edge_bwd_main_kernel(const BwdMainParams P) {
     for (;;) {
       const int64_t row = grab_long_row(P.sched, P.rowptr_t, &sh_ctl);
       if (row < 0) break;
-      bwd_main_row<G, SLOTS, NHT, true, FUSED, FULL, GS>(P, L, row, __ldg(P.rowptr_t + row), __ldg(P.rowptr_t + row + 1), tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, sh_s, part, dyn_smem, stage, sh_flip);
+      bwd_main_row<G, SLOTS, NHT, true, FUSED, FULL, GS, BF16>(P, L, row, __ldg(P.rowptr_t + row), __ldg(P.rowptr_t + row + 1), tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da, sh_s, part, dyn_smem, stage, sh_flip);
     }
   } else {
     int64_t base;
@@ -532,7 +547,7 @@ edge_bwd_main_kernel(const BwdMainParams P) {
         int64_t row;
         int start, end;
         if (prefetched_row<G>(P.sched, k, lane, pr, ps, pe, row, start, end))
-          bwd_main_row<G, SLOTS, NHT, false, FUSED, FULL, GS>(P, L, row, start, end, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da,
+          bwd_main_row<G, SLOTS, NHT, false, FUSED, FULL, GS, BF16>(P, L, row, start, end, tid, gl, gbase, gmask, gmax, corr, sh_dst, sh_gp, sh_w, sh_da,
                                                               sh_s, part, nullptr, stage, sh_flip);
       }
     }
@@ -956,6 +971,41 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
   const size_t push_bytes = (P.push && shape.g == 32) ? (size_t)(kEdgeThreads / 32) * 2 * P.dp * sizeof(float) : 0;
   Q.rowbuf_offset_floats = -1;
   Q.sched_rot = P.push ? (((int64_t)P.my_rank + 1) * P.rows_per_rank) % (n_rows > 0 ? n_rows : 1) : 0;
+  if (P.go_bf16) {   // bf16 variant: fused path, wide unshared rows only (the shapes it is meant for)
+    if (!(FUSED && !P.go_shared && shape.g == 32 && (shape.slots == 2 || shape.slots == 8) && nh <= 4)) {
+      set_error("gat_edge_bwd_fused_bf16: supported for NH <= 4, unshared gradient rows of 132..256 or 772..1024 floats (got NH = %d, %d floats)", nh, P.dp);
+      return GAT_EUNSUPPORTED;
+    }
+#define LAUNCH_BF16(S_)                                                                                                \
+    do {                                                                                                               \
+      const size_t base_ = (main_dyn_smem<32, S_>(P.chunks) + 15) / 16 * 16;                                           \
+      const size_t smem_ = base_ + push_bytes;                                                                         \
+      if (push_bytes) Q.rowbuf_offset_floats = (int)(base_ / sizeof(float));                                           \
+      static size_t optin_bf_ = 0;                                                                                     \
+      if (smem_ > optin_bf_) {                                                                                         \
+        optin_bf_ = smem_;                                                                                             \
+        GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<32, S_, 4, true, FUSED, false, false, true>,                \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin_bf_));                   \
+        GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<32, S_, 4, false, FUSED, false, false, true>,               \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin_bf_));                   \
+      }                                                                                                                \
+      if (coop_launch) {                                                                                               \
+        GAT_CUDA(launch_kernel(edge_bwd_main_kernel<32, S_, 4, true, FUSED, false, false, true>,                       \
+                               persistent_grid(edge_bwd_main_kernel<32, S_, 4, true, FUSED, false, false, true>, kEdgeThreads, smem_, \
+                                               n_long < 0 ? n_rows : n_long),                                          \
+                               kEdgeThreads, smem_, st, Q, false));                                                    \
+        GAT_LAUNCH_CHECK();                                                                                            \
+      }                                                                                                                \
+      GAT_CUDA(launch_kernel(edge_bwd_main_kernel<32, S_, 4, false, FUSED, false, false, true>,                        \
+                             persistent_grid(edge_bwd_main_kernel<32, S_, 4, false, FUSED, false, false, true>, kEdgeThreads, smem_, \
+                                             (n_rows + 7) / 8),                                                        \
+                             kEdgeThreads, smem_, st, Q, coop_launch));                                                \
+      GAT_LAUNCH_CHECK();                                                                                              \
+    } while (0)
+    if (shape.slots == 2) LAUNCH_BF16(2); else LAUNCH_BF16(8);
+#undef LAUNCH_BF16
+    return GAT_OK;
+  }
   // GS: narrow shared upstream-gradient rows are staged through shared memory (see bwd_main_row)
   if (FUSED && P.go_shared && shape.g == 32 && shape.slots <= 2 && nh <= 4 && P.chunks_per_head <= kStageMaxChunks) {
 #define LAUNCH_GS(S_)                                                                                                  \
@@ -1056,7 +1106,7 @@ extern "C" int gat_edge_bwd_main(const int32_t* rowptr_t, const int32_t* col_t, 
   return launch_bwd_main<false>(P, row_order_t, n_long, n_rows, st);
 }
 
-extern "C" int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
+static int edge_bwd_fused_impl(bool go_bf16, const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
                                   int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
                                   const float* s_src, const float* s_tgt, const float* gmax, const float* z,
                                   float dropout_p, uint64_t seed, uint64_t offset,
@@ -1094,8 +1144,42 @@ extern "C" int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t,
   P.s_sum = s_sum; P.tpack = tgt_pack; P.a_src = a_src; P.a_tgt = a_tgt; P.tie_dst = tie_dst; P.tie_src = tie_src; P.header = header;
   P.corr_override = corr_override; P.tgt_lo = tgt_lo; P.tgt_hi = tgt_hi; P.ds_src = ds_src; P.ds_tgt = ds_tgt;
   P.push = n_push > 0; P.my_rank = my_rank; P.rows_per_rank = rows_per_rank > 0 ? rows_per_rank : 1;
+  P.go_bf16 = go_bf16 ? 1 : 0;
   for (int q = 0; q < n_push; ++q) P.push_dst[q] = h_push_dst[q];
   return launch_bwd_main<true>(P, row_order_t, n_long, n_rows, st);
+}
+
+extern "C" int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
+                                  int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                                  const float* s_src, const float* s_tgt, const float* gmax, const float* z,
+                                  float dropout_p, uint64_t seed, uint64_t offset,
+                                  const float* go_padded, int go_shared, const float* s_sum, const float* tgt_pack,
+                                  const float* a_src, const float* a_tgt,
+                                  const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                                  const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
+                                  float* ds_src, float* ds_tgt, float* d_wh,
+                                  float* const* h_push_dst, int n_push, int my_rank, int64_t rows_per_rank,
+                                  void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  return edge_bwd_fused_impl(false, rowptr_t, col_t, pos_t, row_order_t, n_long, eid, n_rows, wh, nh, fp, s_src, s_tgt, gmax, z, dropout_p, seed, offset,
+                             go_padded, go_shared, s_sum, tgt_pack, a_src, a_tgt, tie_dst, tie_src, tie_total, corr_override, tgt_lo, tgt_hi,
+                             ds_src, ds_tgt, d_wh, h_push_dst, n_push, my_rank, rows_per_rank, workspace, workspace_bytes, stream);
+}
+
+// bf16 variant: `go_bf16` is a bfloat16 copy (gat_f32_to_bf16) of the (n_targets, nh*fp) upstream gradient the pass gathers.
+extern "C" int gat_edge_bwd_fused_bf16(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
+                                  int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                                  const float* s_src, const float* s_tgt, const float* gmax, const float* z,
+                                  float dropout_p, uint64_t seed, uint64_t offset,
+                                  const void* go_bf16, int go_shared, const float* s_sum, const float* tgt_pack,
+                                  const float* a_src, const float* a_tgt,
+                                  const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                                  const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
+                                  float* ds_src, float* ds_tgt, float* d_wh,
+                                  float* const* h_push_dst, int n_push, int my_rank, int64_t rows_per_rank,
+                                  void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  return edge_bwd_fused_impl(true, rowptr_t, col_t, pos_t, row_order_t, n_long, eid, n_rows, wh, nh, fp, s_src, s_tgt, gmax, z, dropout_p, seed, offset,
+                             (const float*)go_bf16, go_shared, s_sum, tgt_pack, a_src, a_tgt, tie_dst, tie_src, tie_total, corr_override, tgt_lo, tgt_hi,
+                             ds_src, ds_tgt, d_wh, h_push_dst, n_push, my_rank, rows_per_rank, workspace, workspace_bytes, stream);
 }
 
 extern "C" int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, const int32_t* row_order, int64_t n_long, int64_t n_rows, int nh,

@@ -111,10 +111,24 @@ __device__ __forceinline__ void edge_probs(const EdgeFwdParams& P, int e, bool v
   }
 }
 
+// One 4-element chunk of a gathered feature row.  BF16 = true (the opt-in "bf16 variant" of SURVEY.md 8-d): the gathered
+// matrix is a bfloat16 copy of Wh (half the bytes per edge); the chunk is 8 bytes and is widened to fp32 in registers, all
+// accumulation stays fp32.  `base` points at the matrix, `off` is the chunk's element offset inside the row.
+template <bool BF16>
+__device__ __forceinline__ float4 gather_chunk(const float* base, const int64_t row, const int dp, const int off) {
+  if (BF16) {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(base) + row * dp + off;
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                       __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+  }
+  return ldg4(base + row * dp + off);
+}
+
 // COOP = false: the group owns the whole row.  COOP = true (long rows): the CTA's NG = 256/G groups take the row's
 // batches round-robin; Z and the output row are combined over the groups through `coop` (NG*dp floats of dynamic
 // shared memory) in group order.  Called by ALL threads of the CTA in that case.
-template <int G, int SLOTS, int NHT, bool COOP>
+template <int G, int SLOTS, int NHT, bool COOP, bool BF16 = false>
 __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64_t row, const int start, const int end, const int tid, const int gl,
                                              const int gbase, const unsigned gmask, const float gmax,
                                              int* sh_src, float* sh_w, float* coop) {
@@ -226,9 +240,9 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
       if (t + U <= cnt) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const float* rowp = P.wh + (int64_t)sp[u] * P.dp;
+          const int64_t srow = sp[u];
 #pragma unroll
-          for (int s = 0; s < SLOTS; ++s) v[u][s] = ldg4(rowp + coff[s]);
+          for (int s = 0; s < SLOTS; ++s) v[u][s] = gather_chunk<BF16>(P.wh, srow, P.dp, coff[s]);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -245,10 +259,10 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const bool on = t + u < cnt;
-          const float* rowp = P.wh + (int64_t)(on ? sp[u] : 0) * P.dp;
+          const int64_t srow = on ? sp[u] : 0;
 #pragma unroll
           for (int s = 0; s < SLOTS; ++s)
-            v[u][s] = on ? ldg4(rowp + coff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[u][s] = on ? gather_chunk<BF16>(P.wh, srow, P.dp, coff[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -291,7 +305,7 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
 
 // COOP = false: every warp takes short rows, group per row.  COOP = true: every CTA takes long rows, CTA per row (its
 // own launch, so that neither path pays for the other's registers).
-template <int G, int SLOTS, int NHT, bool COOP>
+template <int G, int SLOTS, int NHT, bool COOP, bool BF16 = false>
 __global__ void __launch_bounds__(kEdgeThreads, (SLOTS <= 2 ? 3 : (SLOTS <= 4 ? 2 : 1)))
 edge_fwd_kernel(const EdgeFwdParams P) {
   extern __shared__ __align__(16) float coop[];   // COOP: (256/G) * dp floats, cross-group reduction
@@ -306,7 +320,7 @@ edge_fwd_kernel(const EdgeFwdParams P) {
     for (;;) {
       const int64_t row = grab_long_row(P.sched, P.rowptr, &sh_ctl);
       if (row < 0) break;
-      edge_fwd_row<G, SLOTS, NHT, true>(P, row, __ldg(P.rowptr + row), __ldg(P.rowptr + row + 1), tid, gl, gbase, gmask, gmax, sh_src, sh_w, coop);
+      edge_fwd_row<G, SLOTS, NHT, true, BF16>(P, row, __ldg(P.rowptr + row), __ldg(P.rowptr + row + 1), tid, gl, gbase, gmask, gmax, sh_src, sh_w, coop);
     }
   } else {
     int64_t base;
@@ -318,7 +332,7 @@ edge_fwd_kernel(const EdgeFwdParams P) {
         int64_t row;
         int start, end;
         if (prefetched_row<G>(P.sched, k, lane, pr, ps, pe, row, start, end))
-          edge_fwd_row<G, SLOTS, NHT, false>(P, row, start, end, tid, gl, gbase, gmask, gmax, sh_src, sh_w, nullptr);
+          edge_fwd_row<G, SLOTS, NHT, false, BF16>(P, row, start, end, tid, gl, gbase, gmask, gmax, sh_src, sh_w, nullptr);
       }
     }
     pdl_wait_for_primary();     // no-op unless launched behind the cooperative kernel
@@ -393,12 +407,12 @@ extern "C" int gat_edge_max(const int32_t* rowptr, const int32_t* col, const int
 
 extern "C" size_t gat_edge_fwd_workspace_bytes(void) { return 256; }
 
-extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
-                            int64_t n, const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
-                            const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
-                            float* out, int out_act, float* alpha_out, float* z_out,
-                            int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
-                            void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+static int edge_fwd_impl(bool gather_bf16, const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
+                         int64_t n, const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
+                         const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
+                         float* out, int out_act, float* alpha_out, float* z_out,
+                         int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
+                         void* workspace, size_t workspace_bytes, gat_stream_t stream) {
   using namespace gat;
   GAT_CHECK_ARG(nh >= 1 && nh <= kMaxHeads, "gat_edge_fwd: num_heads %d not in [1, %d]", nh, kMaxHeads);
   GAT_CHECK_ARG(workspace != nullptr && workspace_bytes >= gat_edge_fwd_workspace_bytes(), "gat_edge_fwd: workspace too small");
@@ -427,6 +441,29 @@ extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int
   // long rows first, CTA per row (skipped when the caller knows there are none; n_long < 0 = unknown); the short-row
   // launch overlaps its tail
   const bool coop_launch = row_order != nullptr && n_long != 0;
+  if (gather_bf16) {   // bf16 variant: instantiated for the wide shapes it is meant for (G = 32; 2 or 8 chunks per lane; NH <= 4)
+    if (!(shape.g == 32 && (shape.slots == 2 || shape.slots == 8) && nh <= 4)) {
+      set_error("gat_edge_fwd_bf16: supported for NH <= 4 and padded rows of 132..256 or 772..1024 floats (got NH = %d, %d floats)", nh, P.dp);
+      return GAT_EUNSUPPORTED;
+    }
+#define LAUNCH_BF16(S_)                                                                                               \
+    do {                                                                                                              \
+      if (coop_launch) {                                                                                              \
+        GAT_CUDA(launch_kernel(edge_fwd_kernel<32, S_, 4, true, true>,                                                \
+                               persistent_grid(edge_fwd_kernel<32, S_, 4, true, true>, kEdgeThreads, coop_smem_bytes(32, P.dp), \
+                                               n_long < 0 ? n : n_long),                                              \
+                               kEdgeThreads, coop_smem_bytes(32, P.dp), st, P, false));                               \
+        GAT_LAUNCH_CHECK();                                                                                           \
+      }                                                                                                               \
+      GAT_CUDA(launch_kernel(edge_fwd_kernel<32, S_, 4, false, true>,                                                 \
+                             persistent_grid(edge_fwd_kernel<32, S_, 4, false, true>, kEdgeThreads, 0, (n + 7) / 8),  \
+                             kEdgeThreads, 0, st, P, coop_launch));                                                   \
+      GAT_LAUNCH_CHECK();                                                                                             \
+    } while (0)
+    if (shape.slots == 2) LAUNCH_BF16(2); else LAUNCH_BF16(8);
+#undef LAUNCH_BF16
+    return GAT_OK;
+  }
   if (coop_launch) {
     const int64_t ctas = n_long < 0 ? n : n_long;
 #define LAUNCH(G_, S_, N_)                                                                                            \
@@ -446,6 +483,27 @@ extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int
 #undef LAUNCH
   GAT_LAUNCH_CHECK();
   return GAT_OK;
+}
+
+extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
+                            int64_t n, const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
+                            const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
+                            float* out, int out_act, float* alpha_out, float* z_out,
+                            int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
+                            void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  return edge_fwd_impl(false, rowptr, col, eid, row_order, n_long, n, wh, nh, fp, s_src, s_tgt, gmax, const_attention, dropout_p, seed,
+                       offset, out, out_act, alpha_out, z_out, tie_dst, tie_src, tie_total, workspace, workspace_bytes, stream);
+}
+
+// bf16 variant: `wh_bf16` is a bfloat16 copy of Wh (gat_f32_to_bf16), same (n, nh*fp) row-major layout; everything else as above.
+extern "C" int gat_edge_fwd_bf16(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
+                                 int64_t n, const void* wh_bf16, int nh, int fp, const float* s_src, const float* s_tgt,
+                                 const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
+                                 float* out, int out_act, float* alpha_out, float* z_out,
+                                 int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
+                                 void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  return edge_fwd_impl(true, rowptr, col, eid, row_order, n_long, n, (const float*)wh_bf16, nh, fp, s_src, s_tgt, gmax, const_attention,
+                       dropout_p, seed, offset, out, out_act, alpha_out, z_out, tie_dst, tie_src, tie_total, workspace, workspace_bytes, stream);
 }
 
 extern "C" int gat_head_merge_fwd(const float* o_padded, int64_t n, int nh, int f, int fp, int concat, float* out,

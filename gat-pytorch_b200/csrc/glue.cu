@@ -163,6 +163,34 @@ extern "C" int gat_attention_degree_scaled(const int32_t* rowptr, const int32_t*
   return GAT_OK;
 }
 
+// ---- bf16 variant: bfloat16 copy of a feature matrix for the per-edge gathers (round to nearest even) ----
+namespace gat {
+__device__ __forceinline__ unsigned bf16_bits(float v) {
+  unsigned u = __float_as_uint(v);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (u >> 16) | 0x40u;     // NaN stays NaN
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+__global__ void __launch_bounds__(256)
+f32_to_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t count4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(src + i);
+    dst[i] = make_uint2(bf16_bits(v.x) | (bf16_bits(v.y) << 16), bf16_bits(v.z) | (bf16_bits(v.w) << 16));
+  }
+}
+}  // namespace gat
+
+extern "C" int gat_f32_to_bf16(const float* src, void* dst, int64_t count, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(src && dst && count >= 0 && count % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0,
+                "gat_f32_to_bf16: count must be a multiple of 4 and the buffers 16 / 8 byte aligned");
+  if (count == 0) return GAT_OK;
+  const int64_t c4 = count / 4, want = (c4 + 255) / 256;
+  f32_to_bf16_kernel<<<(unsigned)(want < kNumSMs * 16 ? want : kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)src, (uint2*)dst, c4);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
 extern "C" size_t gat_attention_norm_workspace_bytes(void) { return (size_t)gat::kNormBlocks * sizeof(double); }
 
 extern "C" int gat_attention_norm_fwd(const void* edge_dst, int index_is_int64, const int32_t* rowptr, const float* alpha,

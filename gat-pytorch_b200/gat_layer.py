@@ -47,7 +47,7 @@ class _GATFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_p, a_src_p, a_tgt_p, st: GraphStructure, nh, f, fp, concat, const_attention,
-                p_drop, want_alpha, gemm_algo, x_act=False, out_act=False):
+                p_drop, want_alpha, gemm_algo, x_act=False, out_act=False, bf16=False):
         lib = _lib.load()
         dev = x.device
         n, f_in, dp = x.size(0), x.size(1), nh * fp
@@ -81,8 +81,12 @@ class _GATFunction(torch.autograd.Function):
             seed = 0
             if p_drop > 0.0:
                 seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator: no device sync
-            _lib.call("gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), st.n_long, n,
-                                        wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax),
+            wh_gather = wh
+            if bf16:    # bf16 variant: the per-edge gathers read a bfloat16 copy of Wh (half the bytes); fp32 Wh is kept for the backward
+                wh_gather = torch.empty((n, dp), dtype=torch.bfloat16, device=dev)
+                _lib.call("gat_f32_to_bf16", wh.data_ptr(), wh_gather.data_ptr(), n * dp, s)
+            _lib.call("gat_edge_fwd_bf16" if bf16 else "gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), st.n_long, n,
+                                        wh_gather.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax),
                                         int(const_attention), float(p_drop), seed, 0,
                                         out_p.data_ptr(), int(out_act), _ptr(alpha), z.data_ptr(),
                                         _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), fws.data_ptr(), fws.numel(), s,
@@ -92,7 +96,7 @@ class _GATFunction(torch.autograd.Function):
                 _lib.call("gat_head_merge_fwd", out_p.data_ptr(), n, nh, f, fp, int(concat), out.data_ptr(), s)
             else:
                 out = out_p
-        ctx.st, ctx.cfg = st, (nh, f, fp, concat, const_attention, float(p_drop), seed, gemm_algo, bool(x_act), bool(out_act))
+        ctx.st, ctx.cfg = st, (nh, f, fp, concat, const_attention, float(p_drop), seed, gemm_algo, bool(x_act), bool(out_act), bool(bf16))
         ctx.save_for_backward(x, w_p, a_src_p, a_tgt_p, wh, s_src, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p)
         if alpha is None:
             return out, None
@@ -103,7 +107,7 @@ class _GATFunction(torch.autograd.Function):
         lib = _lib.load()
         x, w_p, a_src_p, a_tgt_p, wh, s_src, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p = ctx.saved_tensors
         st: GraphStructure = ctx.st
-        nh, f, fp, concat, const_attention, p_drop, seed, gemm_algo, x_act, out_act = ctx.cfg
+        nh, f, fp, concat, const_attention, p_drop, seed, gemm_algo, x_act, out_act, bf16 = ctx.cfg
         dev = x.device
         n, f_in, dp = x.size(0), x.size(1), nh * fp
         with torch.cuda.device(dev):
@@ -148,9 +152,14 @@ class _GATFunction(torch.autograd.Function):
                           ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
                 if out_act:
                     go_p = go_pre
-                _lib.call("gat_edge_bwd_fused", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
+                fused_name, go_gather = "gat_edge_bwd_fused", go_p
+                if bf16 and not go_shared:     # bf16 variant: the gathered upstream gradient is a bfloat16 copy
+                    go_gather = torch.empty((n, dp), dtype=torch.bfloat16, device=dev)
+                    _lib.call("gat_f32_to_bf16", go_p.data_ptr(), go_gather.data_ptr(), n * dp, s)
+                    fused_name = "gat_edge_bwd_fused_bf16"
+                _lib.call(fused_name, st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
                           st.n_long_t, st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, s_src.data_ptr(), s_tgt.data_ptr(), gmax.data_ptr(),
-                          z.data_ptr(), p_drop, seed, 0, go_p.data_ptr(), go_shared, s_sum.data_ptr(), tpack.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
+                          z.data_ptr(), p_drop, seed, 0, go_gather.data_ptr(), go_shared, s_sum.data_ptr(), tpack.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
                           _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total), None, 0, n, ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr(),
                           None, 0, 0, 0, ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
             else:
@@ -186,7 +195,7 @@ class _GATFunction(torch.autograd.Function):
                 sws = torch.empty(sb, dtype=torch.uint8, device=dev)
                 _lib.call("gat_scores_bwd", wh.data_ptr(), n, dp, nh, ds_src.data_ptr(), ds_tgt.data_ptr(),
                           ga_src.data_ptr(), ga_tgt.data_ptr(), sws.data_ptr(), sb, s)
-        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None, None, None
+        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 class GATLayer(nn.Module):
@@ -235,6 +244,10 @@ class GATLayer(nn.Module):
         # the cheaper of the two fusions (measured, profiles/README.md); concat layers without bias only (ELU does not
         # commute with the head mean).
         self.output_activation = None
+        # Opt-in bf16 variant (BASELINE.json north_star "bf16 variant stated separately"): "bf16" makes the edge kernels gather
+        # bfloat16 copies of Wh (forward) and of dL/dout (fused backward) -- half the bytes per edge, fp32 accumulation,
+        # ~2e-3 relative error.  None (default) = fp32 everywhere, the 1e-5 parity path.  NH <= 4, wide rows only.
+        self.feature_dtype = None
         self.structure_cache = GLOBAL_CACHE
         self.reset_parameters()
 
@@ -268,6 +281,13 @@ class GATLayer(nn.Module):
             raise ValueError(f"input_activation must be None or 'elu', got {self.input_activation!r}")
         return True
 
+    def _bf16(self) -> bool:
+        if self.feature_dtype in (None, "f32", "fp32", "float32"):
+            return False
+        if self.feature_dtype not in ("bf16", "bfloat16"):
+            raise ValueError(f"feature_dtype must be None or 'bf16', got {self.feature_dtype!r}")
+        return True
+
     def _out_act(self) -> bool:
         if self.output_activation in (None, "none"):
             return False
@@ -297,7 +317,8 @@ class GATLayer(nn.Module):
         p_drop = float(self.dropout) if (self.training and self.dropout > 0) else 0.0
         out, alpha = _GATFunction.apply(x, w_p, a_src, a_tgt, st, self.num_heads, self.out_features, fp,
                                         bool(self.concat), bool(self.const_attention), p_drop,
-                                        bool(return_attention_weights), int(self.gemm_algo), self._x_act(), self._out_act())
+                                        bool(return_attention_weights), int(self.gemm_algo), self._x_act(), self._out_act(),
+                                        self._bf16())
         self.normalised_attention_coeffs = alpha
         if self.bias:
             out = out + self.bias_param          # gat_layer.py:134-135 (same broadcast rules, same latent shape error)

@@ -304,6 +304,32 @@ GAT_API int gat_attention_entropy(const int32_t* rowptr, const int32_t* eid, int
 GAT_API int gat_attention_degree_scaled(const int32_t* rowptr, const int32_t* eid, int64_t n, const float* alpha, int nh,
                                         float* scaled, gat_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * bf16 variant (BASELINE.json north_star "bf16 variant stated separately").  Opt-in: the matrices the edge
+ * kernels GATHER per edge -- Wh in the forward, the upstream gradient dL/dout in the fused backward -- are bfloat16 copies
+ * (half the bytes per edge); the row a pass owns, every accumulation and every output stay fp32.  Same arguments as the
+ * fp32 entry points except the gathered matrix.  Supported for NH <= 4 and padded rows of 132..256 or 772..1024 floats;
+ * the backward additionally needs an unshared gradient (concat layers).  Parity bar of this variant: 2e-2 tensor-relative.
+ * ------------------------------------------------------------------------------------- */
+GAT_API int gat_f32_to_bf16(const float* src, void* dst, int64_t count, gat_stream_t stream);
+GAT_API int gat_edge_fwd_bf16(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
+                 int64_t n, const void* wh_bf16, int nh, int fp, const float* s_src, const float* s_tgt,
+                 const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
+                 float* out, int out_act, float* alpha_out, float* z_out,
+                 int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
+                 void* workspace, size_t workspace_bytes, gat_stream_t stream);
+GAT_API int gat_edge_bwd_fused_bf16(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
+                               int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                               const float* s_src, const float* s_tgt, const float* gmax, const float* z,
+                               float dropout_p, uint64_t seed, uint64_t offset,
+                               const void* go_bf16, int go_shared, const float* s_sum, const float* tgt_pack,
+                               const float* a_src, const float* a_tgt,
+                               const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                               const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
+                               float* ds_src, float* ds_tgt, float* d_wh,
+                               float* const* h_push_dst, int n_push, int my_rank, int64_t rows_per_rank,
+                               void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -424,3 +424,37 @@ def test_visualisation_feed_matches_reference_loops(small_cases):
         assert O.rel_err(uni.cpu().numpy(), want_uni) < 1e-5, name
         assert scaled.shape == want_scaled.shape
         assert O.rel_err(scaled.cpu().numpy(), want_scaled) < 1e-5, name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["products_L0", "products_L1", "products_L2"])
+def test_bf16_variant_within_its_stated_tolerance(name, small_cases):
+    """BASELINE.json north_star: "bf16 variant stated separately".  `layer.feature_dtype = "bf16"` gathers bfloat16 copies of
+    Wh / dL/dout (fp32 accumulation); bar 2e-2 tensor-relative against the fp64 oracle for out and every gradient, and the
+    returned attention (computed from the fp32 scores) stays at the fp32 bar."""
+    case = small_cases[name]
+    layer = make_layer(case)
+    layer.feature_dtype = "bf16"
+    x = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+    ei = torch.from_numpy(case["edge_index"]).cuda()
+    out = layer(x, ei)
+    go, _ = cases.upstream_grads(case, out.shape[0], out.shape[1], 1)
+    (out * torch.from_numpy(go).cuda()).sum().backward()
+    fw = O.forward(case["x"], case["edge_index"].astype(np.int64), case["W"], case["a"], case["nh"], case["f"], case["concat"],
+                   case["add_self_loops"], case["bias"], case["const_attention"])
+    gr = O.backward(fw, go, None)
+    errs = dict(out=O.rel_err(out.detach().cpu().numpy(), fw["out"]), gx=O.rel_err(x.grad.cpu().numpy(), gr["x"]),
+                gW=O.rel_err(layer.W.weight.grad.cpu().numpy(), gr["W"]), ga=O.rel_err(layer.a.weight.grad.cpu().numpy(), gr["a"]))
+    assert all(e < 2e-2 for e in errs.values()), (name, errs)
+    assert errs["out"] > 1e-6, "the bf16 path did not run (fp32-exact output)"
+    _, (_, alpha) = layer(x.detach(), ei, return_attention_weights=True)
+    assert O.rel_err(alpha.detach().cpu().numpy(), fw["alpha"]) < TOL
+
+
+@pytest.mark.gpu
+def test_bf16_variant_refuses_unsupported_shapes(small_cases):
+    case = small_cases["cora_L0"]          # 8 heads x 8: not a wide-row shape
+    layer = make_layer(case)
+    layer.feature_dtype = "bf16"
+    with pytest.raises(RuntimeError):
+        layer(torch.from_numpy(case["x"]).cuda(), torch.from_numpy(case["edge_index"]).cuda())
