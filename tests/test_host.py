@@ -127,3 +127,24 @@ def test_torch_port_matches_oracle(small_cases):
     fw = O.forward(case["x"], case["edge_index"], case["W"], case["a"], case["nh"], case["f"], True, True)
     assert np.array_equal(ei2.numpy(), fw["edge_index"])
     assert O.rel_err(out.numpy(), fw["out"]) < 1e-5 and O.rel_err(alpha.numpy(), fw["alpha"]) < 1e-5
+
+
+def test_visualisation_oracle_matches_segment_formulas(small_cases):
+    """The oracle restatement of the vis scripts' per-node loops (entropy_histograms.py:103-115, weight_histograms.py:74-87)
+    against closed forms on the CSR segments: uniform entropy = log2(deg), entropy = log2(S) - sum(a log2 a)/S with S the
+    row sum, degree-scaled weights = alpha * deg[dst] in stable target order."""
+    import gat_oracle as O
+    case = small_cases["adv_concat"]
+    fw = O.forward(case["x"], case["edge_index"], case["W"], case["a"], case["nh"], case["f"], case["concat"], True)
+    ei, alpha, n = fw["edge_index"], fw["alpha"].astype(np.float64), case["x"].shape[0]
+    ent, uni = O.neighbourhood_entropy(ei, alpha, n)
+    deg = np.bincount(ei[1], minlength=n)
+    assert np.allclose(uni[deg > 0], np.log2(deg[deg > 0])) and np.all(uni[deg == 0] == 0)
+    ssum = np.zeros((n, alpha.shape[1]))
+    np.add.at(ssum, ei[1], alpha)
+    alog = np.zeros_like(ssum)
+    np.add.at(alog, ei[1], np.where(alpha > 0, alpha * np.log2(np.maximum(alpha, 1e-300)), 0.0))
+    want = np.where(ssum > 0, np.log2(np.maximum(ssum, 1e-300)) - alog / np.maximum(ssum, 1e-300), 0.0)
+    assert np.allclose(ent, want, atol=1e-9)
+    order = np.argsort(ei[1], kind="stable")
+    assert np.allclose(O.degree_scaled_attention(ei, alpha, n), alpha[order] * deg[ei[1][order]][:, None])

@@ -47,12 +47,12 @@ def _worker(rank, world, port, case_name, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case_name", ["adv_concat", "adv_mean_oddF", "adv_ties"])
-def test_two_rank_partition_matches_single_process_oracle(case_name):
+@pytest.mark.parametrize("case_name,world", [("adv_concat", 2), ("adv_mean_oddF", 2), ("adv_ties", 2), ("adv_concat", 3)])
+def test_two_rank_partition_matches_single_process_oracle(case_name, world):
+    """world 3 on 97 nodes: unequal last range (33 + 33 + 31) and a padded gathered buffer."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cases
     import gat_oracle as O
-    world = 2
     ret = mp.Manager().dict()
     port = 29600 + (os.getpid() % 300)
     mp.spawn(_worker, args=(world, port, case_name, ret), nprocs=world, join=True)
