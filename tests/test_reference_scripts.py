@@ -1,0 +1,50 @@
+"""the reference's own `train.py` (-> planetoid_gat.py / GATModel.py / data_utils.py / run_config.py) runs
+UNCHANGED in this offline image on the stand-ins for pytorch_lightning / torch_geometric
+(gat-pytorch_b200/overlay/shims), and the namespace-package overlay makes the same unmodified script construct the B200 layer.
+
+CPU only and only where the reference checkout exists (/root/reference is absent on the GPU box, so nothing here is `gpu`):
+the first test drives the REFERENCE layer through the stand-ins (validating them), the second shows that with the overlay in
+front the script reaches gat_pytorch_b200.GATLayer -- which, on a machine without CUDA, must refuse loudly (no CPU fallback).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+SHIMS = os.path.join(ROOT, "gat-pytorch_b200", "overlay", "shims")
+OVERLAY = os.path.join(ROOT, "gat-pytorch_b200", "overlay")
+
+pytestmark = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "train.py")), reason="reference checkout not present")
+
+
+def _train(args, cwd, pythonpath, safe_path=False):
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join(pythonpath))
+    env.pop("PYTHONSAFEPATH", None)
+    if safe_path:
+        env["PYTHONSAFEPATH"] = "1"      # python >= 3.11: do not put the script's directory in front of PYTHONPATH
+    return subprocess.run([sys.executable, os.path.join(REF, "train.py")] + args, cwd=str(cwd), env=env, capture_output=True,
+                          text=True, timeout=900)
+
+
+def test_reference_train_runs_unchanged_on_the_stand_ins(tmp_path):
+    """`python train.py --dataset Cora` end to end: Planetoid-shaped synthetic graph, LightningModule hooks, Trainer.fit /
+    .test, ModelCheckpoint / EarlyStopping, then `--exec_type test` reloading the checkpoint through data_utils.load."""
+    r = _train(["--dataset", "Cora", "--num_epochs", "1"], tmp_path, [SHIMS])
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "val_loss=" in r.stdout and "test_acc=" in r.stdout
+    assert (tmp_path / "checkpoints" / "Cora-best.ckpt").is_file()
+    r = _train(["--dataset", "Cora", "--exec_type", "test"], tmp_path, [SHIMS])
+    assert r.returncode == 0 and "test_acc=" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="with a GPU the unchanged script simply trains on the B200 layer")
+def test_unchanged_script_reaches_the_b200_layer_through_the_overlay(tmp_path):
+    """overlay first, reference checkout behind it (PYTHONSAFEPATH keeps the script's own directory
+    from jumping the queue).  The unmodified train.py then builds gat_pytorch_b200.GATLayer; without CUDA its forward raises."""
+    r = _train(["--dataset", "Cora", "--num_epochs", "1"], tmp_path, [OVERLAY, ROOT, REF, SHIMS], safe_path=True)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr and os.path.join("gat-pytorch_b200", "gat_layer.py") in r.stderr
