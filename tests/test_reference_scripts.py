@@ -21,13 +21,17 @@ OVERLAY = os.path.join(ROOT, "gat-pytorch_b200", "overlay")
 pytestmark = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "train.py")), reason="reference checkout not present")
 
 
-def _train(args, cwd, pythonpath, safe_path=False):
+def _run(script, args, cwd, pythonpath, safe_path=False):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join(pythonpath))
     env.pop("PYTHONSAFEPATH", None)
     if safe_path:
         env["PYTHONSAFEPATH"] = "1"      # python >= 3.11: do not put the script's directory in front of PYTHONPATH
-    return subprocess.run([sys.executable, os.path.join(REF, "train.py")] + args, cwd=str(cwd), env=env, capture_output=True,
+    return subprocess.run([sys.executable, os.path.join(REF, script)] + args, cwd=str(cwd), env=env, capture_output=True,
                           text=True, timeout=900)
+
+
+def _train(args, cwd, pythonpath, safe_path=False):
+    return _run("train.py", args, cwd, pythonpath, safe_path)
 
 
 def test_reference_train_runs_unchanged_on_the_stand_ins(tmp_path):
@@ -48,3 +52,18 @@ def test_unchanged_script_reaches_the_b200_layer_through_the_overlay(tmp_path):
     r = _train(["--dataset", "Cora", "--num_epochs", "1"], tmp_path, [OVERLAY, ROOT, REF, SHIMS], safe_path=True)
     assert r.returncode != 0
     assert "no CPU fallback" in r.stderr and os.path.join("gat-pytorch_b200", "gat_layer.py") in r.stderr
+
+
+@pytest.mark.parametrize("vis_type", ["Entropy", "Neighbourhood"])
+def test_reference_vis_runs_unchanged_on_the_stand_ins(tmp_path, vis_type):
+    """`python vis.py --dataset Cora --vis_type ...` with the COMMITTED Cora-100epochs.ckpt (a real Lightning 1.2 pickle, loaded
+    through the stand-in's `load_from_checkpoint`), the Planetoid-shaped synthetic graph and recording-only stand-ins for
+    matplotlib / igraph.  ("Weight" needs PPI checkpoints the reference does not ship)"""
+    ckpt = os.path.join(REF, "checkpoints", "Cora-100epochs.ckpt")
+    if not os.path.isfile(ckpt):
+        pytest.skip("committed checkpoint not present")
+    (tmp_path / "checkpoints").mkdir()
+    os.symlink(ckpt, tmp_path / "checkpoints" / "Cora-100epochs.ckpt")
+    (tmp_path / "figures").mkdir()
+    r = _run("vis.py", ["--dataset", "Cora", "--vis_type", vis_type], tmp_path, [SHIMS])
+    assert r.returncode == 0, r.stderr[-2000:]
