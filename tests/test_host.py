@@ -148,3 +148,22 @@ def test_visualisation_oracle_matches_segment_formulas(small_cases):
     assert np.allclose(ent, want, atol=1e-9)
     order = np.argsort(ei[1], kind="stable")
     assert np.allclose(O.degree_scaled_attention(ei, alpha, n), alpha[order] * deg[ei[1][order]][:, None])
+
+
+def test_c_abi_rejects_bad_arguments_with_a_message_before_touching_the_device():
+    """include/gat_b200.h: every entry point returns an int status and leaves a message in gat_last_error(); argument
+    validation happens before any CUDA call, so it can be exercised on a machine without a GPU (no compute is launched)."""
+    from gat_pytorch_b200 import _lib
+    lib = _lib.load()
+    assert lib.gat_version() >= 100
+    assert lib.gat_tgt_pack_stride(4) == 16 and lib.gat_tgt_pack_stride(8) == 32
+    assert lib.gat_edge_fwd_workspace_bytes() == 256
+    assert lib.gat_scores_fwd(None, 10, 64, None, None, 9, None, None, None) != 0
+    assert b"num_heads 9" in lib.gat_last_error()
+    assert lib.gat_f32_to_bf16(None, None, 8, None) != 0 and b"gat_f32_to_bf16" in lib.gat_last_error()
+    assert lib.gat_attention_entropy(None, None, 5, None, 9, None, None, None) != 0 and b"gat_attention_entropy" in lib.gat_last_error()
+    # the tcgen05 path needs 16-byte aligned leading dimensions: Cora's K = 1433 goes to the FFMA kernel (DESIGN.md section 4)
+    assert lib.gat_gemm_tc_supported(0, 1, 100, 64, 1433, 1433, 1433, 64) == 0
+    assert lib.gat_gemm_tc_supported(0, 1, 100, 64, 1024, 1024, 1024, 64) == 1
+    with pytest.raises(RuntimeError, match="gat_scores_fwd"):
+        _lib.call("gat_scores_fwd", None, 10, 64, None, None, 9, None, None, None)
