@@ -972,8 +972,8 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
   Q.rowbuf_offset_floats = -1;
   Q.sched_rot = P.push ? (((int64_t)P.my_rank + 1) * P.rows_per_rank) % (n_rows > 0 ? n_rows : 1) : 0;
   if (P.go_bf16) {   // bf16 variant: fused path, wide unshared rows only (the shapes it is meant for)
-    if (!(FUSED && !P.go_shared && shape.g == 32 && (shape.slots == 2 || shape.slots == 8) && nh <= 4)) {
-      set_error("gat_edge_bwd_fused_bf16: supported for NH <= 4, unshared gradient rows of 132..256 or 772..1024 floats (got NH = %d, %d floats)", nh, P.dp);
+    if (!(FUSED && !P.go_shared && shape.g == 32 && shape.slots == 2 && nh <= 4)) {
+      set_error("gat_edge_bwd_fused_bf16: supported for NH <= 4, unshared gradient rows of 132..256 floats (got NH = %d, %d floats)", nh, P.dp);
       return GAT_EUNSUPPORTED;
     }
 #define LAUNCH_BF16(S_)                                                                                                \
@@ -1002,7 +1002,7 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
                              kEdgeThreads, smem_, st, Q, coop_launch));                                                \
       GAT_LAUNCH_CHECK();                                                                                              \
     } while (0)
-    if (shape.slots == 2) LAUNCH_BF16(2); else LAUNCH_BF16(8);
+    LAUNCH_BF16(2);
 #undef LAUNCH_BF16
     return GAT_OK;
   }

@@ -441,9 +441,9 @@ static int edge_fwd_impl(bool gather_bf16, const int32_t* rowptr, const int32_t*
   // long rows first, CTA per row (skipped when the caller knows there are none; n_long < 0 = unknown); the short-row
   // launch overlaps its tail
   const bool coop_launch = row_order != nullptr && n_long != 0;
-  if (gather_bf16) {   // bf16 variant: instantiated for the wide shapes it is meant for (G = 32; 2 or 8 chunks per lane; NH <= 4)
-    if (!(shape.g == 32 && (shape.slots == 2 || shape.slots == 8) && nh <= 4)) {
-      set_error("gat_edge_fwd_bf16: supported for NH <= 4 and padded rows of 132..256 or 772..1024 floats (got NH = %d, %d floats)", nh, P.dp);
+  if (gather_bf16) {   // bf16 variant: instantiated (and tested) for the shapes it is meant for: G = 32, 2 chunks per lane, NH <= 4
+    if (!(shape.g == 32 && shape.slots == 2 && nh <= 4)) {
+      set_error("gat_edge_fwd_bf16: supported for NH <= 4 and padded rows of 132..256 floats (got NH = %d, %d floats)", nh, P.dp);
       return GAT_EUNSUPPORTED;
     }
 #define LAUNCH_BF16(S_)                                                                                               \
@@ -460,7 +460,7 @@ static int edge_fwd_impl(bool gather_bf16, const int32_t* rowptr, const int32_t*
                              kEdgeThreads, 0, st, P, coop_launch));                                                   \
       GAT_LAUNCH_CHECK();                                                                                             \
     } while (0)
-    if (shape.slots == 2) LAUNCH_BF16(2); else LAUNCH_BF16(8);
+    LAUNCH_BF16(2);
 #undef LAUNCH_BF16
     return GAT_OK;
   }

@@ -246,7 +246,8 @@ class GATLayer(nn.Module):
         self.output_activation = None
         # Opt-in bf16 variant (BASELINE.json north_star "bf16 variant stated separately"): "bf16" makes the edge kernels gather
         # bfloat16 copies of Wh (forward) and of dL/dout (fused backward) -- half the bytes per edge, fp32 accumulation,
-        # ~2e-3 relative error.  None (default) = fp32 everywhere, the 1e-5 parity path.  NH <= 4, wide rows only.
+        # ~2e-3 relative error.  None (default) = fp32 everywhere, the 1e-5 parity path.  NH <= 4 and padded rows of
+        # 132..256 floats only (the products-class shapes it was built and tested for); other shapes raise.
         self.feature_dtype = None
         self.structure_cache = GLOBAL_CACHE
         self.reset_parameters()

@@ -308,7 +308,7 @@ GAT_API int gat_attention_degree_scaled(const int32_t* rowptr, const int32_t* ei
  * bf16 variant (BASELINE.json north_star "bf16 variant stated separately").  Opt-in: the matrices the edge
  * kernels GATHER per edge -- Wh in the forward, the upstream gradient dL/dout in the fused backward -- are bfloat16 copies
  * (half the bytes per edge); the row a pass owns, every accumulation and every output stay fp32.  Same arguments as the
- * fp32 entry points except the gathered matrix.  Supported for NH <= 4 and padded rows of 132..256 or 772..1024 floats;
+ * fp32 entry points except the gathered matrix.  Supported for NH <= 4 and padded rows of 132..256 floats;
  * the backward additionally needs an unshared gradient (concat layers).  Parity bar of this variant: 2e-2 tensor-relative.
  * ------------------------------------------------------------------------------------- */
 GAT_API int gat_f32_to_bf16(const float* src, void* dst, int64_t count, gat_stream_t stream);
