@@ -1,0 +1,102 @@
+"""Static guards on the BUILT library (no GPU needed: cuobjdump reads the sm_100a code here).
+
+Two properties the measured performance depends on and that a recompilation can silently lose:
+  * the hot instantiations fit their register budget without spilling (80 registers = 3 CTAs/SM for the edge kernels,
+    <= 128 for the two-CTA GEMM);
+  * in the gather loops of the edge kernels every load of a group of edges is ISSUED before the first FMA that consumes one
+    (memory-level parallelism).  ptxas once interleaved loads and FMAs under register pressure and the backward pass lost
+    12 %; this test would have caught it without a GPU.
+Also checks the SASS evidence the design claims: tcgen05 MMAs, TMA loads/stores and FP64 tensor-core MMAs in the GEMM,
+bulk copies in the backward.
+"""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "gat-pytorch_b200", "libgat_b200.so")
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.isfile(LIB), reason="needs cuobjdump and the built library")
+
+FWD = "edge_fwd_kernelILi32ELi2ELi4ELb0ELb0E"                      # products hidden layer, short rows
+BWD = "edge_bwd_main_kernelILi32ELi2ELi4ELb0ELb1ELb1ELb0ELb0E"     # fused backward, FULL rows
+BWD_GS = "edge_bwd_main_kernelILi32ELi2ELi4ELb0ELb1ELb0ELb1ELb0E"  # head-mean layer, staged rows
+GEMM_NT = "gemm_tc_kernelILi128ELb0E"
+
+
+@pytest.fixture(scope="module")
+def resources():
+    out = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True).stdout
+    res, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and name:
+            res[name] = (int(m.group(1)), int(m.group(2)))
+    return res
+
+
+def _sass(function_substring):
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", _mangled(function_substring), LIB], capture_output=True, text=True).stdout
+    return [m.group(1).strip() for m in re.finditer(r"^\s+/\*[0-9a-f]{4,5}\*/\s+(.*?);", out, re.M)]
+
+
+_NAMES = None
+
+
+def _mangled(sub):
+    global _NAMES
+    if _NAMES is None:
+        out = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True).stdout
+        _NAMES = re.findall(r"Function (\S+):", out)
+    hits = [n for n in _NAMES if sub in n]
+    assert len(hits) == 1, (sub, hits)
+    return hits[0]
+
+
+def _op(ins):
+    t = ins.split()
+    return (t[1] if t[0].startswith("@") else t[0])
+
+
+@pytest.mark.parametrize("sub,max_regs", [(FWD, 80), (BWD, 80), (BWD_GS, 80), (GEMM_NT, 128)])
+def test_hot_kernels_fit_their_register_budget_without_spills(resources, sub, max_regs):
+    regs, stack = resources[_mangled(sub)]
+    assert regs <= max_regs and stack == 0, (sub, regs, stack)
+
+
+@pytest.mark.parametrize("sub", [FWD, BWD])
+def test_gather_loads_of_a_group_are_issued_before_the_first_fma(sub):
+    ops = [_op(i) for i in _sass(sub)]
+    # the full-group block: a run containing 8 x LDG.E.128 (4 edges x 2 chunks) with nothing but address arithmetic between
+    # them, followed by the FMAs
+    best = 0
+    i = 0
+    while i < len(ops):
+        if ops[i].startswith("LDG.E.128"):
+            j, n_ldg = i, 0
+            while j < len(ops) and not ops[j].startswith(("FFMA", "FMUL", "BRA", "STS")):
+                n_ldg += ops[j].startswith("LDG.E.128")
+                j += 1
+            best = max(best, n_ldg)
+            i = j
+        else:
+            i += 1
+    assert best >= 8, f"{sub}: at most {best} of the 8 gather loads of a group are in flight before the first FMA"
+
+
+def test_sass_carries_the_instructions_the_design_claims():
+    gemm = " ".join(_op(i) for i in _sass(GEMM_NT))
+    assert "UTCHMMA" in gemm or "UTCMMA" in gemm            # tcgen05.mma
+    assert "UTMALDG" in gemm and "UTMASTG" in gemm          # TMA tile loads, TMA stores of the output tile
+    assert "DMMA" in gemm                                   # fused score epilogue on the FP64 tensor cores
+    assert "LDTM" in gemm                                   # tcgen05.ld (TMEM -> registers)
+    bwd = " ".join(_op(i) for i in _sass(BWD))
+    assert "UBLKCP" in bwd or "BLKCP" in bwd                # cp.async.bulk row push (partitioned runs)
+    gs = " ".join(_op(i) for i in _sass(BWD_GS))
+    assert "LDGSTS" in gs                                   # cp.async staging of the narrow shared rows
