@@ -15,9 +15,14 @@ inter-layer glue (layer -> ELU, GATModel.py:120-151).  metric = layer-edges/s = 
   roofline dominant kernel (the fused source-major backward pass gat_edge_bwd_fused on the hidden-layer
            shape) timed live with CUDA events inside the timed region; algorithmic bytes per SURVEY.md
            section 8-d / DESIGN.md section 4; traffic = ncu dram bytes of the same launch (profiles/traffic.json)
-  cpu_baseline / --impl reference: the torch CPU port of the reference layer (oracle/torch_port.py; the
-           reference is Python and cannot travel to the GPU box) on all host cores, on a 1/128-scale
-           products-shaped graph (the reference formulation cannot allocate full scale)
+  cpu_baseline / --impl reference: the reference's OWN `GATLayer` (unmodified copy under oracle/_ref/, written by
+           oracle/make_ref.py; kind "reference") stacked with GATModel.forward's glue, on all host cores, on a 1/64-scale
+           products-shaped graph (the reference formulation cannot allocate full scale, SURVEY
+           5.7); the line's config states the N / E' / scale actually timed.  Falls back to the torch port
+           (oracle/torch_port.py, kind "port") only when oracle/_ref/ is absent.
+  checksums / parity_vs_n1: loss, per-layer sum|dW| / sum|da| (fp64) and an order-independent bit checksum of the final
+           output, printed for every N; at N > 1 rank 0 re-runs the single-GPU model on the same inputs after the timed
+           region and reports the differences (forward must be bit-identical, gradients within reduction-order noise).
 """
 from __future__ import annotations
 
@@ -37,7 +42,7 @@ import torch.nn.functional as F
 
 METRIC = "gat_layer_fwd_bwd_edges_per_s"
 UNIT = "edges/s"
-CPU_SCALE = 1.0 / 128
+CPU_SCALE = 1.0 / 64     # BASELINE.md section 3 / SURVEY 8-d: the scale the reference is timed at
 
 
 def parse():
@@ -125,47 +130,94 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU reference arm (torch port of the reference formulation)
+# CPU reference arm: the reference's own GATLayer (oracle/_ref, an unmodified copy) on the host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_port_step_fn(name, scale):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import torch_port
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REF_DIR, "models", "gat_layer.py"))
+
+
+def cpu_step_fn(name, scale):
+    """fwd+bwd of the stacked model on CPU tensors with GATModel.forward's glue (layer -> ELU, GATModel.py:120-151; dropout 0,
+    no skip connections on this config).  Returns (step, E', layers, N, kind): kind "reference" = the reference's
+    unmodified models/gat_layer.py imported from oracle/_ref, "port" = oracle/torch_port.py (only when _ref is absent)."""
     x, ei, shapes, weights = make_workload(name, scale)
     torch.set_num_threads(os.cpu_count() or 1)
     xt, eit = torch.from_numpy(x), torch.from_numpy(ei)
-    ws = [(torch.from_numpy(w).requires_grad_(True), torch.from_numpy(a).requires_grad_(True)) for w, a in weights]
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port
     e_prime = int(torch_port.rewrite_edges(eit).size(1))
+    if reference_available():
+        sys.path.insert(0, REF_DIR)
+        from models.gat_layer import GATLayer as RefGATLayer      # the reference's file, byte for byte
+        layers = []
+        for (f_in, nh, f, concat), (w, a) in zip(shapes, weights):
+            layer = RefGATLayer(in_features=f_in, out_features=f, num_heads=nh, concat=concat, dropout=0, add_self_loops=True,
+                                bias=False)
+            with torch.no_grad():
+                layer.W.weight.copy_(torch.from_numpy(w))
+                layer.a.weight.copy_(torch.from_numpy(a))
+            layers.append(layer)
+
+        def step():
+            h = xt
+            for i, layer in enumerate(layers):
+                layer.W.weight.grad = layer.a.weight.grad = None
+                h = layer(h, eit)
+                if i != len(layers) - 1:
+                    h = F.elu(h)
+            loss = h.square().mean()
+            loss.backward()
+            return float(loss.detach())
+
+        return step, e_prime, len(shapes), x.shape[0], "reference"
+    ws = [(torch.from_numpy(w).requires_grad_(True), torch.from_numpy(a).requires_grad_(True)) for w, a in weights]
 
     def step():
         for w, a in ws:
             w.grad = a.grad = None
         return torch_port.model_step(xt, eit, ws, shapes)
 
-    return step, e_prime, len(shapes), x.shape[0]
+    return step, e_prime, len(shapes), x.shape[0], "port"
+
+
+def cpu_scale(args):
+    return CPU_SCALE * args.scale if args.workload == "products" else 1.0
+
+
+def cpu_sample_text(args, n, e_prime, n_layers, kind, how):
+    impl = ("the reference's own models/gat_layer.py (unmodified copy in oracle/_ref)" if kind == "reference"
+            else "oracle/torch_port.py (oracle/_ref absent)")
+    return (f"{args.workload}-shaped graph at scale {cpu_scale(args):.6g} of full size (N={n}, E'={e_prime}), {n_layers}-layer fwd+bwd, "
+            f"{how}, {impl}, torch {torch.__version__} CPU on {torch.get_num_threads()} threads")
 
 
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    step, e_prime, n_layers, n = cpu_port_step_fn(args.workload, CPU_SCALE if args.workload == "products" else 1.0)
+    step, e_prime, n_layers, n, kind = cpu_step_fn(args.workload, cpu_scale(args))
+    loss = None
     for _ in range(max(args.warmup, 1)):
-        step()
+        loss = step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        loss = step()
     dt = (time.perf_counter() - t0) / args.steps
     val = n_layers * e_prime / dt
-    sample = (f"{args.workload}-shaped graph at scale 1/128 (N={n}, E'={e_prime}), {n_layers}-layer fwd+bwd, "
-              f"torch {torch.__version__} CPU, {torch.get_num_threads()} threads")
+    sample = cpu_sample_text(args, n, e_prime, n_layers, kind, f"mean of {args.steps} steps after {max(args.warmup, 1)} warm-up")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            # the same workload description as the B200 arm prints (the bounded sample actually timed is in cpu_baseline.sample)
-            "config": dict(workload_config(args.workload, args.gpus), scale=args.scale,
+            # same workload family as the B200 arm; n_nodes / n_edges_rewritten / scale are the bounded sample ACTUALLY timed
+            # here (the reference formulation cannot allocate the full-size graph, SURVEY 5.7), not the B200 arm's full size
+            "config": dict(workload_config(args.workload, args.gpus), scale=cpu_scale(args), n_nodes=n, n_edges_rewritten=e_prime,
                            layers=[list(s) for s in load_synth().LAYER_SHAPES[args.workload]],
-                           **({"n_nodes": 2449029, "n_edges_rewritten": 64308169} if args.workload == "products" and args.scale == 1.0 else {})),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+                           bounded_sample=True, full_size_scale=args.scale),
+            "loss": loss,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -201,6 +253,70 @@ def algorithmic_bytes(kernel, e, n, nh, d, d_out):
     raise KeyError(kernel)
 
 
+class SingleGpuModel:
+    """The stacked drop-in GATLayers of one config on one GPU, with the reference's inter-layer glue (GATModel.py:148-149:
+    F.elu on every layer's output but the last).  The ELU rides in the edge kernel's epilogue and the backward's per-node
+    pass (opt-in fusion); --unfused-glue runs it as separate torch kernels."""
+
+    def __init__(self, g, shapes, weights, dev, args):
+        self.layers = []
+        for (f_in, nh, f, concat), (w, a) in zip(shapes, weights):
+            layer = g.GATLayer(f_in, f, nh, concat, dropout=0.0, add_self_loops=True).to(dev)
+            with torch.no_grad():
+                layer.W.weight.copy_(torch.from_numpy(w))
+                layer.a.weight.copy_(torch.from_numpy(a))
+            self.layers.append(layer)
+        self.fused_glue = [not args.unfused_glue and i != len(self.layers) - 1 and bool(layer.concat)
+                           for i, layer in enumerate(self.layers)]
+        for layer, fz in zip(self.layers, self.fused_glue):
+            layer.output_activation = "elu" if fz else None
+            layer.feature_dtype = None if args.feature_dtype == "f32" else args.feature_dtype
+        self.last_loss = self.last_out = None
+
+    def fwd_bwd(self, x, ei):
+        h = x
+        for i, layer in enumerate(self.layers):
+            layer.W.weight.grad = layer.a.weight.grad = None
+            h = layer(h, ei)
+            if i != len(self.layers) - 1 and not self.fused_glue[i]:
+                h = F.elu(h)
+        loss = h.square().mean()
+        loss.backward()
+        self.last_loss, self.last_out = loss.detach(), h.detach()
+        return loss
+
+
+def checksums(loss, out_rows, grads, world):
+    """Driver-verifiable fingerprints of one step: the loss, per-layer sum|dW| / sum|da| accumulated in fp64, and an
+    order-independent checksum of the final output's BIT PATTERNS (int64 sum of the fp32 words, so equal outputs give equal
+    sums whatever the row partition or summation order).  At N > 1 `out_rows` is this rank's row range and `loss` its share:
+    both are summed over ranks; the gradients are already the global sums on every rank."""
+    bits = out_rows.contiguous().view(torch.int32).to(torch.int64).sum().reshape(1)
+    fsum = torch.stack([loss.double().reshape(()), out_rows.double().abs().sum()])
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(bits)
+        dist.all_reduce(fsum)
+    return {"loss": float(fsum[0].item()), "out_bits_sum": int(bits.item()), "out_abs_sum": float(fsum[1].item()),
+            "grad_abs_sums": [[float(gw.double().abs().sum().item()), float(ga.double().abs().sum().item())] for gw, ga in grads]}
+
+
+def parity_vs_single_gpu(g, shapes, weights, x_host, ei_host, dev, args, multi, multi_grads):
+    """Rank 0 of a multi-GPU run: the single-GPU model on the same inputs and weights, compared with what the partitioned
+    run produced (its checksums and its all-reduced parameter gradients)."""
+    ref = SingleGpuModel(g, shapes, weights, dev, args)
+    ref.fwd_bwd(x_host.to(dev), ei_host.to(dev))
+    one = checksums(ref.last_loss, ref.last_out, [(l.W.weight.grad, l.a.weight.grad) for l in ref.layers], 1)
+    grad_rel = 0.0
+    for (gw, ga), l in zip(multi_grads, ref.layers):
+        for got, want in ((gw, l.W.weight.grad), (ga, l.a.weight.grad)):
+            grad_rel = max(grad_rel, float(((got - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()))
+    return {"n1": one, "forward_bit_identical": multi["out_bits_sum"] == one["out_bits_sum"],
+            "loss_rel_diff": abs(multi["loss"] - one["loss"]) / max(abs(one["loss"]), 1e-30),
+            "out_abs_sum_rel_diff": abs(multi["out_abs_sum"] - one["out_abs_sum"]) / max(abs(one["out_abs_sum"]), 1e-30),
+            "grad_max_rel_diff": grad_rel}
+
+
 def run_b200(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
@@ -219,42 +335,24 @@ def run_b200(args):
     x_host = torch.from_numpy(x_np).pin_memory()
     ei_host = torch.from_numpy(ei_np).pin_memory()
 
+    single = None
     if world > 1:
         from gat_pytorch_b200.partition import PartitionedGAT
         model = PartitionedGAT(shapes, weights, x_host, ei_host, dev, fuse_glue=not args.unfused_glue)
         step_resident, step_e2e, e_prime = model.step_resident, model.step_e2e, model.n_edges_global
+
+        def current_state():
+            return model.last_loss, model.last_out, [(l.W.weight.grad, l.a.weight.grad) for l in model.layers]
     else:
-        layers = []
-        for (f_in, nh, f, concat), (w, a) in zip(shapes, weights):
-            layer = g.GATLayer(f_in, f, nh, concat, dropout=0.0, add_self_loops=True).to(dev)
-            with torch.no_grad():
-                layer.W.weight.copy_(torch.from_numpy(w))
-                layer.a.weight.copy_(torch.from_numpy(a))
-            layers.append(layer)
-        # the reference's inter-layer glue (GATModel.py:148-149: F.elu on every layer's output but the last) rides in the
-        # edge kernel's epilogue and the backward's per-node pass (opt-in fusion); --unfused-glue runs it
-        # as separate torch kernels
-        fused_glue = [not args.unfused_glue and i != len(layers) - 1 and bool(layer.concat) for i, layer in enumerate(layers)]
-        for layer, fz in zip(layers, fused_glue):
-            layer.output_activation = "elu" if fz else None
-            layer.feature_dtype = None if args.feature_dtype == "f32" else args.feature_dtype
-
-        def fwd_bwd(x, ei):
-            h = x
-            for i, layer in enumerate(layers):
-                layer.W.weight.grad = layer.a.weight.grad = None
-                h = layer(h, ei)
-                if i != len(layers) - 1 and not fused_glue[i]:
-                    h = F.elu(h)
-            loss = h.square().mean()
-            loss.backward()
-            return loss
-
+        single = SingleGpuModel(g, shapes, weights, dev, args)
         x_dev, ei_dev = x_host.to(dev), ei_host.to(dev)
         e_prime = g.GLOBAL_CACHE.get(ei_dev, n, True).n_edges
 
         def step_resident():
-            return fwd_bwd(x_dev, ei_dev)
+            return single.fwd_bwd(x_dev, ei_dev)
+
+        def current_state():
+            return single.last_loss, single.last_out, [(l.W.weight.grad, l.a.weight.grad) for l in single.layers]
 
         copy_stream = torch.cuda.Stream(device=dev)
 
@@ -271,7 +369,7 @@ def run_b200(args):
             main.wait_event(ev_ei)
             g.GLOBAL_CACHE.get(eid, n, True)             # Kernel 1 (one host read-back of the sizes) while x is in flight
             main.wait_event(ev_x)
-            return float(fwd_bwd(xd, eid).item())        # D2H read of the step's result
+            return float(single.fwd_bwd(xd, eid).item())  # D2H read of the step's result
 
     def barrier():
         if world > 1:
@@ -339,6 +437,16 @@ def run_b200(args):
                "h2d_bytes_per_step": int(x_host.numel() * 4 + ei_host.numel() * 8), "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps}
 
+    # ---- driver-verifiable fingerprints of the step (every N), and at N > 1 the comparison with the single-GPU model
+    step_resident()
+    loss_t, out_t, grads_t = current_state()
+    sums = checksums(loss_t, out_t, grads_t, world)
+    parity = None
+    if world > 1:
+        if rank == 0:
+            parity = parity_vs_single_gpu(g, shapes, weights, x_host, ei_host, dev, args, sums, grads_t)
+        barrier()
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (hidden-layer shape), timed live above
@@ -365,9 +473,11 @@ def run_b200(args):
     roofline = None
     if dom:
         pk = per_kernel[dom]
+        # DRAM bytes of the same launch from an `ncu --set full` capture (profiles/traffic.json: full-size graph on ONE GPU);
+        # a partitioned run launches the kernel on 1/P of the edges, for which no capture exists -> null
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and world == 1 and args.workload == "products" and args.scale == 1.0 and args.feature_dtype == "f32":
             traffic = json.load(open(tpath)).get(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": pk["GBps"], "peak": peak, "unit": "GB/s", "frac": pk["frac"],
                     "traffic": traffic, "peak_source": peak_src, "ms_avg": pk["ms_avg"], "algorithmic_bytes": pk["algorithmic_bytes"]}
@@ -376,24 +486,22 @@ def run_b200(args):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        step, e_cpu, l_cpu, n_cpu = cpu_port_step_fn(args.workload, CPU_SCALE if args.workload == "products" else 1.0)
+        step, e_cpu, l_cpu, n_cpu, kind = cpu_step_fn(args.workload, cpu_scale(args))
         step()
         best = float("inf")
         for _ in range(2):
             t0 = time.perf_counter()
             step()
             best = min(best, time.perf_counter() - t0)
-        cpu_baseline = {"value": l_cpu * e_cpu / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{args.workload}-shaped graph at scale {'1/128' if args.workload == 'products' else '1'} "
-                                  f"(N={n_cpu}, E'={e_cpu}), {l_cpu}-layer fwd+bwd, best of 2 after 1 warm-up, "
-                                  f"oracle/torch_port.py on {torch.get_num_threads()} threads"}
+        cpu_baseline = {"value": l_cpu * e_cpu / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                        "sample": cpu_sample_text(args, n_cpu, e_cpu, l_cpu, kind, "best of 2 after 1 warm-up")}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if args.feature_dtype == "f32" else "f32 accumulate, bf16 gathered features (variant; parity bar 2e-2)",
             "data": "synthetic", "config": dict(workload_config(args.workload, world), n_nodes=n, n_edges_rewritten=e_prime,
                                                  scale=args.scale, layers=[list(s) for s in shapes]),
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "checksums": sums, "parity_vs_n1": parity, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernels_ms_per_step": breakdown, "edge_kernels": per_kernel,
             "kernel_time_share_of_step": total_kernel_ms / ms_total if ms_total else None}
     print(json.dumps(line), flush=True)

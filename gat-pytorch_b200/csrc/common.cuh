@@ -44,6 +44,16 @@ constexpr int kNumSMs = 148;          // B200
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: the "already opted in" caches of the launchers are
+// therefore indexed by the current device (a process that drives cuda:1 after cuda:0 must opt in again).  A racing
+// second thread at worst repeats the (idempotent) attribute call.
+constexpr int kMaxDevices = 64;
+static inline int cur_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+  return d % kMaxDevices;
+}
+
 // Philox-4x32-10 keyed on (seed), counter = (edge id, head/4 block, offset): one call yields the
 // masks of 4 consecutive heads of one edge.  Stateless, so backward regenerates the same mask.
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset, uint32_t edge, uint32_t blk) {

@@ -981,7 +981,8 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
       const size_t base_ = (main_dyn_smem<32, S_>(P.chunks) + 15) / 16 * 16;                                           \
       const size_t smem_ = base_ + push_bytes;                                                                         \
       if (push_bytes) Q.rowbuf_offset_floats = (int)(base_ / sizeof(float));                                           \
-      static size_t optin_bf_ = 0;                                                                                     \
+      static size_t optin_bf_dev_[kMaxDevices] = {0};                                                                  \
+      size_t& optin_bf_ = optin_bf_dev_[cur_device()];                                                                 \
       if (smem_ > optin_bf_) {                                                                                         \
         optin_bf_ = smem_;                                                                                             \
         GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<32, S_, 4, true, FUSED, false, false, true>,                \
@@ -1015,7 +1016,8 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
       const size_t smem_ = base_ + stage_ + push_bytes;                                                                \
       Q.stage_offset_floats = (int)(base_ / sizeof(float));                                                            \
       if (push_bytes) Q.rowbuf_offset_floats = (int)((base_ + stage_) / sizeof(float));                                \
-      static bool optin_gs_ = false;                                                                                   \
+      static bool optin_gs_dev_[kMaxDevices] = {false};                                                                \
+      bool& optin_gs_ = optin_gs_dev_[cur_device()];                                                                   \
       if (!optin_gs_) {                                                                                                \
         GAT_CUDA(cudaFuncSetAttribute(edge_bwd_main_kernel<32, S_, 4, true, FUSED, false, true>,                       \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024)));                 \
@@ -1043,7 +1045,8 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
 #define LAUNCH_BOTH(G_, S_, N_, FULL_)                                                                                 \
   do {                                                                                                                 \
     /* static + dynamic shared memory can exceed the 48 KB default (wide rows, 8 heads): opt in once per size */       \
-    static size_t optin_ = 0;                                                                                          \
+    static size_t optin_dev_[kMaxDevices] = {0};                                                                       \
+    size_t& optin_ = optin_dev_[cur_device()];                                                                         \
     const size_t base_ = (main_dyn_smem<G_, S_>(P.chunks) + 15) / 16 * 16;                                             \
     const size_t smem_ = base_ + push_bytes;                                                                           \
     if (push_bytes) Q.rowbuf_offset_floats = (int)(base_ / sizeof(float));                                             \

@@ -59,6 +59,7 @@ __device__ __forceinline__ float attn_exp(float logit, float gmax) {
 }
 
 __device__ __forceinline__ float atomic_max_float(float* addr, float value) {
+  value += 0.0f;   // canonicalise -0.0 to +0.0: as an int, -0.0 is INT_MIN and would lose against every stored pattern
   return (value >= 0.f) ? __int_as_float(atomicMax((int*)addr, __float_as_int(value)))
                         : __uint_as_float(atomicMin((unsigned int*)addr, __float_as_uint(value)));
 }

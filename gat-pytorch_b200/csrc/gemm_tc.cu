@@ -544,7 +544,8 @@ static int launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, 
     if (!rc) rc = make_map(&map_b, b, k, n, ldb, BK, kMapMN);
   }
   if (rc) return rc;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {false};     // per device (and per template instantiation)
+  bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
     GAT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, MN>::kTotal));
     attr_set = true;

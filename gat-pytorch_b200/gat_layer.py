@@ -298,9 +298,42 @@ class GATLayer(nn.Module):
             raise ValueError("output_activation='elu' is fused only for concat layers without bias (apply F.elu outside otherwise)")
         return True
 
+    def _forward_host_buffers(self, x, edge_index, return_attention_weights):
+        """HOST-BUFFER mode: a module and inputs that live in host memory (what the reference's own `vis.py` hands the layer:
+        `load_from_checkpoint` restores to the CPU and its DataLoader batch is never moved, vis.py:41-47) are copied to the
+        current CUDA device, the layer runs there, and the results come back as host tensors.  All copies are differentiable
+        `.to()` ops, so gradients flow back to the host-resident parameters.  The arithmetic is still the sm_100a kernels --
+        this is the C ABI called with host buffers, not a CPU implementation; without a CUDA device forward() raises."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        twin = getattr(self, "_device_twin", None)
+        if twin is None:
+            with torch.random.fork_rng(devices=[]):     # the twin's (unused) init must not advance the caller's RNG stream
+                twin = GATLayer(self.in_features, self.out_features, self.num_heads, self.concat, dropout=self.dropout,
+                                add_self_loops=self.add_self_loops, bias=self.bias, const_attention=self.const_attention)
+            for name in ("gemm_algo", "input_activation", "output_activation", "feature_dtype"):
+                setattr(twin, name, getattr(self, name))
+            object.__setattr__(self, "_device_twin", twin)      # not a sub-module: state_dict / parameters() stay the reference's
+        twin.train(self.training)
+        # functional parameters: the twin computes with device copies that stay attached to THIS module's parameters
+        params = {"W.weight": self.W.weight.to(dev)}
+        if not self.const_attention:
+            params["a.weight"] = self.a.weight.to(dev)
+        if self.bias:
+            params["bias_param"] = self.bias_param.to(dev)
+        res = torch.func.functional_call(twin, params, (x.to(dev), edge_index.to(dev), return_attention_weights))
+        if return_attention_weights:
+            out, (ei2, alpha) = res
+            out, ei2, alpha = out.to(x.device), ei2.to(edge_index.device), alpha.to(x.device)
+            self.normalised_attention_coeffs = alpha
+            return out, (ei2, alpha)
+        self.normalised_attention_coeffs = None
+        return res.to(x.device)
+
     def forward(self, x, edge_index, return_attention_weights=False):
         if not x.is_cuda:
-            raise RuntimeError("gat_b200.GATLayer runs on CUDA (sm_100a) only; there is no CPU fallback")
+            if not torch.cuda.is_available():
+                raise RuntimeError("gat_b200.GATLayer runs on CUDA (sm_100a) only; there is no CPU fallback")
+            return self._forward_host_buffers(x, edge_index, return_attention_weights)
         if x.dtype != torch.float32:
             raise RuntimeError(f"expected float32 node features, got {x.dtype}")   # the reference raises a dtype mismatch
         if x.dim() != 2 or x.size(1) != self.in_features:
@@ -316,10 +349,18 @@ class GATLayer(nn.Module):
         if self.num_heads * fp > MAX_ROW_FLOATS:
             raise NotImplementedError(f"num_heads*out_features > {MAX_ROW_FLOATS} is not supported by the sm_100a kernels")
         p_drop = float(self.dropout) if (self.training and self.dropout > 0) else 0.0
+        drop_all = p_drop >= 1.0      # nn.Dropout(p=1) zeroes every coefficient (gat_layer.py:113-115): out = 0, alpha intact
+        if drop_all:
+            p_drop = 0.0
         out, alpha = _GATFunction.apply(x, w_p, a_src, a_tgt, st, self.num_heads, self.out_features, fp,
                                         bool(self.concat), bool(self.const_attention), p_drop,
                                         bool(return_attention_weights), int(self.gemm_algo), self._x_act(), self._out_act(),
                                         self._bf16())
+        if drop_all:
+            out = out * 0.0
+        # The reference stores the coefficients on every forward (gat_layer.py:110; nothing in the repository reads the
+        # attribute).  Here the (E', NH) tensor only exists when the caller asked for it: deliberate deviation,
+        # None otherwise -- ask with return_attention_weights=True to have it materialised.
         self.normalised_attention_coeffs = alpha
         if self.bias:
             out = out + self.bias_param          # gat_layer.py:134-135 (same broadcast rules, same latent shape error)

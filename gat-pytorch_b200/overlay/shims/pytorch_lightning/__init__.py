@@ -89,6 +89,8 @@ class Trainer:
         self.current_epoch = 0
         self.should_stop = False
         self.callback_metrics = {}
+        self.history = []           # per-epoch metric dicts (what ModelCheckpoint / EarlyStopping saw)
+        self.step_losses = []       # training loss of every optimiser step (training-parity tests compare two runs)
 
     def _epoch_metrics(self, model):
         out = {k: float(np.mean(v)) for k, v in model._logged.items() if v}
@@ -111,6 +113,7 @@ class Trainer:
             model.train()
             for i, batch in enumerate(model.train_dataloader()):
                 loss = model.training_step(_to_device(batch, self.device), i)
+                self.step_losses.append(float(loss.detach()))
                 optimizer.zero_grad()
                 loss.backward()
                 model.on_after_backward()
@@ -122,6 +125,7 @@ class Trainer:
                     for i, batch in enumerate(loader):
                         model.validation_step(_to_device(batch, self.device), i)
             self.callback_metrics = self._epoch_metrics(model)
+            self.history.append(dict(self.callback_metrics))
             if scheduler is not None and monitor in self.callback_metrics:
                 scheduler.step(self.callback_metrics[monitor])
             print(f"[shim trainer] epoch {epoch}: " + ", ".join(f"{k}={v:.4f}" for k, v in sorted(self.callback_metrics.items())), flush=True)

@@ -1,7 +1,9 @@
 """Synthetic datasets with the shapes of the ones the reference names (planetoid_gat.py:57-61, ppi_gat.py:61-64,
 pattern_gat.py:72-75), from the generators of gat-pytorch_b200/synth.py (node / edge counts, feature widths,
-split sizes).  Labels are random draws with each dataset's class count / prevalence: the stand-in exercises the code path,
-accuracy numbers on it mean nothing."""
+split sizes).  Labels are PLANTED, not random: a fixed teacher -- two rounds of mean aggregation over the in-neighbourhood
+(a constant-attention GAT, gat_layer.py:89-92) of a seeded random projection of the features -- so that a GAT can learn
+them and loss / accuracy / F1 curves of two layer implementations can be compared (training-parity tests).  Class count and
+prevalence follow each dataset; the absolute numbers say nothing about the real datasets."""
 import importlib.util
 import os
 
@@ -21,6 +23,29 @@ def _synth():
         _SYNTH = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(_SYNTH)
     return _SYNTH
+
+
+def _teacher_scores(x, ei, n_out, seed):
+    """Â²(x P): P a seeded (F_in, n_out) projection, Â = mean over {in-neighbours, self}; columns standardised."""
+    rng = np.random.default_rng(seed)
+    n = x.shape[0]
+    h = x.astype(np.float64) @ rng.standard_normal((x.shape[1], n_out))
+    src, dst = ei[0], ei[1]
+    deg = np.bincount(dst, minlength=n).astype(np.float64) + 1.0
+    for _ in range(2):
+        agg = h.copy()
+        np.add.at(agg, dst, h[src])
+        h = agg / deg[:, None]
+    return (h - h.mean(axis=0)) / (h.std(axis=0) + 1e-12)
+
+
+def planted_classes(x, ei, n_classes, seed=1234):
+    return np.argmax(_teacher_scores(x, ei, n_classes, seed), axis=1).astype(np.int64)
+
+
+def planted_multilabel(x, ei, n_labels, positive_rate, seed=1234):
+    z = _teacher_scores(x, ei, n_labels, seed)
+    return z > np.quantile(z, 1.0 - positive_rate, axis=0, keepdims=True)
 
 
 class _ListDataset:
@@ -46,7 +71,7 @@ class Planetoid(_ListDataset):
         x, ei = gen()
         n, c = x.shape[0], self._CLASSES[name]
         rng = np.random.default_rng(7)
-        y = torch.from_numpy(rng.integers(0, c, n))
+        y = torch.from_numpy(planted_classes(x, ei, c))
         idx = torch.from_numpy(rng.permutation(n))
         masks = [torch.zeros(n, dtype=torch.bool) for _ in range(3)]
         masks[0][idx[:20 * c]] = True
@@ -62,11 +87,10 @@ class PPI(_ListDataset):
 
     def __init__(self, root=None, split="train", **kwargs):
         count, base = {"train": (20, 0), "val": (2, 100), "test": (2, 200)}[split]
-        rng = np.random.default_rng(11 + base)
         graphs = []
         for g in range(count):
             x, ei = _synth().ppi(seed=base + g, graphs=1)
-            y = (rng.random((x.shape[0], 121)) < 0.3).astype(np.float32)
+            y = planted_multilabel(x, ei, 121, 0.3).astype(np.float32)
             graphs.append(Data(x=torch.from_numpy(x), edge_index=torch.from_numpy(ei), y=torch.from_numpy(y)))
         super().__init__(graphs)
 
@@ -79,10 +103,9 @@ class GNNBenchmarkDataset(_ListDataset):
         if name != "PATTERN":
             raise NotImplementedError(name)
         count, base = {"train": (64, 0), "val": (16, 1000), "test": (16, 2000)}[split]
-        rng = np.random.default_rng(13 + base)
         graphs = []
         for g in range(count):
             x, ei = _synth().pattern(seed=base + g, graphs=1)
-            y = (rng.random(x.shape[0]) < 0.1765).astype(np.int64)
+            y = planted_multilabel(x, ei, 1, 0.1765)[:, 0].astype(np.int64)
             graphs.append(Data(x=torch.from_numpy(x), edge_index=torch.from_numpy(ei), y=torch.from_numpy(y)))
         super().__init__(graphs)

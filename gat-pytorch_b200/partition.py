@@ -263,7 +263,8 @@ class CudaBackend:
 # ----------------------------------------------------------------------------------------------
 class _PartitionedGATFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_local, w_p, a_src_p, a_tgt_p, st, plan: Plan, nh, fp, backend, group, gathered, x_act=False, out_act=False):
+    def forward(ctx, x_local, w_p, a_src_p, a_tgt_p, st, plan: Plan, nh, fp, backend, group, gathered, x_act=False, out_act=False,
+                generation=None):
         dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
         rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
         s_src_slab = torch.zeros((R, nh), **f32)
@@ -299,6 +300,9 @@ class _PartitionedGATFunction(torch.autograd.Function):
         if rows:
             backend.edge_fwd(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act)
         ctx.misc = (st, plan, nh, fp, backend, group, bool(x_act), bool(out_act))
+        # wh_full is a persistent symmetric-memory buffer that the peers' TMA stores rewrite behind autograd's back (no
+        # version bump): remember which push filled it, so that backward can refuse a buffer that was re-pushed since
+        ctx.wh_generation = (generation, None if generation is None else generation[0])
         ctx.save_for_backward(x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p)
         return out_p
 
@@ -306,6 +310,12 @@ class _PartitionedGATFunction(torch.autograd.Function):
     def backward(ctx, go_p):
         x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p = ctx.saved_tensors
         st, plan, nh, fp, backend, group, x_act, out_act = ctx.misc
+        gen_cell, gen_at_forward = ctx.wh_generation
+        if gen_cell is not None and gen_cell[0] != gen_at_forward:
+            raise RuntimeError(
+                "PartitionedGATLayer: the gathered feature buffer of this forward has been overwritten by a later forward of the "
+                "same layer (the layer keeps two symmetric-memory buffers: at most ONE other forward may run between a forward "
+                "and its backward).  Run backward before the second-next forward, or use one layer object per application.")
         dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
         rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
         go_p = go_p.contiguous()
@@ -364,7 +374,7 @@ class _PartitionedGATFunction(torch.autograd.Function):
             dist.all_reduce(flat, group=group)                                  # the gradient all-reduce
         gw, ga_src, ga_tgt = flat[:gw.numel()].view_as(gw), flat[gw.numel():gw.numel() + ga_src.numel()].view_as(ga_src), \
             flat[gw.numel() + ga_src.numel():].view_as(ga_tgt)
-        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None
+        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None, None
 
 
 class PartitionedGATLayer(torch.nn.Module):
@@ -379,7 +389,14 @@ class PartitionedGATLayer(torch.nn.Module):
         torch.nn.init.xavier_uniform_(self.W.weight)
         torch.nn.init.xavier_uniform_(self.a.weight)
         self.backend, self.group = backend, group
-        self._gathered = None       # (wh_full, peer pointers) of this layer, allocated once (symmetric memory)
+        # Two (wh_full, peer pointers) symmetric-memory buffers per layer, used alternately: the peers' stores of forward
+        # k+1 must not land in the buffer that forward k's edge kernels (or its pending backward) still read.  With two
+        # buffers the writer of forward k+2 is ordered behind every reader of forward k by the collectives in between
+        # (a rank pushes only after its all_reduce(max) of the previous forward, which needs every peer's contribution,
+        # issued in stream order after that peer's reads).  _generation[i] counts the pushes into buffer i.
+        self._gathered = None
+        self._generation = [[0], [0]]
+        self._forward_count = 0
         self.input_activation = None    # "elu": the layer runs on ELU(x), fused into the GEMMs (see GATLayer)
         self.output_activation = None   # "elu": the layer returns ELU(out), fused into the edge kernel's epilogue (concat only)
 
@@ -400,12 +417,18 @@ class PartitionedGATLayer(torch.nn.Module):
             self.backend = CudaBackend()
         w_p, a_src, a_tgt, fp = self._padded_operands()
         nh, f = self.num_heads, self.out_features
+        gathered = generation = None
         if hasattr(self.backend, "gathered_buffer"):
-            if self._gathered is None or self._gathered[0].shape != (plan.n_pad, nh * fp) or self._gathered[0].device != x_local.device:
-                self._gathered = self.backend.gathered_buffer(plan.n_pad, nh * fp, self.group)
+            if self._gathered is None or self._gathered[0][0].shape != (plan.n_pad, nh * fp) or self._gathered[0][0].device != x_local.device:
+                self._gathered = [self.backend.gathered_buffer(plan.n_pad, nh * fp, self.group) for _ in range(2)]
+                self._generation = [[0], [0]]
+            slot = self._forward_count % 2
+            self._forward_count += 1
+            gathered, generation = self._gathered[slot], self._generation[slot]
+            generation[0] += 1
         out_p = _PartitionedGATFunction.apply(x_local.contiguous(), w_p, a_src, a_tgt, st, plan, nh, fp, self.backend, self.group,
-                                              self._gathered, self.input_activation == "elu",
-                                              self.output_activation == "elu" and bool(self.concat))
+                                              gathered, self.input_activation == "elu",
+                                              self.output_activation == "elu" and bool(self.concat), generation)
         o = out_p.view(-1, nh, fp)[:, :, :f]
         return o.reshape(-1, nh * f) if self.concat else o.mean(dim=1)      # gat_layer.py:129-132
 
@@ -453,6 +476,7 @@ class PartitionedGAT:
                 h = F.elu(h)
         loss = h.square().sum() / (self.plan.n * h.size(1))     # this rank's share of the global mean
         loss.backward()
+        self.last_loss, self.last_out = loss.detach(), h.detach()     # bench.py's checksums (summed over ranks there)
         return loss
 
     def step_resident(self):

@@ -227,3 +227,28 @@ def rel_err(got, want) -> float:
     if want.size == 0:
         return 0.0
     return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+def elementwise_report(got, want, rtol: float = 1e-5) -> dict:
+    """Element-wise companions of `rel_err` (which divides by the LARGEST reference entry, so a few large entries could hide
+    errors in small-magnitude rows):
+      atol_needed_over_mean  smallest atol with |got-want| <= rtol*|want| + atol for EVERY element, as a multiple of mean|want|
+      row_rel_{median,p99,max}  per row r (node / edge / weight row): max_j|got-want| / max_j|want|, rows whose reference is
+                             exactly zero excluded -- a row is judged against its own magnitude
+      frac_within_rtol       fraction of elements with |got-want| <= rtol*|want| + 1e-7*mean|want|"""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    if want.size == 0:
+        return dict(tensor_rel=0.0, atol_needed_over_mean=0.0, row_rel_median=0.0, row_rel_p99=0.0, row_rel_max=0.0, frac_within_rtol=1.0)
+    d = np.abs(got - want)
+    aw = np.abs(want)
+    mean = max(float(aw.mean()), 1e-300)
+    d2, w2 = d.reshape(d.shape[0], -1), aw.reshape(aw.shape[0], -1)
+    row_ref = w2.max(axis=1)
+    ok = row_ref > 0
+    row_rel = d2.max(axis=1)[ok] / row_ref[ok] if ok.any() else np.zeros(1)
+    return dict(tensor_rel=float(d.max() / max(aw.max(), 1e-30)),
+                atol_needed_over_mean=float(np.maximum(d - rtol * aw, 0.0).max() / mean),
+                row_rel_median=float(np.median(row_rel)), row_rel_p99=float(np.percentile(row_rel, 99)),
+                row_rel_max=float(row_rel.max()),
+                frac_within_rtol=float((d <= rtol * aw + 1e-7 * mean).mean()))

@@ -21,6 +21,22 @@ TOL = 1e-5
 TOL_OVERRIDE = {"adv_eps_dominated": 2e-3, "pattern_L2": 5e-5, "pattern_L3": 5e-5}
 
 
+_ELEMENTWISE = {}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_elementwise_report():
+    """After the module ran: gpurun_out/parity_elementwise.json (copied to profiles/ by hand when it is to be cited)."""
+    yield
+    if _ELEMENTWISE:
+        import json
+        import os
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_elementwise.json"), "w") as fh:
+            json.dump(_ELEMENTWISE, fh, indent=1, sort_keys=True)
+
+
 def make_layer(case, device="cuda", gemm_algo=0, dropout=0.0):
     from gat_pytorch_b200 import GATLayer
     layer = GATLayer(case["x"].shape[1], case["f"], case["nh"], case["concat"], dropout=dropout,
@@ -77,6 +93,13 @@ def test_layer_matches_oracle_and_golden(name, small_cases, golden):
     tol = TOL_OVERRIDE.get(name, TOL)
     errs = {k: O.rel_err(got[k], want[k]) for k in want}
     assert all(e <= tol for e in errs.values()), errs
+    # element-wise figures beside the tensor-relative one (a row judged against its own magnitude): recorded for
+    # profiles/parity_elementwise_r02.json; the TYPICAL row must itself meet the bar, and no row may be off by more than
+    # the cancellation noise an fp32 evaluation of the same sums has (measured on the reference's own fp32 run: 1e-3)
+    rep = {k: O.elementwise_report(got[k], want[k]) for k in want}
+    _ELEMENTWISE[name] = rep
+    for k, r in rep.items():
+        assert r["row_rel_median"] <= tol, (k, r)
     # and against the reference's own fp32 outputs (sampled rows), within the same bar + the reference's noise
     for k in want:
         if name == "adv_int32" and k.startswith("g"):
