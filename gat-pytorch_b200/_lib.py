@@ -72,6 +72,8 @@ SIGNATURES = {
     "gat_edge_bwd_finish": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
                                     _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_gamma": (c_int, [_P, c_size_t, _P, _P]),
+    "gat_pack_params": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P]),
+    "gat_unpack_param_grads": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, _P, _P, _P]),
 }
 
 

@@ -222,3 +222,101 @@ extern "C" int gat_attention_norm_bwd(const void* edge_dst, int index_is_int64, 
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Parameter packing (one launch per direction instead of a dozen tiny torch view / pad / slice / cat kernels).
+//   W   (NH*F, F_in)   -> W_p  (NH*Fp, F_in)  padded-head rows (only when Fp != F) and W_pT (F_in, NH*Fp), the K-major
+//                         operand of the dX product, so no transpose kernel runs in the backward
+//   a   (NH, NH*2F)    -> A_src_p, A_tgt_p (NH, NH*Fp): a.view(NH, NH, 2F)[:, :, :F] / [:, :, F:] (gat_layer.py:76-82:
+//                         column h'*2F + j multiplies Wh[src, h', j], column h'*2F + F + j multiplies Wh[dst, h', j])
+// and the adjoint (gradients back to the reference's parameter layouts).
+// ---------------------------------------------------------------------------------------------------------------
+namespace gat {
+
+__global__ void __launch_bounds__(256)
+pack_params_kernel(const float* __restrict__ W, const float* __restrict__ a, int nh, int f, int fp, int64_t f_in,
+                   float* __restrict__ W_p, float* __restrict__ W_pT, float* __restrict__ a_src_p, float* __restrict__ a_tgt_p) {
+  const int64_t dp = (int64_t)nh * fp, n_w = dp * f_in, n_a = (int64_t)nh * dp;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (W_p != nullptr) {       // index over W_p (row r = h*fp + j, column k)
+    for (int64_t i = t0; i < n_w; i += stride) {
+      const int64_t r = i / f_in, k = i - r * f_in;
+      const int h = (int)(r / fp), j = (int)(r - (int64_t)h * fp);
+      W_p[i] = j < f ? __ldg(W + ((int64_t)h * f + j) * f_in + k) : 0.f;
+    }
+  }
+  if (W_pT != nullptr) {      // index over W_pT (row k, column r): coalesced writes, strided (L2-resident) reads
+    for (int64_t i = t0; i < n_w; i += stride) {
+      const int64_t k = i / dp, r = i - k * dp;
+      const int h = (int)(r / fp), j = (int)(r - (int64_t)h * fp);
+      W_pT[i] = j < f ? __ldg(W + ((int64_t)h * f + j) * f_in + k) : 0.f;
+    }
+  }
+  if (a != nullptr) {
+    for (int64_t i = t0; i < n_a; i += stride) {
+      const int64_t row = i / dp, c = i - row * dp;
+      const int h2 = (int)(c / fp), j = (int)(c - (int64_t)h2 * fp);
+      const float* base = a + row * ((int64_t)nh * 2 * f) + (int64_t)h2 * 2 * f + j;
+      a_src_p[i] = j < f ? __ldg(base) : 0.f;
+      a_tgt_p[i] = j < f ? __ldg(base + f) : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_param_grads_kernel(const float* __restrict__ gW_p, const float* __restrict__ ga_src_p, const float* __restrict__ ga_tgt_p,
+                          int nh, int f, int fp, int64_t f_in, float* __restrict__ gW, float* __restrict__ ga) {
+  const int64_t dp = (int64_t)nh * fp;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gW != nullptr) {
+    const int64_t n_w = (int64_t)nh * f * f_in;
+    for (int64_t i = t0; i < n_w; i += stride) {
+      const int64_t r = i / f_in, k = i - r * f_in;
+      const int h = (int)(r / f), j = (int)(r - (int64_t)h * f);
+      gW[i] = __ldg(gW_p + ((int64_t)h * fp + j) * f_in + k);
+    }
+  }
+  if (ga != nullptr) {
+    const int64_t n_a = (int64_t)nh * nh * 2 * f;
+    for (int64_t i = t0; i < n_a; i += stride) {
+      const int64_t row = i / ((int64_t)nh * 2 * f), c = i - row * ((int64_t)nh * 2 * f);
+      const int h2 = (int)(c / (2 * f)), jj = (int)(c - (int64_t)h2 * 2 * f);
+      const int64_t src = row * dp + (int64_t)h2 * fp + (jj < f ? jj : jj - f);
+      ga[i] = jj < f ? __ldg(ga_src_p + src) : __ldg(ga_tgt_p + src);
+    }
+  }
+}
+
+static unsigned pack_grid(int64_t elems) {
+  int64_t b = (elems + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > kNumSMs * 8) b = kNumSMs * 8;
+  return (unsigned)b;
+}
+}  // namespace gat
+
+extern "C" int gat_pack_params(const float* W, const float* a, int nh, int f, int fp, int64_t f_in,
+                               float* W_p, float* W_pT, float* a_src_p, float* a_tgt_p, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(W && nh >= 1 && f >= 1 && fp >= f && fp % 4 == 0 && f_in >= 1, "gat_pack_params: bad arguments");
+  GAT_CHECK_ARG(a == nullptr || (a_src_p && a_tgt_p), "gat_pack_params: a given without a_src_p / a_tgt_p");
+  if (!W_p && !W_pT && !a) return GAT_OK;
+  const int64_t dp = (int64_t)nh * fp;
+  const int64_t elems = (W_p || W_pT) ? dp * f_in : (int64_t)nh * dp;
+  pack_params_kernel<<<pack_grid(elems), 256, 0, (cudaStream_t)stream>>>(W, a, nh, f, fp, f_in, W_p, W_pT, a_src_p, a_tgt_p);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_unpack_param_grads(const float* gW_p, const float* ga_src_p, const float* ga_tgt_p, int nh, int f, int fp,
+                                      int64_t f_in, float* gW, float* ga, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(nh >= 1 && f >= 1 && fp >= f && f_in >= 1, "gat_unpack_param_grads: bad arguments");
+  GAT_CHECK_ARG((gW == nullptr || gW_p) && (ga == nullptr || (ga_src_p && ga_tgt_p)), "gat_unpack_param_grads: missing packed gradient");
+  if (!gW && !ga) return GAT_OK;
+  const int64_t elems = gW ? (int64_t)nh * f * f_in : (int64_t)nh * nh * 2 * f;
+  unpack_param_grads_kernel<<<pack_grid(elems), 256, 0, (cudaStream_t)stream>>>(gW_p, ga_src_p, ga_tgt_p, nh, f, fp, f_in, gW, ga);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}

@@ -330,6 +330,21 @@ GAT_API int gat_edge_bwd_fused_bf16(const int32_t* rowptr_t, const int32_t* col_
                                float* const* h_push_dst, int n_push, int my_rank, int64_t rows_per_rank,
                                void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Parameter packing: the reference's parameter layouts <-> the kernels' operand layouts, ONE launch per direction
+ * (replaces the view / slice / pad / cat / transpose chain and its autograd, a dozen tiny kernels per layer and step).
+ *  W (NH*F, F_in)  [gat_layer.py:27]  -> W_p (NH*Fp, F_in) padded-head rows (NULL: not needed, i.e. Fp == F, use W itself)
+ *                                      -> W_pT (F_in, NH*Fp), the K-major operand of dX = dWh W (NULL: not needed)
+ *  a (NH, NH*2F)   [gat_layer.py:31]  -> a_src_p, a_tgt_p (NH, NH*Fp): a.view(NH, NH, 2F)[:, :, :F] and [:, :, F:]
+ *                                         (gat_layer.py:76-82); a == NULL for const_attention layers
+ * gat_unpack_param_grads is the adjoint: gW (NH*F, F_in) from gW_p (NULL when Fp == F: gW_p already is gW) and
+ * ga (NH, NH*2F) from the two halves.
+ * ------------------------------------------------------------------------------------- */
+GAT_API int gat_pack_params(const float* W, const float* a, int nh, int f, int fp, int64_t f_in,
+                            float* W_p, float* W_pT, float* a_src_p, float* a_tgt_p, gat_stream_t stream);
+GAT_API int gat_unpack_param_grads(const float* gW_p, const float* ga_src_p, const float* ga_tgt_p, int nh, int f, int fp,
+                                   int64_t f_in, float* gW, float* ga, gat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

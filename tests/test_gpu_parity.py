@@ -100,6 +100,9 @@ def test_layer_matches_oracle_and_golden(name, small_cases, golden):
     _ELEMENTWISE[name] = rep
     for k, r in rep.items():
         assert r["row_rel_median"] <= tol, (k, r)
+        if name != "adv_eps_dominated":     # (its alpha / out rows go down to fp32 denormals: 100 % row-relative, 1e-10 absolute)
+            # measured on B200 (profiles/parity_elementwise_r02.json): worst p99 2.1e-5 (pattern_L3 dx), worst atol 2.0e-5
+            assert r["row_rel_p99"] <= 10 * tol and r["atol_needed_over_mean"] <= 10 * tol, (k, r)
     # and against the reference's own fp32 outputs (sampled rows), within the same bar + the reference's noise
     for k in want:
         if name == "adv_int32" and k.startswith("g"):
@@ -230,14 +233,36 @@ def test_dropout_gradient_uses_forward_mask():
     assert abs(fd - an) <= 2e-2 * max(abs(fd), abs(an), 1e-3), (fd, an)
 
 
-def test_cpu_input_raises(small_cases):
+def test_wrong_dtype_raises():
     from gat_pytorch_b200 import GATLayer
-    layer = GATLayer(4, 2, 2, True)
-    with pytest.raises(RuntimeError):
-        layer(torch.randn(3, 4), torch.zeros((2, 2), dtype=torch.long))
-    layer = layer.cuda()
+    layer = GATLayer(4, 2, 2, True).cuda()
     with pytest.raises(RuntimeError):
         layer(torch.randn(3, 4, device="cuda", dtype=torch.float64), torch.zeros((2, 2), dtype=torch.long, device="cuda"))
+
+
+def test_host_buffer_mode_matches_device_mode(small_cases):
+    """A module and inputs that live in HOST memory (what the reference's vis.py hands the layer, vis.py:41-47): the layer
+    copies them to the GPU, runs the same kernels and returns host tensors; gradients reach the host-resident parameters.
+    (Without a CUDA device this raises: tests/test_host.py.)"""
+    case = small_cases["adv_concat"]
+    dev_layer = make_layer(case)
+    host_layer = make_layer(case, device="cpu")
+    x_d = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+    x_h = torch.from_numpy(case["x"]).requires_grad_(True)
+    ei = torch.from_numpy(case["edge_index"])
+    out_d, (ei_d, alpha_d) = dev_layer(x_d, ei.cuda(), return_attention_weights=True)
+    out_h, (ei_h, alpha_h) = host_layer(x_h, ei, return_attention_weights=True)
+    assert not out_h.is_cuda and not alpha_h.is_cuda and not ei_h.is_cuda
+    assert torch.equal(out_h, out_d.cpu()) and torch.equal(alpha_h, alpha_d.cpu()) and torch.equal(ei_h, ei_d.cpu())
+    go = torch.randn_like(out_h)
+    (out_d * go.cuda()).sum().backward()
+    (out_h * go).sum().backward()
+    assert torch.equal(x_h.grad, x_d.grad.cpu())
+    assert torch.equal(host_layer.W.weight.grad, dev_layer.W.weight.grad.cpu())
+    assert torch.equal(host_layer.a.weight.grad, dev_layer.a.weight.grad.cpu())
+    assert list(host_layer.state_dict().keys()) == ["W.weight", "a.weight"]      # the device twin is not a sub-module
+    out_plain = host_layer(x_h.detach(), ei)
+    assert torch.equal(out_plain, out_h.detach())
 
 
 def test_gemm_all_layouts():
