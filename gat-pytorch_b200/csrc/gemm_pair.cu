@@ -171,7 +171,7 @@ struct PairArgs {
   int num_kb;           // ceil(K / 32) (<= 8) A stages per tile; B holds 2 * num_kb 16-wide k-blocks
   int n_tiles;          // ceil(N / 128)
   int m_pairs;          // ceil(M / 256)
-  int clusters_per_tile;// clusters walking the row tiles of one N tile
+  int clusters0;        // clusters walking the row tiles of N tile 0; the remaining gridDim/2 - clusters0 walk N tile 1
   int act_a;            // ELU on the A operand
   int nh;               // heads of the fused score terms (0: none)
   float* s_src;
@@ -203,8 +203,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
-  const int nt = cluster_id % p.n_tiles;                      // this cluster's N tile
-  const int first_pair = cluster_id / p.n_tiles;              // clusters 2j and 2j+1 walk the same rows (second read of A hits L2)
+  // Each cluster owns one N tile (its B half stays resident) and walks the row tiles with a stride.  The two groups of
+  // clusters are sized in proportion to their MMA work per tile (144 : 128 columns when the score columns ride on tile 0),
+  // so both groups advance through the rows at the same pace and the second read of every A tile hits L2 -- with equal
+  // groups the slower one fell ~15 row waves behind by the end and DRAM saw A twice (ncu: 5.0 GB read for 2.5 GB).
+  const int n_clusters = (int)(gridDim.x >> 1);
+  const int nt = cluster_id < p.clusters0 ? 0 : 1;            // this cluster's N tile
+  const int first_pair = nt == 0 ? cluster_id : cluster_id - p.clusters0;
+  const int pair_stride = nt == 0 ? p.clusters0 : n_clusters - p.clusters0;
   const int n0 = nt * PBN;
   const bool scores = (nt == 0) && p.nh > 0;
   const int umma_n = scores ? NBROWS : PBN;
@@ -244,9 +250,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       };
       prefetch_tile(first_pair);
       uint32_t it = 0;
-      for (int pr = first_pair; pr < p.m_pairs; pr += p.clusters_per_tile) {
+      for (int pr = first_pair; pr < p.m_pairs; pr += pair_stride) {
         const int m0 = pr * 256 + (int)rank * PBM;
-        prefetch_tile(pr + p.clusters_per_tile);
+        prefetch_tile(pr + pair_stride);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % kRawStages;
           if (it >= kRawStages) mbar_wait(&raw_empty[s], ((it / kRawStages) - 1) & 1);
@@ -263,7 +269,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t idesc = make_idesc_pair(umma_n);
       const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo);
       uint32_t it = 0, t = 0;
-      for (int pr = first_pair; pr < p.m_pairs; pr += p.clusters_per_tile, ++t) {
+      for (int pr = first_pair; pr < p.m_pairs; pr += pair_stride, ++t) {
         if (t > 0) mbar_wait_cluster(acc_empty, (t - 1) & 1);          // previous tile drained by both epilogues
         tc_fence_after();
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -296,7 +302,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int sw = r & 7;                             // SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r % 8)
     const uint32_t raw_u32 = smem_u32(raw) + r * 128;
     mbar_wait(b_full, 0);                             // the first a_ready arrival also tells the leader that B is resident
-    const int my_tiles = first_pair < p.m_pairs ? (p.m_pairs - first_pair + p.clusters_per_tile - 1) / p.clusters_per_tile : 0;
+    const int my_tiles = first_pair < p.m_pairs ? (p.m_pairs - first_pair + pair_stride - 1) / pair_stride : 0;
     const uint32_t total = (uint32_t)my_tiles * (uint32_t)num_kb;
     // One k-block per iteration; the next k-block's shared-memory loads are issued before this one is processed, so the
     // chain wait -> load -> split -> tcgen05.st -> wait::st -> arrive of one k-block overlaps the next one's load.
@@ -362,10 +368,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     };
     prefetch_mul(first_pair);
-    for (int pr = first_pair; pr < p.m_pairs; pr += p.clusters_per_tile, ++t) {
+    for (int pr = first_pair; pr < p.m_pairs; pr += pair_stride, ++t) {
       const int m0 = pr * 256 + (int)rank * PBM;
       const int64_t grow = (int64_t)m0 + r;
-      prefetch_mul(pr + p.clusters_per_tile);
+      prefetch_mul(pr + pair_stride);
       mbar_wait(acc_full, t & 1);
       tc_fence_after();
       if (scores) {                                   // the 16 score columns first: their registers are dead before the tile is loaded
@@ -491,6 +497,20 @@ int gemm_pair(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, cons
   const int kp = (int)((k + AK - 1) / AK) * AK;      // B is padded with zero k-blocks to whole A stages
   const int n_tiles = (int)((n + PBN - 1) / PBN);
   const int R = n_tiles * NBROWS;
+  // Scratch for the split operand comes from the device's stream-ordered pool.  Its default release threshold is 0: every
+  // synchronisation would hand the memory back to the driver and the next call would map it again (device-wide stalls in
+  // the middle of a step), so the pool is told once per device to keep what it has.
+  static bool pool_set_dev[kMaxDevices] = {false};
+  if (!pool_set_dev[cur_device()]) {
+    cudaMemPool_t pool;
+    int dev_id = 0;
+    if (cudaGetDevice(&dev_id) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev_id) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    pool_set_dev[cur_device()] = true;
+  }
   float* bsplit = nullptr;
   GAT_CUDA(cudaMallocAsync((void**)&bsplit, (size_t)2 * R * kp * sizeof(float), st));
   {
@@ -521,12 +541,18 @@ int gemm_pair(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, cons
   PairArgs p;
   p.M = m; p.N = (int)n; p.num_kb = kp / AK; p.n_tiles = n_tiles; p.m_pairs = (int)((m + 255) / 256);
   int clusters = max_clusters();
-  p.clusters_per_tile = clusters / n_tiles;
-  if (p.clusters_per_tile < 1) p.clusters_per_tile = 1;
-  if (p.clusters_per_tile > p.m_pairs) p.clusters_per_tile = p.m_pairs;
+  if (clusters > n_tiles * p.m_pairs) clusters = n_tiles * p.m_pairs;
+  if (n_tiles == 1) p.clusters0 = clusters;
+  else {
+    if (clusters < 2) clusters = 2;
+    const int w0 = a_src != nullptr ? NBROWS : PBN;     // MMA columns per tile of the two groups
+    p.clusters0 = (clusters * w0 + (w0 + PBN) / 2) / (w0 + PBN);
+    if (p.clusters0 < 1) p.clusters0 = 1;
+    if (p.clusters0 > clusters - 1) p.clusters0 = clusters - 1;
+  }
   p.act_a = act_a; p.nh = a_src != nullptr ? nh : 0; p.s_src = s_src; p.s_tgt = s_tgt; p.mul_src = mul_src; p.mul_ld = mul_ld;
   { const char* e = getenv("GAT_PAIR_DEBUG"); p.debug = e ? atoi(e) : 0; }
-  const unsigned grid = (unsigned)(2 * p.clusters_per_tile * n_tiles);
+  const unsigned grid = (unsigned)(2 * clusters);
   gemm_pair_kernel<<<grid, kPairThreads, kSmemTotal, st>>>(map_a, map_b, cm, p);
   GAT_LAUNCH_CHECK();
   GAT_CUDA(cudaFreeAsync(bsplit, st));
