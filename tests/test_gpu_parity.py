@@ -343,6 +343,64 @@ def test_project_allgather_multi_destination():
         assert torch.equal(s_src, want_s) and torch.equal(s_tgt, want_t)
 
 
+def test_gemm_pair_cta_group2():
+    """Large-M / short-K NT products run on the persistent CTA-pair kernel (csrc/gemm_pair.cu: cta_group::2, B resident, A through
+    tensor memory, score terms as 16 extra MMA columns).  Against torch fp64 on ragged M / N / K, with the ELU operand and
+    the ELU' output multiplier, and the multi-destination (fused all-gather) store with a row offset."""
+    import ctypes
+    from gat_pytorch_b200 import _lib
+    from gat_pytorch_b200.gat_layer import gemm
+    torch.manual_seed(7)
+    st = torch.cuda.current_stream().cuda_stream
+    for (m, dp, k, nh, act) in [(16384, 256, 256, 4, False), (20001, 256, 100, 4, False), (19133, 192, 256, 4, True),
+                                (33000, 64, 64, 8, False), (16500, 128, 48, 1, False), (70001, 100, 256, 2, True)]:
+        x = torch.randn(m, k, device="cuda")
+        w = torch.randn(dp, k, device="cuda") / k ** 0.5
+        a_src, a_tgt = torch.randn(nh, dp, device="cuda") / dp ** 0.5, torch.randn(nh, dp, device="cuda") / dp ** 0.5
+        wh = torch.full((m, dp), float("nan"), device="cuda")
+        s_src, s_tgt = torch.full((m, nh), float("nan"), device="cuda"), torch.full((m, nh), float("nan"), device="cuda")
+        _lib.call("gat_project_fwd", x.data_ptr(), m, k, k, int(act), w.data_ptr(), k, dp, a_src.data_ptr(), a_tgt.data_ptr(), nh,
+                  wh.data_ptr(), s_src.data_ptr(), s_tgt.data_ptr(), 2, None, 0, st)
+        xd = torch.nn.functional.elu(x.double()) if act else x.double()
+        ref = xd @ w.double().T
+        rel = lambda got, want: ((got.double() - want).abs().max() / want.abs().max()).item()
+        assert rel(wh, ref) < 2e-6, (m, dp, k, rel(wh, ref))
+        # the reference forms the logits' node terms from Wh (gat_layer.py:76-82); here they are x (A W)^T, 16 more MMA columns
+        assert rel(s_src, ref @ a_src.double().T) < 2e-6 and rel(s_tgt, ref @ a_tgt.double().T) < 2e-6, (m, dp, k)
+    for (m, n, k, act, mul) in [(16384, 256, 256, False, False), (20001, 100, 256, False, True), (50000, 256, 192, True, True),
+                                (16385, 8, 16, False, False), (25000, 72, 252, False, False), (400000, 256, 256, False, True)]:
+        a = torch.randn(m, k, device="cuda")
+        b = torch.randn(n, k, device="cuda")
+        c = torch.full((m, n), float("nan"), device="cuda")
+        msrc = torch.randn(m, n, device="cuda") if mul else None
+        gemm(False, True, m, n, k, a, k, b, k, c, n, algo=2, act_a=act, mul_elu_grad=msrc)
+        want = (torch.nn.functional.elu(a.double()) if act else a.double()) @ b.double().T
+        if mul:
+            want = want * torch.where(msrc > 0, torch.ones_like(msrc), msrc.exp()).double()
+        err = ((c.double() - want).abs().max() / want.abs().max()).item()
+        assert err < 2e-6, (m, n, k, act, mul, err)
+    # fused projection -> all-gather through the pair kernel: two destinations, slab at a row offset
+    rows, f_in, nh, fp, lo = 20000, 256, 4, 64, 1300
+    dp = nh * fp
+    x = torch.randn(rows, f_in, device="cuda")
+    w = torch.randn(dp, f_in, device="cuda") * 0.1
+    a_src, a_tgt = torch.randn(nh, dp, device="cuda"), torch.randn(nh, dp, device="cuda")
+    want_wh = torch.empty(rows, dp, device="cuda")
+    want_s, want_t = torch.empty(rows, nh, device="cuda"), torch.empty(rows, nh, device="cuda")
+    _lib.call("gat_project_fwd", x.data_ptr(), rows, f_in, f_in, 0, w.data_ptr(), f_in, dp, a_src.data_ptr(), a_tgt.data_ptr(), nh,
+              want_wh.data_ptr(), want_s.data_ptr(), want_t.data_ptr(), 2, None, 0, st)
+    dests = [torch.full((lo + rows + 37, dp), float("nan"), device="cuda") for _ in range(2)]
+    s_src, s_tgt = torch.empty(rows, nh, device="cuda"), torch.empty(rows, nh, device="cuda")
+    arr = (ctypes.c_void_p * 2)(*[d.data_ptr() for d in dests])
+    _lib.call("gat_project_fwd_allgather", x.data_ptr(), rows, f_in, f_in, 0, w.data_ptr(), f_in, dp, a_src.data_ptr(), a_tgt.data_ptr(),
+              nh, arr, 2, lo, s_src.data_ptr(), s_tgt.data_ptr(), st)
+    torch.cuda.synchronize()
+    for d in dests:
+        assert torch.equal(d[lo:lo + rows], want_wh)
+        assert torch.isnan(d[:lo]).all() and torch.isnan(d[lo + rows:]).all()
+    assert torch.equal(s_src, want_s) and torch.equal(s_tgt, want_t)
+
+
 @pytest.mark.parametrize("name", ["adv_concat", "adv_mean_oddF", "adv_1x1", "adv_wide", "adv_ties", "adv_eps_dominated", "adv_bias",
                                   "cora_L0", "cora_L1", "pubmed_L1", "ppi_L2", "pattern_L0", "pattern_L2",
                                   "products_L0", "products_L1", "products_L2"])

@@ -25,6 +25,7 @@ FWD = "edge_fwd_kernelILi32ELi2ELi4ELb0ELb0E"                      # products hi
 BWD = "edge_bwd_main_kernelILi32ELi2ELi4ELb0ELb1ELb1ELb0ELb0E"     # fused backward, FULL rows
 BWD_GS = "edge_bwd_main_kernelILi32ELi2ELi4ELb0ELb1ELb0ELb1ELb0E"  # head-mean layer, staged rows
 GEMM_NT = "gemm_tc_kernelILi128ELb0E"
+GEMM_PAIR = "gemm_pair_kernel"
 
 
 @pytest.fixture(scope="module")
@@ -64,10 +65,11 @@ def _op(ins):
     return (t[1] if t[0].startswith("@") else t[0])
 
 
-@pytest.mark.parametrize("sub,max_regs", [(FWD, 80), (BWD, 80), (BWD_GS, 80), (GEMM_NT, 128)])
+@pytest.mark.parametrize("sub,max_regs", [(FWD, 80), (BWD, 80), (BWD_GS, 80), (GEMM_NT, 128), (GEMM_PAIR, 200)])
 def test_hot_kernels_fit_their_register_budget_without_spills(resources, sub, max_regs):
     regs, stack = resources[_mangled(sub)]
-    assert regs <= max_regs and stack == 0, (sub, regs, stack)
+    # the pair GEMM keeps one loop counter on the stack (8 bytes, outside the hot loops); everything else must be spill-free
+    assert regs <= max_regs and stack <= (16 if sub == GEMM_PAIR else 0), (sub, regs, stack)
 
 
 @pytest.mark.parametrize("sub", [FWD, BWD])
@@ -96,6 +98,16 @@ def test_sass_carries_the_instructions_the_design_claims():
     assert "UTMALDG" in gemm and "UTMASTG" in gemm          # TMA tile loads, TMA stores of the output tile
     assert "DMMA" in gemm                                   # fused score epilogue on the FP64 tensor cores
     assert "LDTM" in gemm                                   # tcgen05.ld (TMEM -> registers)
+    pair = [_op(i) for i in _sass(GEMM_PAIR)]
+    assert any(o.startswith("UTCHMMA.2CTA") for o in pair)              # tcgen05.mma.cta_group::2
+    assert any(o.startswith("UTCBAR.2CTA.MULTICAST") for o in pair)     # commit to both CTAs of the pair
+    assert any(o.startswith("STTM") for o in pair) and any(o.startswith("LDTM") for o in pair)   # A operand written to / accumulators read from TMEM
+    assert any(o.startswith("UTMALDG") for o in pair) and any(o.startswith("UTMASTG") for o in pair) and any(o.startswith("UTMAPF.L2") for o in pair)
+    # the issue loop is warp-uniform: no ELECT / R2UR.BROADCAST re-derivation of the uniform operands between the MMAs
+    first = next(i for i, o in enumerate(pair) if o.startswith("UTCHMMA"))
+    last = max(i for i, o in enumerate(pair) if o.startswith("UTCHMMA"))
+    assert not any(o.startswith("R2UR.BROADCAST") for o in pair[first:last]), "MMA issue loop lost its warp-uniform form"
+    assert last - first <= 12 * 8, "more than ~8 instructions per MMA in the issue loop"
     bwd = " ".join(_op(i) for i in _sass(BWD))
     assert "UBLKCP" in bwd or "BLKCP" in bwd                # cp.async.bulk row push (partitioned runs)
     gs = " ".join(_op(i) for i in _sass(BWD_GS))
