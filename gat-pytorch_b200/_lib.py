@@ -18,6 +18,16 @@ CSRC = os.path.join(_HERE, "csrc")
 _lock = threading.Lock()
 _lib = None
 
+
+class LayerDesc(ctypes.Structure):
+    """struct gat_layer_desc of include/gat_b200.h (graph structure + layer configuration + parameter pointers)."""
+    _fields_ = [(n, c_void_p) for n in ("rowptr", "col", "eid", "order", "rowptr_t", "col_t", "pos_t", "order_t", "tpos")] + [
+        ("n_long", c_int64), ("n_long_t", c_int64), ("n", c_int64), ("n_edges", c_int64), ("f_in", c_int64),
+        ("nh", ctypes.c_int32), ("f", ctypes.c_int32), ("fp", ctypes.c_int32),
+        ("concat", ctypes.c_int32), ("const_attention", ctypes.c_int32), ("x_act", ctypes.c_int32), ("out_act", ctypes.c_int32),
+        ("gemm_algo", ctypes.c_int32), ("p_drop", c_float), ("seed", c_uint64), ("W", c_void_p), ("a", c_void_p)]
+
+
 # name -> (restype, argtypes); mirrors include/gat_b200.h one to one.
 _P = c_void_p
 SIGNATURES = {
@@ -74,6 +84,10 @@ SIGNATURES = {
     "gat_edge_bwd_gamma": (c_int, [_P, c_size_t, _P, _P]),
     "gat_pack_params": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P]),
     "gat_unpack_param_grads": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, _P, _P, _P]),
+    "gat_layer_fwd_arena_bytes": (c_size_t, [_P]),
+    "gat_layer_bwd_scratch_bytes": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
+    "gat_layer_fwd": (c_int, [_P, _P, c_int64, _P, c_size_t, _P, _P, c_int, _P]),
+    "gat_layer_bwd": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, c_size_t, _P, _P, _P, _P]),
 }
 
 

@@ -345,6 +345,43 @@ GAT_API int gat_pack_params(const float* W, const float* a, int nh, int f, int f
 GAT_API int gat_unpack_param_grads(const float* gW_p, const float* ga_src_p, const float* ga_tgt_p, int nh, int f, int fp,
                                    int64_t f_in, float* gW, float* ga, gat_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * One layer per call.  gat_layer_fwd is GATLayer.forward (gat_layer.py:42-140) and gat_layer_bwd its autograd backward,
+ * each issuing the whole kernel sequence above from ONE host call, with the parameters in the REFERENCE's layouts
+ * (W (NH*F, F_in) gat_layer.py:27, a (NH, NH*2F) gat_layer.py:31) on both sides.  On the small named graphs a layer is
+ * 8-10 kernels of a few microseconds; issuing them from one call keeps the GPU fed (csrc/layer.cu).
+ *   desc       graph structure (gat_csr_build outputs) + layer configuration + parameter pointers;
+ *   arena      gat_layer_fwd_arena_bytes(desc) bytes, 256-byte aligned: packed operands, Wh, score terms, Z, tie counts and
+ *              (when a head merge / un-padding is needed) the padded output -- everything the backward reads again.  The
+ *              caller keeps it alive until gat_layer_bwd and must not reuse it for another forward in between;
+ *   out        (n, NH*F) concat or (n, F) head mean; alpha (n_edges, NH) in the rewritten edge order, or NULL;
+ *   want_ties  0 when no gradient will be asked for (inference): the arg-max bookkeeping is skipped;
+ *   scratch    gat_layer_bwd_scratch_bytes(...) bytes, 256-byte aligned, dead after the call;
+ *   grad_alpha (n_edges, NH) or NULL (then the backward is rowdot + ONE fused source-major pass);
+ *   gx (n, F_in) / gW (NH*F, F_in) / ga (NH, NH*2F): outputs, each may be NULL when not needed.
+ * ------------------------------------------------------------------------------------- */
+typedef struct gat_layer_desc {
+  const int32_t *rowptr, *col, *eid, *order;            /* CSR by target + scheduling permutation */
+  const int32_t *rowptr_t, *col_t, *pos_t, *order_t;    /* CSR by source */
+  const int32_t *tpos;
+  int64_t n_long, n_long_t;
+  int64_t n, n_edges;                                   /* nodes, rewritten edges */
+  int64_t f_in;
+  int32_t nh, f, fp;                                    /* heads, out_features, roundup(out_features, 4) */
+  int32_t concat, const_attention, x_act, out_act, gemm_algo;
+  float p_drop;                                         /* 0 outside training */
+  uint64_t seed;
+  const float *W, *a;                                   /* reference layouts; a = NULL for const_attention */
+} gat_layer_desc;
+
+GAT_API size_t gat_layer_fwd_arena_bytes(const gat_layer_desc* desc);
+GAT_API size_t gat_layer_bwd_scratch_bytes(const gat_layer_desc* desc, int has_grad_alpha, int want_gx, int want_gw, int want_ga);
+GAT_API int gat_layer_fwd(const gat_layer_desc* desc, const float* x, int64_t ldx, void* arena, size_t arena_bytes,
+                          float* out, float* alpha, int want_ties, gat_stream_t stream);
+GAT_API int gat_layer_bwd(const gat_layer_desc* desc, const float* x, int64_t ldx, const void* arena, const float* out,
+                          const float* grad_out, const float* grad_alpha, void* scratch, size_t scratch_bytes,
+                          float* gx, float* gW, float* ga, gat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
