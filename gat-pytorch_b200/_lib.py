@@ -74,6 +74,7 @@ SIGNATURES = {
                                    _P, _P, _P, _P, c_int, c_int, c_int64, _P, c_size_t, _P]),
     "gat_attention_entropy": (c_int, [_P, _P, c_int64, _P, c_int, _P, _P, _P]),
     "gat_attention_degree_scaled": (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
+    "gat_attention_neighbourhood": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, _P, _P]),
     "gat_slab_sum": (c_int, [_P, c_int, c_int64, c_int, _P, _P]),
     "gat_head_mean_bwd_shared": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
     "gat_edge_bwd_rowsum": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),

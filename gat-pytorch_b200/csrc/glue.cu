@@ -288,6 +288,31 @@ unpack_param_grads_kernel(const float* __restrict__ gW_p, const float* __restric
   }
 }
 
+// Neighbourhood plot feed (visualisation/neighbourhood_attention_weights.py:45-58): for each requested target node, its
+// neighbours' ids (edge-list order) and the attention of one head over them, divided by its maximum and multiplied by
+// 60 / neighbourhood size -- the edge widths of the star plot.  One CTA per requested node over its CSR segment; the
+// reference builds each with a full-edge-list mask.
+__global__ void __launch_bounds__(128)
+neighbourhood_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ eid,
+                     const float* __restrict__ alpha, int nh, int head, const int64_t* __restrict__ nodes,
+                     const int64_t* __restrict__ out_off, int64_t* __restrict__ out_src, float* __restrict__ out_w) {
+  const int64_t node = nodes[blockIdx.x];
+  const int b = rowptr[node], e = rowptr[node + 1];
+  const int64_t o = out_off[blockIdx.x];
+  __shared__ float red[4];
+  float mx = -INFINITY;
+  for (int j = b + threadIdx.x; j < e; j += blockDim.x) mx = fmaxf(mx, __ldg(alpha + (int64_t)eid[j] * nh + head));
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  const float size = (float)(e - b);
+  for (int j = b + threadIdx.x; j < e; j += blockDim.x) {
+    out_src[o + (j - b)] = col[j];
+    out_w[o + (j - b)] = __ldg(alpha + (int64_t)eid[j] * nh + head) / mx * (60.0f / size);   // :58 then :60, same operation order
+  }
+}
+
 static unsigned pack_grid(int64_t elems) {
   int64_t b = (elems + 255) / 256;
   if (b < 1) b = 1;
@@ -317,6 +342,18 @@ extern "C" int gat_unpack_param_grads(const float* gW_p, const float* ga_src_p, 
   if (!gW && !ga) return GAT_OK;
   const int64_t elems = gW ? (int64_t)nh * f * f_in : (int64_t)nh * nh * 2 * f;
   unpack_param_grads_kernel<<<pack_grid(elems), 256, 0, (cudaStream_t)stream>>>(gW_p, ga_src_p, ga_tgt_p, nh, f, fp, f_in, gW, ga);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_attention_neighbourhood(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const float* alpha, int nh,
+                                           int head, const int64_t* nodes, int64_t n_nodes_req, const int64_t* out_off,
+                                           int64_t* out_src, float* out_w, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(rowptr && col && eid && alpha && nodes && out_off && out_src && out_w, "gat_attention_neighbourhood: null buffer");
+  GAT_CHECK_ARG(nh >= 1 && head >= 0 && head < nh && n_nodes_req >= 0, "gat_attention_neighbourhood: bad head / count");
+  if (n_nodes_req == 0) return GAT_OK;
+  neighbourhood_kernel<<<(unsigned)n_nodes_req, 128, 0, (cudaStream_t)stream>>>(rowptr, col, eid, alpha, nh, head, nodes, out_off, out_src, out_w);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }

@@ -113,3 +113,31 @@ def degree_scaled_attention(edge_index: torch.Tensor, attention: torch.Tensor, n
         _lib.call("gat_attention_degree_scaled", st.rowptr.data_ptr(), st.eid.data_ptr(), st.n, alpha.data_ptr(), nh,
                   out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
     return out
+
+
+def neighbourhood_attention(edge_index: torch.Tensor, attention: torch.Tensor, node_ids, head: int, n_nodes: int | None = None):
+    """Visualisation feed of `visualisation/neighbourhood_attention_weights.py:45-60`: for every node in
+    `node_ids`, `(neighbour_ids, edge_widths)` where `neighbour_ids == edge_index[0][edge_index[1] == node]` and
+    `edge_widths == attention[edge_index[1] == node, head] / max(...) * 60 / len(neighbour_ids)` -- what the script feeds to
+    igraph, built from the node's CSR segment instead of a mask over the whole edge list.  Returns a list of (int64, float32)
+    tensor pairs, one per requested node, in request order."""
+    st = _structure_for(edge_index, n_nodes, "neighbourhood_attention")
+    alpha = attention.detach().to(torch.float32).contiguous()
+    if alpha.dim() != 2 or alpha.size(0) != st.n_edges:
+        raise ValueError(f"attention must be (E', NH) with E' = {st.n_edges}")
+    dev, nh = alpha.device, alpha.size(1)
+    if not 0 <= int(head) < nh:
+        raise IndexError(f"head {head} out of range for {nh} heads")
+    nodes = torch.as_tensor(list(node_ids), dtype=torch.int64, device=dev)
+    if nodes.numel() and (int(nodes.min()) < 0 or int(nodes.max()) >= st.n):
+        raise IndexError("node id out of range")
+    with torch.cuda.device(dev):
+        deg = (st.rowptr[nodes + 1] - st.rowptr[nodes]).to(torch.int64)
+        off = torch.cumsum(deg, 0) - deg
+        sizes = deg.tolist()
+        total = int(sum(sizes))
+        src = torch.empty(total, dtype=torch.int64, device=dev)
+        w = torch.empty(total, dtype=torch.float32, device=dev)
+        _lib.call("gat_attention_neighbourhood", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), alpha.data_ptr(), nh, int(head),
+                  nodes.data_ptr(), nodes.numel(), off.data_ptr(), src.data_ptr(), w.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    return list(zip(torch.split(src, sizes), torch.split(w, sizes)))

@@ -69,6 +69,43 @@ def local_edge_list(edge_index: torch.Tensor, n_idx: int, lo: int, hi: int, add_
     return edge_index[:, keep]
 
 
+def edge_slice(n_edges: int, world: int, rank: int):
+    """Columns [c0, c1) of the global edge list that rank `rank` uploads: consecutive, in rank order."""
+    per = (n_edges + world - 1) // world
+    return min(rank * per, n_edges), min((rank + 1) * per, n_edges)
+
+
+def exchange_edge_list(ei_part: torch.Tensor, plan: Plan, group=None, add_self_loops: bool = True):
+    """Rank-local rewritten edge list from a DISTRIBUTED edge list: every rank holds only its consecutive slice of the global
+    (2, E) list (`edge_slice`), buckets its edges by the owner of their target and sends each bucket to that owner (one
+    all-to-all over NVLink).  Buckets arrive in sender-rank order and every step keeps the input order inside a bucket, so the
+    result equals `local_edge_list(whole list, ...)` edge for edge -- the CSR rows, and with them the forward, stay
+    bit-identical -- while each rank uploads and filters 1/P of the list instead of all of it.
+    Returns (local (2, E_r) list, n_idx).  One host read-back (bucket sizes + max id)."""
+    world, dev = plan.world, ei_part.device
+    src, dst = ei_part[0], ei_part[1]
+    if add_self_loops:
+        keep = src != dst                                    # the loops are re-created by their owner (utils.py:61-65)
+        src, dst = src[keep], dst[keep]
+    owner = torch.div(dst, plan.rows_per_rank, rounding_mode="floor").clamp_(0, world - 1)
+    order = torch.sort(owner, stable=True).indices           # stable: input order inside a bucket
+    send = torch.stack([src[order], dst[order]], dim=1).contiguous()        # (m, 2), bucket after bucket
+    cnt_in = torch.bincount(owner, minlength=world)[:world].to(torch.int64)
+    mx = ei_part.max().reshape(1) if ei_part.numel() else torch.full((1,), -1, dtype=ei_part.dtype, device=dev)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)   # utils.py:72: num_nodes = max id + 1, over the WHOLE list
+    cnt_out = torch.empty_like(cnt_in)
+    dist.all_to_all_single(cnt_out, cnt_in, group=group)
+    sizes = torch.cat([cnt_in, cnt_out, mx.to(torch.int64)]).tolist()       # the one host sync
+    n_in, n_out, n_idx = sizes[:world], sizes[world:2 * world], int(sizes[-1]) + 1
+    recv = torch.empty((sum(n_out), 2), dtype=ei_part.dtype, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=n_out, input_split_sizes=n_in, group=group)
+    local = recv.t()
+    if add_self_loops:
+        loops = torch.arange(plan.lo, max(min(plan.hi, n_idx), plan.lo), dtype=ei_part.dtype, device=dev)
+        local = torch.cat([local, torch.stack([loops, loops])], dim=1)
+    return local.contiguous(), n_idx
+
+
 # ----------------------------------------------------------------------------------------------
 # product backend: the C ABI
 # ----------------------------------------------------------------------------------------------
@@ -455,16 +492,20 @@ class PartitionedGAT:
         self.x_local_host = x_host[self.plan.lo:self.plan.hi].contiguous()
         if x_host.is_pinned():
             self.x_local_host = self.x_local_host.pin_memory()
+        # every rank uploads only ITS consecutive 1/P of the edge list; the buckets are exchanged over NVLink (exchange_edge_list)
+        c0, c1 = edge_slice(ei_host.size(1), self.world, self.rank)
+        self.ei_part_host = ei_host[:, c0:c1].contiguous()
+        if ei_host.is_pinned():
+            self.ei_part_host = self.ei_part_host.pin_memory()
         self.x_local, self.st = self._upload()
         counts = torch.tensor([self.backend.n_edges(self.st)], dtype=torch.int64, device=dev)
         dist.all_reduce(counts)
         self.n_edges_local, self.n_edges_global, self.n_local = self.backend.n_edges(self.st), int(counts.item()), self.plan.rows
 
     def _upload(self):
+        ei_part = self.ei_part_host.to(self.dev, non_blocking=True)
         x_local = self.x_local_host.to(self.dev, non_blocking=True)
-        ei = self.ei_host.to(self.dev, non_blocking=True)
-        n_idx = int(ei.max().item()) + 1
-        local = local_edge_list(ei, n_idx, self.plan.lo, self.plan.hi, True)
+        local, _ = exchange_edge_list(ei_part, self.plan, None, True)
         return x_local, self.backend.build_structure(local, self.plan.n)
 
     def _fwd_bwd(self, x_local, st):

@@ -304,6 +304,14 @@ GAT_API int gat_attention_entropy(const int32_t* rowptr, const int32_t* eid, int
 GAT_API int gat_attention_degree_scaled(const int32_t* rowptr, const int32_t* eid, int64_t n, const float* alpha, int nh,
                                         float* scaled, gat_stream_t stream);
 
+/*   gat_attention_neighbourhood:  the star-plot feed of visualisation/neighbourhood_attention_weights.py:45-58.  For request i
+ *                                 (target node nodes[i]) writes, at out_off[i] (a prefix sum of the requested in-degrees),
+ *                                 out_src = its neighbours' ids in edge-list order and
+ *                                 out_w   = alpha[.., head] over them / its maximum * 60 / neighbourhood size. */
+GAT_API int gat_attention_neighbourhood(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const float* alpha, int nh,
+                                        int head, const int64_t* nodes, int64_t n_nodes_req, const int64_t* out_off,
+                                        int64_t* out_src, float* out_w, gat_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * bf16 variant (BASELINE.json north_star "bf16 variant stated separately").  Opt-in: the matrices the edge
  * kernels GATHER per edge -- Wh in the forward, the upstream gradient dL/dout in the fused backward -- are bfloat16 copies

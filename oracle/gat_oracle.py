@@ -252,3 +252,19 @@ def elementwise_report(got, want, rtol: float = 1e-5) -> dict:
                 row_rel_median=float(np.median(row_rel)), row_rel_p99=float(np.percentile(row_rel, 99)),
                 row_rel_max=float(row_rel.max()),
                 frac_within_rtol=float((d <= rtol * aw + 1e-7 * mean).mean()))
+
+
+def neighbourhood_attention(edge_index, alpha, node_ids, head):
+    """visualisation/neighbourhood_attention_weights.py:41-60, statement for statement: per requested node the mask over the
+    whole edge list, the neighbours' ids, the head's weights over them divided by their maximum, times 60 / size."""
+    source_nodes, target_nodes = edge_index[0], edge_index[1]
+    out = []
+    for node_id in node_ids:
+        neighbour_node_indices = target_nodes == node_id                                   # :46
+        neighbour_nodes_ids = source_nodes[neighbour_node_indices]                         # :49
+        size_of_neighborhood = len(neighbour_nodes_ids)                                    # :50
+        w = np.array(alpha[neighbour_node_indices, head], dtype=np.float32)                # :53
+        w /= np.max(w)                                                                     # :56
+        w *= (60 / size_of_neighborhood)                                                   # :58
+        out.append((neighbour_nodes_ids.astype(np.int64), w))
+    return out

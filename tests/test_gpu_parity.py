@@ -530,6 +530,17 @@ def test_visualisation_feed_matches_reference_loops(small_cases):
         assert O.rel_err(uni.cpu().numpy(), want_uni) < 1e-5, name
         assert scaled.shape == want_scaled.shape
         assert O.rel_err(scaled.cpu().numpy(), want_scaled) < 1e-5, name
+        # star-plot feed (neighbourhood_attention_weights.py:45-60): neighbours' ids bit-exact, edge widths to fp32 rounding
+        from gat_pytorch_b200 import neighbourhood_attention
+        ei_np, al_np = ei2.cpu().numpy(), alpha.detach().cpu().numpy()
+        picks = [int(v) for v in np.unique(ei_np[1])[::max(1, n // 12)][:12]]
+        for head in (0, alpha.size(1) - 1):
+            got = neighbourhood_attention(ei2, alpha, picks, head)
+            want = O.neighbourhood_attention(ei_np, al_np, picks, head)
+            assert len(got) == len(want)
+            for (gs, gw), (ws_, ww) in zip(got, want):
+                assert np.array_equal(gs.cpu().numpy(), ws_), name
+                assert np.allclose(gw.cpu().numpy(), ww, rtol=2e-6, atol=0), name
 
 
 @pytest.mark.gpu

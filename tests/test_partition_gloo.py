@@ -74,6 +74,37 @@ def test_two_rank_partition_matches_single_process_oracle(case_name, world):
         assert np.array_equal(ret[r]["edges"], ei2[:, sel])
 
 
+def _exchange_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gat_pytorch_b200.partition import edge_slice, exchange_edge_list, local_edge_list, make_plan
+        g = torch.Generator().manual_seed(5)
+        n = 101
+        ei = torch.randint(0, n - 3, (2, 1500), generator=g)        # existing self-loops, duplicates, trailing isolated nodes
+        ei[:, 7] = ei[:, 3]
+        ei[1, 20:40] = ei[0, 20:40]
+        plan = make_plan(n, world, rank)
+        c0, c1 = edge_slice(ei.size(1), world, rank)
+        got, n_idx = exchange_edge_list(ei[:, c0:c1].contiguous(), plan, None, True)
+        want = local_edge_list(ei, int(ei.max()) + 1, plan.lo, plan.hi, True)
+        ret[rank] = (bool(torch.equal(got, want)), n_idx == int(ei.max()) + 1, tuple(got.shape))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_edge_exchange_equals_the_local_filter(world):
+    """Each rank uploads 1/P of the edge list and the buckets are exchanged (all-to-all): the rank-local rewritten list must be
+    identical, edge for edge and in order, to filtering the whole list (so the CSR rows and the forward stay bit-identical)."""
+    ret = mp.Manager().dict()
+    port = 29950 + (os.getpid() % 40)
+    mp.spawn(_exchange_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r][0] and ret[r][1], (r, ret[r])
+
+
 def test_plan_covers_all_rows():
     from gat_pytorch_b200.partition import make_plan
     for n, world in [(97, 2), (10, 4), (8, 8), (5, 8)]:
