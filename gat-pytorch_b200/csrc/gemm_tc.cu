@@ -21,6 +21,11 @@ namespace gat {
 
 namespace tc {
 
+// TN products (dW, K = number of nodes): the split-K plan caps one accumulator at 2048 rows and sums the partials in fp64, so
+// the truncation split of the NT path (hi = the raw word, only lo is written) is accurate enough here too (measured in
+// tests/test_gpu_parity.py::test_gemm_tcgen05_3xtf32) and saves one of the three shared-memory writes per element.
+constexpr bool kRoundSplitTN = false;
+
 template <int BN, bool MN>
 struct Smem {
   static constexpr int kABytes = BM * BK * 4;     // 8 KB
@@ -147,7 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 4
       for (int i = t; i < S::kABytes / 16; i += kSplitThreads) {
         float4 v = a_hi[i];
-        if (MN) {   // long-K products (dW): round-to-nearest hi, written back -- 4x smaller representation error
+        if (MN && kRoundSplitTN) {   // round-to-nearest hi, written back (4x smaller representation error, one more shared-memory write per element)
           if (act_a) v = elu4(v);
           const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
           a_hi[i] = h;
@@ -160,7 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 4
       for (int i = t; i < S::kBBytes / 16; i += kSplitThreads) {
         float4 v = b_hi[i];
-        if (MN) {
+        if (MN && kRoundSplitTN) {
           if (act_b) v = elu4(v);
           const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
           b_hi[i] = h;
