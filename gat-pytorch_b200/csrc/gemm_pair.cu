@@ -453,6 +453,220 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// ======================================================================================================================
+// TN form for the weight gradient: C[M <= 256, N <= 256] = A[K, M]^T B[K, N], K = number of nodes (dW = dWh^T x, the adjoint of
+// gat_layer.py:64).  Same machinery as above with the roles of the operands adapted to the long contraction:
+//   * every cluster owns one 128-column half of C and one contiguous range of node rows (split-K); per 32-node stage each
+//     CTA loads a [32 x 128] slice of A (its half of the M = 256 rows of C) and a [32 x 64] slice of B (its half of the
+//     cluster's 128 C columns) by TMA;
+//   * A goes through tensor memory: thread m reads COLUMN m of the raw tile (conflict-free LDS.32), i.e. the transposition the
+//     MN-major operand would need happens on the way into TMEM (lane = m, column = node), hi = raw word, lo = round_tf32(v - trunc);
+//   * B stays in shared memory in the MN-major SWIZZLE_128B_BASE32B layout the tensor core reads (see gemm_tc.cu); the
+//     splitters write only its lo companion tile (position preserving);
+//   * the tensor core rounds its fp32 accumulator toward zero at every MMA, so one accumulator sees at most 64 stages (2048
+//     node rows): then both CTAs drain it and add it IN FP64 into the cluster's own slot of a (splits, 256, 256) fp64 buffer
+//     (read-modify-write by one owner: deterministic); a small kernel sums the slots.
+// The one-CTA-per-tile TN kernel it replaces on the products shapes ran at 2.1 ms (shared-memory bound: both operands split in
+// shared memory and read three times); this one moves 88 KB of shared memory per stage and CTA against 768 clk of MMA.
+constexpr int TK = 32;                       // node rows per stage
+constexpr int kTnStages = 6;
+constexpr int kTnABytes = TK * 128 * 4;      // raw A slice [32][128], unswizzled (read by columns)
+constexpr int kTnBBytes = TK * 64 * 4;       // B slice: two boxes of [32 k][32 n] in the MN-major atom layout
+constexpr int kTnStageBytes = kTnABytes + 2 * kTnBBytes;     // + lo companion of B
+constexpr int kTnSmemTotal = kTnStages * kTnStageBytes + 1024 + 256;
+static_assert(kTnSmemTotal <= 227 * 1024, "shared memory budget");
+constexpr int kTnAStages = 3, kTnAccCross = 128, kTnACol0 = 256;   // TMEM: [0,128) main, [128,256) cross, 3 x 64 A columns
+constexpr int kTnFlushStages = 64;
+
+struct PairTnArgs {
+  int64_t K;             // nodes
+  int M, N;              // C is M x N
+  int n_halves;          // ceil(N / 128)
+  int n_splits;          // clusters per half
+  int stages_per_split;  // 32-node stages per split (multiple of 1)
+  int act_b;             // ELU on the B operand (fused input activation of the layer)
+  double* slots;         // (n_splits, 256, 256) fp64
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+gemm_pair_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const PairTnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + kTnStages * kTnStageBytes);
+  uint64_t* full = bars;                         // TMA landed stage s                          (1 + tx)
+  uint64_t* stage_free = full + kTnStages;       // the MMAs that read B of stage s completed   (commit, both CTAs)
+  uint64_t* a_ready = stage_free + kTnStages;    // A hi/lo in TMEM + B lo written, both CTAs   (8 warps, leader's copy)
+  uint64_t* a_free = a_ready + kTnAStages;       // the MMAs that read TMEM stage a completed   (commit, both CTAs)
+  uint64_t* acc_full = a_free + kTnAStages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_ptr = (uint32_t*)(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int nhalf = cluster_id % p.n_halves, split = cluster_id / p.n_halves;
+  const int64_t total_stages = (p.K + TK - 1) / TK;
+  const int64_t st0 = (int64_t)split * p.stages_per_split;
+  const int my_stages = (int)max((int64_t)0, min((int64_t)p.stages_per_split, total_stages - st0));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTnStages; ++s) { mbar_init(&full[s], 1); mbar_init(&stage_free[s], 1); }
+    for (int s = 0; s < kTnAStages; ++s) { mbar_init(&a_ready[s], 8); mbar_init(&a_free[s], 1); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const int m_col = (int)rank * 128;                           // this CTA's rows of C = columns of A
+      const int n_col = nhalf * 128 + (int)rank * 64;              // this CTA's half of the cluster's C columns = columns of B
+      for (int it = 0; it < my_stages; ++it) {
+        const int s = it % kTnStages;
+        if (it >= kTnStages) mbar_wait(&stage_free[s], ((it / kTnStages) - 1) & 1);
+        uint8_t* st = smem + s * kTnStageBytes;
+        const int krow = (int)((st0 + it) * TK);
+        mbar_expect_tx(&full[s], kTnABytes + kTnBBytes);
+        tma_load_2d(st, &map_a, &full[s], m_col, krow);
+        tma_load_2d(st + kTnABytes, &map_b, &full[s], n_col, krow);
+        tma_load_2d(st + kTnABytes + TK * 128, &map_b, &full[s], n_col + 32, krow);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA), warp-uniform, one elected lane issues =====
+    if (rank == 0) {
+      const uint32_t elected = elect_one();
+      // D = f32, A = B = tf32, A K-major (TMEM), B MN-major, M = 256, N = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      uint32_t flush = 0;
+      for (int it = 0; it < my_stages; ++it) {
+        const uint32_t s = it % kTnStages, a = it % kTnAStages;
+        const int in_flush = it % kTnFlushStages;
+        if (in_flush == 0 && it > 0) { mbar_wait_cluster(acc_empty, (flush - 1) & 1); tc_fence_after(); }
+        mbar_wait_cluster(&a_ready[a], (it / kTnAStages) & 1);
+        tc_fence_after();
+        const uint32_t acol = tmem_base + kTnACol0 + a * 64;
+        const uint32_t b_hi = smem_u32(smem + s * kTnStageBytes + kTnABytes), b_lo = b_hi + kTnBBytes;
+#pragma unroll
+        for (int k = 0; k < TK / UMMA_K; ++k) {
+          const uint32_t first = (in_flush | k) != 0;
+          const uint32_t a_hi = acol + k * UMMA_K, a_lo = a_hi + TK;
+          const uint64_t d_hi = make_desc_mn_sw128(b_hi + k * 1024, TK * 128, 512);     // 8 node rows = two 4-row atoms = 1 KB
+          const uint64_t d_lo = make_desc_mn_sw128(b_lo + k * 1024, TK * 128, 512);
+          umma_tf32_ts2(tmem_base + kTnAccCross, a_hi, d_lo, idesc, first, elected);
+          umma_tf32_ts2(tmem_base + kTnAccCross, a_lo, d_hi, idesc, 1, elected);
+          umma_tf32_ts2(tmem_base, a_hi, d_hi, idesc, first, elected);
+        }
+        umma_commit2(&a_free[a], elected);
+        umma_commit2(&stage_free[s], elected);
+        if (in_flush == kTnFlushStages - 1 || it == my_stages - 1) { umma_commit2(acc_full, elected); ++flush; }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // ===== splitters: column m of the raw A slice -> hi / lo in tensor memory; lo companion of the B slice =====
+    // (measured: giving the B half of this work to the epilogue warps, with its own barrier ring, was SLOWER -- 2.13 vs 1.77 ms)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                      // row of C inside the CTA's half = column of the A slice
+    const int t = (warp - 2) * 32 + lane;             // 0..127, for the B slice
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + kTnACol0;
+    for (int it = 0; it < my_stages; ++it) {
+      const uint32_t s = it % kTnStages, a = it % kTnAStages;
+      mbar_wait(&full[s], (it / kTnStages) & 1);
+      const uint32_t st = smem_u32(smem + s * kTnStageBytes);
+      float hi[TK], lo[TK];
+#pragma unroll
+      for (int k = 0; k < TK; ++k) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[k]) : "r"(st + k * 512 + r * 4));
+#pragma unroll
+      for (int k = 0; k < TK; ++k) lo[k] = lo1(hi[k]);
+      // B: 512 16-byte chunks per CTA and stage, 4 per thread; hi stays where TMA put it unless the ELU is applied
+      const uint32_t bh = st + kTnABytes, bl = bh + kTnBBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = (uint32_t)(t + i * 128) * 16;
+        float4 v = lds128(bh + off);
+        if (p.act_b) { v = elu4(v); sts128(bh + off, v.x, v.y, v.z, v.w); }
+        const float4 l = lo4(v);
+        sts128(bl + off, l.x, l.y, l.z, l.w);
+      }
+      fence_proxy_async();                            // generic-proxy writes of B lo -> visible to the tensor core
+      if (it >= kTnAStages) { mbar_wait(&a_free[a], ((it / kTnAStages) - 1) & 1); tc_fence_after(); }
+      tmem_st32(trow + a * 64, hi);
+      tmem_st32(trow + a * 64 + TK, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&a_ready[a], 0);
+    }
+  } else {
+    // ===== epilogue: every 64 stages drain main + cross and add them in fp64 into this cluster's slot =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int m = (int)rank * 128 + r;
+    double* slot = p.slots + ((int64_t)split * 256 + m) * 256 + nhalf * 128;
+    const int n_flush = (my_stages + kTnFlushStages - 1) / kTnFlushStages;
+    for (int f = 0; f < n_flush; ++f) {
+      mbar_wait(acc_full, f & 1);
+      tc_fence_after();
+      float v[4][32];
+      {
+        float x[32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(trow + c * 32, v[c]);
+          tmem_ld32(trow + kTnAccCross + c * 32, x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[c][j] += x[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty, 0);
+      if (m < p.M) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            double2* dp = reinterpret_cast<double2*>(slot + c * 32 + j);
+            double2 acc = f == 0 ? make_double2(0.0, 0.0) : *dp;
+            acc.x += (double)v[c][j]; acc.y += (double)v[c][j + 1];
+            *dp = acc;
+          }
+        }
+      }
+    }
+    if (n_flush == 0 && m < p.M) {                    // a cluster without rows still owns a slot: zero it
+      for (int j = 0; j < 128; ++j) slot[j] = 0.0;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+__global__ void pair_tn_reduce_kernel(const double* __restrict__ slots, int n_splits, int M, int N, float* __restrict__ C, int64_t ldc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int m = idx / N, n = idx - m * N;
+  double s = 0.0;
+  for (int z = 0; z < n_splits; ++z) s += slots[((int64_t)z * 256 + m) * 256 + n];
+  C[(int64_t)m * ldc + n] = (float)s;
+}
+
 static int max_clusters() {
   static int cached[kMaxDevices] = {0};
   int& c = cached[cur_device()];
@@ -556,6 +770,74 @@ int gemm_pair(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, cons
   gemm_pair_kernel<<<grid, kPairThreads, kSmemTotal, st>>>(map_a, map_b, cm, p);
   GAT_LAUNCH_CHECK();
   GAT_CUDA(cudaFreeAsync(bsplit, st));
+  return GAT_OK;
+}
+
+// dW-shaped products: both operands row-major with the contraction over rows.
+bool pair_tn_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("GAT_GEMM_PAIR"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return false;
+  if (m < 8 || m > 256 || n < 8 || n > 256 || k < 65536 || k >= ((int64_t)1 << 31) - 64) return false;
+  if (lda % 4 || ldb % 4 || ldc < n) return false;
+  return true;
+}
+
+static int make_map_plain(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols, bool atom32) {
+  tc::EncodeTiledFn fn = tc::encode_fn();
+  if (!fn) { set_error("gat_gemm: cuTensorMapEncodeTiled is unavailable"); return GAT_EUNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gat_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r); return GAT_EINVAL; }
+  return GAT_OK;
+}
+
+int gemm_pair_tn(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
+                 int act_b, cudaStream_t st) {
+  using namespace tcp;
+  CUtensorMap map_a, map_b;
+  int rc = make_map_plain(&map_a, a, k, m, lda, TK, 128, false);
+  if (!rc) rc = make_map_plain(&map_b, b, k, n, ldb, TK, 32, true);
+  if (rc) return rc;
+  PairTnArgs p;
+  p.K = k; p.M = (int)m; p.N = (int)n; p.n_halves = n > 128 ? 2 : 1; p.act_b = act_b;
+  const int64_t total_stages = (k + TK - 1) / TK;
+  int clusters = max_clusters();
+  int splits = clusters / p.n_halves;
+  if (splits < 1) splits = 1;
+  if (splits > total_stages) splits = (int)total_stages;
+  p.stages_per_split = (int)((total_stages + splits - 1) / splits);
+  p.n_splits = (int)((total_stages + p.stages_per_split - 1) / p.stages_per_split);
+  static bool pool_set_dev[kMaxDevices] = {false};
+  if (!pool_set_dev[cur_device()]) {
+    cudaMemPool_t pool;
+    int dev_id = 0;
+    if (cudaGetDevice(&dev_id) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev_id) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    pool_set_dev[cur_device()] = true;
+  }
+  double* slots = nullptr;
+  GAT_CUDA(cudaMallocAsync((void**)&slots, (size_t)p.n_splits * 256 * 256 * sizeof(double), st));
+  p.slots = slots;
+  static bool attr_set_dev[kMaxDevices] = {false};
+  bool& attr_set = attr_set_dev[cur_device()];
+  if (!attr_set) {
+    GAT_CUDA(cudaFuncSetAttribute(gemm_pair_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnSmemTotal));
+    attr_set = true;
+  }
+  gemm_pair_tn_kernel<<<(unsigned)(2 * p.n_splits * p.n_halves), kPairThreads, kTnSmemTotal, st>>>(map_a, map_b, p);
+  GAT_LAUNCH_CHECK();
+  pair_tn_reduce_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, st>>>(slots, p.n_splits, (int)m, (int)n, c, ldc);
+  GAT_LAUNCH_CHECK();
+  GAT_CUDA(cudaFreeAsync(slots, st));
   return GAT_OK;
 }
 

@@ -433,6 +433,10 @@ int gemm_pair(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, cons
               float* const* dests, int n_dests, int64_t row_offset,
               int act_a, const float* mul_src, int64_t mul_ld, cudaStream_t st);
 
+bool pair_tn_supported(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc);
+int gemm_pair_tn(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t ldb, float* c, int64_t ldc,
+                 int act_b, cudaStream_t st);
+
 bool tc_supported(int ta, int tb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc) {
   const bool nt = (ta == 0 && tb == 1), tn = (ta == 1 && tb == 0);
   if (!nt && !tn) return false;
@@ -491,6 +495,8 @@ int gemm_tc(int ta, int tb, int64_t m, int64_t n, int64_t k, const float* a, int
     return tc::launch<64, false>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
   }
   if (mul_src != nullptr) { set_error("gat_gemm: the ELU' output multiplier is only implemented for ta = 0"); return GAT_EUNSUPPORTED; }
+  if (act_a == 0 && pair_tn_supported(m, n, k, lda, ldb, ldc))     // dW of a large graph: persistent CTA-pair kernel
+    return gemm_pair_tn(m, n, k, a, lda, b, ldb, c, ldc, act_b, st);
   if (bn == 256) return tc::launch<256, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
   if (bn == 128) return tc::launch<128, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);
   return tc::launch<64, true>(m, n, k, a, lda, b, ldb, c, ldc, workspace, workspace_bytes, st, nf, nd, g);

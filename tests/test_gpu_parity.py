@@ -379,6 +379,17 @@ def test_gemm_pair_cta_group2():
             want = want * torch.where(msrc > 0, torch.ones_like(msrc), msrc.exp()).double()
         err = ((c.double() - want).abs().max() / want.abs().max()).item()
         assert err < 2e-6, (m, n, k, act, mul, err)
+    # TN (dW = dWh^T x over >= 65536 node rows): A through tensor memory (transposed on the way in), B MN-major in shared memory,
+    # fp64 slots every 2048 rows.  The bar is the accumulator's round-toward-zero over 2048 rows (same as the one-CTA kernel).
+    for (m, n, k, act) in [(256, 256, 70000, False), (192, 256, 100003, False), (256, 100, 66000, True), (64, 72, 131072, False),
+                           (8, 8, 65536, False)]:
+        a = torch.randn(k, m, device="cuda")
+        b = torch.randn(k, n, device="cuda")
+        c = torch.full((m, n), float("nan"), device="cuda")
+        gemm(True, False, m, n, k, a, m, b, n, c, n, algo=2, act_b=act)
+        want = a.double().T @ (torch.nn.functional.elu(b.double()) if act else b.double())
+        err = ((c.double() - want).abs().max() / want.abs().max()).item()
+        assert err < 8e-6, ("TN", m, n, k, act, err)
     # fused projection -> all-gather through the pair kernel: two destinations, slab at a row offset
     rows, f_in, nh, fp, lo = 20000, 256, 4, 64, 1300
     dp = nh * fp

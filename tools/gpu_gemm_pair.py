@@ -95,3 +95,29 @@ for (n, k, mul) in [(256, 256, True), (100, 256, False), (256, 192, True)]:
     err, ms = plain(M, n, k, False, mul, reps=5)
     gb = 4.0 * M * (n + k + (n if mul else 0)) / 1e9
     print(f"dX-like m={M} n={n} k={k} elu_grad_out={mul}: {ms:.3f} ms  {gb / ms:.0f} GB/s  err {err:.2e}", flush=True)
+
+print("---- TN (dW): CTA-pair kernel for K >= 65536 ----", flush=True)
+def tn(m, n, k, act_b=False, reps=0):
+    torch.manual_seed(k + m)
+    a = torch.randn((k, m), device=dev); b = torch.randn((k, n), device=dev)
+    c = torch.full((m, n), float("nan"), device=dev)
+    gemm(True, False, m, n, k, a, m, b, n, c, n, algo=2, act_b=act_b)
+    torch.cuda.synchronize()
+    bd = torch.nn.functional.elu(b.double()) if act_b else b.double()
+    want = a.double().T @ bd
+    err = rel(c, want)
+    ms = None
+    if reps:
+        for _ in range(2): gemm(True, False, m, n, k, a, m, b, n, c, n, algo=2, act_b=act_b)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps): gemm(True, False, m, n, k, a, m, b, n, c, n, algo=2, act_b=act_b)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+    return err, ms
+for (m, n, k, act) in [(256, 256, 70000, False), (192, 256, 100003, False), (256, 100, 66000, True), (64, 72, 131072, False), (8, 8, 65536, False)]:
+    err, _ = tn(m, n, k, act)
+    print(f"TN m={m} n={n} k={k} elu_b={act}: err {err:.2e}", flush=True)
+for (m, n) in [(256, 256), (192, 256), (256, 100)]:
+    err, ms = tn(m, n, M, False, reps=5)
+    print(f"TN m={m} n={n} k={M}: {ms:.3f} ms err {err:.2e}", flush=True)

@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 $CMD > gpurun_out/plain_${tag}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_${tag}.csv $CMD > gpurun_out/ncu_launch_${tag}.log 2>&1 &&
 ncu --set full --clock-control none --import-source on \
-    -k 'regex:edge_bwd_main_kernel|edge_fwd_kernel|gemm_tc_kernel|edge_bwd_rowdot_kernel|edge_max_kernel|scores_bwd_partial' -s 90 -c 32 \
+    -k 'regex:edge_bwd_main_kernel|edge_fwd_kernel|gemm_tc_kernel|gemm_pair_kernel|edge_bwd_rowdot_kernel|edge_max_kernel|scores_bwd_partial' -s 100 -c 36 \
     -f -o /tmp/prof_${tag} $CMD > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "profile exit $?"
 python tools/ncu_summary.py /tmp/prof_${tag}.ncu-rep gpurun_out/ncu_${tag}_kernels.csv > /dev/null
