@@ -73,9 +73,46 @@ def gpu_epoch(data, epochs, penalty):
         opt.step()
         return float(loss.detach()), f1
 
+    def breakdown(x, ei, y):
+        """The same step with a device synchronisation after every part: where an epoch's time goes (ms per step)."""
+        def tick(t=[None]):
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            dt = None if t[0] is None else (now - t[0]) * 1e3
+            t[0] = now
+            return dt
+        parts = {}
+        tick()
+        att, h = [], x
+        for i, layer in enumerate(layers):
+            inp = h
+            h, (ei, a) = layer(h, ei, return_attention_weights=True)
+            att.append(a)
+            if skip[i]:
+                h = h + inp
+            if i != len(layers) - 1:
+                h = F.elu(h)
+        parts["forward (3 layers + glue)"] = tick()
+        loss = F.binary_cross_entropy_with_logits(h, y)
+        norm = g.attention_norm(ei, att)
+        loss = loss + penalty * norm
+        parts["loss + attention_norm"] = tick()
+        f1_micro(h, y)
+        parts["sklearn micro-F1 on the CPU (D2H + f1_score)"] = tick()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        parts["backward"] = tick()
+        opt.step()
+        parts["Adam step"] = tick()
+        return parts
+
     for x, ei, y in dd[:3]:
         step(x, ei, y)
     torch.cuda.synchronize()
+    gpu_epoch.breakdown = {}
+    for x, ei, y in dd:
+        for k, v in breakdown(x, ei, y).items():
+            gpu_epoch.breakdown[k] = gpu_epoch.breakdown.get(k, 0.0) + v / len(dd)
     times = []
     for _ in range(epochs):
         t0 = time.perf_counter()
@@ -137,6 +174,7 @@ def main():
                                              "4x256 / 4x256+skip / 6x121 mean, BCE + attention penalty, sklearn micro-F1, Adam",
                                  "attention_penalty": args.penalty},
                       "last_step": {"loss": loss, "train_f1": f1},
+                      "ms_per_step_breakdown_synchronised": {k: round(v, 3) for k, v in gpu_epoch.breakdown.items()},
                       "cpu_baseline": None if cpu_s is None else {"value": cpu_s, "unit": "s", "cores": torch.get_num_threads(), "kind": "port",
                                                                   "sample": f"{args.cpu_steps} steps of oracle/torch_port.py scaled to 10"}}))
 
