@@ -37,10 +37,16 @@ from .graph import build_structure
 class Plan:
     world: int
     rank: int
-    n: int            # global node count
+    n: int            # size of the node-id space the kernels see: the global node count, or P*R slab ids for a balanced plan
     rows_per_rank: int
     lo: int
     hi: int
+    n_real: int = -1          # global node count (== n unless the plan is edge-balanced)
+    bounds: tuple = None      # edge-balanced plans: global node boundaries b_0 = 0 <= ... <= b_P = n_real; rank r owns [b_r, b_r+1)
+
+    def __post_init__(self):
+        if self.n_real < 0:
+            self.n_real = self.n
 
     @property
     def n_pad(self) -> int:
@@ -54,6 +60,44 @@ class Plan:
 def make_plan(n: int, world: int, rank: int) -> Plan:
     r = (n + world - 1) // world
     return Plan(world, rank, n, r, min(rank * r, n), min((rank + 1) * r, n))
+
+
+def make_balanced_plan(bounds, rank: int) -> Plan:
+    """Edge-balanced destination ranges ("boundaries chosen to equalise edge counts").  Rank r owns the global
+    nodes [b_r, b_r+1); the kernels keep their uniform slab arithmetic (owner = id // R, gathered buffers of P slabs of R rows)
+    because the partitioned pipeline runs on SLAB ids: node g of rank r becomes r*R + (g - b_r), with R = the largest range.
+    The relabelling is monotone, so every row keeps its edges in input order and the forward stays bit-identical; slab rows
+    beyond a rank's range are empty (no edges, zero features)."""
+    bounds = tuple(int(b) for b in bounds)
+    world = len(bounds) - 1
+    r = max(1, max(bounds[i + 1] - bounds[i] for i in range(world)))
+    return Plan(world, rank, r * world, r, rank * r, rank * r + (bounds[rank + 1] - bounds[rank]), bounds[-1], bounds)
+
+
+def to_slab_ids(ids: torch.Tensor, plan: Plan) -> torch.Tensor:
+    """Global node ids -> the ids the partitioned kernels use (identity for an equal-range plan)."""
+    if plan.bounds is None:
+        return ids
+    b = torch.as_tensor(plan.bounds, dtype=ids.dtype, device=ids.device)
+    owner = torch.searchsorted(b[1:], ids, right=True).clamp_(max=plan.world - 1)
+    return owner * plan.rows_per_rank + (ids - b[owner])
+
+
+def edge_balanced_bounds(ei_part: torch.Tensor, n: int, world: int, group=None):
+    """Boundaries that give every rank the same number of rewritten edges (in-degree without existing self loops + the one
+    appended loop per node), from the DISTRIBUTED edge list: local in-degree histogram, all-reduce, prefix sum, P-quantiles."""
+    src, dst = ei_part[0], ei_part[1]
+    deg = torch.bincount(dst[src != dst], minlength=n)[:n].to(torch.int64) + 1
+    dist.all_reduce(deg, group=group)
+    deg -= (world - 1)                                       # the +1 loop was counted on every rank
+    csum = torch.cumsum(deg, 0)
+    targets = (csum[-1].to(torch.float64) * torch.arange(1, world, dtype=torch.float64, device=deg.device) / world).to(torch.int64)
+    cuts = (torch.searchsorted(csum, targets, right=False) + 1).clamp_(max=n).tolist() if world > 1 else []
+    bounds = [0]
+    for c in cuts:
+        bounds.append(max(int(c), bounds[-1]))
+    bounds.append(n)
+    return tuple(bounds)
 
 
 def local_edge_list(edge_index: torch.Tensor, n_idx: int, lo: int, hi: int, add_self_loops: bool = True) -> torch.Tensor:
@@ -87,7 +131,11 @@ def exchange_edge_list(ei_part: torch.Tensor, plan: Plan, group=None, add_self_l
     if add_self_loops:
         keep = src != dst                                    # the loops are re-created by their owner (utils.py:61-65)
         src, dst = src[keep], dst[keep]
-    owner = torch.div(dst, plan.rows_per_rank, rounding_mode="floor").clamp_(0, world - 1)
+    if plan.bounds is None:
+        owner = torch.div(dst, plan.rows_per_rank, rounding_mode="floor").clamp_(0, world - 1)
+    else:                                                    # edge-balanced ranges: owner by boundary search, ids -> slab ids
+        src, dst = to_slab_ids(src, plan), to_slab_ids(dst, plan)
+        owner = torch.div(dst, plan.rows_per_rank, rounding_mode="floor").clamp_(0, world - 1)
     order = torch.sort(owner, stable=True).indices           # stable: input order inside a bucket
     send = torch.stack([src[order], dst[order]], dim=1).contiguous()        # (m, 2), bucket after bucket
     cnt_in = torch.bincount(owner, minlength=world)[:world].to(torch.int64)
@@ -101,7 +149,11 @@ def exchange_edge_list(ei_part: torch.Tensor, plan: Plan, group=None, add_self_l
     dist.all_to_all_single(recv, send, output_split_sizes=n_out, input_split_sizes=n_in, group=group)
     local = recv.t()
     if add_self_loops:
-        loops = torch.arange(plan.lo, max(min(plan.hi, n_idx), plan.lo), dtype=ei_part.dtype, device=dev)
+        if plan.bounds is None:
+            loops = torch.arange(plan.lo, max(min(plan.hi, n_idx), plan.lo), dtype=ei_part.dtype, device=dev)
+        else:                                                # owned GLOBAL nodes below n_idx, as slab ids
+            g_lo = plan.bounds[plan.rank]
+            loops = torch.arange(plan.lo, plan.lo + max(min(plan.bounds[plan.rank + 1], n_idx) - g_lo, 0), dtype=ei_part.dtype, device=dev)
         local = torch.cat([local, torch.stack([loops, loops])], dim=1)
     return local.contiguous(), n_idx
 
@@ -473,11 +525,17 @@ class PartitionedGATLayer(torch.nn.Module):
 class PartitionedGAT:
     """bench.py's multi-GPU model: the stacked layers of one config over a partitioned graph."""
 
-    def __init__(self, shapes, weights, x_host, ei_host, dev, backend=None, fuse_glue=False):
+    def __init__(self, shapes, weights, x_host, ei_host, dev, backend=None, fuse_glue=False, balance="edges"):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.fuse_glue = fuse_glue      # the inter-layer ELU rides in the next layer's GEMMs (SURVEY.md 8-f1)
         self.dev, self.x_host, self.ei_host = dev, x_host, ei_host
-        self.plan = make_plan(x_host.size(0), self.world, self.rank)
+        c0, c1 = edge_slice(ei_host.size(1), self.world, self.rank)
+        if balance == "edges" and self.world > 1:
+            # destination ranges with equal EDGE counts (part of the plan: computed once, from the distributed edge list)
+            bounds = edge_balanced_bounds(ei_host[:, c0:c1].to(dev), x_host.size(0), self.world)
+            self.plan = make_balanced_plan(bounds, self.rank)
+        else:
+            self.plan = make_plan(x_host.size(0), self.world, self.rank)
         self.backend = backend or CudaBackend()
         self.layers = []
         for (f_in, nh, f, concat), (w, a) in zip(shapes, weights):
@@ -489,11 +547,11 @@ class PartitionedGAT:
         if fuse_glue:   # F.elu after every layer but the last (GATModel.py:148-149), in the edge kernel's epilogue
             for layer in self.layers[:-1]:
                 layer.output_activation = "elu" if layer.concat else None
-        self.x_local_host = x_host[self.plan.lo:self.plan.hi].contiguous()
+        g_lo, g_hi = (self.plan.lo, self.plan.hi) if self.plan.bounds is None else (self.plan.bounds[self.rank], self.plan.bounds[self.rank + 1])
+        self.x_local_host = x_host[g_lo:g_hi].contiguous()
         if x_host.is_pinned():
             self.x_local_host = self.x_local_host.pin_memory()
         # every rank uploads only ITS consecutive 1/P of the edge list; the buckets are exchanged over NVLink (exchange_edge_list)
-        c0, c1 = edge_slice(ei_host.size(1), self.world, self.rank)
         self.ei_part_host = ei_host[:, c0:c1].contiguous()
         if ei_host.is_pinned():
             self.ei_part_host = self.ei_part_host.pin_memory()
@@ -515,7 +573,7 @@ class PartitionedGAT:
             h = layer(h, st, self.plan)
             if i != len(self.layers) - 1 and layer.output_activation != "elu":
                 h = F.elu(h)
-        loss = h.square().sum() / (self.plan.n * h.size(1))     # this rank's share of the global mean
+        loss = h.square().sum() / (self.plan.n_real * h.size(1))     # this rank's share of the global mean
         loss.backward()
         self.last_loss, self.last_out = loss.detach(), h.detach()     # bench.py's checksums (summed over ranks there)
         return loss

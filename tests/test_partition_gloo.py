@@ -105,6 +105,80 @@ def test_distributed_edge_exchange_equals_the_local_filter(world):
         assert ret[r][0] and ret[r][1], (r, ret[r])
 
 
+def _balanced_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from _oracle_backend import OracleBackend
+        from gat_pytorch_b200.partition import (PartitionedGATLayer, edge_balanced_bounds, edge_slice, exchange_edge_list,
+                                                make_balanced_plan)
+        x, ei, w, a, nh, f = _skewed_case()
+        n = x.size(0)
+        c0, c1 = edge_slice(ei.size(1), world, rank)
+        bounds = edge_balanced_bounds(ei[:, c0:c1].contiguous(), n, world)
+        plan = make_balanced_plan(bounds, rank)
+        backend = OracleBackend()
+        local, n_idx = exchange_edge_list(ei[:, c0:c1].contiguous(), plan, None, True)
+        st = backend.build_structure(local, plan.n)
+        layer = PartitionedGATLayer(x.size(1), f, nh, True, backend)
+        with torch.no_grad():
+            layer.W.weight.copy_(w)
+            layer.a.weight.copy_(a)
+        xl = x[bounds[rank]:bounds[rank + 1]].clone().requires_grad_(True)
+        out = layer(xl, st, plan)
+        g = torch.Generator().manual_seed(11)
+        go = torch.randn(n, out.size(1), generator=g)
+        (out * go[bounds[rank]:bounds[rank + 1]]).sum().backward()
+        ret[rank] = dict(bounds=bounds, n_edges=int(local.size(1)), out=out.detach().numpy(), gx=xl.grad.numpy(),
+                         gW=layer.W.weight.grad.numpy(), ga=layer.a.weight.grad.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _skewed_case():
+    """Degree-sorted graph: the first nodes are hubs (what equal node ranges split badly)."""
+    g = torch.Generator().manual_seed(3)
+    n, e, nh, f, f_in = 120, 2400, 2, 4, 6
+    dst = (torch.rand(e, generator=g) ** 3 * (n - 5)).long()            # mass concentrated on low ids
+    src = torch.randint(0, n - 5, (e,), generator=g)
+    ei = torch.stack([src, dst])
+    x = torch.randn(n, f_in, generator=g)
+    w = torch.randn(nh * f, f_in, generator=g) * 0.3
+    a = torch.randn(nh, nh * 2 * f, generator=g) * 0.3
+    return x, ei, w, a, nh, f
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_edge_balanced_partition_matches_single_process_oracle(world):
+    """destination ranges chosen to equalise EDGE counts.  The pipeline then runs on slab ids (rank r's node g is
+    r*R + g - b_r); outputs and gradients must still equal the single-process oracle, and the edge counts must be balanced where
+    equal node ranges are not."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gat_oracle as O
+    ret = mp.Manager().dict()
+    port = 29900 + (os.getpid() % 40)
+    mp.spawn(_balanced_worker, args=(world, port, ret), nprocs=world, join=True)
+    x, ei, w, a, nh, f = _skewed_case()
+    fw = O.forward(x.numpy(), ei.numpy(), w.numpy(), a.numpy(), nh, f, True, True)
+    g = torch.Generator().manual_seed(11)
+    go = torch.randn(x.size(0), fw["out"].shape[1], generator=g).numpy()
+    gr = O.backward(fw, go, None)
+    assert O.rel_err(np.concatenate([ret[r]["out"] for r in range(world)]), fw["out"]) < 1e-5
+    assert O.rel_err(np.concatenate([ret[r]["gx"] for r in range(world)]), gr["x"]) < 1e-5
+    for r in range(world):
+        assert O.rel_err(ret[r]["gW"], gr["W"]) < 1e-5 and O.rel_err(ret[r]["ga"], gr["a"]) < 1e-5
+    counts = [ret[r]["n_edges"] for r in range(world)]
+    assert sum(counts) == fw["edge_index"].shape[1]
+    assert max(counts) <= 1.25 * sum(counts) / world, counts                  # balanced ...
+    dst = fw["edge_index"][1]
+    per = (x.size(0) + world - 1) // world
+    naive = [int(((dst >= r * per) & (dst < (r + 1) * per)).sum()) for r in range(world)]
+    assert max(naive) > 1.5 * sum(naive) / world, naive                      # ... where equal node ranges are not
+
+
 def test_plan_covers_all_rows():
     from gat_pytorch_b200.partition import make_plan
     for n, world in [(97, 2), (10, 4), (8, 8), (5, 8)]:

@@ -25,14 +25,17 @@ def main():
         if i != len(model.layers) - 1:
             h = F.elu(h)
     out_local = h
-    loss = out_local.square().sum() / (plan.n * out_local.size(1))
+    loss = out_local.square().sum() / (plan.n_real * out_local.size(1))
     loss.backward()
     outs = [torch.zeros((plan.rows_per_rank, out_local.size(1)), device=dev) for _ in range(world)]
     pad = torch.zeros((plan.rows_per_rank, out_local.size(1)), device=dev); pad[:plan.rows] = out_local.detach()
     dist.all_gather(outs, pad)
     ok = True
     if rank == 0:
-        out_part = torch.cat(outs)[:plan.n]
+        if plan.bounds is None:
+            out_part = torch.cat(outs)[:plan.n]
+        else:       # edge-balanced ranges: rank r's rows are the first b_{r+1} - b_r rows of its slab
+            out_part = torch.cat([o[:plan.bounds[r + 1] - plan.bounds[r]] for r, o in enumerate(outs)])
         layers = []
         for (f_in, nh, f, concat), (w, a) in zip(shapes, weights):
             l = g.GATLayer(f_in, f, nh, concat, add_self_loops=True).to(dev)
@@ -48,7 +51,7 @@ def main():
         h.square().mean().backward()
         same = torch.equal(out_part, h.detach())
         rel = ((out_part - h.detach()).abs().max() / h.detach().abs().max()).item()
-        print(f"forward bit-identical: {same} (rel diff {rel:.2e}) N={plan.n} E'={model.n_edges_global}")
+        print(f"forward bit-identical: {same} (rel diff {rel:.2e}) N={plan.n_real} E'={model.n_edges_global} bounds={plan.bounds}")
         ok = ok and rel < 1e-6
         for i, (lp, ls) in enumerate(zip(model.layers, layers)):
             for nm in ("W", "a"):
