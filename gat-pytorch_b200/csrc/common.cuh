@@ -78,6 +78,29 @@ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t offset, u
   return u < p ? 0.0f : 1.0f / (1.0f - p);
 }
 
+// Output glue: what GATModel.forward does between a layer and the next one -- skip add, ELU, the next layer's
+// input dropout (GATModel.py:130, :135-149) -- folded into the kernel that produces the layer's output:
+//     y = keep(row, col) * E(out + skip),   E = ELU or identity,   keep = 0 or 1/(1-p) from Philox keyed on (row, col/4)
+// so the mask is never stored; the backward regenerates it.
+__device__ __forceinline__ float4 glue_keep4(uint64_t seed, int64_t row, int chunk, float p) {
+  const uint4 r = philox4x32(seed, 0x676c7565ull, (uint32_t)row, (uint32_t)chunk);
+  const float keep = 1.0f / (1.0f - p);
+  return make_float4(((float)(r.x >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : keep, ((float)(r.y >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : keep,
+                     ((float)(r.z >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : keep, ((float)(r.w >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : keep);
+}
+__device__ __forceinline__ float glue_keep1(uint64_t seed, int64_t row, int col, float p) {
+  const float4 k = glue_keep4(seed, row, col >> 2, p);
+  return (col & 3) == 0 ? k.x : (col & 3) == 1 ? k.y : (col & 3) == 2 ? k.z : k.w;
+}
+__device__ __forceinline__ float glue_elu(float v) { return v > 0.f ? v : expm1f(v); }
+// adjoint of one element: dL/d(out+skip) from dL/dy and the stored y (keep = this element's keep scale, 1 without dropout)
+__device__ __forceinline__ float glue_adjoint1(float g, float y, int act, float keep, float one_minus_p) {
+  if (keep == 0.f) return 0.f;
+  const float hval = y * one_minus_p;                       // E(out + skip)
+  const float d = (act && hval <= 0.f) ? hval + 1.0f : 1.0f;   // ELU' = 1 (h > 0) or h + 1
+  return g * keep * d;
+}
+
 // Order-preserving float <-> uint mapping so that a float max can use atomicMax (deterministic).
 __device__ __forceinline__ unsigned int float_to_ordered(float f) {
   unsigned int u = __float_as_uint(f);

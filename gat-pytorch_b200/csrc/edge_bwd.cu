@@ -564,6 +564,10 @@ static size_t main_dyn_smem(int chunks) {
   return part > coop ? part : coop;
 }
 
+}  // namespace gat
+#include "edge_bwd_hm.cuh"   // head-mean layers with four heads: lane = (edge slot, head, quarter)
+namespace gat {
+
 // ------------------------------------------------------------------------------------------------------------
 // pass 2: per target row, S[h] = sum_e alpha*d_alpha; ds_tgt[h] = 0.01 * S * eps / (Z + eps)
 // ------------------------------------------------------------------------------------------------------------
@@ -658,6 +662,8 @@ struct BwdRowdotParams {
   // then recovers out = h > 0 ? h : log1p(h) and ELU'(out) = h > 0 ? 1 : h + 1, forms the gradient w.r.t. the pre-activation
   // output go*ELU', writes it to go_out (what the source-major pass gathers) and uses it in S -- the ELU backward fused.
   int out_is_act; float* go_out;
+  // the rest of the output glue (common.cuh): `out` holds y = keep * E(out + skip); `glue` is set when any part is active
+  int glue; const float* skip; int64_t ld_skip; float drop_p; uint64_t drop_seed;
   float* s_sum; float* ds_tgt;
   const float* s_tgt; float* tpack;   // optional: write the per-target record {s_tgt | Z | S} for gat_edge_bwd_fused
 };
@@ -696,19 +702,27 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
         g[r] = on ? ldg4(P.go + (row0 + r) * P.go_ld + (P.go_shared ? gc : c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         o[r] = on ? ldg4(P.out + (row0 + r) * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (P.out_is_act) {
+      if (P.glue) {
+        const float omp = 1.0f - P.drop_p;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           float* gv = reinterpret_cast<float*>(&g[r]);
           float* ov = reinterpret_cast<float*>(&o[r]);
+          const bool on = row0 + r < P.n;
+          float4 k4 = make_float4(1.f, 1.f, 1.f, 1.f), s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (P.drop_p > 0.f) k4 = glue_keep4(P.drop_seed, row0 + r, c, P.drop_p);
+          if (P.skip && on) s4 = ldg4(P.skip + (row0 + r) * P.ld_skip + c * 4);
+          const float* kv = reinterpret_cast<const float*>(&k4);
+          const float* sv = reinterpret_cast<const float*>(&s4);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float h = ov[j];
-            const bool neg = h <= 0.f;
-            gv[j] = neg ? gv[j] * (h + 1.0f) : gv[j];      // dL/dout = dL/dh * ELU'(out)
-            ov[j] = neg ? log1p_neg_fast(h) : h;           // out recovered from h = ELU(out)
+            const float h = ov[j] * omp;                   // E(out + skip) where the element was kept
+            const bool neg = P.out_is_act && h <= 0.f;
+            gv[j] = glue_adjoint1(gv[j], ov[j], P.out_is_act, kv[j], omp);      // dL/d(out + skip)
+            // out recovered from the stored value; a dropped element's gradient is 0, so its (unknown) out never matters
+            ov[j] = kv[j] == 0.f ? 0.f : (neg ? log1p_neg_fast(h) : h) - sv[j];
           }
-          if (row0 + r < P.n) *reinterpret_cast<float4*>(P.go_out + (row0 + r) * P.dp + c * 4) = g[r];
+          if (on) *reinterpret_cast<float4*>(P.go_out + (row0 + r) * P.dp + c * 4) = g[r];
         }
       }
 #pragma unroll
@@ -1032,14 +1046,36 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
                                kEdgeThreads, smem_, st, Q, false));                                                    \
         GAT_LAUNCH_CHECK();                                                                                            \
       }                                                                                                                \
-      GAT_CUDA(launch_kernel(edge_bwd_main_kernel<32, S_, 4, false, FUSED, false, true>,                               \
-                             persistent_grid(edge_bwd_main_kernel<32, S_, 4, false, FUSED, false, true>, kEdgeThreads, smem_, \
-                                             (n_rows + 7) / 8),                                                        \
-                             kEdgeThreads, smem_, st, Q, coop_launch));                                                \
-      GAT_LAUNCH_CHECK();                                                                                              \
+      if (hm_cpl == 0) {                                                                                               \
+        GAT_CUDA(launch_kernel(edge_bwd_main_kernel<32, S_, 4, false, FUSED, false, true>,                             \
+                               persistent_grid(edge_bwd_main_kernel<32, S_, 4, false, FUSED, false, true>, kEdgeThreads, smem_, \
+                                               (n_rows + 7) / 8),                                                      \
+                               kEdgeThreads, smem_, st, Q, coop_launch));                                              \
+        GAT_LAUNCH_CHECK();                                                                                            \
+      }                                                                                                                \
     } while (0)
+    // short rows of a four-head head-mean layer: the (edge slot, head, quarter) kernel of edge_bwd_hm.cuh (the long rows keep
+    // the cooperative launch above)
+    const int hm_cpl = (FUSED && nh == 4 && P.tpack != nullptr && !P.push && getenv("GAT_BWD_HM_OFF") == nullptr) ? (P.chunks_per_head + 3) / 4 : 0;
     if (shape.slots == 1) LAUNCH_GS(1); else LAUNCH_GS(2);
 #undef LAUNCH_GS
+#define LAUNCH_HM(C_, X_)                                                                                              \
+    do {                                                                                                               \
+      static bool optin_hm_dev_[kMaxDevices] = {false};                                                                \
+      bool& optin_hm_ = optin_hm_dev_[cur_device()];                                                                   \
+      if (!optin_hm_) {                                                                                                \
+        GAT_CUDA(cudaFuncSetAttribute(edge_bwd_hm4_kernel<C_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      (int)HmShape<C_>::kSmem));                                                       \
+        optin_hm_ = true;                                                                                              \
+      }                                                                                                                \
+      GAT_CUDA(launch_kernel(edge_bwd_hm4_kernel<C_, X_>,                                                              \
+                             persistent_grid(edge_bwd_hm4_kernel<C_, X_>, kEdgeThreads, HmShape<C_>::kSmem, (n_rows + 7) / 8), \
+                             kEdgeThreads, HmShape<C_>::kSmem, st, Q, coop_launch));                                   \
+      GAT_LAUNCH_CHECK();                                                                                              \
+    } while (0)
+    if (hm_cpl == 3 && P.chunks_per_head == 12) LAUNCH_HM(3, true);
+    else if (hm_cpl == 2) LAUNCH_HM(2, false); else if (hm_cpl == 3) LAUNCH_HM(3, false); else if (hm_cpl == 4) LAUNCH_HM(4, false);
+#undef LAUNCH_HM
     return GAT_OK;
   }
 #define LAUNCH_BOTH(G_, S_, N_, FULL_)                                                                                 \
@@ -1209,14 +1245,19 @@ extern "C" int gat_edge_bwd_rowsum(const int32_t* rowptr, const int32_t* tpos, c
 
 extern "C" int gat_tgt_pack_stride(int nh) { return nh <= 4 ? 16 : 32; }
 
-extern "C" int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const float* out_padded, int out_is_act, float* go_out,
+static int edge_bwd_rowdot_impl(const float* go_padded, int go_shared, const float* out_padded, int out_is_act, float* go_out,
                                    const float* z, int64_t n_rows, int nh, int fp,
                                    float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
-                                   void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+                                   void* workspace, size_t workspace_bytes, gat_stream_t stream,
+                                   const float* skip, int64_t ld_skip, float drop_p, uint64_t drop_seed) {
   using namespace gat;
   int rc = check_common("gat_edge_bwd_rowdot", nh, fp, workspace, workspace_bytes);
   if (rc) return rc;
-  GAT_CHECK_ARG(!out_is_act || (go_out != nullptr && !go_shared), "gat_edge_bwd_rowdot: out_is_act needs go_out and an unshared gradient");
+  const bool glue = out_is_act || skip != nullptr || drop_p > 0.f;
+  GAT_CHECK_ARG(!glue || (go_out != nullptr && !go_shared), "gat_edge_bwd_rowdot: a fused output glue needs go_out and an unshared gradient");
+  GAT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "gat_edge_bwd_rowdot: output dropout %f not in [0, 1)", drop_p);
+  GAT_CHECK_ARG(skip == nullptr || (ld_skip >= (int64_t)nh * fp && ld_skip % 4 == 0 && ((uintptr_t)skip & 15) == 0),
+                "gat_edge_bwd_rowdot: skip rows must be 16-byte aligned with a stride of at least nh*fp floats");
   GAT_CHECK_ARG(tgt_pack == nullptr || (s_tgt != nullptr && ((uintptr_t)tgt_pack & 15) == 0), "gat_edge_bwd_rowdot: tgt_pack needs s_tgt and 16-byte alignment");
   if (n_rows == 0) return GAT_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1225,6 +1266,7 @@ extern "C" int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const 
   P.chunks_per_head = fp / 4; P.s_sum = s_sum; P.ds_tgt = ds_tgt;
   P.go_shared = go_shared ? 1 : 0; P.go_ld = go_shared ? fp : nh * fp;
   P.out_is_act = out_is_act ? 1 : 0; P.go_out = go_out;
+  P.glue = glue ? 1 : 0; P.skip = skip; P.ld_skip = ld_skip; P.drop_p = drop_p; P.drop_seed = drop_seed;
   P.s_tgt = s_tgt; P.tpack = tgt_pack;
   int64_t want = (n_rows + 31) / 32;
   const unsigned grid = (unsigned)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8);
@@ -1234,6 +1276,24 @@ extern "C" int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const 
   gamma_partial_kernel<<<kGammaBlocks, 256, 0, st>>>(ds_tgt, n_rows * nh, (BwdHeader*)workspace, (double*)((char*)workspace + kBwdHeaderBytes));
   GAT_LAUNCH_CHECK();
   return GAT_OK;
+}
+
+extern "C" int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const float* out_padded, int out_is_act, float* go_out,
+                                   const float* z, int64_t n_rows, int nh, int fp,
+                                   float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
+                                   void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  return edge_bwd_rowdot_impl(go_padded, go_shared, out_padded, out_is_act, go_out, z, n_rows, nh, fp, s_sum, ds_tgt, s_tgt, tgt_pack,
+                              workspace, workspace_bytes, stream, nullptr, 0, 0.f, 0);
+}
+
+// gat_edge_bwd_rowdot for a forward that ran with the whole output glue (gat_edge_fwd_glue): out_padded holds y = keep * E(out + skip)
+extern "C" int gat_edge_bwd_rowdot_glue(const float* go_padded, const float* y_padded, int out_is_act, const float* skip, int64_t ld_skip,
+                                        float drop_p, uint64_t drop_seed, float* go_out,
+                                        const float* z, int64_t n_rows, int nh, int fp,
+                                        float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
+                                        void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  return edge_bwd_rowdot_impl(go_padded, 0, y_padded, out_is_act, go_out, z, n_rows, nh, fp, s_sum, ds_tgt, s_tgt, tgt_pack,
+                              workspace, workspace_bytes, stream, skip, ld_skip, drop_p, drop_seed);
 }
 
 extern "C" int gat_edge_bwd_gamma(void* workspace, size_t workspace_bytes, double* gamma_out, gat_stream_t stream) {

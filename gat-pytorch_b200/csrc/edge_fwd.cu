@@ -79,11 +79,27 @@ struct EdgeFwdParams {
   float* out; float* alpha_out; float* z_out;
   int out_act;   // 1: the stored row is ELU(out) -- the F.elu that follows a hidden layer (GATModel.py:148-149), fused
   int32_t* tie_dst; int32_t* tie_src; unsigned long long* tie_total;
+  // rest of the output glue (common.cuh): skip rows added before the activation, dropout of the stored row
+  const float* skip; int64_t ld_skip; float out_drop_p; uint64_t out_drop_seed;
 };
 
 __device__ __forceinline__ float4 elu_f4(float4 v) {
   return make_float4(v.x > 0.f ? v.x : expm1f(v.x), v.y > 0.f ? v.y : expm1f(v.y), v.z > 0.f ? v.z : expm1f(v.z),
                      v.w > 0.f ? v.w : expm1f(v.w));
+}
+
+// what is stored for chunk c of row `row`: keep * E(t + skip)
+__device__ __forceinline__ float4 out_glue(const EdgeFwdParams& P, const int64_t row, const int c, float4 t) {
+  if (P.skip) {
+    const float4 k = ldg4(P.skip + row * P.ld_skip + c * 4);
+    t.x += k.x; t.y += k.y; t.z += k.z; t.w += k.w;
+  }
+  if (P.out_act) t = elu_f4(t);
+  if (P.out_drop_p > 0.f) {
+    const float4 k = glue_keep4(P.out_drop_seed, row, c, P.out_drop_p);
+    t.x *= k.x; t.y *= k.y; t.z *= k.z; t.w *= k.w;
+  }
+  return t;
 }
 
 template <int NHT>
@@ -292,14 +308,13 @@ __device__ __forceinline__ void edge_fwd_row(const EdgeFwdParams& P, const int64
         const float4 v = *reinterpret_cast<const float4*>(coop + j * P.dp + c * 4);
         t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
       }
-      if (P.out_act) t = elu_f4(t);
-      *reinterpret_cast<float4*>(P.out + row * P.dp + c * 4) = t;
+      *reinterpret_cast<float4*>(P.out + row * P.dp + c * 4) = out_glue(P, row, c, t);
     }
     // the next grab_long_row() starts with a __syncthreads(), which also protects `coop`
   } else {
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s)
-      if (ok[s]) *reinterpret_cast<float4*>(P.out + row * P.dp + (s * G + gl) * 4) = P.out_act ? elu_f4(acc[s]) : acc[s];
+      if (ok[s]) *reinterpret_cast<float4*>(P.out + row * P.dp + (s * G + gl) * 4) = out_glue(P, row, s * G + gl, acc[s]);
   }
 }
 
@@ -361,6 +376,43 @@ __global__ void head_merge_fwd_kernel(const float* __restrict__ o, int64_t n, in
   }
 }
 
+// Head merge with the output glue applied to the MERGED row (layers whose padded rows are not the caller's rows: head-mean layers,
+// F % 4 != 0): out = keep * E(merge(o) + skip).
+__global__ void head_merge_fwd_glue_kernel(const float* __restrict__ o, int64_t n, int nh, int f, int fp, int concat,
+                                           const float* __restrict__ skip, int64_t ld_skip, int act, float drop_p, uint64_t drop_seed,
+                                           float* __restrict__ out) {
+  const int width = concat ? nh * f : f;
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * width) return;
+  int64_t i = idx / width;
+  int c = (int)(idx % width);
+  const float* r = o + i * (int64_t)nh * fp;
+  float v;
+  if (concat) {
+    v = r[(c / f) * fp + (c % f)];
+  } else {
+    float s = 0.f;
+    for (int h = 0; h < nh; ++h) s += r[h * fp + c];
+    v = s / (float)nh;
+  }
+  if (skip) v += skip[i * ld_skip + c];
+  if (act) v = glue_elu(v);
+  if (drop_p > 0.f) v *= glue_keep1(drop_seed, i, c, drop_p);
+  out[idx] = v;
+}
+
+// dL/d(out + skip) from dL/dy and the stored y = keep * E(out + skip), element-wise over an (n, width) matrix
+__global__ void out_glue_adjoint_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t n, int width, int act,
+                                        float drop_p, uint64_t drop_seed, float* __restrict__ out) {
+  const float omp = 1.0f - drop_p;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n * width; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / width;
+    const int c = (int)(idx - i * width);
+    const float keep = drop_p > 0.f ? glue_keep1(drop_seed, i, c, drop_p) : 1.0f;
+    out[idx] = glue_adjoint1(g[idx], y[idx], act, keep, omp);
+  }
+}
+
 // Head-mean layers: the adjoint of mean(dim=1) hands every head the same vector g/NH, so it is stored ONCE as a padded
 // (n, fp) row that the backward kernels share across heads (go_shared) -- a quarter of the gather traffic at NH = 4.
 __global__ void head_mean_bwd_shared_kernel(const float* __restrict__ g, int64_t n, int nh, int f, int fp, float* __restrict__ go) {
@@ -412,9 +464,13 @@ static int edge_fwd_impl(bool gather_bf16, const int32_t* rowptr, const int32_t*
                          const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
                          float* out, int out_act, float* alpha_out, float* z_out,
                          int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
-                         void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+                         void* workspace, size_t workspace_bytes, gat_stream_t stream,
+                         const float* skip = nullptr, int64_t ld_skip = 0, float out_drop_p = 0.f, uint64_t out_drop_seed = 0) {
   using namespace gat;
   GAT_CHECK_ARG(nh >= 1 && nh <= kMaxHeads, "gat_edge_fwd: num_heads %d not in [1, %d]", nh, kMaxHeads);
+  GAT_CHECK_ARG(out_drop_p >= 0.f && out_drop_p < 1.f, "gat_edge_fwd: output dropout %f not in [0, 1)", out_drop_p);
+  GAT_CHECK_ARG(skip == nullptr || (ld_skip >= (int64_t)nh * fp && ld_skip % 4 == 0 && ((uintptr_t)skip & 15) == 0),
+                "gat_edge_fwd: skip rows must be 16-byte aligned with a stride of at least nh*fp floats");
   GAT_CHECK_ARG(workspace != nullptr && workspace_bytes >= gat_edge_fwd_workspace_bytes(), "gat_edge_fwd: workspace too small");
   GAT_CHECK_ARG(fp > 0 && fp % 4 == 0, "gat_edge_fwd: padded head width %d must be a positive multiple of 4", fp);
   GAT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "gat_edge_fwd: dropout %f not in [0, 1)", dropout_p);
@@ -429,6 +485,7 @@ static int edge_fwd_impl(bool gather_bf16, const int32_t* rowptr, const int32_t*
   P.s_src = s_src; P.s_tgt = s_tgt; P.gmax = gmax; P.const_attention = const_attention;
   P.dropout_p = dropout_p; P.seed = seed; P.offset = offset;
   P.out = out; P.alpha_out = alpha_out; P.z_out = z_out; P.out_act = out_act ? 1 : 0;
+  P.skip = skip; P.ld_skip = ld_skip; P.out_drop_p = out_drop_p; P.out_drop_seed = out_drop_seed;
   P.tie_dst = const_attention ? nullptr : tie_dst; P.tie_src = const_attention ? nullptr : tie_src;
   P.tie_total = const_attention ? nullptr : tie_total;
   GroupShape shape = pick_group(P.chunks);
@@ -495,6 +552,19 @@ extern "C" int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int
                        offset, out, out_act, alpha_out, z_out, tie_dst, tie_src, tie_total, workspace, workspace_bytes, stream);
 }
 
+// gat_edge_fwd with the whole output glue (include/gat_b200.h): out = keep * E(out + skip)
+extern "C" int gat_edge_fwd_glue(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
+                                 int64_t n, const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
+                                 const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
+                                 float* out, int out_act, const float* skip, int64_t ld_skip, float out_drop_p, uint64_t out_drop_seed,
+                                 float* alpha_out, float* z_out,
+                                 int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
+                                 void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  return edge_fwd_impl(false, rowptr, col, eid, row_order, n_long, n, wh, nh, fp, s_src, s_tgt, gmax, const_attention, dropout_p, seed,
+                       offset, out, out_act, alpha_out, z_out, tie_dst, tie_src, tie_total, workspace, workspace_bytes, stream,
+                       skip, ld_skip, out_drop_p, out_drop_seed);
+}
+
 // bf16 variant: `wh_bf16` is a bfloat16 copy of Wh (gat_f32_to_bf16), same (n, nh*fp) row-major layout; everything else as above.
 extern "C" int gat_edge_fwd_bf16(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
                                  int64_t n, const void* wh_bf16, int nh, int fp, const float* s_src, const float* s_tgt,
@@ -513,6 +583,35 @@ extern "C" int gat_head_merge_fwd(const float* o_padded, int64_t n, int nh, int 
   int64_t total = n * (concat ? nh * f : f);
   if (total == 0) return GAT_OK;
   head_merge_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(o_padded, n, nh, f, fp, concat, out);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_head_merge_fwd_glue(const float* o_padded, int64_t n, int nh, int f, int fp, int concat,
+                                       const float* skip, int64_t ld_skip, int act, float drop_p, uint64_t drop_seed, float* out,
+                                       gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(nh >= 1 && f >= 1 && fp >= f, "gat_head_merge_fwd_glue: bad shape");
+  GAT_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "gat_head_merge_fwd_glue: dropout %f not in [0, 1)", drop_p);
+  const int64_t width = concat ? (int64_t)nh * f : f;
+  GAT_CHECK_ARG(skip == nullptr || ld_skip >= width, "gat_head_merge_fwd_glue: skip stride too small");
+  const int64_t total = n * width;
+  if (total == 0) return GAT_OK;
+  head_merge_fwd_glue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(o_padded, n, nh, f, fp, concat, skip, ld_skip,
+                                                                                                 act ? 1 : 0, drop_p, drop_seed, out);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_out_glue_adjoint(const float* grad_y, const float* y, int64_t n, int width, int act, float drop_p, uint64_t drop_seed,
+                                    float* grad_pre, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(grad_y && y && grad_pre && width >= 1 && drop_p >= 0.f && drop_p < 1.f, "gat_out_glue_adjoint: bad arguments");
+  const int64_t total = n * width;
+  if (total == 0) return GAT_OK;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  out_glue_adjoint_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_y, y, n, width, act ? 1 : 0, drop_p, drop_seed, grad_pre);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }

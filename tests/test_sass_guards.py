@@ -24,6 +24,7 @@ pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path
 FWD = "edge_fwd_kernelILi32ELi2ELi4ELb0ELb0E"                      # products hidden layer, short rows
 BWD = "edge_bwd_main_kernelILi32ELi2ELi4ELb0ELb1ELb1ELb0ELb0E"     # fused backward, FULL rows
 BWD_GS = "edge_bwd_main_kernelILi32ELi2ELi4ELb0ELb1ELb0ELb1ELb0E"  # head-mean layer, staged rows
+BWD_HM = "edge_bwd_hm4_kernelILi3ELb1EE"                             # head-mean layer (4 heads), short rows: lane = (edge slot, head, quarter)
 GEMM_NT = "gemm_tc_kernelILi128ELb0E"
 GEMM_PAIR = "gemm_pair_kernel"
 
@@ -65,7 +66,7 @@ def _op(ins):
     return (t[1] if t[0].startswith("@") else t[0])
 
 
-@pytest.mark.parametrize("sub,max_regs", [(FWD, 80), (BWD, 80), (BWD_GS, 80), (GEMM_NT, 128), (GEMM_PAIR, 200)])
+@pytest.mark.parametrize("sub,max_regs", [(FWD, 80), (BWD, 80), (BWD_GS, 80), (BWD_HM, 80), (GEMM_NT, 128), (GEMM_PAIR, 200)])
 def test_hot_kernels_fit_their_register_budget_without_spills(resources, sub, max_regs):
     regs, stack = resources[_mangled(sub)]
     # the pair GEMM keeps one loop counter on the stack (8 bytes, outside the hot loops); everything else must be spill-free
@@ -112,3 +113,6 @@ def test_sass_carries_the_instructions_the_design_claims():
     assert "UBLKCP" in bwd or "BLKCP" in bwd                # cp.async.bulk row push (partitioned runs)
     gs = " ".join(_op(i) for i in _sass(BWD_GS))
     assert "LDGSTS" in gs                                   # cp.async staging of the narrow shared rows
+    hm = [_op(i) for i in _sass(BWD_HM)]
+    assert any(o.startswith("LDGSTS") for o in hm)          # the four-head head-mean kernel stages its gathers the same way
+    assert not any(o.startswith("BAR") for o in hm)         # and is warp-autonomous: no CTA barrier anywhere
