@@ -20,6 +20,8 @@ inter-layer glue (layer -> ELU, GATModel.py:120-151).  metric = layer-edges/s = 
            products-shaped graph (the reference formulation cannot allocate full scale, SURVEY
            5.7); the line's config states the N / E' / scale actually timed.  Falls back to the torch port
            (oracle/torch_port.py, kind "port") only when oracle/_ref/ is absent.
+  extra    (default single-GPU run only) the other figures of BASELINE.json's metric, driver-run in the same command: the four
+           small named shapes at 1 GPU (`named_shapes`, same method as --workload NAME) and the PPI epoch time (`ppi_epoch`)
   checksums / parity_vs_n1: loss, per-layer sum|dW| / sum|da| (fp64) and an order-independent bit checksum of the final
            output, printed for every N; at N > 1 rank 0 re-runs the single-GPU model on the same inputs after the timed
            region and reports the differences (forward must be bit-identical, gradients within reduction-order noise).
@@ -55,6 +57,7 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the named-shape lines and the PPI epoch appended to the default run")
     ap.add_argument("--unfused-glue", action="store_true", help="run the inter-layer ELU as separate torch kernels")
     ap.add_argument("--feature-dtype", default="f32", choices=["f32", "bf16"],
                     help="bf16: the opt-in variant whose per-edge gathers read bfloat16 copies (stated separately from the fp32 headline)")
@@ -317,6 +320,69 @@ def parity_vs_single_gpu(g, shapes, weights, x_host, ei_host, dev, args, multi, 
             "grad_max_rel_diff": grad_rel}
 
 
+def measure_named_shape(g, _lib, lib, name, dev, steps=20, warmup=5):
+    """One of the small BASELINE shapes (Cora / Pubmed / PPI x2 / PATTERN x128) on the product path, the way `--workload NAME`
+    times it: device-resident inputs, structure cached, 512 MB written between steps to flush L2, CUDA events per step."""
+    x_np, ei_np, shapes, weights = make_workload(name, 1.0)
+
+    class _A:
+        unfused_glue, feature_dtype = False, "f32"
+    model = SingleGpuModel(g, shapes, weights, dev, _A)
+    x, ei = torch.from_numpy(x_np).to(dev), torch.from_numpy(ei_np).to(dev)
+    e_prime = g.GLOBAL_CACHE.get(ei, x_np.shape[0], True).n_edges
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def timed_pass():
+        pairs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model.fwd_bwd(x, ei)
+            e1.record()
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in pairs)
+
+    for _ in range(warmup):
+        model.fwd_bwd(x, ei)
+    torch.cuda.synchronize()
+    l0 = lib.gat_launch_count()
+    ms = timed_pass() / steps
+    launches = int(lib.gat_launch_count() - l0) / steps
+    with _lib.KernelTimer() as kt:
+        model.fwd_bwd(x, ei)
+        torch.cuda.synchronize()
+        kt.records.clear()
+        ms_pk = timed_pass()
+    kernel_ms = sum(v["ms_total"] for v in kt.summary().values())
+    return {"graph": name, "n_nodes": int(x_np.shape[0]), "n_edges_rewritten": int(e_prime), "layers": [list(sh) for sh in shapes],
+            "ms_per_step": ms, "value": len(shapes) * e_prime / (ms * 1e-3), "unit": UNIT, "steps": steps, "warmup": warmup,
+            "gpu_launches_per_step": launches, "kernel_time_share_of_step_per_kernel_pass": kernel_ms / ms_pk if ms_pk else None}
+
+
+def extras(g, _lib, lib, dev):
+    """Appended to the default single-GPU line so that the other figures BASELINE.json's metric names are driver-run too: the
+    four small named shapes at 1 GPU and the PPI epoch time (tools/ppi_epoch.py: `PPI_GAT.training_step` in a plain loop)."""
+    out = {"named_shapes": [], "ppi_epoch": None}
+    for name in ("cora", "pubmed", "ppi", "pattern"):
+        try:
+            out["named_shapes"].append(measure_named_shape(g, _lib, lib, name, dev))
+        except Exception as exc:   # never lose the headline line over an extra
+            out["named_shapes"].append({"graph": name, "error": repr(exc)[:300]})
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ppi_epoch
+        data = ppi_epoch.batches(10)
+        secs, (loss, f1) = ppi_epoch.gpu_epoch(data, 2, 1.0)
+        out["ppi_epoch"] = {"metric": "ppi_epoch_time", "value": secs, "unit": "s", "higher_is_better": False, "steps_per_epoch": len(data),
+                            "attention_penalty": 1.0, "last_step": {"loss": loss, "train_f1": f1},
+                            "ms_per_step_breakdown_synchronised": {k: round(v, 3) for k, v in ppi_epoch.gpu_epoch.breakdown.items()}}
+    except Exception as exc:
+        out["ppi_epoch"] = {"error": repr(exc)[:300]}
+    return out
+
+
 def run_b200(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
@@ -499,6 +565,10 @@ def run_b200(args):
     total_kernel_ms = sum(v["ms_total"] for v in kernels.values())
     breakdown = {f"{k[0]}{'' if k[1] is None else list(k[1])}": round(v["ms_total"] / args.steps, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_total"])}
 
+    extra = None
+    if world == 1 and args.workload == "products" and not args.no_extras:
+        extra = extras(g, _lib, lib, dev)
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         step, e_cpu, l_cpu, n_cpu, kind = cpu_step_fn(args.workload, cpu_scale(args))
@@ -518,7 +588,7 @@ def run_b200(args):
                                                  scale=args.scale, layers=[list(s) for s in shapes]),
             "e2e": e2e, "checksums": sums, "parity_vs_n1": parity, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernels_ms_per_step": breakdown, "edge_kernels": per_kernel,
-            "kernel_time_share_of_step": total_kernel_ms / ms_total if ms_total else None}
+            "kernel_time_share_of_step": total_kernel_ms / ms_total if ms_total else None, "extra": extra}
     print(json.dumps(line), flush=True)
 
 

@@ -6,7 +6,8 @@ Only what the path needs lives here:
   graph.py         host side of the CSR / transposed-CSR builder + per-graph cache
   gat_layer.py     drop-in `GATLayer` (reference: models/gat_layer.py)
   glue.py          caller-side glue on the cached structure: GATModel.calc_attention_norm, the visualisation
-                   feed (per-node attention entropy, degree-scaled weights)
+                   feed (per-node attention entropy, degree-scaled weights), GATModel.forward with the skip add /
+                   ELU / input dropout between layers folded into the layers' kernels (model_forward)
   partition.py     destination-range partitioned layer for graphs spanning several GPUs
   synth.py         seeded synthetic graphs of the BASELINE shapes
   overlay/models/  namespace-package overlay so `from models.gat_layer import GATLayer` resolves here
@@ -16,8 +17,8 @@ through the `gat_pytorch_b200` shim module at the repository root.
 """
 from .gat_layer import GATLayer  # noqa: F401
 from .graph import GLOBAL_CACHE, GraphStructure, StructureCache, build_structure  # noqa: F401
-from .glue import attention_norm, degree_scaled_attention, neighbourhood_attention, neighbourhood_entropy  # noqa: F401
+from .glue import attention_norm, degree_scaled_attention, model_forward, neighbourhood_attention, neighbourhood_entropy  # noqa: F401
 from . import synth  # noqa: F401
 
 __all__ = ["GATLayer", "GraphStructure", "StructureCache", "build_structure", "GLOBAL_CACHE", "attention_norm", "neighbourhood_entropy",
-           "degree_scaled_attention", "neighbourhood_attention", "synth"]
+           "degree_scaled_attention", "neighbourhood_attention", "model_forward", "synth"]

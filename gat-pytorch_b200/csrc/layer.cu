@@ -35,6 +35,10 @@ struct FwdPlan {        // everything the backward needs again lives here (the "
 };
 
 bool needs_merge(const gat_layer_desc* d) { return d->fp != d->f || !d->concat; }
+// output glue (include/gat_b200.h): applied in the edge kernel's epilogue when the padded rows are the caller's rows, else
+// to the merged rows by the head-merge kernel
+bool has_glue(const gat_layer_desc* d) { return d->out_act || d->skip != nullptr || d->out_drop_p > 0.f; }
+int64_t out_width(const gat_layer_desc* d) { return d->concat ? (int64_t)d->nh * d->f : d->f; }
 
 void plan_fwd(const gat_layer_desc* d, Bump& b, FwdPlan& p) {
   const int64_t n = d->n, dp = (int64_t)d->nh * d->fp;
@@ -63,6 +67,7 @@ void plan_fwd(const gat_layer_desc* d, Bump& b, FwdPlan& p) {
 
 struct BwdPlan {
   float *go_p, *d_wh, *ds_src, *ds_tgt, *s_sum, *go_pre, *tpack, *rec, *gw_p, *ga_src_p, *ga_tgt_p;
+  float* grad_pre;      // dL/d(out + skip) in the caller's layout (glue applied to merged rows, or the three-pass backward)
   void* ws; size_t ws_bytes;
   void* gws; size_t gws_bytes;
   void* sws; size_t sws_bytes;
@@ -74,7 +79,10 @@ void plan_bwd(const gat_layer_desc* d, bool has_grad_alpha, bool want_gx, bool w
   const int64_t n = d->n, dp = (int64_t)d->nh * d->fp;
   const bool fused = !d->const_attention && !has_grad_alpha;
   p.go_shared = (!d->concat && d->nh > 1) ? 1 : 0;
-  p.go_is_user = !p.go_shared && !needs_merge(d) && !(d->out_act && !fused);
+  const bool glue = has_glue(d), glue_in_edge = glue && !needs_merge(d);
+  // the adjoint kernel runs wherever rowdot cannot apply it: merged rows, and the three-pass backward
+  p.grad_pre = (glue && !(glue_in_edge && fused)) ? b.take<float>((size_t)n * out_width(d)) : nullptr;
+  p.go_is_user = !p.go_shared && !needs_merge(d);
   p.go_p = p.go_is_user ? nullptr : b.take<float>((size_t)n * (p.go_shared ? d->fp : dp));
   p.d_wh = b.take<float>((size_t)n * dp);
   p.ds_src = p.ds_tgt = p.s_sum = p.go_pre = p.tpack = p.rec = nullptr;
@@ -83,7 +91,7 @@ void plan_bwd(const gat_layer_desc* d, bool has_grad_alpha, bool want_gx, bool w
     p.ds_tgt = b.take<float>((size_t)n * d->nh);
     p.s_sum = b.take<float>((size_t)n * d->nh);
     if (fused) {
-      if (d->out_act) p.go_pre = b.take<float>((size_t)n * dp);
+      if (glue_in_edge) p.go_pre = b.take<float>((size_t)n * dp);
       p.tpack = b.take<float>((size_t)n * gat_tgt_pack_stride(d->nh));
     } else {
       p.rec = b.take<float>((size_t)d->n_edges * 2 * d->nh);
@@ -113,7 +121,8 @@ int check_desc(const gat_layer_desc* d, const char* who, bool need_params = true
     return GAT_EINVAL;
   }
   if (need_params && (d->W == nullptr || (!d->const_attention && d->a == nullptr))) { set_error("%s: parameter pointer missing", who); return GAT_EINVAL; }
-  if (d->out_act && (!d->concat)) { set_error("%s: out_act is fused only for concat layers", who); return GAT_EINVAL; }
+  if (!(d->out_drop_p >= 0.f && d->out_drop_p < 1.f)) { set_error("%s: output dropout %f not in [0, 1)", who, d->out_drop_p); return GAT_EINVAL; }
+  if (d->skip != nullptr && d->ld_skip < out_width(d)) { set_error("%s: skip stride %lld below the output width", who, (long long)d->ld_skip); return GAT_EINVAL; }
   return GAT_OK;
 }
 
@@ -122,15 +131,6 @@ __global__ void layer_init_kernel(float* gmax, int32_t* ties, int64_t n_ties) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i == 0) *gmax = -INFINITY;
   for (int64_t j = i; j < n_ties; j += (int64_t)gridDim.x * blockDim.x) ties[j] = 0;
-}
-
-// dL/dout = dL/dh * ELU'(out) from the stored h = ELU(out): ELU' = 1 (h > 0) or h + 1.  Only on the path where an upstream
-// dL/dalpha arrives together with a fused output activation (the fused backward applies the adjoint inside rowdot).
-__global__ void elu_adjoint_kernel(const float* __restrict__ go, const float* __restrict__ h, float* __restrict__ out, int64_t count) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-    const float hv = h[i];
-    out[i] = go[i] * (hv > 0.f ? 1.f : hv + 1.f);
-  }
 }
 
 unsigned grid_for(int64_t elems) {
@@ -200,10 +200,22 @@ extern "C" int gat_layer_fwd(const gat_layer_desc* d, const float* x, int64_t ld
     }
     GAT_TRY(gat_edge_max(d->rowptr, d->col, d->order, d->n_long, n, p.s_src, p.s_tgt, d->nh, p.gmax, p.fws, p.fws_bytes, stream));
   }
-  GAT_TRY(gat_edge_fwd(d->rowptr, d->col, d->eid, d->order, d->n_long, n, p.wh, d->nh, d->fp, p.s_src, p.s_tgt, p.gmax,
-                       d->const_attention, d->p_drop, d->seed, 0, out_p, d->out_act, alpha, p.z, tie_dst, tie_src, tie_total,
-                       p.fws, p.fws_bytes, stream));
-  if (!p.out_is_user) GAT_TRY(gat_head_merge_fwd(out_p, n, d->nh, d->f, d->fp, d->concat, out, stream));
+  const bool glue = has_glue(d);
+  if (glue && p.out_is_user) {
+    // a skip matrix whose rows cannot be read as float4 (odd stride / alignment) is not expected from torch; reject it loudly
+    GAT_TRY(gat_edge_fwd_glue(d->rowptr, d->col, d->eid, d->order, d->n_long, n, p.wh, d->nh, d->fp, p.s_src, p.s_tgt, p.gmax,
+                              d->const_attention, d->p_drop, d->seed, 0, out_p, d->out_act, d->skip, d->ld_skip, d->out_drop_p,
+                              d->out_drop_seed, alpha, p.z, tie_dst, tie_src, tie_total, p.fws, p.fws_bytes, stream));
+  } else {
+    GAT_TRY(gat_edge_fwd(d->rowptr, d->col, d->eid, d->order, d->n_long, n, p.wh, d->nh, d->fp, p.s_src, p.s_tgt, p.gmax,
+                         d->const_attention, d->p_drop, d->seed, 0, out_p, 0, alpha, p.z, tie_dst, tie_src, tie_total,
+                         p.fws, p.fws_bytes, stream));
+  }
+  if (!p.out_is_user) {
+    if (glue) GAT_TRY(gat_head_merge_fwd_glue(out_p, n, d->nh, d->f, d->fp, d->concat, d->skip, d->ld_skip, d->out_act, d->out_drop_p,
+                                              d->out_drop_seed, out, stream));
+    else GAT_TRY(gat_head_merge_fwd(out_p, n, d->nh, d->f, d->fp, d->concat, out, stream));
+  }
   return GAT_OK;
 }
 
@@ -236,24 +248,35 @@ extern "C" int gat_layer_bwd(const gat_layer_desc* d, const float* x, int64_t ld
     tie_dst = f.ties + 2;
     tie_src = f.ties + 2 + n * d->nh;
   }
+  // output glue: dL/d(out + skip) from dL/dy and the stored y = `out` -- inside rowdot when the glue ran in the edge kernel and
+  // the one-pass backward follows, by the element-wise adjoint kernel otherwise; either way it is also dL/dskip
+  const bool glue = has_glue(d), glue_in_edge = glue && f.out_is_user;
+  GAT_CHECK_ARG(!glue || out != nullptr, "gat_layer_bwd: the forward's output y is needed for the output glue (out)");
+  const float* go_user = grad_out;
+  if (glue && !(glue_in_edge && fused)) {
+    float* gp = d->grad_skip ? d->grad_skip : p.grad_pre;
+    GAT_TRY(gat_out_glue_adjoint(grad_out, out, n, (int)out_width(d), d->out_act, d->out_drop_p, d->out_drop_seed, gp, stream));
+    go_user = gp;
+  }
   // upstream gradient -> padded-head layout (shared single row for a head mean)
-  const float* go = grad_out;
+  const float* go = go_user;
   if (p.go_shared) {
-    GAT_TRY(gat_head_mean_bwd_shared(grad_out, n, d->nh, d->f, d->fp, p.go_p, stream));
+    GAT_TRY(gat_head_mean_bwd_shared(go_user, n, d->nh, d->f, d->fp, p.go_p, stream));
     go = p.go_p;
   } else if (needs_merge(d)) {
-    GAT_TRY(gat_head_merge_bwd(grad_out, n, d->nh, d->f, d->fp, d->concat, p.go_p, stream));
-    go = p.go_p;
-  }
-  if (d->out_act && !fused) {
-    elu_adjoint_kernel<<<grid_for(n * dp), 256, 0, st>>>(go, out_p, p.go_p, n * dp);
-    GAT_LAUNCH_CHECK();
+    GAT_TRY(gat_head_merge_bwd(go_user, n, d->nh, d->f, d->fp, d->concat, p.go_p, stream));
     go = p.go_p;
   }
   if (fused) {
-    GAT_TRY(gat_edge_bwd_rowdot(go, p.go_shared, out_p, d->out_act, p.go_pre, f.z, n, d->nh, d->fp, p.s_sum, p.ds_tgt, f.s_tgt, p.tpack,
-                                p.ws, p.ws_bytes, stream));
-    if (d->out_act) go = p.go_pre;
+    if (glue_in_edge) {
+      float* go_pre = d->grad_skip ? d->grad_skip : p.go_pre;
+      GAT_TRY(gat_edge_bwd_rowdot_glue(go, out_p, d->out_act, d->skip, d->ld_skip, d->out_drop_p, d->out_drop_seed, go_pre, f.z, n, d->nh,
+                                       d->fp, p.s_sum, p.ds_tgt, f.s_tgt, p.tpack, p.ws, p.ws_bytes, stream));
+      go = go_pre;
+    } else {
+      GAT_TRY(gat_edge_bwd_rowdot(go, p.go_shared, out_p, 0, nullptr, f.z, n, d->nh, d->fp, p.s_sum, p.ds_tgt, f.s_tgt, p.tpack,
+                                  p.ws, p.ws_bytes, stream));
+    }
     GAT_TRY(gat_edge_bwd_fused(d->rowptr_t, d->col_t, d->pos_t, d->order_t, d->n_long_t, d->eid, n, f.wh, d->nh, d->fp, f.s_src, f.s_tgt,
                                f.gmax, f.z, d->p_drop, d->seed, 0, go, p.go_shared, p.s_sum, p.tpack, f.a_src_p, f.a_tgt_p,
                                tie_dst, tie_src, tie_total, nullptr, 0, n, p.ds_src, p.ds_tgt, p.d_wh, nullptr, 0, 0, 0,

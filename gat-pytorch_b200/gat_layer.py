@@ -206,14 +206,15 @@ class _GATLayerFunction(torch.autograd.Function):
     arena tensor.  Same arithmetic, same kernels as _GATFunction; used whenever no per-kernel timer is active."""
 
     @staticmethod
-    def forward(ctx, x, w, a, st: GraphStructure, desc_proto, arena_bytes, d_out, want_alpha):
+    def forward(ctx, x, w, a, skip, st: GraphStructure, desc_proto, arena_bytes, d_out, want_alpha):
         lib = _lib.load()
         dev = x.device
         n = x.size(0)
-        needs_grad = any(ctx.needs_input_grad[:3])
+        needs_grad = any(ctx.needs_input_grad[:4])
         desc = _lib.LayerDesc.from_buffer_copy(desc_proto)     # this call's own copy (seed, parameter pointers)
         desc.W = w.data_ptr()
         desc.a = None if a is None else a.data_ptr()
+        desc.skip, desc.ld_skip, desc.grad_skip = (None, 0, None) if skip is None else (skip.data_ptr(), skip.stride(0), None)
         with torch.cuda.device(dev):
             arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
             out = torch.empty((n, d_out), dtype=torch.float32, device=dev)
@@ -222,7 +223,7 @@ class _GATLayerFunction(torch.autograd.Function):
                                    _ptr(alpha), int(needs_grad), _stream(dev))
             _lib.check(rc, "gat_layer_fwd")
         ctx.st, ctx.desc = st, desc
-        ctx.save_for_backward(x, w, a, arena, out)
+        ctx.save_for_backward(x, w, a, arena, out, skip)
         if alpha is None:
             return out, None
         return out, alpha
@@ -230,7 +231,7 @@ class _GATLayerFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, grad_alpha):
         lib = _lib.load()
-        x, w, a, arena, out = ctx.saved_tensors
+        x, w, a, arena, out, skip = ctx.saved_tensors
         desc = ctx.desc
         dev = x.device
         with torch.cuda.device(dev):
@@ -246,10 +247,13 @@ class _GATLayerFunction(torch.autograd.Function):
             gx = torch.empty_like(x) if want[0] else None
             gw = torch.empty_like(w) if want[1] else None
             ga = torch.empty_like(a) if want_ga else None
+            gskip = torch.empty_like(out) if (skip is not None and want[3]) else None
+            desc.grad_skip = _ptr(gskip)
             rc = lib.gat_layer_bwd(ctypes.byref(desc), x.data_ptr(), x.stride(0), arena.data_ptr(), out.data_ptr(), grad_out.data_ptr(),
                                    _ptr(grad_alpha), scratch.data_ptr(), sb, _ptr(gx), _ptr(gw), _ptr(ga), _stream(dev))
+            desc.grad_skip = None
             _lib.check(rc, "gat_layer_bwd")
-        return gx, gw, ga, None, None, None, None, None
+        return gx, gw, ga, gskip, None, None, None, None, None
 
 
 class GATLayer(nn.Module):
@@ -298,6 +302,11 @@ class GATLayer(nn.Module):
         # the cheaper of the two fusions (measured, profiles/README.md); concat layers without bias only (ELU does not
         # commute with the head mean).
         self.output_activation = None
+        # The rest of the output glue (include/gat_b200.h "OUTPUT GLUE"): `output_dropout` = p makes a training-mode forward
+        # return dropout_p(ELU?(out + skip)) -- the NEXT layer's input dropout (GATModel.py:130) applied where this layer's
+        # output is written, Philox mask regenerated in the backward -- and forward(..., skip=t) adds the skip connection's
+        # rows (GATModel.py:135-145; for a head-mean layer the caller passes skip_output.mean(dim=1)) before the activation.
+        self.output_dropout = 0.0
         # Opt-in bf16 variant (BASELINE.json north_star "bf16 variant stated separately"): "bf16" makes the edge kernels gather
         # bfloat16 copies of Wh (forward) and of dL/dout (fused backward) -- half the bytes per edge, fp32 accumulation,
         # ~2e-3 relative error.  None (default) = fp32 everywhere, the 1e-5 parity path.  NH <= 4 and padded rows of
@@ -346,10 +355,13 @@ class GATLayer(nn.Module):
             hit = [st, d, None, None]
             cache[id(st)] = hit
         d = hit[1]
-        d.x_act, d.out_act, d.gemm_algo = int(self._x_act()), int(self._out_act()), int(self.gemm_algo)
-        d.W = d.a = None          # set per call from the tensors actually used (functional_call may substitute them)
+        d.x_act, d.out_act, d.gemm_algo = int(self._x_act()), int(self._out_act(one_call=True)), int(self.gemm_algo)
+        d.W = d.a = d.skip = d.grad_skip = None   # set per call from the tensors actually used (functional_call may substitute them)
+        d.ld_skip = 0
         d.p_drop = p_drop
         d.seed = int(torch.empty((), dtype=torch.int64).random_().item()) if p_drop > 0.0 else 0   # CPU generator: no device sync
+        d.out_drop_p = self._out_drop()
+        d.out_drop_seed = int(torch.empty((), dtype=torch.int64).random_().item()) if d.out_drop_p > 0.0 else 0
         key = (d.x_act, d.out_act, d.gemm_algo)
         if hit[2] != key:
             hit[2], hit[3] = key, int(_lib.load().gat_layer_fwd_arena_bytes(ctypes.byref(d)))
@@ -371,14 +383,25 @@ class GATLayer(nn.Module):
             raise ValueError(f"feature_dtype must be None or 'bf16', got {self.feature_dtype!r}")
         return True
 
-    def _out_act(self) -> bool:
+    def _out_act(self, one_call: bool = False) -> bool:
         if self.output_activation in (None, "none"):
             return False
         if self.output_activation != "elu":
             raise ValueError(f"output_activation must be None or 'elu', got {self.output_activation!r}")
-        if not self.concat or self.bias:
-            raise ValueError("output_activation='elu' is fused only for concat layers without bias (apply F.elu outside otherwise)")
+        if self.bias:
+            raise ValueError("output_activation='elu' is fused only for layers without bias (apply F.elu outside otherwise)")
+        if not self.concat and not one_call:
+            raise ValueError("output_activation='elu' on a head-mean layer is applied by the merge kernel of the one-call path only "
+                             "(not under a per-kernel timer / the bf16 variant)")
         return True
+
+    def _out_drop(self) -> float:
+        p = float(self.output_dropout or 0.0)
+        if not 0.0 <= p < 1.0:
+            raise ValueError(f"output_dropout must be in [0, 1), got {p}")
+        if p > 0.0 and self.bias:
+            raise ValueError("output_dropout is fused only for layers without bias")
+        return p if self.training else 0.0
 
     def _forward_host_buffers(self, x, edge_index, return_attention_weights):
         """HOST-BUFFER mode: a module and inputs that live in host memory (what the reference's own `vis.py` hands the layer:
@@ -411,10 +434,12 @@ class GATLayer(nn.Module):
         self.normalised_attention_coeffs = None
         return res.to(x.device)
 
-    def forward(self, x, edge_index, return_attention_weights=False):
+    def forward(self, x, edge_index, return_attention_weights=False, skip=None):
         if not x.is_cuda:
             if not torch.cuda.is_available():
                 raise RuntimeError("gat_b200.GATLayer runs on CUDA (sm_100a) only; there is no CPU fallback")
+            if skip is not None:
+                raise NotImplementedError("skip= is not available in host-buffer mode")
             return self._forward_host_buffers(x, edge_index, return_attention_weights)
         if x.dtype != torch.float32:
             raise RuntimeError(f"expected float32 node features, got {x.dtype}")   # the reference raises a dtype mismatch
@@ -437,6 +462,17 @@ class GATLayer(nn.Module):
         drop_all = p_drop >= 1.0      # nn.Dropout(p=1) zeroes every coefficient (gat_layer.py:113-115): out = 0, alpha intact
         if drop_all:
             p_drop = 0.0
+        if skip is not None:
+            d_out = self.num_heads * self.out_features if self.concat else self.out_features
+            if skip.device != x.device or skip.dtype != torch.float32 or tuple(skip.shape) != (x.size(0), d_out):
+                raise RuntimeError(f"skip must be a float32 ({x.size(0)}, {d_out}) tensor on {x.device}")
+            if self.bias:
+                raise ValueError("skip= is fused only for layers without bias")
+            if skip.stride(1) != 1 or skip.stride(0) % 4 != 0 or skip.data_ptr() % 16 != 0:
+                skip = skip.contiguous()
+        if per_kernel and (skip is not None or self._out_drop() > 0.0):
+            raise NotImplementedError("skip= / output_dropout are implemented by the one-call path (gat_layer_fwd); not available under a "
+                                      "per-kernel timer or with the bf16 variant")
         if per_kernel:
             # per-kernel path: the bf16 variant and runs under a per-kernel timer (bench.py's live roofline measurement)
             out, alpha = _GATFunction.apply(x, w_p, a_src, a_tgt, st, self.num_heads, self.out_features, fp,
@@ -447,7 +483,7 @@ class GATLayer(nn.Module):
             desc, arena_bytes = self._layer_desc(st, fp, p_drop)
             d_out = self.num_heads * self.out_features if self.concat else self.out_features
             out, alpha = _GATLayerFunction.apply(x, self.W.weight.contiguous(),
-                                                 None if self.const_attention else self.a.weight.contiguous(), st, desc,
+                                                 None if self.const_attention else self.a.weight.contiguous(), skip, st, desc,
                                                  arena_bytes, d_out, bool(return_attention_weights))
         if drop_all:
             out = out * 0.0

@@ -70,6 +70,61 @@ def attention_norm(edge_index: torch.Tensor, attention_list, n_nodes: int | None
     return total / len(attention_list)
 
 
+def model_forward(model, data, return_attention_weights=None):
+    """`GATModel.forward` (GATModel.py:118-151) / `GATModel.forward_and_return_attention` (:153-187) for a model whose
+    `gat_layer_list` holds B200 `GATLayer`s, with the inter-layer glue folded into the layers' kernels:
+
+      * the skip connection's rows (Identity / Linear of the layer input, head-averaged for a head-mean layer, :135-145) are
+        added where the layer's output is written (`forward(..., skip=)`),
+      * the ELU between layers (:148-149) is applied in the same place (`output_activation`),
+      * the NEXT layer's input dropout (:130) as well (`output_dropout`, Philox mask regenerated in the backward) -- unless that
+        layer has a skip connection and therefore needs the undropped tensor too; then, and for the raw input of the first
+        layer, the dropout stays a torch op.
+
+    `return_attention_weights=None` returns what `forward` returns (the output); True / False what
+    `forward_and_return_attention(data, flag)` returns: `(x, edge_index, attention_weights_list)`.  Same arithmetic as the
+    reference's op-by-op sequence; the layers' own attributes are restored before returning, so the unchanged callers keep
+    working on the same modules."""
+    import torch.nn.functional as F
+    x, edge_index = data.x, data.edge_index
+    layers = model.gat_layer_list
+    n_layers = len(layers)
+    p = float(model.dropout) if model.training else 0.0
+    want_attention = bool(return_attention_weights)
+    attention, skip_count, dropped = [], 0, False
+    for i, layer in enumerate(layers):
+        layer_input = x
+        if p > 0.0 and not dropped:
+            x = F.dropout(x, p=p, training=True)
+        skip = None
+        if model.add_skip_connection[i]:
+            skip = model.skip_layer_list[skip_count](layer_input)
+            skip_count += 1
+            if not model.heads_concat_per_layer[i]:
+                skip = skip.view(-1, model.num_heads_per_layer[i + 1], model.head_output_features_per_layer[i + 1]).mean(dim=1)
+        last = i == n_layers - 1
+        fold_dropout = (not last) and p > 0.0 and not model.add_skip_connection[i + 1]
+        saved = (layer.output_activation, layer.output_dropout)
+        layer.output_activation, layer.output_dropout = (None if last else "elu"), (p if fold_dropout else 0.0)
+        try:
+            if return_attention_weights is None:
+                x = layer(x, edge_index, skip=skip)
+            else:
+                res = layer(x, edge_index, return_attention_weights=want_attention, skip=skip)
+                if want_attention:
+                    x, (edge_index, alpha) = res
+                    attention.append(alpha)
+                else:       # the reference unpacks a tuple here and fails for False (GATModel.py:166); this path just works
+                    x = res
+                    attention.append(None)
+        finally:
+            layer.output_activation, layer.output_dropout = saved
+        dropped = fold_dropout
+    if return_attention_weights is None:
+        return x
+    return x, edge_index, attention
+
+
 def _structure_for(edge_index: torch.Tensor, n_nodes: int | None, who: str):
     if not edge_index.is_cuda:
         raise RuntimeError(f"gat_b200.{who} runs on CUDA only; there is no CPU fallback")

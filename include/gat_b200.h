@@ -175,6 +175,21 @@ GAT_API int gat_edge_fwd(const int32_t* rowptr, const int32_t* col, const int32_
                  int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
                  void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
+/* OUTPUT GLUE (opt-in): everything GATModel.forward does between this layer and the next one --
+ *     x_next = dropout_p( ELU( layer(x) + skip ) )          GATModel.py:130 (next layer's input dropout), :135-145 (skip add), :148-149
+ * -- folded into the kernel that writes the layer's output, so no (n, D) pass of its own exists in either direction:
+ *     y[i, c] = keep(i, c) * E(out[i, c] + skip[i, c]),   E = ELU (out_act) or identity, keep = 0 or 1/(1 - out_drop_p) from Philox keyed
+ *     on (out_drop_seed, row i, column c / 4) -- the mask is never stored, the backward regenerates it.
+ * gat_edge_fwd_glue = gat_edge_fwd with the whole glue in its epilogue, for layers whose padded rows ARE the caller's rows
+ * (concat, F % 4 == 0); `skip` (n, ld_skip >= nh*fp) is indexed like `out`, 16-byte aligned rows, or NULL. */
+GAT_API int gat_edge_fwd_glue(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
+                 int64_t n, const float* wh, int nh, int fp, const float* s_src, const float* s_tgt,
+                 const float* gmax, int const_attention, float dropout_p, uint64_t seed, uint64_t offset,
+                 float* out, int out_act, const float* skip, int64_t ld_skip, float out_drop_p, uint64_t out_drop_seed,
+                 float* alpha_out, float* z_out,
+                 int32_t* tie_dst, int32_t* tie_src, unsigned long long* tie_total,
+                 void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
 /* Head merge (gat_layer.py:129-132): padded (n, nh, fp) -> (n, nh*f) concat or (n, f) head mean. */
 GAT_API int gat_head_merge_fwd(const float* o_padded, int64_t n, int nh, int f, int fp, int concat,
                        float* out, gat_stream_t stream);
@@ -259,6 +274,26 @@ GAT_API int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const flo
                                 const float* z, int64_t n_rows, int nh, int fp,
                                 float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
                                 void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
+/* gat_edge_bwd_rowdot behind gat_edge_fwd_glue: y_padded holds y = keep * E(out + skip) and go_padded is dL/dy; the pass
+ * regenerates the mask, recovers out = E^-1(y * (1 - drop_p)) - skip, writes dL/d(out + skip) = go * keep * E' to go_out
+ * (n_rows, nh*fp) -- which is ALSO dL/dskip, and the buffer the source-major pass gathers -- and uses both in S. */
+GAT_API int gat_edge_bwd_rowdot_glue(const float* go_padded, const float* y_padded, int out_is_act, const float* skip, int64_t ld_skip,
+                                     float drop_p, uint64_t drop_seed, float* go_out,
+                                     const float* z, int64_t n_rows, int nh, int fp,
+                                     float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
+                                     void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
+/* The output glue for layers whose padded rows are NOT the caller's rows (head-mean layers, F % 4 != 0): applied to the
+ * merged row, out[i, c] = keep * E(merge(o_padded)[i, c] + skip[i, c]), skip (n, ld_skip >= width) or NULL. */
+GAT_API int gat_head_merge_fwd_glue(const float* o_padded, int64_t n, int nh, int f, int fp, int concat,
+                                    const float* skip, int64_t ld_skip, int act, float drop_p, uint64_t drop_seed, float* out,
+                                    gat_stream_t stream);
+
+/* Adjoint of the output glue, element-wise over an (n, width) matrix: grad_pre = dL/d(out + skip) (= dL/dskip) from grad_y = dL/dy
+ * and the stored y.  Used where the glue was applied to merged rows, and on the three-pass backward (upstream dL/dalpha). */
+GAT_API int gat_out_glue_adjoint(const float* grad_y, const float* y, int64_t n, int width, int act, float drop_p, uint64_t drop_seed,
+                                 float* grad_pre, gat_stream_t stream);
 
 /* Partitioned graphs only: *gamma_out = this rank's Gamma.  The caller all-reduces Gamma and tie_total over ranks and hands
  * Gamma/|T| to gat_edge_bwd_finish as `corr_override` (a device scalar).  On one GPU pass corr_override = NULL. */
@@ -367,6 +402,9 @@ GAT_API int gat_unpack_param_grads(const float* gW_p, const float* ga_src_p, con
  *   scratch    gat_layer_bwd_scratch_bytes(...) bytes, 256-byte aligned, dead after the call;
  *   grad_alpha (n_edges, NH) or NULL (then the backward is rowdot + ONE fused source-major pass);
  *   gx (n, F_in) / gW (NH*F, F_in) / ga (NH, NH*2F): outputs, each may be NULL when not needed.
+ * Output glue (see gat_edge_fwd_glue): out_act, skip (n, ld_skip; same columns as `out`), out_drop_p / out_drop_seed make
+ * gat_layer_fwd return y = keep * E(out + skip); gat_layer_bwd then takes grad_out = dL/dy, `out` = y, and writes dL/dskip
+ * (n, width of out; contiguous) to grad_skip when it is not NULL.
  * ------------------------------------------------------------------------------------- */
 typedef struct gat_layer_desc {
   const int32_t *rowptr, *col, *eid, *order;            /* CSR by target + scheduling permutation */
@@ -380,6 +418,11 @@ typedef struct gat_layer_desc {
   float p_drop;                                         /* 0 outside training */
   uint64_t seed;
   const float *W, *a;                                   /* reference layouts; a = NULL for const_attention */
+  const float* skip;                                    /* output glue: rows added before the activation, or NULL */
+  int64_t ld_skip;
+  float out_drop_p;                                     /* output glue: dropout of the stored output (the next layer's input dropout) */
+  uint64_t out_drop_seed;
+  float* grad_skip;                                     /* gat_layer_bwd: dL/dskip output, or NULL */
 } gat_layer_desc;
 
 GAT_API size_t gat_layer_fwd_arena_bytes(const gat_layer_desc* desc);

@@ -2,7 +2,7 @@
 # Full-set + per-instruction capture of a few named kernels of one steady-state bench step (1 GPU), summarised on the box.
 #   bash tools/profile_kernels.sh <tag> '<kernel regex>' <skip> <count> '<source-page regex 1>' ['<source-page regex 2>' ...]
 tag=$1; regex=$2; skip=$3; count=$4; shift 4
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_${tag}.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k "regex:${regex}" -s ${skip} -c ${count} -f -o /tmp/prof_${tag} $CMD > gpurun_out/ncu_full_${tag}.log 2>&1

@@ -4,7 +4,7 @@
 # The .ncu-rep files are summarised ON THE BOX (tools/ncu_summary.py -> CSV) and removed, so that what travels back in
 # gpurun_out/ stays small: launches_<tag>.csv, ncu_<tag>_kernels.csv, ncu_<tag>_top_source.csv.
 tag=${1:-r01}
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_${tag}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_${tag}.csv $CMD > gpurun_out/ncu_launch_${tag}.log 2>&1 &&
