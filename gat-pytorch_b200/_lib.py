@@ -26,7 +26,8 @@ class LayerDesc(ctypes.Structure):
         ("nh", ctypes.c_int32), ("f", ctypes.c_int32), ("fp", ctypes.c_int32),
         ("concat", ctypes.c_int32), ("const_attention", ctypes.c_int32), ("x_act", ctypes.c_int32), ("out_act", ctypes.c_int32),
         ("gemm_algo", ctypes.c_int32), ("p_drop", c_float), ("seed", c_uint64), ("W", c_void_p), ("a", c_void_p),
-        ("skip", c_void_p), ("ld_skip", c_int64), ("out_drop_p", c_float), ("out_drop_seed", c_uint64), ("grad_skip", c_void_p)]
+        ("skip", c_void_p), ("ld_skip", c_int64), ("out_drop_p", c_float), ("out_drop_seed", c_uint64), ("grad_skip", c_void_p),
+        ("norm_out", c_void_p), ("grad_norm", c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/gat_b200.h one to one.
@@ -58,8 +59,12 @@ SIGNATURES = {
                              _P, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_fwd_glue": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, c_int, c_int, _P, _P, _P, c_int, c_float, c_uint64, c_uint64,
                                   _P, c_int, _P, c_int64, c_float, c_uint64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "gat_edge_bwd_rowdot_glue": (c_int, [_P, _P, c_int, _P, c_int64, c_float, c_uint64, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P,
-                                         _P, c_size_t, _P]),
+    "gat_edge_bwd_rowdot_glue": (c_int, [_P, c_int, _P, c_int, _P, c_int64, c_float, c_uint64, _P, _P, _P, _P, c_float,
+                                         _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gat_edge_bwd_fused_norm": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P,
+                                        c_float, c_uint64, c_uint64, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float,
+                                        _P, _P, _P, _P, c_size_t, _P]),
+    "gat_attention_norm_scores": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "gat_head_merge_fwd_glue": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, c_int, c_float, c_uint64, _P, _P]),
     "gat_out_glue_adjoint": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, c_uint64, _P, _P]),
     "gat_head_merge_fwd": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),

@@ -76,6 +76,10 @@ struct BwdMainParams {
   // 4.4 ms pass); rank r starts at the slab of owner r+1 instead.
   int64_t sched_rot;
   int go_bf16;               // host-side switch: launch the BF16 instantiation (go is a bfloat16 matrix)
+  // attention-norm regulariser fused: the loss carries c * |alpha*deg - 1|_1 with c = *norm_coef * norm_scale
+  // (upstream gradient of the layer's norm, device scalar, times 1/E'); dL/dalpha[e,h] = c*deg(d)*sign(alpha*deg(d) - 1) is
+  // formed here from the recomputed alpha and deg(d) -- float 3*NHT of the target's record -- and S[d] already includes its share
+  const float* norm_coef; float norm_scale;
 };
 
 __device__ __forceinline__ float* dwh_row_ptr(const BwdMainParams& P, const int64_t row) {
@@ -217,6 +221,14 @@ __device__ __forceinline__ void bwd_main_row(const BwdMainParams& P, const LaneS
 #pragma unroll
           for (int h = 0; h < NHT; ++h)
             if (h < nh) alpha[h] = attn_exp(ss[h] + tv[h], gmax) / (zv[h] + kSoftmaxEps);
+          if (P.norm_coef != nullptr) {   // g = 0.01*alpha*(m*<dOut,Wh> + dL/dalpha - S): fold dL/dalpha into the S term
+            const float cn = __ldg(P.norm_coef) * P.norm_scale, deg = __ldg(pk + 3 * NHT);
+#pragma unroll
+            for (int h = 0; h < NHT; ++h) {
+              const float u = alpha[h] * deg - 1.0f;
+              sv[h] -= u > 0.f ? cn * deg : (u < 0.f ? -cn * deg : 0.f);
+            }
+          }
         } else {
           if (FUSED) {   // S[dst] travels with s_tgt[dst] / Z[dst] (same round trip) and waits in shared memory
             const float* sp = P.s_sum + (int64_t)d * nh;
@@ -664,6 +676,8 @@ struct BwdRowdotParams {
   int out_is_act; float* go_out;
   // the rest of the output glue (common.cuh): `out` holds y = keep * E(out + skip); `glue` is set when any part is active
   int glue; const float* skip; int64_t ld_skip; float drop_p; uint64_t drop_seed;
+  // fused attention-norm regulariser: S[d,h] += c * deg(d) * norm_t[d,h]; deg(d) is also packed into the target's record
+  const int32_t* rowptr; const float* norm_t; const float* norm_coef; float norm_scale;
   float* s_sum; float* ds_tgt;
   const float* s_tgt; float* tpack;   // optional: write the per-target record {s_tgt | Z | S} for gat_edge_bwd_fused
 };
@@ -674,7 +688,9 @@ __device__ __forceinline__ float log1p_neg_fast(float h) {
   return h > -1e-3f ? h * fmaf(h, fmaf(h, 0.33333334f, -0.5f), 1.0f) : __logf(1.0f + h);
 }
 
-template <int NHT>
+// FULLGLUE: skip rows and / or output dropout are part of the glue (Philox per chunk: its registers stay out of the plain
+// instantiation, which the headline's hidden layers run with the ELU adjoint only).
+template <int NHT, bool FULLGLUE>
 __global__ void __launch_bounds__(256)
 edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
   constexpr int R = 4;   // rows per warp iteration: 2*R*chunks/32 independent 16-byte loads in flight per lane
@@ -702,7 +718,22 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
         g[r] = on ? ldg4(P.go + (row0 + r) * P.go_ld + (P.go_shared ? gc : c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         o[r] = on ? ldg4(P.out + (row0 + r) * P.dp + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (P.glue) {
+      if (!FULLGLUE && P.out_is_act) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float* gv = reinterpret_cast<float*>(&g[r]);
+          float* ov = reinterpret_cast<float*>(&o[r]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float h = ov[j];
+            const bool neg = h <= 0.f;
+            gv[j] = neg ? gv[j] * (h + 1.0f) : gv[j];      // dL/dout = dL/dh * ELU'(out)
+            ov[j] = neg ? log1p_neg_fast(h) : h;           // out recovered from h = ELU(out)
+          }
+          if (row0 + r < P.n) *reinterpret_cast<float4*>(P.go_out + (row0 + r) * P.dp + c * 4) = g[r];
+        }
+      }
+      if (FULLGLUE) {
         const float omp = 1.0f - P.drop_p;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -743,10 +774,16 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
       }
       if (lane == 0 && row0 + r < P.n) {
         float zrow[NHT], trow[NHT], srow[NHT];
+        float deg = 0.f, cdeg = 0.f;
+        if (P.rowptr) {
+          deg = (float)(__ldg(P.rowptr + row0 + r + 1) - __ldg(P.rowptr + row0 + r));
+          if (P.norm_coef) cdeg = __ldg(P.norm_coef) * P.norm_scale * deg;
+        }
 #pragma unroll
         for (int h = 0; h < NHT; ++h) {
           zrow[h] = 0.f; trow[h] = 0.f; srow[h] = 0.f;
           if (h < nh) {
+            if (P.norm_t) s[r][h] = fmaf(cdeg, __ldg(P.norm_t + (row0 + r) * nh + h), s[r][h]);
             const float zz = __ldg(P.z + (row0 + r) * nh + h);
             P.s_sum[(row0 + r) * nh + h] = s[r][h];
             P.ds_tgt[(row0 + r) * nh + h] = kLeakySlope * s[r][h] * (kSoftmaxEps / (zz + kSoftmaxEps));
@@ -762,6 +799,7 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
             *reinterpret_cast<float4*>(pk + NHT + 4 * q) = make_float4(zrow[4 * q], zrow[4 * q + 1], zrow[4 * q + 2], zrow[4 * q + 3]);
             *reinterpret_cast<float4*>(pk + 2 * NHT + 4 * q) = make_float4(srow[4 * q], srow[4 * q + 1], srow[4 * q + 2], srow[4 * q + 3]);
           }
+          if (P.rowptr) pk[3 * NHT] = deg;
         }
       }
     }
@@ -1155,9 +1193,11 @@ static int edge_bwd_fused_impl(bool go_bf16, const int32_t* rowptr_t, const int3
                                   const float* corr_override, int64_t tgt_lo, int64_t tgt_hi,
                                   float* ds_src, float* ds_tgt, float* d_wh,
                                   float* const* h_push_dst, int n_push, int my_rank, int64_t rows_per_rank,
-                                  void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+                                  void* workspace, size_t workspace_bytes, gat_stream_t stream,
+                                  const float* norm_coef = nullptr, float norm_scale = 0.f) {
   using namespace gat;
   int rc = check_common("gat_edge_bwd_fused", nh, fp, workspace, workspace_bytes);
+  GAT_CHECK_ARG(norm_coef == nullptr || (tgt_pack != nullptr && !go_bf16), "gat_edge_bwd_fused_norm: needs the per-target records (tgt_pack)");
   if (rc) return rc;
   GAT_CHECK_ARG(s_src && gmax && (tgt_pack || (s_tgt && z && s_sum)) && a_src && a_tgt && ds_src && ds_tgt && (d_wh || n_push > 0),
                 "gat_edge_bwd_fused: buffers missing");
@@ -1184,6 +1224,7 @@ static int edge_bwd_fused_impl(bool go_bf16, const int32_t* rowptr_t, const int3
   P.corr_override = corr_override; P.tgt_lo = tgt_lo; P.tgt_hi = tgt_hi; P.ds_src = ds_src; P.ds_tgt = ds_tgt;
   P.push = n_push > 0; P.my_rank = my_rank; P.rows_per_rank = rows_per_rank > 0 ? rows_per_rank : 1;
   P.go_bf16 = go_bf16 ? 1 : 0;
+  P.norm_coef = norm_coef; P.norm_scale = norm_scale;
   for (int q = 0; q < n_push; ++q) P.push_dst[q] = h_push_dst[q];
   return launch_bwd_main<true>(P, row_order_t, n_long, n_rows, st);
 }
@@ -1202,6 +1243,23 @@ extern "C" int gat_edge_bwd_fused(const int32_t* rowptr_t, const int32_t* col_t,
   return edge_bwd_fused_impl(false, rowptr_t, col_t, pos_t, row_order_t, n_long, eid, n_rows, wh, nh, fp, s_src, s_tgt, gmax, z, dropout_p, seed, offset,
                              go_padded, go_shared, s_sum, tgt_pack, a_src, a_tgt, tie_dst, tie_src, tie_total, corr_override, tgt_lo, tgt_hi,
                              ds_src, ds_tgt, d_wh, h_push_dst, n_push, my_rank, rows_per_rank, workspace, workspace_bytes, stream);
+}
+
+// gat_edge_bwd_fused for a loss that also carries c * |alpha*deg - 1|_1 of this layer (c = *norm_coef * norm_scale): see
+// BwdMainParams::norm_coef; the records must come from gat_edge_bwd_rowdot_glue called with the same coefficient.
+extern "C" int gat_edge_bwd_fused_norm(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
+                                  int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                                  const float* s_src, const float* s_tgt, const float* gmax, const float* z,
+                                  float dropout_p, uint64_t seed, uint64_t offset,
+                                  const float* go_padded, int go_shared, const float* s_sum, const float* tgt_pack,
+                                  const float* a_src, const float* a_tgt,
+                                  const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                                  const float* norm_coef, float norm_scale,
+                                  float* ds_src, float* ds_tgt, float* d_wh,
+                                  void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  return edge_bwd_fused_impl(false, rowptr_t, col_t, pos_t, row_order_t, n_long, eid, n_rows, wh, nh, fp, s_src, s_tgt, gmax, z, dropout_p, seed, offset,
+                             go_padded, go_shared, s_sum, tgt_pack, a_src, a_tgt, tie_dst, tie_src, tie_total, nullptr, 0, n_rows,
+                             ds_src, ds_tgt, d_wh, nullptr, 0, 0, 0, workspace, workspace_bytes, stream, norm_coef, norm_scale);
 }
 
 // bf16 variant: `go_bf16` is a bfloat16 copy (gat_f32_to_bf16) of the (n_targets, nh*fp) upstream gradient the pass gathers.
@@ -1249,9 +1307,13 @@ static int edge_bwd_rowdot_impl(const float* go_padded, int go_shared, const flo
                                    const float* z, int64_t n_rows, int nh, int fp,
                                    float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
                                    void* workspace, size_t workspace_bytes, gat_stream_t stream,
-                                   const float* skip, int64_t ld_skip, float drop_p, uint64_t drop_seed) {
+                                   const float* skip, int64_t ld_skip, float drop_p, uint64_t drop_seed,
+                                   const int32_t* rowptr = nullptr, const float* norm_t = nullptr, const float* norm_coef = nullptr,
+                                   float norm_scale = 0.f) {
   using namespace gat;
   int rc = check_common("gat_edge_bwd_rowdot", nh, fp, workspace, workspace_bytes);
+  GAT_CHECK_ARG((norm_t == nullptr) == (norm_coef == nullptr) && (norm_t == nullptr || (rowptr != nullptr && tgt_pack != nullptr)),
+                "gat_edge_bwd_rowdot: the fused attention norm needs rowptr, norm_t, norm_coef and tgt_pack together");
   if (rc) return rc;
   const bool glue = out_is_act || skip != nullptr || drop_p > 0.f;
   GAT_CHECK_ARG(!glue || (go_out != nullptr && !go_shared), "gat_edge_bwd_rowdot: a fused output glue needs go_out and an unshared gradient");
@@ -1267,11 +1329,13 @@ static int edge_bwd_rowdot_impl(const float* go_padded, int go_shared, const flo
   P.go_shared = go_shared ? 1 : 0; P.go_ld = go_shared ? fp : nh * fp;
   P.out_is_act = out_is_act ? 1 : 0; P.go_out = go_out;
   P.glue = glue ? 1 : 0; P.skip = skip; P.ld_skip = ld_skip; P.drop_p = drop_p; P.drop_seed = drop_seed;
+  P.rowptr = rowptr; P.norm_t = norm_t; P.norm_coef = norm_coef; P.norm_scale = norm_scale;
   P.s_tgt = s_tgt; P.tpack = tgt_pack;
   int64_t want = (n_rows + 31) / 32;
   const unsigned grid = (unsigned)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8);
-  if (nh <= 4) edge_bwd_rowdot_kernel<4><<<grid, 256, 0, st>>>(P);
-  else edge_bwd_rowdot_kernel<8><<<grid, 256, 0, st>>>(P);
+  const bool full = skip != nullptr || drop_p > 0.f;
+  if (nh <= 4) { if (full) edge_bwd_rowdot_kernel<4, true><<<grid, 256, 0, st>>>(P); else edge_bwd_rowdot_kernel<4, false><<<grid, 256, 0, st>>>(P); }
+  else { if (full) edge_bwd_rowdot_kernel<8, true><<<grid, 256, 0, st>>>(P); else edge_bwd_rowdot_kernel<8, false><<<grid, 256, 0, st>>>(P); }
   GAT_LAUNCH_CHECK();
   gamma_partial_kernel<<<kGammaBlocks, 256, 0, st>>>(ds_tgt, n_rows * nh, (BwdHeader*)workspace, (double*)((char*)workspace + kBwdHeaderBytes));
   GAT_LAUNCH_CHECK();
@@ -1287,13 +1351,14 @@ extern "C" int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const 
 }
 
 // gat_edge_bwd_rowdot for a forward that ran with the whole output glue (gat_edge_fwd_glue): out_padded holds y = keep * E(out + skip)
-extern "C" int gat_edge_bwd_rowdot_glue(const float* go_padded, const float* y_padded, int out_is_act, const float* skip, int64_t ld_skip,
-                                        float drop_p, uint64_t drop_seed, float* go_out,
+extern "C" int gat_edge_bwd_rowdot_glue(const float* go_padded, int go_shared, const float* y_padded, int out_is_act, const float* skip,
+                                        int64_t ld_skip, float drop_p, uint64_t drop_seed, float* go_out,
+                                        const int32_t* rowptr, const float* norm_t, const float* norm_coef, float norm_scale,
                                         const float* z, int64_t n_rows, int nh, int fp,
                                         float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
                                         void* workspace, size_t workspace_bytes, gat_stream_t stream) {
-  return edge_bwd_rowdot_impl(go_padded, 0, y_padded, out_is_act, go_out, z, n_rows, nh, fp, s_sum, ds_tgt, s_tgt, tgt_pack,
-                              workspace, workspace_bytes, stream, skip, ld_skip, drop_p, drop_seed);
+  return edge_bwd_rowdot_impl(go_padded, go_shared, y_padded, out_is_act, go_out, z, n_rows, nh, fp, s_sum, ds_tgt, s_tgt, tgt_pack,
+                              workspace, workspace_bytes, stream, skip, ld_skip, drop_p, drop_seed, rowptr, norm_t, norm_coef, norm_scale);
 }
 
 extern "C" int gat_edge_bwd_gamma(void* workspace, size_t workspace_bytes, double* gamma_out, gat_stream_t stream) {

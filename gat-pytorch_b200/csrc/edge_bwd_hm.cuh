@@ -130,6 +130,15 @@ edge_bwd_hm4_kernel(const BwdMainParams P) {
           al.z = attn_exp(ss.z + t4.z, gmax) / (z4.z + kSoftmaxEps);
           al.w = attn_exp(ss.w + t4.w, gmax) / (z4.w + kSoftmaxEps);
           w = al;
+          float4 s4e = s4;
+          if (P.norm_coef != nullptr) {   // fused attention-norm regulariser: dL/dalpha folded into the S term (BwdMainParams::norm_coef)
+            const float cn = __ldg(P.norm_coef) * P.norm_scale, deg = __ldg(pk + 12);
+            const float ux = al.x * deg - 1.0f, uy = al.y * deg - 1.0f, uz = al.z * deg - 1.0f, uw = al.w * deg - 1.0f;
+            s4e.x -= ux > 0.f ? cn * deg : (ux < 0.f ? -cn * deg : 0.f);
+            s4e.y -= uy > 0.f ? cn * deg : (uy < 0.f ? -cn * deg : 0.f);
+            s4e.z -= uz > 0.f ? cn * deg : (uz < 0.f ? -cn * deg : 0.f);
+            s4e.w -= uw > 0.f ? cn * deg : (uw < 0.f ? -cn * deg : 0.f);
+          }
           if (P.dropout_p > 0.f && valid) {
             float msk[4];
             const int edge_id = __ldg(P.eid + __ldg(P.pos_t + e));
@@ -138,7 +147,7 @@ edge_bwd_hm4_kernel(const BwdMainParams P) {
           }
           if (!valid) { w = make_float4(0.f, 0.f, 0.f, 0.f); al = w; }
           sh_w[lane] = w;
-          sh_s[lane] = make_float4(al.x * s4.x, al.y * s4.y, al.z * s4.z, al.w * s4.w);
+          sh_s[lane] = make_float4(al.x * s4e.x, al.y * s4e.y, al.z * s4e.z, al.w * s4e.w);
         }
         // ---- the two halves ----
 #pragma unroll

@@ -67,6 +67,75 @@ __global__ void attn_norm_bwd_kernel(const T* __restrict__ dst, const int32_t* _
   grad_alpha[idx] = __ldg(upstream) * sgn * deg * inv_edges;
 }
 
+// ---- the regulariser straight from the layer's score terms (fused form) -----------------------------------
+// alpha[e,h] = exp(LeakyReLU(s_src[src_e,h] + s_tgt[d,h] - M)) / (Z[d,h] + eps) is recomputed per CSR slot from what the layer
+// keeps anyway (16-byte gathers of s_src, L2 resident), so the (E', NH) attention tensor is never written or read:
+//   norm      = sum_{d,e,h} |alpha*deg(d) - 1| / E'                      (value, two fixed-order fp64 stages)
+//   tsum[d,h] = sum_{e in row d} alpha[e,h] * sign(alpha[e,h]*deg(d) - 1)
+// tsum is all the backward needs besides a scalar: with dL/dalpha[e,h] = c*deg*sign(.) the per-target sum of the softmax
+// adjoint, S[d,h] = sum_e alpha*dL/dalpha, gains c*deg(d)*tsum[d,h] (gat_edge_bwd_rowdot_glue) and the per-edge term is formed
+// inside the one-pass source-major backward (gat_edge_bwd_fused_norm) -- the regularised training step keeps the ONE-pass
+// backward and no per-edge record.
+__global__ void __launch_bounds__(256)
+attn_norm_scores_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n, const float* __restrict__ s_src,
+                        const float* __restrict__ s_tgt, const float* __restrict__ gmax, const float* __restrict__ z, int nh,
+                        int const_attention, float* __restrict__ tsum, double* __restrict__ partials) {
+  __shared__ double sh[8];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  const float m = const_attention ? 0.f : __ldg(gmax);
+  double total = 0.0;
+  for (int64_t row = warp; row < n; row += nwarps) {
+    const int start = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    const float deg = (float)(end - start);
+    float st[8], zz[8], ns[8], ts[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      ns[h] = 0.f; ts[h] = 0.f;
+      st[h] = (!const_attention && h < nh) ? __ldg(s_tgt + row * nh + h) : 0.f;
+      zz[h] = h < nh ? __ldg(z + row * nh + h) + kSoftmaxEps : 1.f;
+    }
+    for (int j = start + lane; j < end; j += 32) {
+      const float* sp = s_src + (int64_t)__ldg(col + j) * nh;
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        if (h < nh) {
+          float p = 1.f;
+          if (!const_attention) {
+            const float t = __ldg(sp + h) + st[h] - m;
+            p = expf(t >= 0.f ? t : t * kLeakySlope);
+          }
+          const float a = p / zz[h];
+          const float u = a * deg - 1.0f;
+          ns[h] += fabsf(u);
+          ts[h] += u > 0.f ? a : (u < 0.f ? -a : 0.f);
+        }
+      }
+    }
+    float rowsum = 0.f;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      if (h < nh) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          ns[h] += __shfl_xor_sync(0xffffffffu, ns[h], o);
+          ts[h] += __shfl_xor_sync(0xffffffffu, ts[h], o);
+        }
+        rowsum += ns[h];
+        if (lane == 0) tsum[row * nh + h] = ts[h];
+      }
+    }
+    total += (double)rowsum;
+  }
+  if (lane == 0) sh[threadIdx.x >> 5] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    partials[blockIdx.x] = t;
+  }
+}
+
 // ---- visualisation feed -----------------------------------------------------------------------------
 // visualisation/entropy_histograms.py:103-115 loops over every node, masks the whole edge list with
 // `target_nodes == node_id` (O(N * E')) and calls scipy.stats.entropy(weights, base=2) on the node's incoming attention;
@@ -205,6 +274,22 @@ extern "C" int gat_attention_norm_fwd(const void* edge_dst, int index_is_int64, 
   else attn_norm_partial_kernel<int32_t><<<kNormBlocks, 256, 0, st>>>((const int32_t*)edge_dst, rowptr, alpha, n_edges, nh, partials);
   GAT_LAUNCH_CHECK();
   attn_norm_finalize_kernel<<<1, 1024, 0, st>>>(partials, 1.0 / (double)n_edges, norm_out);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
+
+extern "C" int gat_attention_norm_scores(const int32_t* rowptr, const int32_t* col, int64_t n, int64_t n_edges, const float* s_src,
+                                         const float* s_tgt, const float* gmax, const float* z, int nh, int const_attention,
+                                         float* tsum, float* norm_out, void* workspace, size_t workspace_bytes, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(rowptr && col && z && tsum && norm_out && n >= 1 && n_edges >= 1 && nh >= 1 && nh <= 8, "gat_attention_norm_scores: bad arguments");
+  GAT_CHECK_ARG(const_attention || (s_src && s_tgt && gmax), "gat_attention_norm_scores: score buffers missing");
+  GAT_CHECK_ARG(workspace && workspace_bytes >= gat_attention_norm_workspace_bytes(), "gat_attention_norm_scores: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  attn_norm_scores_kernel<<<kNormBlocks, 256, 0, st>>>(rowptr, col, n, s_src, s_tgt, gmax, z, nh, const_attention ? 1 : 0, tsum,
+                                                       (double*)workspace);
+  GAT_LAUNCH_CHECK();
+  attn_norm_finalize_kernel<<<1, 1024, 0, st>>>((const double*)workspace, 1.0 / (double)n_edges, norm_out);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }

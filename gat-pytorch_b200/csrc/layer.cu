@@ -28,6 +28,8 @@ struct Bump {           // sizes a plan (base == nullptr) or carves it out of an
 
 struct FwdPlan {        // everything the backward needs again lives here (the "saved tensors" of the layer)
   float *w_p, *w_pT, *a_src_p, *a_tgt_p, *wh, *s_src, *s_tgt, *gmax, *z, *out_p;
+  float* norm_t;        // (n, nh) per-target sums of the fused attention-norm regulariser (desc->norm_out given)
+  void* nws; size_t nws_bytes;
   int32_t* ties;        // [tie_total (2 x int32 = one uint64) | tie_dst (n*nh) | tie_src (n*nh)]
   void* fws; size_t fws_bytes;
   void* gws; size_t gws_bytes;
@@ -58,6 +60,10 @@ void plan_fwd(const gat_layer_desc* d, Bump& b, FwdPlan& p) {
   p.z = b.take<float>((size_t)n * d->nh);
   p.out_is_user = !needs_merge(d);
   p.out_p = p.out_is_user ? nullptr : b.take<float>((size_t)n * dp);
+  // always planned (n*nh floats), so that the arena layout does not depend on whether the norm was asked for
+  p.norm_t = b.take<float>((size_t)n * d->nh);
+  p.nws_bytes = gat_attention_norm_workspace_bytes();
+  p.nws = b.take<char>(p.nws_bytes);
   // forward-only scratch at the tail
   p.fws_bytes = gat_edge_fwd_workspace_bytes();
   p.fws = b.take<char>(p.fws_bytes);
@@ -211,6 +217,9 @@ extern "C" int gat_layer_fwd(const gat_layer_desc* d, const float* x, int64_t ld
                          d->const_attention, d->p_drop, d->seed, 0, out_p, 0, alpha, p.z, tie_dst, tie_src, tie_total,
                          p.fws, p.fws_bytes, stream));
   }
+  if (d->norm_out != nullptr)
+    GAT_TRY(gat_attention_norm_scores(d->rowptr, d->col, n, d->n_edges, p.s_src, p.s_tgt, p.gmax, p.z, d->nh, d->const_attention, p.norm_t,
+                                      d->norm_out, p.nws, p.nws_bytes, stream));
   if (!p.out_is_user) {
     if (glue) GAT_TRY(gat_head_merge_fwd_glue(out_p, n, d->nh, d->f, d->fp, d->concat, d->skip, d->ld_skip, d->out_act, d->out_drop_p,
                                               d->out_drop_seed, out, stream));
@@ -267,20 +276,32 @@ extern "C" int gat_layer_bwd(const gat_layer_desc* d, const float* x, int64_t ld
     GAT_TRY(gat_head_merge_bwd(go_user, n, d->nh, d->f, d->fp, d->concat, p.go_p, stream));
     go = p.go_p;
   }
+  GAT_CHECK_ARG(d->grad_norm == nullptr || fused || d->const_attention,
+                "gat_layer_bwd: the fused attention norm and an upstream dL/dalpha cannot be combined (use one or the other)");
   if (fused) {
-    if (glue_in_edge) {
-      float* go_pre = d->grad_skip ? d->grad_skip : p.go_pre;
-      GAT_TRY(gat_edge_bwd_rowdot_glue(go, out_p, d->out_act, d->skip, d->ld_skip, d->out_drop_p, d->out_drop_seed, go_pre, f.z, n, d->nh,
+    const float* norm_coef = d->grad_norm;          // NULL: no regulariser on this layer
+    const float norm_scale = d->n_edges > 0 ? 1.0f / (float)d->n_edges : 0.f;
+    if (glue_in_edge || norm_coef) {
+      float* go_pre = glue_in_edge ? (d->grad_skip ? d->grad_skip : p.go_pre) : nullptr;
+      GAT_TRY(gat_edge_bwd_rowdot_glue(go, p.go_shared, out_p, glue_in_edge ? d->out_act : 0, glue_in_edge ? d->skip : nullptr,
+                                       glue_in_edge ? d->ld_skip : 0, glue_in_edge ? d->out_drop_p : 0.f, d->out_drop_seed, go_pre,
+                                       d->rowptr, norm_coef ? f.norm_t : nullptr, norm_coef, norm_scale, f.z, n, d->nh,
                                        d->fp, p.s_sum, p.ds_tgt, f.s_tgt, p.tpack, p.ws, p.ws_bytes, stream));
-      go = go_pre;
+      if (glue_in_edge) go = go_pre;
     } else {
       GAT_TRY(gat_edge_bwd_rowdot(go, p.go_shared, out_p, 0, nullptr, f.z, n, d->nh, d->fp, p.s_sum, p.ds_tgt, f.s_tgt, p.tpack,
                                   p.ws, p.ws_bytes, stream));
     }
-    GAT_TRY(gat_edge_bwd_fused(d->rowptr_t, d->col_t, d->pos_t, d->order_t, d->n_long_t, d->eid, n, f.wh, d->nh, d->fp, f.s_src, f.s_tgt,
-                               f.gmax, f.z, d->p_drop, d->seed, 0, go, p.go_shared, p.s_sum, p.tpack, f.a_src_p, f.a_tgt_p,
-                               tie_dst, tie_src, tie_total, nullptr, 0, n, p.ds_src, p.ds_tgt, p.d_wh, nullptr, 0, 0, 0,
-                               p.ws, p.ws_bytes, stream));
+    if (norm_coef) {
+      GAT_TRY(gat_edge_bwd_fused_norm(d->rowptr_t, d->col_t, d->pos_t, d->order_t, d->n_long_t, d->eid, n, f.wh, d->nh, d->fp, f.s_src, f.s_tgt,
+                                      f.gmax, f.z, d->p_drop, d->seed, 0, go, p.go_shared, p.s_sum, p.tpack, f.a_src_p, f.a_tgt_p,
+                                      tie_dst, tie_src, tie_total, norm_coef, norm_scale, p.ds_src, p.ds_tgt, p.d_wh, p.ws, p.ws_bytes, stream));
+    } else {
+      GAT_TRY(gat_edge_bwd_fused(d->rowptr_t, d->col_t, d->pos_t, d->order_t, d->n_long_t, d->eid, n, f.wh, d->nh, d->fp, f.s_src, f.s_tgt,
+                                 f.gmax, f.z, d->p_drop, d->seed, 0, go, p.go_shared, p.s_sum, p.tpack, f.a_src_p, f.a_tgt_p,
+                                 tie_dst, tie_src, tie_total, nullptr, 0, n, p.ds_src, p.ds_tgt, p.d_wh, nullptr, 0, 0, 0,
+                                 p.ws, p.ws_bytes, stream));
+    }
   } else {
     GAT_TRY(gat_edge_bwd_main(d->rowptr_t, d->col_t, d->pos_t, d->order_t, d->n_long_t, d->eid, n, f.wh, d->nh, d->fp, f.s_src, f.s_tgt,
                               f.gmax, f.z, d->const_attention, d->p_drop, d->seed, 0, go, p.go_shared, grad_alpha, p.rec, p.d_wh,

@@ -206,7 +206,7 @@ class _GATLayerFunction(torch.autograd.Function):
     arena tensor.  Same arithmetic, same kernels as _GATFunction; used whenever no per-kernel timer is active."""
 
     @staticmethod
-    def forward(ctx, x, w, a, skip, st: GraphStructure, desc_proto, arena_bytes, d_out, want_alpha):
+    def forward(ctx, x, w, a, skip, st: GraphStructure, desc_proto, arena_bytes, d_out, want_alpha, want_norm=False):
         lib = _lib.load()
         dev = x.device
         n = x.size(0)
@@ -219,17 +219,18 @@ class _GATLayerFunction(torch.autograd.Function):
             arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
             out = torch.empty((n, d_out), dtype=torch.float32, device=dev)
             alpha = torch.empty((st.n_edges, desc.nh), dtype=torch.float32, device=dev) if want_alpha else None
+            norm = torch.empty((), dtype=torch.float32, device=dev) if want_norm else None
+            desc.norm_out, desc.grad_norm = _ptr(norm), None
             rc = lib.gat_layer_fwd(ctypes.byref(desc), x.data_ptr(), x.stride(0), arena.data_ptr(), arena_bytes, out.data_ptr(),
                                    _ptr(alpha), int(needs_grad), _stream(dev))
             _lib.check(rc, "gat_layer_fwd")
+        desc.norm_out = None
         ctx.st, ctx.desc = st, desc
         ctx.save_for_backward(x, w, a, arena, out, skip)
-        if alpha is None:
-            return out, None
-        return out, alpha
+        return out, alpha, norm
 
     @staticmethod
-    def backward(ctx, grad_out, grad_alpha):
+    def backward(ctx, grad_out, grad_alpha, grad_norm=None):
         lib = _lib.load()
         x, w, a, arena, out, skip = ctx.saved_tensors
         desc = ctx.desc
@@ -249,11 +250,17 @@ class _GATLayerFunction(torch.autograd.Function):
             ga = torch.empty_like(a) if want_ga else None
             gskip = torch.empty_like(out) if (skip is not None and want[3]) else None
             desc.grad_skip = _ptr(gskip)
+            if grad_norm is not None and a is not None:
+                if grad_alpha is not None:
+                    raise RuntimeError("GATLayer: the fused attention norm (layer.attention_norm) and a gradient through the returned "
+                                       "attention weights cannot be combined in one backward; use one of the two")
+                grad_norm = grad_norm.to(torch.float32).contiguous()
+                desc.grad_norm = grad_norm.data_ptr()
             rc = lib.gat_layer_bwd(ctypes.byref(desc), x.data_ptr(), x.stride(0), arena.data_ptr(), out.data_ptr(), grad_out.data_ptr(),
                                    _ptr(grad_alpha), scratch.data_ptr(), sb, _ptr(gx), _ptr(gw), _ptr(ga), _stream(dev))
-            desc.grad_skip = None
+            desc.grad_skip = desc.grad_norm = None
             _lib.check(rc, "gat_layer_bwd")
-        return gx, gw, ga, gskip, None, None, None, None, None
+        return gx, gw, ga, gskip, None, None, None, None, None, None
 
 
 class GATLayer(nn.Module):
@@ -307,6 +314,12 @@ class GATLayer(nn.Module):
         # output is written, Philox mask regenerated in the backward -- and forward(..., skip=t) adds the skip connection's
         # rows (GATModel.py:135-145; for a head-mean layer the caller passes skip_output.mean(dim=1)) before the activation.
         self.output_dropout = 0.0
+        # Opt-in fused regulariser: True makes every forward also compute this layer's term of
+        # GATModel.calc_attention_norm, sum |alpha*deg - 1| / E' (GATModel.py:207-224), from the score terms -- no (E', NH)
+        # tensor -- and leaves it in `attention_norm_value` as a differentiable scalar whose backward rides in the one-pass
+        # source-major kernel (include/gat_b200.h: gat_attention_norm_scores, gat_edge_bwd_fused_norm).
+        self.attention_norm = False
+        self.attention_norm_value = None
         # Opt-in bf16 variant (BASELINE.json north_star "bf16 variant stated separately"): "bf16" makes the edge kernels gather
         # bfloat16 copies of Wh (forward) and of dL/dout (fused backward) -- half the bytes per edge, fp32 accumulation,
         # ~2e-3 relative error.  None (default) = fp32 everywhere, the 1e-5 parity path.  NH <= 4 and padded rows of
@@ -470,9 +483,9 @@ class GATLayer(nn.Module):
                 raise ValueError("skip= is fused only for layers without bias")
             if skip.stride(1) != 1 or skip.stride(0) % 4 != 0 or skip.data_ptr() % 16 != 0:
                 skip = skip.contiguous()
-        if per_kernel and (skip is not None or self._out_drop() > 0.0):
-            raise NotImplementedError("skip= / output_dropout are implemented by the one-call path (gat_layer_fwd); not available under a "
-                                      "per-kernel timer or with the bf16 variant")
+        if per_kernel and (skip is not None or self._out_drop() > 0.0 or self.attention_norm):
+            raise NotImplementedError("skip= / output_dropout / attention_norm are implemented by the one-call path (gat_layer_fwd); not "
+                                      "available under a per-kernel timer or with the bf16 variant")
         if per_kernel:
             # per-kernel path: the bf16 variant and runs under a per-kernel timer (bench.py's live roofline measurement)
             out, alpha = _GATFunction.apply(x, w_p, a_src, a_tgt, st, self.num_heads, self.out_features, fp,
@@ -482,9 +495,10 @@ class GATLayer(nn.Module):
         else:
             desc, arena_bytes = self._layer_desc(st, fp, p_drop)
             d_out = self.num_heads * self.out_features if self.concat else self.out_features
-            out, alpha = _GATLayerFunction.apply(x, self.W.weight.contiguous(),
-                                                 None if self.const_attention else self.a.weight.contiguous(), skip, st, desc,
-                                                 arena_bytes, d_out, bool(return_attention_weights))
+            out, alpha, norm = _GATLayerFunction.apply(x, self.W.weight.contiguous(),
+                                                       None if self.const_attention else self.a.weight.contiguous(), skip, st, desc,
+                                                       arena_bytes, d_out, bool(return_attention_weights), bool(self.attention_norm))
+            self.attention_norm_value = norm
         if drop_all:
             out = out * 0.0
         # The reference stores the coefficients on every forward (gat_layer.py:110; nothing in the repository reads the

@@ -70,7 +70,7 @@ def attention_norm(edge_index: torch.Tensor, attention_list, n_nodes: int | None
     return total / len(attention_list)
 
 
-def model_forward(model, data, return_attention_weights=None):
+def model_forward(model, data, return_attention_weights=None, attention_norm=False):
     """`GATModel.forward` (GATModel.py:118-151) / `GATModel.forward_and_return_attention` (:153-187) for a model whose
     `gat_layer_list` holds B200 `GATLayer`s, with the inter-layer glue folded into the layers' kernels:
 
@@ -84,14 +84,19 @@ def model_forward(model, data, return_attention_weights=None):
     `return_attention_weights=None` returns what `forward` returns (the output); True / False what
     `forward_and_return_attention(data, flag)` returns: `(x, edge_index, attention_weights_list)`.  Same arithmetic as the
     reference's op-by-op sequence; the layers' own attributes are restored before returning, so the unchanged callers keep
-    working on the same modules."""
+    working on the same modules.
+
+    `attention_norm=True` appends `GATModel.calc_attention_norm(edge_index, attention_weights_list)` (GATModel.py:189-234: the
+    mean over layers of sum |alpha*deg - 1| / E') to the result, computed by the layers from their score terms
+    (`GATLayer.attention_norm`): the training steps of planetoid_gat.py:19-27 / ppi_gat.py:22-33 then need no attention tensor
+    at all (`return_attention_weights=None`) and their backward stays the one-pass source-major kernel."""
     import torch.nn.functional as F
     x, edge_index = data.x, data.edge_index
     layers = model.gat_layer_list
     n_layers = len(layers)
     p = float(model.dropout) if model.training else 0.0
     want_attention = bool(return_attention_weights)
-    attention, skip_count, dropped = [], 0, False
+    attention, norms, skip_count, dropped = [], [], 0, False
     for i, layer in enumerate(layers):
         layer_input = x
         if p > 0.0 and not dropped:
@@ -104,8 +109,9 @@ def model_forward(model, data, return_attention_weights=None):
                 skip = skip.view(-1, model.num_heads_per_layer[i + 1], model.head_output_features_per_layer[i + 1]).mean(dim=1)
         last = i == n_layers - 1
         fold_dropout = (not last) and p > 0.0 and not model.add_skip_connection[i + 1]
-        saved = (layer.output_activation, layer.output_dropout)
+        saved = (layer.output_activation, layer.output_dropout, layer.attention_norm)
         layer.output_activation, layer.output_dropout = (None if last else "elu"), (p if fold_dropout else 0.0)
+        layer.attention_norm = bool(attention_norm)
         try:
             if return_attention_weights is None:
                 x = layer(x, edge_index, skip=skip)
@@ -118,11 +124,14 @@ def model_forward(model, data, return_attention_weights=None):
                     x = res
                     attention.append(None)
         finally:
-            layer.output_activation, layer.output_dropout = saved
+            layer.output_activation, layer.output_dropout, layer.attention_norm = saved
+        if attention_norm:
+            norms.append(layer.attention_norm_value)
         dropped = fold_dropout
+    norm = (sum(norms) / len(norms),) if attention_norm else ()
     if return_attention_weights is None:
-        return x
-    return x, edge_index, attention
+        return (x,) + norm if attention_norm else x
+    return (x, edge_index, attention) + norm
 
 
 def _structure_for(edge_index: torch.Tensor, n_nodes: int | None, who: str):

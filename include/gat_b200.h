@@ -275,14 +275,35 @@ GAT_API int gat_edge_bwd_rowdot(const float* go_padded, int go_shared, const flo
                                 float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
                                 void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
-/* gat_edge_bwd_rowdot behind gat_edge_fwd_glue: y_padded holds y = keep * E(out + skip) and go_padded is dL/dy; the pass
- * regenerates the mask, recovers out = E^-1(y * (1 - drop_p)) - skip, writes dL/d(out + skip) = go * keep * E' to go_out
- * (n_rows, nh*fp) -- which is ALSO dL/dskip, and the buffer the source-major pass gathers -- and uses both in S. */
-GAT_API int gat_edge_bwd_rowdot_glue(const float* go_padded, const float* y_padded, int out_is_act, const float* skip, int64_t ld_skip,
-                                     float drop_p, uint64_t drop_seed, float* go_out,
+/* gat_edge_bwd_rowdot with the opt-in extras:
+ *  - behind gat_edge_fwd_glue (out_is_act / skip / drop_p): y_padded holds y = keep * E(out + skip) and go_padded is dL/dy; the pass
+ *    regenerates the mask, recovers out = E^-1(y * (1 - drop_p)) - skip, writes dL/d(out + skip) = go * keep * E' to go_out
+ *    (n_rows, nh*fp) -- which is ALSO dL/dskip, and the buffer the source-major pass gathers -- and uses both in S;
+ *  - fused attention-norm regulariser (norm_t / norm_coef / rowptr given, tgt_pack required): the loss carries
+ *    c * sum |alpha*deg - 1| of this layer with c = *norm_coef * norm_scale (device scalar = upstream gradient of the layer's
+ *    norm, host scale = 1/E'); then S[d,h] += c * deg(d) * norm_t[d,h] (norm_t from gat_attention_norm_scores) and deg(d) is
+ *    stored in the target's record for gat_edge_bwd_fused_norm.  rowptr is the CSR by target of the rows handled here. */
+GAT_API int gat_edge_bwd_rowdot_glue(const float* go_padded, int go_shared, const float* y_padded, int out_is_act, const float* skip,
+                                     int64_t ld_skip, float drop_p, uint64_t drop_seed, float* go_out,
+                                     const int32_t* rowptr, const float* norm_t, const float* norm_coef, float norm_scale,
                                      const float* z, int64_t n_rows, int nh, int fp,
                                      float* s_sum, float* ds_tgt, const float* s_tgt, float* tgt_pack,
                                      void* workspace, size_t workspace_bytes, gat_stream_t stream);
+
+/* gat_edge_bwd_fused (one GPU) for a loss that also carries c * sum |alpha*deg - 1| of this layer: dL/dalpha[e,h] =
+ * c * deg(d) * sign(alpha*deg(d) - 1) is formed inside the pass from the recomputed alpha and the deg(d) of the target's record,
+ * so the attention-regularised training step (planetoid_gat.py:19-27, ppi_gat.py:22-33) keeps the ONE-pass backward and writes
+ * no per-edge record.  The records must come from gat_edge_bwd_rowdot_glue called with the same coefficient. */
+GAT_API int gat_edge_bwd_fused_norm(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* pos_t, const int32_t* row_order_t,
+                                    int64_t n_long, const int32_t* eid, int64_t n_rows, const float* wh, int nh, int fp,
+                                    const float* s_src, const float* s_tgt, const float* gmax, const float* z,
+                                    float dropout_p, uint64_t seed, uint64_t offset,
+                                    const float* go_padded, int go_shared, const float* s_sum, const float* tgt_pack,
+                                    const float* a_src, const float* a_tgt,
+                                    const int32_t* tie_dst, const int32_t* tie_src, const unsigned long long* tie_total,
+                                    const float* norm_coef, float norm_scale,
+                                    float* ds_src, float* ds_tgt, float* d_wh,
+                                    void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* The output glue for layers whose padded rows are NOT the caller's rows (head-mean layers, F % 4 != 0): applied to the
  * merged row, out[i, c] = keep * E(merge(o_padded)[i, c] + skip[i, c]), skip (n, ld_skip >= width) or NULL. */
@@ -323,6 +344,13 @@ GAT_API int gat_attention_norm_fwd(const void* edge_dst, int index_is_int64, con
                                    gat_stream_t stream);
 GAT_API int gat_attention_norm_bwd(const void* edge_dst, int index_is_int64, const int32_t* rowptr, const float* alpha,
                                    int64_t n_edges, int nh, const float* upstream, float* grad_alpha, gat_stream_t stream);
+/* The same regulariser WITHOUT the (n_edges, nh) attention tensor: alpha is recomputed per CSR slot from the layer's score
+ * terms (s_src, s_tgt, gmax, z as gat_project_fwd / gat_edge_max / gat_edge_fwd left them; pre-dropout, like the returned
+ * attention).  *norm_out = sum |alpha*deg - 1| / n_edges; tsum[d,h] = sum_{e into d} alpha*sign(alpha*deg(d) - 1) is what the
+ * backward needs (gat_edge_bwd_rowdot_glue / gat_edge_bwd_fused_norm).  workspace: gat_attention_norm_workspace_bytes(). */
+GAT_API int gat_attention_norm_scores(const int32_t* rowptr, const int32_t* col, int64_t n, int64_t n_edges, const float* s_src,
+                                      const float* s_tgt, const float* gmax, const float* z, int nh, int const_attention,
+                                      float* tsum, float* norm_out, void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Visualisation feed.  Replaces the per-node `target_nodes == node_id` masks of
@@ -405,6 +433,9 @@ GAT_API int gat_unpack_param_grads(const float* gW_p, const float* ga_src_p, con
  * Output glue (see gat_edge_fwd_glue): out_act, skip (n, ld_skip; same columns as `out`), out_drop_p / out_drop_seed make
  * gat_layer_fwd return y = keep * E(out + skip); gat_layer_bwd then takes grad_out = dL/dy, `out` = y, and writes dL/dskip
  * (n, width of out; contiguous) to grad_skip when it is not NULL.
+ * Fused attention-norm regulariser: norm_out makes gat_layer_fwd also return this layer's
+ * sum |alpha*deg - 1| / E' (GATModel.py:196-225, one layer) without materialising alpha; grad_norm hands its upstream gradient
+ * to gat_layer_bwd, which stays rowdot + ONE source-major pass.
  * ------------------------------------------------------------------------------------- */
 typedef struct gat_layer_desc {
   const int32_t *rowptr, *col, *eid, *order;            /* CSR by target + scheduling permutation */
@@ -423,6 +454,9 @@ typedef struct gat_layer_desc {
   float out_drop_p;                                     /* output glue: dropout of the stored output (the next layer's input dropout) */
   uint64_t out_drop_seed;
   float* grad_skip;                                     /* gat_layer_bwd: dL/dskip output, or NULL */
+  float* norm_out;                                      /* gat_layer_fwd: device scalar receiving sum |alpha*deg - 1| / E' of this layer
+                                                           (gat_attention_norm_scores), or NULL */
+  const float* grad_norm;                               /* gat_layer_bwd: device scalar dL/dnorm, or NULL; needs grad_alpha == NULL */
 } gat_layer_desc;
 
 GAT_API size_t gat_layer_fwd_arena_bytes(const gat_layer_desc* desc);

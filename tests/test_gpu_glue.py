@@ -231,3 +231,63 @@ def test_glue_refuses_what_it_does_not_implement(small_cases):
     layer.train()
     with pytest.raises(ValueError):
         layer(torch.from_numpy(case["x"]).cuda(), torch.from_numpy(case["edge_index"]).cuda())
+
+
+@pytest.mark.parametrize("name", ["adv_concat", "adv_mean_oddF", "adv_ties", "cora_L0", "cora_L1", "pubmed_L1", "ppi_L1", "ppi_L2",
+                                  "pattern_L1", "products_L1", "products_L2"])
+def test_fused_attention_norm_matches_the_materialised_one(name, small_cases):
+    """SURVEY.md 8-f3, fused form: layer.attention_norm computes sum |alpha*deg - 1| / E' from the score terms and its gradient
+    rides in the one-pass backward.  Must equal attention_norm(edge_index', [alpha]) on the returned attention (itself pinned
+    against GATModel.calc_attention_norm in test_gpu_parity.py) in value and in every gradient of task loss + lambda * norm."""
+    from gat_pytorch_b200 import attention_norm
+    case = small_cases[name]
+    ei = torch.from_numpy(case["edge_index"]).cuda()
+    lam = 3.0
+    res = []
+    for fused in (False, True):
+        layer = make_layer(case)
+        x = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+        if fused:
+            layer.attention_norm = True
+            out = layer(x, ei)
+            norm = layer.attention_norm_value
+        else:
+            out, (ei2, alpha) = layer(x, ei, return_attention_weights=True)
+            norm = attention_norm(ei2, [alpha])
+        go, _ = cases.upstream_grads(case, out.shape[0], out.shape[1], 1)
+        ((out * torch.from_numpy(go).cuda()).sum() + lam * norm).backward()
+        res.append({"norm": norm.detach().reshape(1), "out": out.detach(), "gx": x.grad, "gW": layer.W.weight.grad, "ga": layer.a.weight.grad})
+    for k in res[0]:
+        assert _rel(res[1][k], res[0][k]) <= 1e-5, (name, k, _rel(res[1][k], res[0][k]))
+    # the regulariser really reached the gradients (the comparison above is not between two copies of the task gradient)
+    layer = make_layer(case)
+    x = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+    out = layer(x, ei)
+    (out * torch.from_numpy(go).cuda()).sum().backward()
+    assert _rel(layer.a.weight.grad, res[1]["ga"]) > 1e-3
+
+
+def test_model_forward_with_fused_norm_equals_calc_attention_norm():
+    """The PPI training step's ingredients (ppi_gat.py:22-33): forward_and_return_attention + calc_attention_norm, against
+    model_forward(..., attention_norm=True) which needs no attention tensor."""
+    from gat_pytorch_b200 import attention_norm, model_forward, synth
+    shapes, add_skip = [(50, 4, 64, True), (256, 4, 64, True), (256, 6, 121, False)], [False, True, False]
+    x0, ei = synth.ppi()
+    x0, ei = torch.from_numpy(x0).cuda(), torch.from_numpy(ei).cuda()
+    model = _toy_model(shapes, add_skip, dropout=0.0)
+    res = []
+    for fused in (False, True):
+        model.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True)
+        data = types.SimpleNamespace(x=x, edge_index=ei)
+        if fused:
+            out, norm = model_forward(model, data, attention_norm=True)
+        else:
+            out, ei2, att = _reference_forward(model, x, ei, True)
+            norm = attention_norm(ei2, att)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        ((out * torch.randn(out.shape, device="cuda", generator=g)).sum() + 2.0 * norm).backward()
+        res.append(dict(out=out.detach(), norm=norm.detach().reshape(1), gx=x.grad.clone(),
+                        **{f"g:{k}": v.grad.clone() for k, v in model.named_parameters()}))
+    for k in res[0]:
+        assert _rel(res[1][k], res[0][k]) <= 2e-5, (k, _rel(res[1][k], res[0][k]))
