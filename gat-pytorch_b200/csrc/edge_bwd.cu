@@ -1011,7 +1011,7 @@ namespace gat {
 template <bool FUSED>
 static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, int64_t n_long, int64_t n_rows, cudaStream_t st) {
   const int nh = P.nh;
-  GroupShape shape = pick_group(P.chunks);
+  GroupShape shape = pick_group(P.chunks, n_rows);
   if (shape.slots < 0) {
     set_error("gat_edge_bwd_main: row width %d floats exceeds the supported 1024", P.dp);
     return GAT_EUNSUPPORTED;
@@ -1094,7 +1094,8 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
     } while (0)
     // short rows of a four-head head-mean layer: the (edge slot, head, quarter) kernel of edge_bwd_hm.cuh (the long rows keep
     // the cooperative launch above)
-    const int hm_cpl = (FUSED && nh == 4 && P.tpack != nullptr && !P.push && getenv("GAT_BWD_HM_OFF") == nullptr) ? (P.chunks_per_head + 3) / 4 : 0;
+    int hm_cpl = (FUSED && nh == 4 && P.tpack != nullptr && !P.push && getenv("GAT_BWD_HM_OFF") == nullptr) ? (P.chunks_per_head + 3) / 4 : 0;
+    if (hm_cpl < 2 || hm_cpl > 4) hm_cpl = 0;     // 5..16 chunks per head (narrower rows: the general kernel's lane grid fits them)
     if (shape.slots == 1) LAUNCH_GS(1); else LAUNCH_GS(2);
 #undef LAUNCH_GS
 #define LAUNCH_HM(C_, X_)                                                                                              \
@@ -1398,7 +1399,7 @@ extern "C" int gat_edge_bwd_finish(const int32_t* rowptr_t, const int32_t* col_t
   P.rec = rec; P.s_sum = s_sum; P.a_src = a_src; P.a_tgt = a_tgt;
   P.tie_dst = tie_dst; P.tie_src = tie_src; P.header = header; P.corr_override = corr_override;
   P.tgt_lo = tgt_lo; P.tgt_hi = tgt_hi; P.ds_src = ds_src; P.ds_tgt = ds_tgt; P.d_wh = d_wh;
-  GroupShape shape = pick_group(P.chunks);
+  GroupShape shape = pick_group(P.chunks, n_rows);
   if (shape.slots < 0) {
     set_error("gat_edge_bwd_finish: row width %d floats exceeds the supported 1024", P.dp);
     return GAT_EUNSUPPORTED;

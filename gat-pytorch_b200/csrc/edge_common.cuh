@@ -161,14 +161,20 @@ __device__ __forceinline__ bool prefetched_row(const RowSched& S, const int k, c
 }
 
 // Host-side choice of (G, SLOTS) for a padded row of `chunks` float4s.
+// Narrow rows on SMALL graphs: the narrowest group that covers the row leaves most of the machine idle (PATTERN's 1x1 output
+// layer: 15 341 rows of one chunk = 480 warps for 3 552 warp slots) and walks a hub row edge by edge (Cora's 169-edge row on a
+// 2-lane group: 60 us of a 500 us step).  While the whole launch still fits one wave of resident warps the group is widened:
+// a batch is then G edges whose softmax terms are computed by G lanes in parallel; the surplus lanes of the gather loop re-read
+// chunk 0 (never stored).  Which G a row gets depends on (row width, rows in the launch) only, so results stay deterministic.
 struct GroupShape { int g, slots; };
-static inline GroupShape pick_group(int chunks) {
+static inline GroupShape pick_group(int chunks, int64_t n_rows = -1) {
   GroupShape s;
-  if (chunks <= 1) { s.g = 1; s.slots = 1; }
-  else if (chunks <= 2) { s.g = 2; s.slots = 1; }
-  else if (chunks <= 4) { s.g = 4; s.slots = 1; }
-  else if (chunks <= 8) { s.g = 8; s.slots = 1; }
-  else if (chunks <= 16) { s.g = 16; s.slots = 1; }
+  if (chunks <= 16) {
+    s.slots = 1;
+    s.g = chunks <= 1 ? 1 : (chunks <= 2 ? 2 : (chunks <= 4 ? 4 : (chunks <= 8 ? 8 : 16)));
+    constexpr int64_t kWave = (int64_t)kNumSMs * 24;                 // resident warps at 3 CTAs of 8 warps per SM
+    while (n_rows >= 0 && s.g < 32 && n_rows * (2 * s.g) <= kWave * 32) s.g *= 2;
+  }
   else {
     s.g = 32;
     int need = (chunks + 31) / 32;

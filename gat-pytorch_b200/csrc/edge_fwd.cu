@@ -488,7 +488,7 @@ static int edge_fwd_impl(bool gather_bf16, const int32_t* rowptr, const int32_t*
   P.skip = skip; P.ld_skip = ld_skip; P.out_drop_p = out_drop_p; P.out_drop_seed = out_drop_seed;
   P.tie_dst = const_attention ? nullptr : tie_dst; P.tie_src = const_attention ? nullptr : tie_src;
   P.tie_total = const_attention ? nullptr : tie_total;
-  GroupShape shape = pick_group(P.chunks);
+  GroupShape shape = pick_group(P.chunks, n);
   if (shape.slots < 0) {
     set_error("gat_edge_fwd: row width %d floats exceeds the supported 1024", P.dp);
     return GAT_EUNSUPPORTED;

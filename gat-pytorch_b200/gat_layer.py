@@ -200,6 +200,180 @@ class _GATFunction(torch.autograd.Function):
         return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None, None, None, None
 
 
+def _head_groups(nh: int, fp: int):
+    """Head ranges [(h0, h1), ...] such that every group fits the edge kernels' limits (<= MAX_HEADS heads, <= MAX_ROW_FLOATS floats)."""
+    per = max(1, min(MAX_HEADS, MAX_ROW_FLOATS // fp))
+    return [(h0, min(nh, h0 + per)) for h0 in range(0, nh, per)]
+
+
+class _GATWideFunction(torch.autograd.Function):
+    """(x, W_p, A_src_p, A_tgt_p) -> (out, alpha) for layers BEYOND the edge kernels' limits (num_heads > 8 or a padded row of more
+    than 1024 floats), which the reference constructor accepts like any other (gat_layer.py:13).  The edge stage is independent per
+    head once the score terms exist, so the heads are processed in GROUPS that fit the kernels, on contiguous copies of their
+    columns; what couples the heads is handled around the groups:
+      * `a` is a full cross-head matrix (gat_layer.py:76-82): s_src / s_tgt of ALL heads come from two GEMMs over the whole Wh row,
+        and the backward adds  dWh += ds_src A_src + ds_tgt A_tgt  over all heads as two GEMMs (the per-group kernels get zero
+        matrices for that term);
+      * the ONE global max M (gat_layer.py:85): every group's gat_edge_max accumulates into the same scalar;
+      * the gradient through max(): Gamma and |T| are summed over the groups and handed to the per-group source-major passes as
+        `corr_override` -- the same mechanism the partitioned layer uses across ranks.
+    Same kernels, same arithmetic per head as the common path; the extra column copies make it slower per byte, which is the price
+    of a shape none of the reference's configurations uses."""
+
+    @staticmethod
+    def forward(ctx, x, w_p, a_src_p, a_tgt_p, st: GraphStructure, nh, f, fp, concat, const_attention, p_drop, want_alpha, gemm_algo):
+        lib = _lib.load()
+        dev = x.device
+        n, f_in, dp = x.size(0), x.size(1), nh * fp
+        needs_grad = any(ctx.needs_input_grad[:4])
+        groups = _head_groups(nh, fp)
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            wh = torch.empty((n, dp), **f32)
+            gemm(False, True, n, dp, f_in, x, x.stride(0), w_p, w_p.stride(0), wh, dp, gemm_algo)
+            s_src = s_tgt = gmax = None
+            fws = torch.empty(int(lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=dev)
+            if not const_attention:
+                s_src, s_tgt = torch.empty((n, nh), **f32), torch.empty((n, nh), **f32)
+                gemm(False, True, n, nh, dp, wh, dp, a_src_p, dp, s_src, nh, 1)
+                gemm(False, True, n, nh, dp, wh, dp, a_tgt_p, dp, s_tgt, nh, 1)
+                gmax = torch.full((1,), float("-inf"), **f32)
+            seed = int(torch.empty((), dtype=torch.int64).random_().item()) if p_drop > 0.0 else 0
+            per_group = []
+            for gi, (h0, h1) in enumerate(groups):
+                g_nh = h1 - h0
+                wh_g = wh[:, h0 * fp:h1 * fp].contiguous()
+                ss_g = st_g = None
+                if not const_attention:
+                    ss_g, st_g = s_src[:, h0:h1].contiguous(), s_tgt[:, h0:h1].contiguous()
+                    _lib.call("gat_edge_max", st.rowptr.data_ptr(), st.col.data_ptr(), st.order.data_ptr(), st.n_long, n, ss_g.data_ptr(),
+                              st_g.data_ptr(), g_nh, gmax.data_ptr(), fws.data_ptr(), fws.numel(), s)
+                per_group.append([g_nh, wh_g, ss_g, st_g])
+            outs, alphas = [], []
+            for gi, (g_nh, wh_g, ss_g, st_g) in enumerate(per_group):
+                out_g = torch.empty((n, g_nh * fp), **f32)
+                alpha_g = torch.empty((st.n_edges, g_nh), **f32) if want_alpha else None
+                z_g = torch.empty((n, g_nh), **f32)
+                tie_dst = tie_src = tie_total = None
+                if needs_grad and not const_attention:
+                    ties = torch.zeros(2 * n * g_nh + 2, dtype=torch.int32, device=dev)
+                    tie_total, tie_dst, tie_src = ties[:2], ties[2:2 + n * g_nh], ties[2 + n * g_nh:]
+                _lib.call("gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), st.n_long, n,
+                          wh_g.data_ptr(), g_nh, fp, _ptr(ss_g), _ptr(st_g), _ptr(gmax), int(const_attention), float(p_drop), seed, gi,
+                          out_g.data_ptr(), 0, _ptr(alpha_g), z_g.data_ptr(), _ptr(tie_dst), _ptr(tie_src), _ptr(tie_total),
+                          fws.data_ptr(), fws.numel(), s, tag=(g_nh, fp))
+                per_group[gi] += [out_g, z_g, tie_dst, tie_src, tie_total]
+                outs.append(out_g)
+                alphas.append(alpha_g)
+            out_p = torch.cat(outs, dim=1)
+            if fp != f or not concat:
+                out = torch.empty((n, nh * f if concat else f), **f32)
+                _lib.call("gat_head_merge_fwd", out_p.data_ptr(), n, nh, f, fp, int(concat), out.data_ptr(), s)
+            else:
+                out = out_p
+            alpha = torch.cat(alphas, dim=1) if want_alpha else None
+        ctx.st, ctx.cfg, ctx.groups = st, (nh, f, fp, concat, const_attention, float(p_drop), seed, gemm_algo), per_group
+        ctx.save_for_backward(x, w_p, a_src_p, a_tgt_p, wh, gmax)
+        return out, alpha
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_alpha):
+        lib = _lib.load()
+        x, w_p, a_src_p, a_tgt_p, wh, gmax = ctx.saved_tensors
+        st: GraphStructure = ctx.st
+        nh, f, fp, concat, const_attention, p_drop, seed, gemm_algo = ctx.cfg
+        dev = x.device
+        n, f_in, dp = x.size(0), x.size(1), nh * fp
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            if grad_out is None:
+                grad_out = torch.zeros((n, nh * f if concat else f), **f32)
+            grad_out = grad_out.contiguous()
+            go_p = torch.empty((n, dp), **f32)
+            _lib.call("gat_head_merge_bwd", grad_out.data_ptr(), n, nh, f, fp, int(concat), go_p.data_ptr(), s)
+            fused = not const_attention and grad_alpha is None
+            ws_bytes = int(lib.gat_edge_bwd_workspace_bytes(n, st.n_edges, nh))
+            work, h0 = [], 0
+            gammas, ties = [], []
+            # stage 1 per group: S (and with an upstream dL/dalpha the per-edge records), Gamma partials
+            for g_nh, wh_g, ss_g, st_g, out_g, z_g, tie_dst, tie_src, tie_total in ctx.groups:
+                h1 = h0 + g_nh
+                go_g = go_p[:, h0 * fp:h1 * fp].contiguous()
+                d_wh_g = torch.empty((n, g_nh * fp), **f32)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                item = dict(g_nh=g_nh, wh=wh_g, ss=ss_g, st=st_g, z=z_g, go=go_g, d_wh=d_wh_g, ws=ws, tie_dst=tie_dst, tie_src=tie_src)
+                if not const_attention:
+                    item["ds_src"], item["ds_tgt"], item["s_sum"] = (torch.empty((n, g_nh), **f32) for _ in range(3))
+                    item["zeros_a"] = torch.zeros((g_nh, g_nh * fp), **f32)
+                if fused:
+                    item["tpack"] = torch.empty((n, int(lib.gat_tgt_pack_stride(g_nh))), **f32)
+                    _lib.call("gat_edge_bwd_rowdot", go_g.data_ptr(), 0, out_g.data_ptr(), 0, None, z_g.data_ptr(), n, g_nh, fp,
+                              item["s_sum"].data_ptr(), item["ds_tgt"].data_ptr(), st_g.data_ptr(), item["tpack"].data_ptr(),
+                              ws.data_ptr(), ws_bytes, s, tag=(g_nh, fp))
+                else:
+                    ga_g = grad_alpha[:, h0:h1].contiguous() if grad_alpha is not None else None
+                    item["rec"] = torch.empty((st.n_edges, 2 * g_nh), **f32) if not const_attention else None
+                    _lib.call("gat_edge_bwd_main", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
+                              st.n_long_t, st.eid.data_ptr(), n, wh_g.data_ptr(), g_nh, fp, _ptr(ss_g), _ptr(st_g), _ptr(gmax), z_g.data_ptr(),
+                              int(const_attention), p_drop, seed, len(work), go_g.data_ptr(), 0, _ptr(ga_g), _ptr(item["rec"]),
+                              d_wh_g.data_ptr(), ws.data_ptr(), ws_bytes, s, tag=(g_nh, fp))
+                    if not const_attention:
+                        _lib.call("gat_edge_bwd_rowsum", st.rowptr.data_ptr(), st.tpos.data_ptr(), st.order.data_ptr(), st.n_long, n, g_nh,
+                                  item["rec"].data_ptr(), z_g.data_ptr(), item["s_sum"].data_ptr(), item["ds_tgt"].data_ptr(),
+                                  ws.data_ptr(), ws_bytes, s, tag=(g_nh, fp))
+                if not const_attention:
+                    gamma = torch.empty(1, dtype=torch.float64, device=dev)
+                    _lib.call("gat_edge_bwd_gamma", ws.data_ptr(), ws_bytes, gamma.data_ptr(), s)
+                    gammas.append(gamma)
+                    ties.append(tie_total.view(torch.int64)[:1].to(torch.float64))
+                work.append(item)
+                h0 = h1
+            ds_src = ds_tgt = None
+            if not const_attention:
+                # the gradient through the ONE global max(): Gamma / |T| over all heads (SURVEY.md 9.2)
+                g_tot, t_tot = torch.stack(gammas).sum(), torch.stack(ties).sum()
+                corr = torch.where(t_tot > 0, g_tot / t_tot.clamp(min=1.0), torch.zeros_like(g_tot)).to(torch.float32).reshape(1)
+                # stage 2 per group: the source-major pass with the shared correction; the cross-head A terms follow as GEMMs
+                for gi, it in enumerate(work):
+                    g_nh = it["g_nh"]
+                    if fused:
+                        _lib.call("gat_edge_bwd_fused", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
+                                  st.n_long_t, st.eid.data_ptr(), n, it["wh"].data_ptr(), g_nh, fp, it["ss"].data_ptr(), it["st"].data_ptr(),
+                                  gmax.data_ptr(), it["z"].data_ptr(), p_drop, seed, gi, it["go"].data_ptr(), 0, it["s_sum"].data_ptr(),
+                                  it["tpack"].data_ptr(), it["zeros_a"].data_ptr(), it["zeros_a"].data_ptr(), it["tie_dst"].data_ptr(),
+                                  it["tie_src"].data_ptr(), None, corr.data_ptr(), 0, n, it["ds_src"].data_ptr(), it["ds_tgt"].data_ptr(),
+                                  it["d_wh"].data_ptr(), None, 0, 0, 0, it["ws"].data_ptr(), ws_bytes, s, tag=(g_nh, fp))
+                    else:
+                        _lib.call("gat_edge_bwd_finish", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.order_t.data_ptr(), st.n_long_t, n, g_nh, fp,
+                                  it["rec"].data_ptr(), it["s_sum"].data_ptr(), it["zeros_a"].data_ptr(), it["zeros_a"].data_ptr(),
+                                  it["tie_dst"].data_ptr(), it["tie_src"].data_ptr(), None, corr.data_ptr(), 0, n,
+                                  it["ds_src"].data_ptr(), it["ds_tgt"].data_ptr(), it["d_wh"].data_ptr(), it["ws"].data_ptr(), ws_bytes, s,
+                                  tag=(g_nh, fp))
+                ds_src = torch.cat([it["ds_src"] for it in work], dim=1)
+                ds_tgt = torch.cat([it["ds_tgt"] for it in work], dim=1)
+            d_wh = torch.cat([it["d_wh"] for it in work], dim=1)
+            if not const_attention:
+                cross = torch.empty((n, dp), **f32)
+                gemm(False, False, n, dp, nh, ds_src, nh, a_src_p, dp, cross, dp, 1)
+                d_wh += cross
+                gemm(False, False, n, dp, nh, ds_tgt, nh, a_tgt_p, dp, cross, dp, 1)
+                d_wh += cross
+            gx = gw = ga_src = ga_tgt = None
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty((n, f_in), **f32)
+                gemm(False, False, n, f_in, dp, d_wh, dp, w_p, w_p.stride(0), gx, f_in, gemm_algo)
+            if ctx.needs_input_grad[1]:
+                gw = torch.empty((dp, f_in), **f32)
+                gemm(True, False, dp, f_in, n, d_wh, dp, x, x.stride(0), gw, f_in, gemm_algo)
+            if not const_attention and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
+                ga_src, ga_tgt = torch.empty((nh, dp), **f32), torch.empty((nh, dp), **f32)
+                gemm(True, False, nh, dp, n, ds_src, nh, wh, dp, ga_src, dp, 1)
+                gemm(True, False, nh, dp, n, ds_tgt, nh, wh, dp, ga_tgt, dp, 1)
+        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None
+
+
 class _GATLayerFunction(torch.autograd.Function):
     """(x, W, a) -> (out, alpha) through gat_layer_fwd / gat_layer_bwd: ONE C-ABI call per direction (csrc/layer.cu issues the
     whole kernel sequence), parameters in the reference's own layouts.  Everything the backward reads again lives in one
@@ -458,8 +632,6 @@ class GATLayer(nn.Module):
             raise RuntimeError(f"expected float32 node features, got {x.dtype}")   # the reference raises a dtype mismatch
         if x.dim() != 2 or x.size(1) != self.in_features:
             raise RuntimeError(f"x must have shape (N, {self.in_features}), got {tuple(x.shape)}")
-        if self.num_heads > MAX_HEADS:
-            raise NotImplementedError(f"num_heads > {MAX_HEADS} is not supported by the sm_100a kernels")
         if edge_index.device != x.device:
             raise RuntimeError("x and edge_index must be on the same device")
         if x.stride(1) != 1 or (x.size(0) > 1 and x.stride(0) < x.size(1)):
@@ -469,8 +641,13 @@ class GATLayer(nn.Module):
         fp = (self.out_features + 3) // 4 * 4
         if per_kernel:
             w_p, a_src, a_tgt, fp = self._padded_operands()
-        if self.num_heads * fp > MAX_ROW_FLOATS:
-            raise NotImplementedError(f"num_heads*out_features > {MAX_ROW_FLOATS} is not supported by the sm_100a kernels")
+        wide = self.num_heads > MAX_HEADS or self.num_heads * fp > MAX_ROW_FLOATS
+        if wide and fp > MAX_ROW_FLOATS:
+            raise NotImplementedError(f"out_features > {MAX_ROW_FLOATS} per head is not supported by the sm_100a kernels")
+        if wide and (self._x_act() or self._out_act(one_call=True) or self._bf16() or skip is not None or self._out_drop() > 0.0
+                     or self.attention_norm):
+            raise NotImplementedError("the fused glue / bf16 variant / fused attention norm are not available for layers processed in head "
+                                      f"groups (num_heads > {MAX_HEADS} or more than {MAX_ROW_FLOATS} floats per row)")
         p_drop = float(self.dropout) if (self.training and self.dropout > 0) else 0.0
         drop_all = p_drop >= 1.0      # nn.Dropout(p=1) zeroes every coefficient (gat_layer.py:113-115): out = 0, alpha intact
         if drop_all:
@@ -486,7 +663,12 @@ class GATLayer(nn.Module):
         if per_kernel and (skip is not None or self._out_drop() > 0.0 or self.attention_norm):
             raise NotImplementedError("skip= / output_dropout / attention_norm are implemented by the one-call path (gat_layer_fwd); not "
                                       "available under a per-kernel timer or with the bf16 variant")
-        if per_kernel:
+        if wide:
+            # beyond the edge kernels' limits: the same kernels over groups of heads (see _GATWideFunction)
+            w_p, a_src, a_tgt, fp = self._padded_operands()
+            out, alpha = _GATWideFunction.apply(x, w_p, a_src, a_tgt, st, self.num_heads, self.out_features, fp, bool(self.concat),
+                                                bool(self.const_attention), p_drop, bool(return_attention_weights), int(self.gemm_algo))
+        elif per_kernel:
             # per-kernel path: the bf16 variant and runs under a per-kernel timer (bench.py's live roofline measurement)
             out, alpha = _GATFunction.apply(x, w_p, a_src, a_tgt, st, self.num_heads, self.out_features, fp,
                                             bool(self.concat), bool(self.const_attention), p_drop,
