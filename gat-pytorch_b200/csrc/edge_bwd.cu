@@ -1094,22 +1094,25 @@ static int launch_bwd_main(const BwdMainParams& P, const int32_t* row_order_t, i
     } while (0)
     // short rows of a four-head head-mean layer: the (edge slot, head, quarter) kernel of edge_bwd_hm.cuh (the long rows keep
     // the cooperative launch above)
-    int hm_cpl = (FUSED && nh == 4 && P.tpack != nullptr && !P.push && getenv("GAT_BWD_HM_OFF") == nullptr) ? (P.chunks_per_head + 3) / 4 : 0;
+    int hm_cpl = (FUSED && nh == 4 && P.tpack != nullptr && getenv("GAT_BWD_HM_OFF") == nullptr) ? (P.chunks_per_head + 3) / 4 : 0;
     if (hm_cpl < 2 || hm_cpl > 4) hm_cpl = 0;     // 5..16 chunks per head (narrower rows: the general kernel's lane grid fits them)
     if (shape.slots == 1) LAUNCH_GS(1); else LAUNCH_GS(2);
 #undef LAUNCH_GS
 #define LAUNCH_HM(C_, X_)                                                                                              \
     do {                                                                                                               \
-      static bool optin_hm_dev_[kMaxDevices] = {false};                                                                \
-      bool& optin_hm_ = optin_hm_dev_[cur_device()];                                                                   \
-      if (!optin_hm_) {                                                                                                \
+      const size_t hm_smem_ = HmShape<C_>::kSmem + push_bytes;                                                         \
+      BwdMainParams H = Q;                                                                                             \
+      H.rowbuf_offset_floats = push_bytes ? (int)(HmShape<C_>::kSmem / sizeof(float)) : -1;                            \
+      static size_t optin_hm_dev_[kMaxDevices] = {0};                                                                  \
+      size_t& optin_hm_ = optin_hm_dev_[cur_device()];                                                                 \
+      if (hm_smem_ > optin_hm_) {                                                                                      \
+        optin_hm_ = hm_smem_;                                                                                          \
         GAT_CUDA(cudaFuncSetAttribute(edge_bwd_hm4_kernel<C_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                      (int)HmShape<C_>::kSmem));                                                       \
-        optin_hm_ = true;                                                                                              \
+                                      (int)optin_hm_));                                                                \
       }                                                                                                                \
       GAT_CUDA(launch_kernel(edge_bwd_hm4_kernel<C_, X_>,                                                              \
-                             persistent_grid(edge_bwd_hm4_kernel<C_, X_>, kEdgeThreads, HmShape<C_>::kSmem, (n_rows + 7) / 8), \
-                             kEdgeThreads, HmShape<C_>::kSmem, st, Q, coop_launch));                                   \
+                             persistent_grid(edge_bwd_hm4_kernel<C_, X_>, kEdgeThreads, hm_smem_, (n_rows + 7) / 8),   \
+                             kEdgeThreads, hm_smem_, st, H, coop_launch));                                             \
       GAT_LAUNCH_CHECK();                                                                                              \
     } while (0)
     if (hm_cpl == 3 && P.chunks_per_head == 12) LAUNCH_HM(3, true);

@@ -66,6 +66,7 @@ edge_bwd_hm4_kernel(const BwdMainParams P) {
   const int q32 = 32 / cph, r32 = 32 - q32 * cph;
   const int k0s = lane / cph, j0s = lane - k0s * cph;
 
+  int flip = 0;             // which of the warp's two push buffers is next
   int64_t base_rows;
   while (grab_rows<32>(P.sched, lane, base_rows)) {
     int pr, ps, pe;
@@ -217,6 +218,14 @@ edge_bwd_hm4_kernel(const BwdMainParams P) {
         }
       }
       float* const drow = dwh_row_ptr(P, row);
+      // PUSH (partitioned graphs): the finished row is staged in one of the warp's two row buffers and leaves as ONE bulk copy
+      // into its owner's receive slab over NVLink (see BwdMainParams::rowbuf_offset_floats); otherwise straight to d_wh
+      float* dst = drow;
+      if (P.rowbuf_offset_floats >= 0) {
+        dst = reinterpret_cast<float*>(hm_smem) + P.rowbuf_offset_floats + (warp * 2 + flip) * P.dp;
+        if (lane == 0) bulk_wait_read_keep1();          // the copy issued from this buffer two rows ago has read it
+        __syncwarp();
+      }
 #pragma unroll
       for (int i = 0; i < CPL; ++i) {
         acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, 16);
@@ -224,10 +233,17 @@ edge_bwd_hm4_kernel(const BwdMainParams P) {
         acc[i].z += __shfl_xor_sync(0xffffffffu, acc[i].z, 16);
         acc[i].w += __shfl_xor_sync(0xffffffffu, acc[i].w, 16);
         // chunk i leaves from half (i & 1): both halves hold the same sum (x + y is commutative bit for bit)
-        if (ok[i] && j == (i & 1)) *reinterpret_cast<float4*>(drow + coff[i]) = acc[i];
+        if (ok[i] && j == (i & 1)) *reinterpret_cast<float4*>(dst + coff[i]) = acc[i];
+      }
+      if (P.rowbuf_offset_floats >= 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk copy
+        __syncwarp();
+        if (lane == 0) bulk_store(drow, dst, (unsigned)(P.dp * sizeof(float)));
+        flip ^= 1;
       }
     }
   }
+  if (P.rowbuf_offset_floats >= 0 && lane == 0) bulk_wait_all();   // every pushed row has left before the grid may complete
   pdl_wait_for_primary();     // no-op unless launched behind the cooperative long-row kernel
 }
 

@@ -240,9 +240,10 @@ class CudaBackend:
         """Kernel 2: wh = [ELU](x) W^T with the score terms emitted by the GEMM epilogue (gat_project_fwd)."""
         ws_bytes = int(self.lib.gat_gemm_workspace_bytes(0, 1, rows, dp, f_in, self.gemm_algo))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
+        p = lambda t: None if t is None else t.data_ptr()   # noqa: E731  (const_attention: no attention halves, no score terms)
         _lib.call("gat_project_fwd", x.data_ptr(), rows, f_in, x.stride(0), int(x_act), w_p.data_ptr(), w_p.stride(0), dp,
-                  a_src.data_ptr(), a_tgt.data_ptr(), nh, wh.data_ptr(), s_src.data_ptr(), s_tgt.data_ptr(), self.gemm_algo,
-                  ws.data_ptr(), ws_bytes, self._s(x.device), tag=(rows, dp, f_in))
+                  p(a_src), p(a_tgt), nh, wh.data_ptr(), p(s_src) if a_src is not None else None, p(s_tgt) if a_src is not None else None,
+                  self.gemm_algo, ws.data_ptr(), ws_bytes, self._s(x.device), tag=(rows, dp, f_in))
 
     def scores(self, wh, rows, dp, a_src, a_tgt, nh, s_src, s_tgt):
         _lib.call("gat_scores_fwd", wh.data_ptr(), rows, dp, a_src.data_ptr(), a_tgt.data_ptr(), nh,
@@ -255,15 +256,19 @@ class CudaBackend:
                   plan.rows, s_src_full.data_ptr(), s_tgt_local.data_ptr(), nh, gmax.data_ptr(), ws.data_ptr(), ws.numel(),
                   self._s(gmax.device))
 
-    def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act=False):
+    def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act=False,
+                 p_drop=0.0, seed=0, alpha=None, const_attention=False):
+        """Kernel 3 over the owned rows.  p_drop / seed: attention dropout (gat_layer.py:113-115; the Philox counter offset is
+        the rank, so equal local edge positions on different ranks draw different masks); alpha: (local E', nh) output in the
+        order of the rank-local rewritten edge list, pre-dropout; const_attention: gat_layer.py:89-92 (no score terms)."""
         p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
         fws = torch.empty(int(self.lib.gat_edge_fwd_workspace_bytes()), dtype=torch.uint8, device=out_p.device)
         order, n_long = self.local_order(st, plan)
         _lib.call("gat_edge_fwd", st.rowptr.data_ptr() + 4 * plan.lo, st.col.data_ptr(), st.eid.data_ptr(),
                   order.data_ptr(), n_long, plan.rows,
-                  wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(), s_tgt_local.data_ptr(), gmax.data_ptr(),
-                  0, 0.0, 0, 0, out_p.data_ptr(), int(out_act), None, z.data_ptr(), p(tie_dst), p(tie_src), p(tie_total),
-                  fws.data_ptr(), fws.numel(), self._s(out_p.device), tag=(nh, fp))
+                  wh_full.data_ptr(), nh, fp, p(s_src_full), p(s_tgt_local), p(gmax),
+                  int(const_attention), float(p_drop), int(seed), plan.rank, out_p.data_ptr(), int(out_act), p(alpha), z.data_ptr(),
+                  p(tie_dst), p(tie_src), p(tie_total), fws.data_ptr(), fws.numel(), self._s(out_p.device), tag=(nh, fp))
 
     def scores_bwd(self, wh, n, dp, nh, ds_src, ds_tgt, da_src, da_tgt):
         sb = int(self.lib.gat_scores_bwd_workspace_bytes(dp, nh))
@@ -275,15 +280,19 @@ class CudaBackend:
         ws_bytes = int(self.lib.gat_edge_bwd_workspace_bytes(0, 0, nh))
         return torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes
 
-    def edge_bwd_main(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh):
+    def edge_bwd_main(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh, p_drop=0.0, seed=0,
+                      const_attention=False):
         """Pass 1 over ALL source rows with this rank's edges; target-indexed arrays are local, so their base
-        pointers are shifted by plan.lo rows (col_t holds GLOBAL target ids, all in [lo, hi))."""
+        pointers are shifted by plan.lo rows (col_t holds GLOBAL target ids, all in [lo, hi)).  const_attention: the whole
+        backward of the edge stage (alpha = 1/(deg+eps) carries no gradient): d_wh only, no records."""
         dp, lo = nh * fp, plan.lo
         ws, ws_bytes = self._bwd_ws(go_p.device, nh)
+        sh = lambda t, w: None if t is None else t.data_ptr() - 4 * w * lo   # noqa: E731
         _lib.call("gat_edge_bwd_main", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
-                  st.n_long_t, st.eid.data_ptr(), plan.n, wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(),
-                  s_tgt_local.data_ptr() - 4 * nh * lo, gmax.data_ptr(), z_local.data_ptr() - 4 * nh * lo,
-                  0, 0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, 0, None, rec.data_ptr(), d_wh.data_ptr(),
+                  st.n_long_t, st.eid.data_ptr(), plan.n, wh_full.data_ptr(), nh, fp, None if s_src_full is None else s_src_full.data_ptr(),
+                  sh(s_tgt_local, nh), None if gmax is None else gmax.data_ptr(), sh(z_local, nh),
+                  int(const_attention), float(p_drop), int(seed), plan.rank, go_p.data_ptr() - 4 * dp * lo, 0, None,
+                  None if rec is None else rec.data_ptr(), d_wh.data_ptr(),
                   ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
 
     def recv_buffer(self, plan, dp, group):
@@ -301,7 +310,7 @@ class CudaBackend:
         _lib.call("gat_slab_sum", recv.data_ptr(), n_slabs, slab_rows, dp, out.data_ptr(), self._s(out.device), tag=(n_slabs, dp))
 
     def edge_bwd_fused(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, s_sum_local,
-                       a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh, push_ptrs=None):
+                       a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh, push_ptrs=None, p_drop=0.0, seed=0, go_shared=False):
         """The backward's one heavy pass (gat_edge_bwd_fused) over ALL source rows with this rank's edges; target-indexed
         arrays are local, so their base pointers are shifted by plan.lo rows (col_t holds GLOBAL target ids in [lo, hi)).
         With push_ptrs (the ranks' receive buffers) every finished dWh row goes straight to its owner over NVLink."""
@@ -313,14 +322,28 @@ class CudaBackend:
         _lib.call("gat_edge_bwd_fused", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
                   st.n_long_t, st.eid.data_ptr(), plan.n, wh_full.data_ptr(), nh, fp, s_src_full.data_ptr(),
                   s_tgt_local.data_ptr() - 4 * nh * lo, gmax.data_ptr(), z_local.data_ptr() - 4 * nh * lo,
-                  0.0, 0, 0, go_p.data_ptr() - 4 * dp * lo, 0, s_sum_local.data_ptr() - 4 * nh * lo,
+                  float(p_drop), int(seed), plan.rank, go_p.data_ptr() - 4 * (fp if go_shared else dp) * lo, int(go_shared),
+                  s_sum_local.data_ptr() - 4 * nh * lo,
                   (tpack.data_ptr() - 4 * tpack.size(1) * lo) if tpack is not None else None,
                   a_src.data_ptr(), a_tgt.data_ptr(), tie_dst.data_ptr(), tie_src.data_ptr(), None, corr.data_ptr(),
                   plan.lo, plan.hi, ds_src.data_ptr(), ds_tgt.data_ptr(), d_wh.data_ptr() if d_wh is not None else None,
                   arr, len(push_ptrs) if push_ptrs else 0, plan.rank, plan.rows_per_rank, ws.data_ptr(), ws_bytes,
                   self._s(go_p.device), tag=(nh, fp))
 
-    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt, go_pre=None, s_tgt_local=None):
+    def head_merge(self, out_p, rows, nh, f, fp, concat):
+        """gat_layer.py:129-132 on the owned rows: padded (rows, nh, fp) -> (rows, nh*f) or the head mean (rows, f)."""
+        out = torch.empty((rows, nh * f if concat else f), dtype=torch.float32, device=out_p.device)
+        _lib.call("gat_head_merge_fwd", out_p.data_ptr(), rows, nh, f, fp, int(concat), out.data_ptr(), self._s(out_p.device))
+        return out
+
+    def head_mean_bwd_shared(self, go, rows, nh, f, fp):
+        """Adjoint of the head mean as ONE shared (rows, fp) row per target (every head receives go/nh): what the backward
+        kernels gather with go_shared = 1 -- a quarter of the bytes per edge at nh = 4, and the lane mapping built for it."""
+        out = torch.empty((max(rows, 1), fp), dtype=torch.float32, device=go.device)
+        _lib.call("gat_head_mean_bwd_shared", go.data_ptr(), rows, nh, f, fp, out.data_ptr(), self._s(go.device))
+        return out
+
+    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt, go_pre=None, s_tgt_local=None, go_shared=False):
         """Pass 2 without per-edge data: S = <dOut, out> over the owned rows; returns this rank's Gamma.  With go_pre
         (the forward stored ELU(out)) the ELU adjoint is applied on the way and dL/dout is written to go_pre.  With
         s_tgt_local the pass also writes the per-target records {s_tgt | Z | S} that the next edge_bwd_fused call gathers."""
@@ -330,7 +353,7 @@ class CudaBackend:
         if s_tgt_local is not None:
             tpack = torch.empty((max(plan.rows, 1), int(self.lib.gat_tgt_pack_stride(nh))), dtype=torch.float32, device=go_p.device)
         self._tpack = tpack
-        _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), 0, out_p.data_ptr(), int(go_pre is not None),
+        _lib.call("gat_edge_bwd_rowdot", go_p.data_ptr(), int(go_shared), out_p.data_ptr(), int(go_pre is not None),
                   go_pre.data_ptr() if go_pre is not None else None, z_local.data_ptr(), plan.rows, nh, fp,
                   s_sum.data_ptr(), ds_tgt.data_ptr(), s_tgt_local.data_ptr() if tpack is not None else None,
                   tpack.data_ptr() if tpack is not None else None, ws.data_ptr(), ws_bytes, self._s(go_p.device), tag=(nh, fp))
@@ -353,7 +376,7 @@ class CudaBackend:
 class _PartitionedGATFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_local, w_p, a_src_p, a_tgt_p, st, plan: Plan, nh, fp, backend, group, gathered, x_act=False, out_act=False,
-                generation=None):
+                generation=None, p_drop=0.0, want_alpha=False, mean_f=0):
         dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
         rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
         s_src_slab = torch.zeros((R, nh), **f32)
@@ -386,19 +409,34 @@ class _PartitionedGATFunction(torch.autograd.Function):
         z = torch.zeros((max(rows, 1), nh), **f32)
         ties = torch.zeros(2 + max(rows, 1) * nh + plan.n_pad * nh, dtype=torch.int32, device=dev)
         tie_total, tie_dst, tie_src = ties[:2], ties[2:2 + max(rows, 1) * nh], ties[2 + max(rows, 1) * nh:]
+        seed = int(torch.empty((), dtype=torch.int64).random_().item()) if p_drop > 0.0 else 0     # CPU generator: no device sync
+        alpha = torch.empty((backend.n_edges(st), nh), **f32) if want_alpha else None
         if rows:
-            backend.edge_fwd(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act)
+            backend.edge_fwd(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act,
+                             **({"p_drop": p_drop, "seed": seed} if p_drop > 0.0 else {}), **({"alpha": alpha} if want_alpha else {}))
         ctx.misc = (st, plan, nh, fp, backend, group, bool(x_act), bool(out_act))
+        ctx.drop = (float(p_drop), seed)
+        ctx.mean_f = int(mean_f)
         # wh_full is a persistent symmetric-memory buffer that the peers' TMA stores rewrite behind autograd's back (no
         # version bump): remember which push filled it, so that backward can refuse a buffer that was re-pushed since
         ctx.wh_generation = (generation, None if generation is None else generation[0])
         ctx.save_for_backward(x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p)
-        return out_p
+        # head-mean layers (gat_layer.py:131-132) merge inside the function, so that the backward sees the (rows, F) gradient and
+        # can hand the kernels ONE shared row per target instead of nh copies of it
+        res = backend.head_merge(out_p, rows, nh, mean_f, fp, False) if (mean_f and rows) else (out_p[:, :mean_f] if mean_f else out_p)
+        if want_alpha:
+            # the returned attention is an OUTPUT of the partitioned layer, not a differentiable one: a loss term on it would need
+            # the three-pass backward across ranks (single-GPU layers have it; here it raises instead of being silently ignored)
+            ctx.mark_non_differentiable(alpha)
+            return res, alpha
+        return res
 
     @staticmethod
-    def backward(ctx, go_p):
+    def backward(ctx, go_p, *unused):
         x_local, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p = ctx.saved_tensors
         st, plan, nh, fp, backend, group, x_act, out_act = ctx.misc
+        p_drop, seed = ctx.drop
+        drop_kw = {"p_drop": p_drop, "seed": seed} if p_drop > 0.0 else {}
         gen_cell, gen_at_forward = ctx.wh_generation
         if gen_cell is not None and gen_cell[0] != gen_at_forward:
             raise RuntimeError(
@@ -408,6 +446,10 @@ class _PartitionedGATFunction(torch.autograd.Function):
         dev, f32 = x_local.device, dict(dtype=torch.float32, device=x_local.device)
         rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
         go_p = go_p.contiguous()
+        shared = bool(ctx.mean_f)
+        if shared:
+            go_p = backend.head_mean_bwd_shared(go_p, rows, nh, ctx.mean_f, fp)
+        sh_kw = {"go_shared": True} if shared else {}
         ds_tgt_full = torch.zeros((plan.n_pad + 1, nh), **f32)     # owned rows live at [lo, hi); the rest stays zero
         ds_tgt = ds_tgt_full[plan.lo:plan.lo + max(rows, 1)]
         s_sum = torch.zeros((max(rows, 1), nh), **f32)
@@ -416,7 +458,7 @@ class _PartitionedGATFunction(torch.autograd.Function):
         gamma = torch.zeros(1, dtype=torch.float64, device=dev)
         if rows:    # S = <dOut, out> over the owned rows first: no per-edge data needed
             go_pre = torch.empty_like(go_p) if out_act else None     # dL/dout when the forward stored ELU(out)
-            gamma = backend.edge_bwd_rowdot(plan, nh, fp, go_p, out_p, z, s_sum, ds_tgt, go_pre, s_tgt)
+            gamma = backend.edge_bwd_rowdot(plan, nh, fp, go_p, out_p, z, s_sum, ds_tgt, go_pre, s_tgt, **sh_kw)
             if out_act:
                 go_p = go_pre
         red = torch.stack([gamma[0], tie_total.view(torch.int64)[0].to(torch.float64)])
@@ -428,7 +470,7 @@ class _PartitionedGATFunction(torch.autograd.Function):
             # fused reduce-scatter: the pass stores every finished dWh row into its owner's receive slab over NVLink;
             # a tiny collective is the barrier, then the owner adds its P slabs in rank order
             backend.edge_bwd_fused(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, s_sum, a_src_p, a_tgt_p,
-                                   tie_dst, tie_src, corr, ds_src_part, ds_tgt, None, push_ptrs=push_ptrs)
+                                   tie_dst, tie_src, corr, ds_src_part, ds_tgt, None, push_ptrs=push_ptrs, **drop_kw, **sh_kw)
             with _lib.timed("nccl:barrier(push)"):
                 dist.all_reduce(torch.zeros(1, **f32), group=group)            # barrier: every rank's pushes have landed
             backend.slab_sum(recv, plan.world, R, dp, d_wh)
@@ -437,7 +479,7 @@ class _PartitionedGATFunction(torch.autograd.Function):
             if plan.n_pad > plan.n:
                 d_wh_part[plan.n:].zero_()
             backend.edge_bwd_fused(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, s_sum, a_src_p, a_tgt_p,
-                                   tie_dst, tie_src, corr, ds_src_part, ds_tgt, d_wh_part)
+                                   tie_dst, tie_src, corr, ds_src_part, ds_tgt, d_wh_part, **drop_kw, **sh_kw)
             dist.reduce_scatter_tensor(d_wh, d_wh_part, group=group)        # transpose of the all-gather (NCCL)
         gx = None
         if ctx.needs_input_grad[0] and rows:
@@ -463,20 +505,79 @@ class _PartitionedGATFunction(torch.autograd.Function):
             dist.all_reduce(flat, group=group)                                  # the gradient all-reduce
         gw, ga_src, ga_tgt = flat[:gw.numel()].view_as(gw), flat[gw.numel():gw.numel() + ga_src.numel()].view_as(ga_src), \
             flat[gw.numel() + ga_src.numel():].view_as(ga_tgt)
-        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None, None
+        return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None, None, None, None, None
+
+
+class _PartitionedConstGATFunction(torch.autograd.Function):
+    """The partitioned layer with `const_attention` (gat_layer.py:89-92: e = 0, alpha = 1/(deg + 1e-8), no `a`): projection,
+    feature all-gather, Kernel 3 with its const flag; backward = the source-major pass alone (alpha carries no gradient), the
+    reduce-scatter of dWh and the two GEMMs.  The exchanges go through NCCL (the fused peer-memory kernels carry the score
+    epilogue this variant does not have)."""
+
+    @staticmethod
+    def forward(ctx, x_local, w_p, st, plan: Plan, nh, fp, backend, group, p_drop=0.0, want_alpha=False):
+        f32 = dict(dtype=torch.float32, device=x_local.device)
+        rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
+        wh_slab = torch.zeros((R, dp), **f32)
+        if rows:
+            backend.project(x_local, rows, f_in, w_p, dp, None, None, nh, wh_slab, None, None)
+        wh_full = torch.empty((plan.n_pad, dp), **f32)
+        dist.all_gather_into_tensor(wh_full, wh_slab, group=group)
+        out_p = torch.empty((max(rows, 1), dp), **f32)[:rows]
+        z = torch.zeros((max(rows, 1), nh), **f32)
+        seed = int(torch.empty((), dtype=torch.int64).random_().item()) if p_drop > 0.0 else 0
+        alpha = torch.empty((backend.n_edges(st), nh), **f32) if want_alpha else None
+        if rows:
+            backend.edge_fwd(st, plan, wh_full, nh, fp, None, None, None, out_p, z, None, None, None, False,
+                             p_drop=p_drop, seed=seed, alpha=alpha, const_attention=True)
+        ctx.misc = (st, plan, nh, fp, backend, group, float(p_drop), seed)
+        ctx.save_for_backward(x_local, w_p, wh_full, z)
+        if want_alpha:
+            ctx.mark_non_differentiable(alpha)
+            return out_p, alpha
+        return out_p
+
+    @staticmethod
+    def backward(ctx, go_p, *unused):
+        x_local, w_p, wh_full, z = ctx.saved_tensors
+        st, plan, nh, fp, backend, group, p_drop, seed = ctx.misc
+        f32 = dict(dtype=torch.float32, device=x_local.device)
+        rows, dp, f_in, R = plan.rows, nh * fp, x_local.size(1), plan.rows_per_rank
+        go_p = go_p.contiguous()
+        d_wh_part = torch.zeros((plan.n_pad, dp), **f32)
+        if backend.n_edges(st):
+            backend.edge_bwd_main(st, plan, wh_full, nh, fp, None, None, None, z, go_p, None, d_wh_part, p_drop=p_drop, seed=seed,
+                                  const_attention=True)
+        d_wh = torch.empty((R, dp), **f32)
+        dist.reduce_scatter_tensor(d_wh, d_wh_part, group=group)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.zeros((rows, f_in), **f32)
+            if rows:
+                backend.gemm(False, True, rows, f_in, dp, d_wh, dp, w_p.t().contiguous(), dp, gx, f_in)
+        gw = torch.zeros((dp, f_in), **f32)
+        if rows:
+            backend.gemm(True, False, dp, f_in, rows, d_wh, dp, x_local, x_local.stride(0), gw, f_in)
+        dist.all_reduce(gw, group=group)
+        return gx, gw, None, None, None, None, None, None, None, None
 
 
 class PartitionedGATLayer(torch.nn.Module):
-    """`GATLayer` semantics (add_self_loops=True, dropout 0, attention not returned) for one rank's rows.
-    forward(x_local, st, plan) -> out_local.  Parameters are replicated; their .grad is the global sum."""
+    """`GATLayer` semantics (gat_layer.py:13-140 with add_self_loops=True, bias=False -- what GATModel.py:76-77 constructs) for one
+    rank's rows: forward(x_local, st, plan, return_attention_weights=False) -> out_local or (out_local, (edge_index_local',
+    alpha_local)).  `dropout` (training mode) and `const_attention` as in the reference; the returned attention covers the
+    rank-local rewritten edge list (the edges whose target this rank owns, in the order of `exchange_edge_list`) and is not
+    differentiable.  Parameters are replicated; their .grad is the global sum."""
 
-    def __init__(self, in_features, out_features, num_heads, concat, backend=None, group=None):
+    def __init__(self, in_features, out_features, num_heads, concat, backend=None, group=None, dropout=0.0, const_attention=False):
         super().__init__()
         self.in_features, self.out_features, self.num_heads, self.concat = in_features, out_features, num_heads, concat
+        self.dropout, self.const_attention = dropout, const_attention
         self.W = torch.nn.Linear(in_features, num_heads * out_features, bias=False)
-        self.a = torch.nn.Linear(num_heads * 2 * out_features, num_heads, bias=False)
         torch.nn.init.xavier_uniform_(self.W.weight)
-        torch.nn.init.xavier_uniform_(self.a.weight)
+        if not const_attention:     # same construction order as the reference (gat_layer.py:27-31)
+            self.a = torch.nn.Linear(num_heads * 2 * out_features, num_heads, bias=False)
+            torch.nn.init.xavier_uniform_(self.a.weight)
         self.backend, self.group = backend, group
         # Two (wh_full, peer pointers) symmetric-memory buffers per layer, used alternately: the peers' stores of forward
         # k+1 must not land in the buffer that forward k's edge kernels (or its pending backward) still read.  With two
@@ -495,17 +596,27 @@ class PartitionedGATLayer(torch.nn.Module):
         w = self.W.weight
         if fp != f:
             w = F.pad(w.view(nh, f, self.in_features), (0, 0, 0, fp - f)).reshape(nh * fp, self.in_features)
+        if self.const_attention:
+            return w, None, None, fp
         a3 = self.a.weight.view(nh, nh, 2 * f)
         a_src, a_tgt = a3[:, :, :f], a3[:, :, f:]
         if fp != f:
             a_src, a_tgt = F.pad(a_src, (0, fp - f)), F.pad(a_tgt, (0, fp - f))
         return w, a_src.reshape(nh, nh * fp).contiguous(), a_tgt.reshape(nh, nh * fp).contiguous(), fp
 
-    def forward(self, x_local, st, plan: Plan):
+    def forward(self, x_local, st, plan: Plan, return_attention_weights=False):
         if self.backend is None:
             self.backend = CudaBackend()
         w_p, a_src, a_tgt, fp = self._padded_operands()
         nh, f = self.num_heads, self.out_features
+        p_drop = float(self.dropout) if (self.training and self.dropout > 0) else 0.0
+        if not 0.0 <= p_drop < 1.0:
+            raise ValueError(f"dropout must be in [0, 1) for the partitioned layer, got {p_drop}")
+        want_alpha = bool(return_attention_weights)
+        if self.const_attention:
+            res = _PartitionedConstGATFunction.apply(x_local.contiguous(), w_p, st, plan, nh, fp, self.backend, self.group, p_drop, want_alpha)
+            out_p, alpha = res if want_alpha else (res, None)
+            return self._finish(out_p, alpha, st, nh, f, fp, want_alpha)
         gathered = generation = None
         if hasattr(self.backend, "gathered_buffer"):
             if self._gathered is None or self._gathered[0][0].shape != (plan.n_pad, nh * fp) or self._gathered[0][0].device != x_local.device:
@@ -515,11 +626,23 @@ class PartitionedGATLayer(torch.nn.Module):
             self._forward_count += 1
             gathered, generation = self._gathered[slot], self._generation[slot]
             generation[0] += 1
-        out_p = _PartitionedGATFunction.apply(x_local.contiguous(), w_p, a_src, a_tgt, st, plan, nh, fp, self.backend, self.group,
-                                              gathered, self.input_activation == "elu",
-                                              self.output_activation == "elu" and bool(self.concat), generation)
+        mean_f = f if (not self.concat and nh > 1 and hasattr(self.backend, "head_merge")) else 0
+        res = _PartitionedGATFunction.apply(x_local.contiguous(), w_p, a_src, a_tgt, st, plan, nh, fp, self.backend, self.group,
+                                            gathered, self.input_activation == "elu",
+                                            self.output_activation == "elu" and bool(self.concat), generation, p_drop, want_alpha, mean_f)
+        out_p, alpha = res if want_alpha else (res, None)
+        if mean_f:      # already merged (and averaged) inside the function
+            edges = st.edge_index if hasattr(st, "edge_index") else torch.stack([st["src"], st["dst"]])
+            return (out_p, (edges, alpha)) if want_alpha else out_p
+        return self._finish(out_p, alpha, st, nh, f, fp, want_alpha)
+
+    def _finish(self, out_p, alpha, st, nh, f, fp, want_alpha):
         o = out_p.view(-1, nh, fp)[:, :, :f]
-        return o.reshape(-1, nh * f) if self.concat else o.mean(dim=1)      # gat_layer.py:129-132
+        out = o.reshape(-1, nh * f) if self.concat else o.mean(dim=1)      # gat_layer.py:129-132
+        if not want_alpha:
+            return out
+        edges = st.edge_index if hasattr(st, "edge_index") else torch.stack([st["src"], st["dst"]])
+        return out, (edges, alpha)
 
 
 class PartitionedGAT:

@@ -33,7 +33,8 @@ class OracleBackend:
         if x_act:
             x = torch.nn.functional.elu(x)
         self.gemm(False, True, rows, dp, f_in, x, x.stride(0), w_p, w_p.stride(0), wh, dp)
-        self.scores(wh, rows, dp, a_src, a_tgt, nh, s_src, s_tgt)
+        if a_src is not None:       # const_attention has no score terms
+            self.scores(wh, rows, dp, a_src, a_tgt, nh, s_src, s_tgt)
 
     def scores(self, wh, rows, dp, a_src, a_tgt, nh, s_src, s_tgt):
         s_src[:rows] = (wh[:rows].double() @ a_src.double().T).float()
@@ -54,14 +55,25 @@ class OracleBackend:
         z = torch.zeros((rows, nh)).index_add_(0, st["dst"] - plan.lo, p)
         return l, p, z
 
-    def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act=False):
+    def edge_fwd(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act=False,
+                 p_drop=0.0, seed=0, alpha=None, const_attention=False):
+        assert p_drop == 0.0, "the oracle backend has no Philox: dropout is covered by the GPU tests"
         rows = plan.rows
-        l, p, zz = self._alpha(st, plan, s_src_full, s_tgt_local, gmax, rows, nh)
+        if const_attention:         # gat_layer.py:89-92: e = 0 -> p = 1, Z = in-degree
+            p = torch.ones((st["src"].numel(), nh))
+            zz = torch.zeros((rows, nh)).index_add_(0, st["dst"] - plan.lo, p)
+            l = None
+        else:
+            l, p, zz = self._alpha(st, plan, s_src_full, s_tgt_local, gmax, rows, nh)
         z[:rows] = zz
-        alpha = p / (zz[st["dst"] - plan.lo] + EPS)
-        msg = alpha[:, :, None] * wh_full[st["src"]].view(-1, nh, fp)
+        al = p / (zz[st["dst"] - plan.lo] + EPS)
+        if alpha is not None:
+            alpha.copy_(al)
+        msg = al[:, :, None] * wh_full[st["src"]].view(-1, nh, fp)
         out_p.zero_()
         out_p.view(-1, nh, fp).index_add_(0, st["dst"] - plan.lo, msg)
+        if const_attention:
+            return
         tie = (l == gmax).to(torch.int32)
         tie_dst.view(-1, nh).index_add_(0, st["dst"] - plan.lo, tie)
         tie_src.view(-1, nh).index_add_(0, st["src"], tie)
@@ -69,9 +81,30 @@ class OracleBackend:
         if out_act:
             out_p.copy_(torch.nn.functional.elu(out_p))
 
-    def edge_bwd_main(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh):
+    def head_merge(self, out_p, rows, nh, f, fp, concat):
+        o = out_p.view(-1, nh, fp)[:rows, :, :f]
+        return o.reshape(rows, nh * f).clone() if concat else o.mean(dim=1)
+
+    def head_mean_bwd_shared(self, go, rows, nh, f, fp):
+        out = torch.zeros((max(rows, 1), fp))
+        out[:rows, :f] = go[:rows] / nh
+        return out
+
+    @staticmethod
+    def _per_head(go_p, nh, fp, go_shared):
+        return go_p.view(-1, 1, fp).expand(-1, nh, fp).reshape(-1, nh * fp) if go_shared else go_p
+
+    def edge_bwd_main(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh, p_drop=0.0, seed=0,
+                      const_attention=False):
+        assert p_drop == 0.0
         rows = plan.rows
         dl = st["dst"] - plan.lo
+        if const_attention:
+            alpha = 1.0 / (z_local[:rows][dl] + EPS)
+            go_e = go_p.view(-1, nh, fp)[dl]
+            d_wh.zero_()
+            d_wh.view(-1, nh, fp).index_add_(0, st["src"], alpha[:, :, None] * go_e)
+            return
         l, p, _ = self._alpha(st, plan, s_src_full, s_tgt_local, gmax, rows, nh)
         alpha = p / (z_local[:rows][dl] + EPS)
         go_e = go_p.view(-1, nh, fp)[dl]
@@ -83,14 +116,17 @@ class OracleBackend:
         d_wh.view(-1, nh, fp).index_add_(0, st["src"], alpha[:, :, None] * go_e)
 
     def edge_bwd_fused(self, st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, s_sum_local,
-                       a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh, push_ptrs=None):
+                       a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh, push_ptrs=None, p_drop=0.0, seed=0, go_shared=False):
+        assert p_drop == 0.0
+        go_p = self._per_head(go_p, nh, fp, go_shared)
         assert push_ptrs is None   # peer-memory push is a CUDA-only path (the oracle backend has no recv_buffer)
         rec = torch.zeros((max(self.n_edges(st), 1), 2 * nh))
         self.edge_bwd_main(st, plan, wh_full, nh, fp, s_src_full, s_tgt_local, gmax, z_local, go_p, rec, d_wh)
         self.edge_bwd_finish(st, plan, nh, fp, rec, s_sum_local, a_src, a_tgt, tie_dst, tie_src, corr, ds_src, ds_tgt, d_wh)
 
-    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt, go_pre=None, s_tgt_local=None):
+    def edge_bwd_rowdot(self, plan, nh, fp, go_p, out_p, z_local, s_sum, ds_tgt, go_pre=None, s_tgt_local=None, go_shared=False):
         rows = plan.rows
+        go_p = self._per_head(go_p, nh, fp, go_shared)
         if go_pre is not None:     # out_p holds h = ELU(out): recover out and apply ELU'
             h = out_p
             go_pre.copy_(go_p * torch.where(h > 0, torch.ones_like(h), h + 1.0))

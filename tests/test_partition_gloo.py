@@ -74,6 +74,69 @@ def test_two_rank_partition_matches_single_process_oracle(case_name, world):
         assert np.array_equal(ret[r]["edges"], ei2[:, sel])
 
 
+def _extras_worker(rank, world, port, case_name, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import cases
+        from _oracle_backend import OracleBackend
+        from gat_pytorch_b200.partition import PartitionedGATLayer, local_edge_list, make_plan
+        case = {c["name"]: c for c in cases.adversarial_cases()}[case_name]
+        x, ei = torch.from_numpy(case["x"]), torch.from_numpy(case["edge_index"].astype(np.int64))
+        plan = make_plan(x.size(0), world, rank)
+        backend = OracleBackend()
+        st = backend.build_structure(local_edge_list(ei, int(ei.max()) + 1, plan.lo, plan.hi, True), plan.n)
+        layer = PartitionedGATLayer(x.size(1), case["f"], case["nh"], case["concat"], backend, const_attention=case["const_attention"])
+        with torch.no_grad():
+            layer.W.weight.copy_(torch.from_numpy(case["W"]))
+            if not case["const_attention"]:
+                layer.a.weight.copy_(torch.from_numpy(case["a"]))
+        xl = x[plan.lo:plan.hi].clone().requires_grad_(True)
+        out, (edges, alpha) = layer(xl, st, plan, return_attention_weights=True)
+        go_full, _ = cases.upstream_grads(case, x.size(0), out.size(1), 1)
+        (out * torch.from_numpy(go_full[plan.lo:plan.hi])).sum().backward()
+        ret[rank] = dict(lo=plan.lo, hi=plan.hi, out=out.detach().numpy(), gx=xl.grad.numpy(), gW=layer.W.weight.grad.numpy(),
+                         ga=None if case["const_attention"] else layer.a.weight.grad.numpy(),
+                         edges=edges.numpy(), alpha=alpha.numpy(), alpha_requires_grad=bool(alpha.requires_grad),
+                         has_a=hasattr(layer, "a"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case_name", ["adv_const", "adv_concat"])
+def test_partitioned_layer_const_attention_and_returned_attention(case_name):
+    """`const_attention` (gat_layer.py:89-92) and `return_attention_weights` in the partitioned layer: outputs and gradients
+    against the single-process oracle; the returned attention is the oracle's, restricted to the edges whose target the rank
+    owns, in the rewritten order; it is an output only (not differentiable)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cases
+    import gat_oracle as O
+    world = 2
+    ret = mp.Manager().dict()
+    port = 29950 + (os.getpid() % 40)
+    mp.spawn(_extras_worker, args=(world, port, case_name, ret), nprocs=world, join=True)
+    case = {c["name"]: c for c in cases.adversarial_cases()}[case_name]
+    fw = O.forward(case["x"], case["edge_index"], case["W"], case["a"], case["nh"], case["f"], case["concat"], True, None,
+                   case["const_attention"])
+    go, _ = cases.upstream_grads(case, fw["out"].shape[0], fw["out"].shape[1], 1)
+    gr = O.backward(fw, go, None)
+    assert O.rel_err(np.concatenate([ret[r]["out"] for r in range(world)]), fw["out"]) < 1e-5
+    assert O.rel_err(np.concatenate([ret[r]["gx"] for r in range(world)]), gr["x"]) < 1e-5
+    ei2 = fw["edge_index"]
+    for r in range(world):
+        assert O.rel_err(ret[r]["gW"], gr["W"]) < 1e-5
+        if not case["const_attention"]:
+            assert O.rel_err(ret[r]["ga"], gr["a"]) < 1e-5
+        assert ret[r]["has_a"] == (not case["const_attention"])
+        sel = (ei2[1] >= ret[r]["lo"]) & (ei2[1] < ret[r]["hi"])
+        assert np.array_equal(ret[r]["edges"], ei2[:, sel])
+        assert O.rel_err(ret[r]["alpha"], fw["alpha"][sel]) < 1e-5
+        assert not ret[r]["alpha_requires_grad"]
+
+
 def _exchange_worker(rank, world, port, ret):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
