@@ -508,6 +508,92 @@ class _PartitionedGATFunction(torch.autograd.Function):
         return gx, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
+class _ReplicatedInputGATFunction(torch.autograd.Function):
+    """The partitioned layer when the layer INPUT is replicated on every rank (the first layer: the node features are data, the
+    same every step, F_in narrower than the projection -- products: 100 against 256 floats per node).  Then nothing as wide as
+    Wh has to cross NVLink in either direction:
+      forward   every rank projects ALL nodes itself (one local GEMM over N rows; bit-identical to the slab-wise product, whose
+                K loop per output element is the same) instead of exchanging (P-1)/P of Wh: at 8 GPUs 0.97 ms against 3.2 ms;
+      backward  the source-major pass writes its partial dWh for all sources LOCALLY; dW = dWh_partial^T x over all nodes is a
+                local GEMM whose sum over ranks the parameter all-reduce forms anyway, so the reduce-scatter of dWh (the push)
+                disappears: the pass runs at its compute time.
+    The input carries no gradient in this mode (it raises if one is asked for).  What still crosses the links: the max, Gamma and
+    the tie count, the small dS_src reduce-scatter for dA, the parameter all-reduce."""
+
+    @staticmethod
+    def forward(ctx, x_full, w_p, a_src_p, a_tgt_p, st, plan: Plan, nh, fp, backend, group, out_act=False, mean_f=0):
+        dev, f32 = x_full.device, dict(dtype=torch.float32, device=x_full.device)
+        rows, dp, f_in = plan.rows, nh * fp, x_full.size(1)
+        n_all = x_full.size(0)                       # n_pad rows (slab rows beyond a rank's range are zero)
+        wh_full = torch.empty((n_all, dp), **f32)
+        s_src_full = torch.empty((n_all, nh), **f32)
+        s_tgt_full = torch.empty((n_all, nh), **f32)
+        backend.project(x_full, n_all, f_in, w_p, dp, a_src_p, a_tgt_p, nh, wh_full, s_src_full, s_tgt_full, False)
+        s_tgt = s_tgt_full[plan.lo:plan.lo + max(rows, 1)]
+        gmax = torch.full((1,), float("-inf"), **f32)
+        if rows:
+            backend.edge_max(st, plan, s_src_full, s_tgt, nh, gmax)
+        with _lib.timed("nccl:all_reduce(max)"):
+            dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+        out_p = torch.empty((max(rows, 1), dp), **f32)[:rows]
+        z = torch.zeros((max(rows, 1), nh), **f32)
+        ties = torch.zeros(2 + max(rows, 1) * nh + n_all * nh, dtype=torch.int32, device=dev)
+        tie_total, tie_dst, tie_src = ties[:2], ties[2:2 + max(rows, 1) * nh], ties[2 + max(rows, 1) * nh:]
+        if rows:
+            backend.edge_fwd(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, out_p, z, tie_dst, tie_src, tie_total, out_act)
+        ctx.misc = (st, plan, nh, fp, backend, group, bool(out_act), int(mean_f))
+        ctx.save_for_backward(x_full, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p)
+        return backend.head_merge(out_p, rows, nh, mean_f, fp, False) if (mean_f and rows) else (out_p[:, :mean_f] if mean_f else out_p)
+
+    @staticmethod
+    def backward(ctx, go_p):
+        x_full, w_p, a_src_p, a_tgt_p, wh_full, s_src_full, s_tgt, gmax, z, tie_dst, tie_src, tie_total, out_p = ctx.saved_tensors
+        st, plan, nh, fp, backend, group, out_act, mean_f = ctx.misc
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("PartitionedGATLayer(replicated input): the replicated input carries no gradient")
+        dev, f32 = x_full.device, dict(dtype=torch.float32, device=x_full.device)
+        rows, dp, f_in, R = plan.rows, nh * fp, x_full.size(1), plan.rows_per_rank
+        n_all = x_full.size(0)
+        go_p = go_p.contiguous()
+        sh_kw = {}
+        if mean_f:
+            go_p, sh_kw = backend.head_mean_bwd_shared(go_p, rows, nh, mean_f, fp), {"go_shared": True}
+        ds_tgt_full = torch.zeros((n_all + 1, nh), **f32)
+        ds_tgt = ds_tgt_full[plan.lo:plan.lo + max(rows, 1)]
+        s_sum = torch.zeros((max(rows, 1), nh), **f32)
+        ds_src_part = torch.zeros((n_all, nh), **f32)
+        gamma = torch.zeros(1, dtype=torch.float64, device=dev)
+        if rows:
+            go_pre = torch.empty_like(go_p) if out_act else None
+            gamma = backend.edge_bwd_rowdot(plan, nh, fp, go_p, out_p, z, s_sum, ds_tgt, go_pre, s_tgt, **sh_kw)
+            if out_act:
+                go_p = go_pre
+        red = torch.stack([gamma[0], tie_total.view(torch.int64)[0].to(torch.float64)])
+        with _lib.timed("nccl:all_reduce(gamma,ties)"):
+            dist.all_reduce(red, group=group)
+        corr = torch.where(red[1] > 0, red[0] / red[1].clamp(min=1.0), torch.zeros_like(red[0])).to(torch.float32).reshape(1)
+        d_wh_part = torch.empty((n_all, dp), **f32)      # rows [0, n) are all written by the source-major pass
+        if n_all > plan.n:
+            d_wh_part[plan.n:].zero_()
+        backend.edge_bwd_fused(st, plan, wh_full, nh, fp, s_src_full, s_tgt, gmax, z, go_p, s_sum, a_src_p, a_tgt_p,
+                               tie_dst, tie_src, corr, ds_src_part, ds_tgt, d_wh_part, **sh_kw)
+        gw = torch.zeros((dp, f_in), **f32)
+        backend.gemm(True, False, dp, f_in, n_all, d_wh_part, dp, x_full, x_full.stride(0), gw, f_in)    # partial dW over ALL nodes
+        ga_src = torch.zeros((nh, dp), **f32)
+        ga_tgt = torch.zeros((nh, dp), **f32)
+        ds_src_local = torch.empty((R, nh), **f32)
+        with _lib.timed("nccl:reduce_scatter(ds_src)"):
+            dist.reduce_scatter_tensor(ds_src_local, ds_src_part, group=group)
+        if rows:
+            backend.scores_bwd(wh_full[plan.lo:plan.lo + rows], rows, dp, nh, ds_src_local, ds_tgt, ga_src, ga_tgt)
+        flat = torch.cat([gw.reshape(-1), ga_src.reshape(-1), ga_tgt.reshape(-1)])
+        with _lib.timed("nccl:all_reduce(grads)"):
+            dist.all_reduce(flat, group=group)
+        gw, ga_src, ga_tgt = flat[:gw.numel()].view_as(gw), flat[gw.numel():gw.numel() + ga_src.numel()].view_as(ga_src), \
+            flat[gw.numel() + ga_src.numel():].view_as(ga_tgt)
+        return None, gw, ga_src, ga_tgt, None, None, None, None, None, None, None, None
+
+
 class _PartitionedConstGATFunction(torch.autograd.Function):
     """The partitioned layer with `const_attention` (gat_layer.py:89-92: e = 0, alpha = 1/(deg + 1e-8), no `a`): projection,
     feature all-gather, Kernel 3 with its const flag; backward = the source-major pass alone (alpha carries no gradient), the
@@ -636,6 +722,21 @@ class PartitionedGATLayer(torch.nn.Module):
             return (out_p, (edges, alpha)) if want_alpha else out_p
         return self._finish(out_p, alpha, st, nh, f, fp, want_alpha)
 
+    def forward_replicated(self, x_full, st, plan: Plan):
+        """The layer on a REPLICATED input: `x_full` holds the features of all nodes in the plan's id space ((plan.n_pad, F_in); rows
+        that belong to no node are zero) on every rank.  No feature exchange in either direction (_ReplicatedInputGATFunction);
+        meant for the first layer, whose input is data.  Returns this rank's rows, like forward()."""
+        if self.backend is None:
+            self.backend = CudaBackend()
+        if self.const_attention or (self.training and self.dropout > 0) or self.input_activation == "elu":
+            raise NotImplementedError("forward_replicated covers the plain layer (no const_attention / dropout / input activation)")
+        w_p, a_src, a_tgt, fp = self._padded_operands()
+        nh, f = self.num_heads, self.out_features
+        mean_f = f if (not self.concat and nh > 1 and hasattr(self.backend, "head_merge")) else 0
+        out_p = _ReplicatedInputGATFunction.apply(x_full.contiguous(), w_p, a_src, a_tgt, st, plan, nh, fp, self.backend, self.group,
+                                                  self.output_activation == "elu" and bool(self.concat), mean_f)
+        return out_p if mean_f else self._finish(out_p, None, st, nh, f, fp, False)
+
     def _finish(self, out_p, alpha, st, nh, f, fp, want_alpha):
         o = out_p.view(-1, nh, fp)[:, :, :f]
         out = o.reshape(-1, nh * f) if self.concat else o.mean(dim=1)      # gat_layer.py:129-132
@@ -648,8 +749,12 @@ class PartitionedGATLayer(torch.nn.Module):
 class PartitionedGAT:
     """bench.py's multi-GPU model: the stacked layers of one config over a partitioned graph."""
 
-    def __init__(self, shapes, weights, x_host, ei_host, dev, backend=None, fuse_glue=False, balance="edges"):
+    def __init__(self, shapes, weights, x_host, ei_host, dev, backend=None, fuse_glue=False, balance="edges", replicate_input=None):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        # the first layer's input is data: when it is narrower than the projection, every rank keeps ALL of it (all-gathered once per
+        # upload) and that layer needs no feature exchange at all (PartitionedGATLayer.forward_replicated)
+        f_in0, nh0, f0, _ = shapes[0]
+        self.replicate_input = (f_in0 < nh0 * f0) if replicate_input is None else bool(replicate_input)
         self.fuse_glue = fuse_glue      # the inter-layer ELU rides in the next layer's GEMMs (SURVEY.md 8-f1)
         self.dev, self.x_host, self.ei_host = dev, x_host, ei_host
         c0, c1 = edge_slice(ei_host.size(1), self.world, self.rank)
@@ -687,13 +792,19 @@ class PartitionedGAT:
         ei_part = self.ei_part_host.to(self.dev, non_blocking=True)
         x_local = self.x_local_host.to(self.dev, non_blocking=True)
         local, _ = exchange_edge_list(ei_part, self.plan, None, True)
+        self.x_full = None
+        if self.replicate_input:
+            slab = torch.zeros((self.plan.rows_per_rank, x_local.size(1)), dtype=x_local.dtype, device=self.dev)
+            slab[:x_local.size(0)] = x_local
+            self.x_full = torch.empty((self.plan.n_pad, x_local.size(1)), dtype=x_local.dtype, device=self.dev)
+            dist.all_gather_into_tensor(self.x_full, slab)            # once per upload: 1/2.5 of ONE step's Wh exchange on products
         return x_local, self.backend.build_structure(local, self.plan.n)
 
     def _fwd_bwd(self, x_local, st):
         h = x_local
         for i, layer in enumerate(self.layers):
             layer.W.weight.grad = layer.a.weight.grad = None
-            h = layer(h, st, self.plan)
+            h = layer.forward_replicated(self.x_full, st, self.plan) if (i == 0 and self.x_full is not None) else layer(h, st, self.plan)
             if i != len(self.layers) - 1 and layer.output_activation != "elu":
                 h = F.elu(h)
         loss = h.square().sum() / (self.plan.n_real * h.size(1))     # this rank's share of the global mean

@@ -74,6 +74,55 @@ def test_two_rank_partition_matches_single_process_oracle(case_name, world):
         assert np.array_equal(ret[r]["edges"], ei2[:, sel])
 
 
+def _replicated_worker(rank, world, port, case_name, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import cases
+        from _oracle_backend import OracleBackend
+        from gat_pytorch_b200.partition import PartitionedGATLayer, local_edge_list, make_plan
+        case = {c["name"]: c for c in cases.adversarial_cases()}[case_name]
+        x, ei = torch.from_numpy(case["x"]), torch.from_numpy(case["edge_index"].astype(np.int64))
+        plan = make_plan(x.size(0), world, rank)
+        backend = OracleBackend()
+        st = backend.build_structure(local_edge_list(ei, int(ei.max()) + 1, plan.lo, plan.hi, True), plan.n)
+        layer = PartitionedGATLayer(x.size(1), case["f"], case["nh"], case["concat"], backend)
+        with torch.no_grad():
+            layer.W.weight.copy_(torch.from_numpy(case["W"]))
+            layer.a.weight.copy_(torch.from_numpy(case["a"]))
+        x_full = torch.zeros((plan.n_pad, x.size(1)))
+        x_full[:x.size(0)] = x                      # every rank holds all node features (what PartitionedGAT all-gathers once per upload)
+        out = layer.forward_replicated(x_full, st, plan)
+        go_full, _ = cases.upstream_grads(case, x.size(0), out.size(1), 1)
+        (out * torch.from_numpy(go_full[plan.lo:plan.hi])).sum().backward()
+        ret[rank] = dict(out=out.detach().numpy(), gW=layer.W.weight.grad.numpy(), ga=layer.a.weight.grad.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case_name,world", [("adv_concat", 2), ("adv_mean_oddF", 3), ("adv_ties", 2)])
+def test_replicated_input_layer_matches_single_process_oracle(case_name, world):
+    """The first partitioned layer on a replicated input (no feature exchange in either direction: every rank projects all nodes,
+    dW is formed from the rank's partial dWh over all nodes and summed by the parameter all-reduce)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cases
+    import gat_oracle as O
+    ret = mp.Manager().dict()
+    port = 29900 + (os.getpid() % 40)
+    mp.spawn(_replicated_worker, args=(world, port, case_name, ret), nprocs=world, join=True)
+    case = {c["name"]: c for c in cases.adversarial_cases()}[case_name]
+    fw = O.forward(case["x"], case["edge_index"], case["W"], case["a"], case["nh"], case["f"], case["concat"], True)
+    go, _ = cases.upstream_grads(case, fw["out"].shape[0], fw["out"].shape[1], 1)
+    gr = O.backward(fw, go, None)
+    assert O.rel_err(np.concatenate([ret[r]["out"] for r in range(world)]), fw["out"]) < 1e-5
+    for r in range(world):
+        assert O.rel_err(ret[r]["gW"], gr["W"]) < 1e-5
+        assert O.rel_err(ret[r]["ga"], gr["a"]) < 1e-5
+
+
 def _extras_worker(rank, world, port, case_name, ret):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
