@@ -98,3 +98,62 @@ def test_wide_layer_refuses_what_it_does_not_implement():
     layer.output_activation = "elu"
     with pytest.raises(NotImplementedError):
         layer(torch.from_numpy(case["x"]).cuda(), torch.from_numpy(case["edge_index"]).cuda())
+
+
+# ---- the four-head head-mean backward kernel (csrc/edge_bwd_hm.cuh) over every chunk count it is instantiated for ----
+@pytest.mark.parametrize("f", [18, 20, 29, 32, 36, 45, 47, 52, 61, 64])
+@pytest.mark.parametrize("graph", ["adversarial", "products"])
+def test_head_mean_four_heads_every_width(f, graph):
+    """NH = 4, concat = False, F = 18 .. 64 (5 .. 16 float4 chunks per head: chunks-per-lane 2, 3, 4, exact and ragged), on the
+    adversarial graph (duplicates, existing loops, isolated nodes) and on a products-shaped graph with hub rows (> 256 edges: the
+    cooperative long-row launch runs next to the new kernel).  Fused backward (nothing consumes the attention) against the oracle."""
+    from gat_pytorch_b200 import synth
+    rng = np.random.default_rng(100 + f)
+    if graph == "adversarial":
+        x, ei = synth.adversarial()
+    else:
+        x, ei = synth.products(scale=1.0 / 512)
+        x = x[:, :24].copy()
+    f_in = x.shape[1]
+    case = dict(name=f"hm4_{graph}_{f}", x=x, edge_index=ei, add_self_loops=True, const_attention=False, bias=None,
+                W=synth.xavier_uniform(rng, 4 * f, f_in), a=synth.xavier_uniform(rng, 4, 8 * f), nh=4, f=f, concat=False)
+    layer = make_layer(case)
+    xt = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+    out = layer(xt, torch.from_numpy(case["edge_index"]).cuda())
+    fw = O.forward(case["x"], case["edge_index"].astype(np.int64), case["W"], case["a"], 4, f, False, True)
+    go, _ = cases.upstream_grads(case, out.shape[0], out.shape[1], 1)
+    (out * torch.from_numpy(go).cuda()).sum().backward()
+    gr = O.backward(fw, go, None)
+    errs = {"out": O.rel_err(out.detach().cpu().numpy(), fw["out"]), "gx": O.rel_err(xt.grad.cpu().numpy(), gr["x"]),
+            "gW": O.rel_err(layer.W.weight.grad.cpu().numpy(), gr["W"]), "ga": O.rel_err(layer.a.weight.grad.cpu().numpy(), gr["a"])}
+    assert all(e <= 1e-5 for e in errs.values()), errs
+
+
+@pytest.mark.parametrize("name,nh,f,concat", [("narrow_1x1", 1, 1, False), ("narrow_1x7", 1, 7, False), ("narrow_2x3_mean", 2, 3, False),
+                                              ("narrow_8x3_mean", 8, 3, False), ("narrow_4x4", 4, 4, True), ("narrow_3x5", 3, 5, True)])
+@pytest.mark.parametrize("graph", ["adversarial", "pattern"])
+def test_narrow_rows_with_widened_groups(name, nh, f, concat, graph):
+    """Rows of 1 .. 16 chunks on SMALL graphs run with lane groups wider than the row needs (pick_group(chunks, n_rows)): every
+    group width from the minimal one up to 32, on the 97-node adversarial graph (G = 32 everywhere) and a PATTERN batch; both
+    backward families against the oracle."""
+    from gat_pytorch_b200 import synth
+    rng = np.random.default_rng(hash((name, graph)) % 2 ** 32)
+    x, ei = synth.adversarial() if graph == "adversarial" else synth.pattern(graphs=24)
+    f_in = x.shape[1]
+    case = dict(name=f"{name}_{graph}", x=x, edge_index=ei, add_self_loops=True, const_attention=False, bias=None,
+                W=synth.xavier_uniform(rng, nh * f, f_in), a=synth.xavier_uniform(rng, nh, 2 * nh * f), nh=nh, f=f, concat=concat)
+    got, ei2 = run_cuda(case)
+    fw, want = run_oracle(case)
+    assert np.array_equal(ei2, fw["edge_index"])
+    errs = {k: O.rel_err(got[k], want[k]) for k in want}
+    tol = 5e-5 if (nh, f) == (1, 1) else 1e-5          # 1x1 rows: the reference's own fp32 run is 2.6e-5 from its fp64 run (pattern_L3)
+    assert all(e <= tol for e in errs.values()), errs
+    layer = make_layer(case)
+    xt = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+    out = layer(xt, torch.from_numpy(case["edge_index"]).cuda())
+    go, _ = cases.upstream_grads(case, out.shape[0], out.shape[1], 1)
+    (out * torch.from_numpy(go).cuda()).sum().backward()
+    gr = O.backward(fw, go, None)
+    errs = {"gx": O.rel_err(xt.grad.cpu().numpy(), gr["x"]), "gW": O.rel_err(layer.W.weight.grad.cpu().numpy(), gr["W"]),
+            "ga": O.rel_err(layer.a.weight.grad.cpu().numpy(), gr["a"])}
+    assert all(e <= tol for e in errs.values()), errs

@@ -167,3 +167,64 @@ def test_c_abi_rejects_bad_arguments_with_a_message_before_touching_the_device()
     assert lib.gat_gemm_tc_supported(0, 1, 100, 64, 1024, 1024, 1024, 64) == 1
     with pytest.raises(RuntimeError, match="gat_scores_fwd"):
         _lib.call("gat_scores_fwd", None, 10, 64, None, None, 9, None, None, None)
+
+
+def test_model_forward_folds_the_glue_as_documented():
+    """glue.model_forward on mock layers, no GPU: which switches each layer gets -- ELU on every layer but the last,
+    the next layer's input dropout folded into a layer's output unless that next layer has a skip connection (it then needs the
+    undropped tensor too), the skip rows head-averaged for a head-mean layer (GATModel.py:139-145) -- and that the layers come
+    back with their own settings."""
+    import types
+    import torch
+    from gat_pytorch_b200.glue import model_forward
+
+    calls = []
+
+    class MockLayer(torch.nn.Module):
+        def __init__(self, out_dim):
+            super().__init__()
+            self.out_dim, self.output_activation, self.output_dropout, self.attention_norm = out_dim, None, 0.0, False
+            self.attention_norm_value = None
+
+        def forward(self, x, edge_index, return_attention_weights=False, skip=None):
+            calls.append(dict(act=self.output_activation, drop=self.output_dropout, norm=self.attention_norm,
+                              skip=None if skip is None else tuple(skip.shape), x_zero_frac=float((x == 0).float().mean())))
+            self.attention_norm_value = torch.tensor(float(len(calls)))
+            out = torch.ones(x.size(0), self.out_dim)
+            if return_attention_weights:
+                return out, (edge_index, torch.full((edge_index.size(1), 2), 0.5))
+            return out
+
+    def model(add_skip, concat, dims, heads, feats, p):
+        m = torch.nn.Module()
+        m.gat_layer_list = torch.nn.ModuleList([MockLayer(d) for d in dims])
+        m.skip_layer_list = torch.nn.ModuleList([torch.nn.Identity() for s in add_skip if s])
+        m.add_skip_connection, m.heads_concat_per_layer = add_skip, concat
+        m.num_heads_per_layer, m.head_output_features_per_layer, m.dropout = heads, feats, p
+        return m
+
+    data = types.SimpleNamespace(x=torch.ones(6, 8), edge_index=torch.zeros((2, 5), dtype=torch.long))
+    # three layers, skip on the middle one (PPI's pattern), dropout 0.5 in training mode
+    m = model([False, True, False], [True, True, False], [8, 8, 4], [1, 2, 2, 2], [8, 4, 4, 2], 0.5)
+    m.train()
+    out = model_forward(m, data)
+    assert tuple(out.shape) == (6, 4)
+    assert [c["act"] for c in calls] == ["elu", "elu", None]
+    # layer 0 may NOT fold layer 1's dropout (layer 1 has a skip and needs the undropped tensor); layer 1 folds layer 2's
+    assert [c["drop"] for c in calls] == [0.0, 0.5, 0.0]
+    assert [c["skip"] for c in calls] == [None, (6, 8), None]
+    assert calls[0]["x_zero_frac"] > 0.2          # raw input: torch dropout in front of the first layer
+    assert calls[1]["x_zero_frac"] > 0.2          # not folded -> torch dropout in front of layer 1
+    assert calls[2]["x_zero_frac"] == 0.0         # folded into layer 1's output kernel: no torch dropout here
+    assert all(l.output_activation is None and l.output_dropout == 0.0 and l.attention_norm is False for l in m.gat_layer_list)
+    # eval mode: nothing dropped anywhere; attention requested -> the reference's triple; the norm is the mean over layers
+    calls.clear()
+    m.eval()
+    out, ei2, att, norm = model_forward(m, data, True, attention_norm=True)
+    assert [c["drop"] for c in calls] == [0.0, 0.0, 0.0] and all(c["x_zero_frac"] == 0.0 for c in calls)
+    assert all(c["norm"] for c in calls) and len(att) == 3 and float(norm) == 2.0
+    # a head-mean layer with a skip connection receives the head-averaged skip rows
+    calls.clear()
+    m2 = model([True], [False], [4], [1, 2], [8, 4], 0.0)
+    model_forward(m2, types.SimpleNamespace(x=torch.arange(48.).view(6, 8), edge_index=data.edge_index))
+    assert calls[0]["skip"] == (6, 4) and calls[0]["act"] is None
