@@ -691,7 +691,7 @@ __device__ __forceinline__ float log1p_neg_fast(float h) {
 // FULLGLUE: skip rows and / or output dropout are part of the glue (Philox per chunk: its registers stay out of the plain
 // instantiation, which the headline's hidden layers run with the ELU adjoint only).
 template <int NHT, bool FULLGLUE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NHT == 4 && !FULLGLUE) ? 3 : 2)
 edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
   constexpr int R = 4;   // rows per warp iteration: 2*R*chunks/32 independent 16-byte loads in flight per lane
   const int lane = threadIdx.x & 31;
@@ -707,6 +707,23 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int h = 0; h < NHT; ++h) s[r][h] = 0.f;
+    // this lane's (row, head) pair of the epilogue below: its scalars are requested now, used after the streaming loop
+    float pre_z = 1.f, pre_t = 0.f, pre_nt = 0.f, pre_deg = 0.f, pre_cdeg = 0.f;
+    {
+      constexpr int V0 = R * NHT;
+      const int v0 = V0 == 32 ? (((lane >> 4) & 1) << 4 | ((lane >> 3) & 1) << 3 | ((lane >> 2) & 1) << 2 | ((lane >> 1) & 1) << 1 | (lane & 1))
+                              : (((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 2 | ((lane >> 2) & 1) << 1 | ((lane >> 1) & 1));
+      const int pr = v0 / NHT, ph = v0 - pr * NHT;
+      const int64_t prow = row0 + pr;
+      if (prow < P.n && ph < nh) {
+        pre_z = __ldg(P.z + prow * nh + ph);
+        if (P.tpack) pre_t = __ldg(P.s_tgt + prow * nh + ph);
+        if (P.rowptr) {
+          pre_deg = (float)(__ldg(P.rowptr + prow + 1) - __ldg(P.rowptr + prow));
+          if (P.norm_coef) { pre_cdeg = __ldg(P.norm_coef) * P.norm_scale * pre_deg; pre_nt = __ldg(P.norm_t + prow * nh + ph); }
+        }
+      }
+    }
     int hh = hh0 - q32, gc = gc0 - r32;
     for (int c = lane; c < P.chunks; c += 32) {
       hh += q32; gc += r32;
@@ -763,45 +780,55 @@ edge_bwd_rowdot_kernel(const BwdRowdotParams P) {
         for (int h = 0; h < NHT; ++h) s[r][h] += (h == hh) ? d : 0.f;
       }
     }
+    // ---- the R*NHT per-(row, head) sums of the 32 lanes are TRANSPOSE-REDUCED: at butterfly distance o a lane keeps the half of
+    // its values whose index has the matching bit and sends the other half, so R*NHT - 1 (+1) shuffles reduce all values at once
+    // (16 for 16 values; the plain butterfly takes 80) and lane L ends up with the COMPLETE sum of ONE (row, head) pair -- whose
+    // epilogue it then runs itself, in parallel with the others: the scalars it needs were requested before the streaming loop,
+    // its stores are contiguous across lanes.  (Was: 80 shuffles, then lane 0 alone loaded, computed and stored all 16 pairs
+    // while the warp waited; the pass ran at 0.6 of the DRAM rate with half its issue slots idle.)
+    constexpr int V = R * NHT;                     // 16 or 32 values, index v = r*NHT + h
+    float val[V];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int h = 0; h < NHT; ++h) {
-        if (h < nh) {
+      for (int h = 0; h < NHT; ++h) val[r * NHT + h] = s[r][h];
+    int width = V;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s[r][h] += __shfl_xor_sync(0xffffffffu, s[r][h], o);
-        }
-      }
-      if (lane == 0 && row0 + r < P.n) {
-        float zrow[NHT], trow[NHT], srow[NHT];
-        float deg = 0.f, cdeg = 0.f;
-        if (P.rowptr) {
-          deg = (float)(__ldg(P.rowptr + row0 + r + 1) - __ldg(P.rowptr + row0 + r));
-          if (P.norm_coef) cdeg = __ldg(P.norm_coef) * P.norm_scale * deg;
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+      if (width > 1) {
+        const bool up = (lane & o) != 0;           // keep the upper half of the indices
+        const int half = width / 2;
 #pragma unroll
-        for (int h = 0; h < NHT; ++h) {
-          zrow[h] = 0.f; trow[h] = 0.f; srow[h] = 0.f;
-          if (h < nh) {
-            if (P.norm_t) s[r][h] = fmaf(cdeg, __ldg(P.norm_t + (row0 + r) * nh + h), s[r][h]);
-            const float zz = __ldg(P.z + (row0 + r) * nh + h);
-            P.s_sum[(row0 + r) * nh + h] = s[r][h];
-            P.ds_tgt[(row0 + r) * nh + h] = kLeakySlope * s[r][h] * (kSoftmaxEps / (zz + kSoftmaxEps));
-            zrow[h] = zz; srow[h] = s[r][h];
-            if (P.tpack) trow[h] = __ldg(P.s_tgt + (row0 + r) * nh + h);
+        for (int i = 0; i < V / 2; ++i) {
+          if (i < half) {
+            const float send = up ? val[i] : val[i + half];
+            const float keep = up ? val[i + half] : val[i];
+            val[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
           }
         }
-        if (P.tpack) {
-          float* pk = P.tpack + (row0 + r) * (4 * NHT);
-#pragma unroll
-          for (int q = 0; q < NHT / 4; ++q) {
-            *reinterpret_cast<float4*>(pk + 4 * q) = make_float4(trow[4 * q], trow[4 * q + 1], trow[4 * q + 2], trow[4 * q + 3]);
-            *reinterpret_cast<float4*>(pk + NHT + 4 * q) = make_float4(zrow[4 * q], zrow[4 * q + 1], zrow[4 * q + 2], zrow[4 * q + 3]);
-            *reinterpret_cast<float4*>(pk + 2 * NHT + 4 * q) = make_float4(srow[4 * q], srow[4 * q + 1], srow[4 * q + 2], srow[4 * q + 3]);
-          }
-          if (P.rowptr) pk[3 * NHT] = deg;
-        }
+        width = half;
+      } else {
+        val[0] += __shfl_xor_sync(0xffffffffu, val[0], o);     // V = 16: the last stage sums two lanes holding the same index
       }
+    }
+    // lane -> value index: the stages at o = 16, 8, 4, 2 (, 1) consumed index bits from the top
+    const int vidx = V == 32 ? (((lane >> 4) & 1) << 4 | ((lane >> 3) & 1) << 3 | ((lane >> 2) & 1) << 2 | ((lane >> 1) & 1) << 1 | (lane & 1))
+                             : (((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 2 | ((lane >> 2) & 1) << 1 | ((lane >> 1) & 1));
+    const int er = vidx / NHT, eh = vidx - er * NHT;
+    const int64_t erow = row0 + er;
+    if ((V == 32 || (lane & 1) == 0) && erow < P.n && eh < nh) {
+      float sv = val[0];
+      if (P.norm_t) sv = fmaf(pre_cdeg, pre_nt, sv);
+      P.s_sum[erow * nh + eh] = sv;
+      P.ds_tgt[erow * nh + eh] = kLeakySlope * sv * (kSoftmaxEps / (pre_z + kSoftmaxEps));
+      if (P.tpack) {
+        float* pk = P.tpack + erow * (4 * NHT);
+        pk[eh] = pre_t; pk[NHT + eh] = pre_z; pk[2 * NHT + eh] = sv;
+        if (P.rowptr && eh == 0) pk[3 * NHT] = pre_deg;
+      }
+    } else if ((V == 32 || (lane & 1) == 0) && erow < P.n && P.tpack) {   // head slots beyond nh: defined (zero) record fields
+      float* pk = P.tpack + erow * (4 * NHT);
+      pk[eh] = 0.f; pk[NHT + eh] = 1.f; pk[2 * NHT + eh] = 0.f;
     }
   }
 }
