@@ -79,6 +79,8 @@ SIGNATURES = {
     "gat_attention_norm_fwd": (c_int, [_P, c_int, _P, _P, c_int64, c_int, _P, _P, c_size_t, _P]),
     "gat_attention_norm_bwd": (c_int, [_P, c_int, _P, _P, c_int64, c_int, _P, _P, _P]),
     "gat_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "gat_f32_round_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "gat_edge_bf16_native": (c_int, [c_int, c_int, c_int]),
     "gat_edge_fwd_bf16": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, c_int, c_int, _P, _P, _P, c_int, c_float, c_uint64, c_uint64,
                              _P, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gat_edge_bwd_fused_bf16": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P,

@@ -246,7 +246,33 @@ f32_to_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int6
     dst[i] = make_uint2(bf16_bits(v.x) | (bf16_bits(v.y) << 16), bf16_bits(v.z) | (bf16_bits(v.w) << 16));
   }
 }
+// the same rounding, kept in fp32 storage: dst = float(bfloat16(src))
+__global__ void __launch_bounds__(256)
+f32_round_bf16_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t count4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(src + i);
+    dst[i] = make_float4(__uint_as_float(bf16_bits(v.x) << 16), __uint_as_float(bf16_bits(v.y) << 16),
+                         __uint_as_float(bf16_bits(v.z) << 16), __uint_as_float(bf16_bits(v.w) << 16));
+  }
+}
 }  // namespace gat
+
+extern "C" int gat_edge_bf16_native(int nh, int fp, int go_shared) {
+  const int chunks = nh * fp / 4;
+  return (nh >= 1 && nh <= 4 && fp > 0 && fp % 4 == 0 && chunks > 32 && chunks <= 64 && !go_shared) ? 1 : 0;
+}
+
+extern "C" int gat_f32_round_bf16(const float* src, float* dst, int64_t count, gat_stream_t stream) {
+  using namespace gat;
+  GAT_CHECK_ARG(src && dst && count >= 0 && count % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0,
+                "gat_f32_round_bf16: count must be a multiple of 4 and the buffers 16-byte aligned");
+  if (count == 0) return GAT_OK;
+  const int64_t c4 = count / 4, want = (c4 + 255) / 256;
+  f32_round_bf16_kernel<<<(unsigned)(want < kNumSMs * 16 ? want : kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)src, (float4*)dst, c4);
+  GAT_LAUNCH_CHECK();
+  return GAT_OK;
+}
 
 extern "C" int gat_f32_to_bf16(const float* src, void* dst, int64_t count, gat_stream_t stream) {
   using namespace gat;

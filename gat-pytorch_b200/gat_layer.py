@@ -84,10 +84,14 @@ class _GATFunction(torch.autograd.Function):
             if p_drop > 0.0:
                 seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator: no device sync
             wh_gather = wh
-            if bf16:    # bf16 variant: the per-edge gathers read a bfloat16 copy of Wh (half the bytes); fp32 Wh is kept for the backward
+            bf16_native = bf16 and bool(lib.gat_edge_bf16_native(nh, fp, 0))
+            if bf16_native:    # bf16 variant: the per-edge gathers read a bfloat16 copy of Wh (half the bytes); fp32 Wh is kept for the backward
                 wh_gather = torch.empty((n, dp), dtype=torch.bfloat16, device=dev)
                 _lib.call("gat_f32_to_bf16", wh.data_ptr(), wh_gather.data_ptr(), n * dp, s)
-            _lib.call("gat_edge_fwd_bf16" if bf16 else "gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), st.n_long, n,
+            elif bf16:         # no bf16 kernel for this shape: same numerics (Wh rounded to bfloat16), fp32 storage and kernels
+                wh_gather = torch.empty((n, dp), **f32)
+                _lib.call("gat_f32_round_bf16", wh.data_ptr(), wh_gather.data_ptr(), n * dp, s)
+            _lib.call("gat_edge_fwd_bf16" if bf16_native else "gat_edge_fwd", st.rowptr.data_ptr(), st.col.data_ptr(), st.eid.data_ptr(), st.order.data_ptr(), st.n_long, n,
                                         wh_gather.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax),
                                         int(const_attention), float(p_drop), seed, 0,
                                         out_p.data_ptr(), int(out_act), _ptr(alpha), z.data_ptr(),
@@ -155,10 +159,13 @@ class _GATFunction(torch.autograd.Function):
                 if out_act:
                     go_p = go_pre
                 fused_name, go_gather = "gat_edge_bwd_fused", go_p
-                if bf16 and not go_shared:     # bf16 variant: the gathered upstream gradient is a bfloat16 copy
+                if bf16 and lib.gat_edge_bf16_native(nh, fp, go_shared):     # bf16 variant: the gathered upstream gradient is a bfloat16 copy
                     go_gather = torch.empty((n, dp), dtype=torch.bfloat16, device=dev)
                     _lib.call("gat_f32_to_bf16", go_p.data_ptr(), go_gather.data_ptr(), n * dp, s)
                     fused_name = "gat_edge_bwd_fused_bf16"
+                elif bf16:                                                   # same numerics on the fp32 kernel
+                    go_gather = torch.empty_like(go_p)
+                    _lib.call("gat_f32_round_bf16", go_p.data_ptr(), go_gather.data_ptr(), go_p.numel(), s)
                 _lib.call(fused_name, st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
                           st.n_long_t, st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, s_src.data_ptr(), s_tgt.data_ptr(), gmax.data_ptr(),
                           z.data_ptr(), p_drop, seed, 0, go_gather.data_ptr(), go_shared, s_sum.data_ptr(), tpack.data_ptr(), a_src_p.data_ptr(), a_tgt_p.data_ptr(),
@@ -166,6 +173,10 @@ class _GATFunction(torch.autograd.Function):
                           None, 0, 0, 0, ws.data_ptr(), ws_bytes, s, tag=(nh, fp))
             else:
                 rec = torch.empty((st.n_edges, 2 * nh), **f32) if not const_attention else None
+                if bf16:    # three-pass backward of the bf16 variant: the gathered gradient rounded to bfloat16, fp32 kernels
+                    go_r = torch.empty_like(go_p)
+                    _lib.call("gat_f32_round_bf16", go_p.data_ptr(), go_r.data_ptr(), go_p.numel(), s)
+                    go_p = go_r
                 # pass 1 (source-major, the only feature gather of the backward)
                 _lib.call("gat_edge_bwd_main", st.rowptr_t.data_ptr(), st.col_t.data_ptr(), st.pos_t.data_ptr(), st.order_t.data_ptr(),
                           st.n_long_t, st.eid.data_ptr(), n, wh.data_ptr(), nh, fp, _ptr(s_src), _ptr(s_tgt), _ptr(gmax), z.data_ptr(),
@@ -496,8 +507,9 @@ class GATLayer(nn.Module):
         self.attention_norm_value = None
         # Opt-in bf16 variant (BASELINE.json north_star "bf16 variant stated separately"): "bf16" makes the edge kernels gather
         # bfloat16 copies of Wh (forward) and of dL/dout (fused backward) -- half the bytes per edge, fp32 accumulation,
-        # ~2e-3 relative error.  None (default) = fp32 everywhere, the 1e-5 parity path.  NH <= 4 and padded rows of
-        # 132..256 floats only (the products-class shapes it was built and tested for); other shapes raise.
+        # ~2e-3 relative error.  None (default) = fp32 everywhere, the 1e-5 parity path.  bf16 kernels exist for NH <= 4 and padded
+        # rows of 132..256 floats with an unshared gradient (the products-class shapes, where the bytes are the bound); every other
+        # shape / backward path keeps the variant's numerics (gathered matrix rounded to bfloat16) on the fp32 kernels.
         self.feature_dtype = None
         self.structure_cache = GLOBAL_CACHE
         self.reset_parameters()

@@ -381,7 +381,13 @@ GAT_API int gat_attention_neighbourhood(const int32_t* rowptr, const int32_t* co
  * (half the bytes per edge); the row a pass owns, every accumulation and every output stay fp32.  Same arguments as the
  * fp32 entry points except the gathered matrix.  Supported for NH <= 4 and padded rows of 132..256 floats;
  * the backward additionally needs an unshared gradient (concat layers).  Parity bar of this variant: 2e-2 tensor-relative.
+ * gat_edge_bf16_native(nh, fp, go_shared) tells whether such a kernel exists for a shape.  Everywhere else (narrow or very wide
+ * rows, more than 4 heads, shared head-mean gradients, the three-pass backward) the variant keeps its NUMERICS -- the gathered
+ * matrix is rounded to bfloat16 by gat_f32_round_bf16, stored as fp32 -- and runs the fp32 kernels: same results as a bf16
+ * gather, without the halved bytes (those shapes are the L2-resident small graphs, where the bytes are not the bound).
  * ------------------------------------------------------------------------------------- */
+GAT_API int gat_edge_bf16_native(int nh, int fp, int go_shared);
+GAT_API int gat_f32_round_bf16(const float* src, float* dst, int64_t count, gat_stream_t stream);
 GAT_API int gat_f32_to_bf16(const float* src, void* dst, int64_t count, gat_stream_t stream);
 GAT_API int gat_edge_fwd_bf16(const int32_t* rowptr, const int32_t* col, const int32_t* eid, const int32_t* row_order, int64_t n_long,
                  int64_t n, const void* wh_bf16, int nh, int fp, const float* s_src, const float* s_tgt,

@@ -582,9 +582,37 @@ def test_bf16_variant_within_its_stated_tolerance(name, small_cases):
 
 
 @pytest.mark.gpu
-def test_bf16_variant_refuses_unsupported_shapes(small_cases):
-    case = small_cases["cora_L0"]          # 8 heads x 8: not a wide-row shape
+@pytest.mark.parametrize("name", ["cora_L0", "pubmed_L1", "ppi_L1", "ppi_L2", "pattern_L1", "adv_wide"])
+@pytest.mark.parametrize("with_alpha", [False, True])
+def test_bf16_variant_on_shapes_without_a_bf16_kernel(name, with_alpha, small_cases):
+    """The variant is available for EVERY shape and both backward families: where no bf16 kernel exists (more than 4 heads, narrow
+    or very wide rows, shared head-mean gradients, an upstream dL/dalpha) the gathered matrices are rounded to bfloat16 and the fp32
+    kernels run -- the variant's numerics, same 2e-2 bar; the returned attention stays at the fp32 bar (fp32 scores)."""
+    from gat_pytorch_b200 import _lib
+    case = small_cases[name]
+    fp = (case["f"] + 3) // 4 * 4
+    assert not (_lib.load().gat_edge_bf16_native(case["nh"], fp, int(not case["concat"] and case["nh"] > 1)) and not with_alpha)
     layer = make_layer(case)
     layer.feature_dtype = "bf16"
-    with pytest.raises(RuntimeError):
-        layer(torch.from_numpy(case["x"]).cuda(), torch.from_numpy(case["edge_index"]).cuda())
+    x = torch.from_numpy(case["x"]).cuda().requires_grad_(True)
+    ei = torch.from_numpy(case["edge_index"]).cuda()
+    fw = O.forward(case["x"], case["edge_index"].astype(np.int64), case["W"], case["a"], case["nh"], case["f"], case["concat"],
+                   case["add_self_loops"], case["bias"], case["const_attention"])
+    if with_alpha:
+        out, (_, alpha) = layer(x, ei, return_attention_weights=True)
+        go, ga = cases.upstream_grads(case, out.shape[0], out.shape[1], alpha.shape[0])
+        ((out * torch.from_numpy(go).cuda()).sum() + (alpha * torch.from_numpy(ga).cuda()).sum()).backward()
+        gr = O.backward(fw, go, ga)
+        assert O.rel_err(alpha.detach().cpu().numpy(), fw["alpha"]) < TOL
+    else:
+        out = layer(x, ei)
+        go, _ = cases.upstream_grads(case, out.shape[0], out.shape[1], 1)
+        (out * torch.from_numpy(go).cuda()).sum().backward()
+        gr = O.backward(fw, go, None)
+    errs = dict(out=O.rel_err(out.detach().cpu().numpy(), fw["out"]), gx=O.rel_err(x.grad.cpu().numpy(), gr["x"]),
+                gW=O.rel_err(layer.W.weight.grad.cpu().numpy(), gr["W"]), ga=O.rel_err(layer.a.weight.grad.cpu().numpy(), gr["a"]))
+    # da is a sum of g = alpha*(dalpha - S): the cancellation amplifies the 2^-9 rounding of the gathered rows on heads of 3-8
+    # features and on PATTERN's epsilon-dominated checkpoint weights (measured: 3.1e-2 on pubmed_L1, 5.9e-2 on pattern_L1, <= 3e-3
+    # elsewhere), hence its own bar
+    assert all(e < (1e-1 if k == "ga" else 2e-2) for k, e in errs.items()), (name, errs)
+    assert errs["out"] > 1e-6, "the bf16 rounding did not happen (fp32-exact output)"
