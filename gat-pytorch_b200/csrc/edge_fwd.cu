@@ -359,20 +359,26 @@ static size_t coop_smem_bytes(int g, int dp) { return (size_t)(kEdgeThreads / g)
 // ------------------------------------------------------------------------------------------
 // Head merge: padded (n, NH, Fp) -> (n, NH*F) or head mean (n, F)   (gat_layer.py:129-132)
 // ------------------------------------------------------------------------------------------
-__global__ void head_merge_fwd_kernel(const float* __restrict__ o, int64_t n, int nh, int f, int fp, int concat,
-                                      float* __restrict__ out) {
+// 2-D indexing (threadIdx.x walks the columns of a row, blockIdx.x / threadIdx.y the rows): no 64-bit division per element, which
+// made these streaming kernels instruction bound (0.56 / 0.46 ms on the products output layer for 0.36 / 0.14 ms of traffic).
+constexpr int kMergeRows = 8;      // rows per CTA (blockDim = 32 x 8)
+
+__global__ void __launch_bounds__(256)
+head_merge_fwd_kernel(const float* __restrict__ o, int64_t n, int nh, int f, int fp, int concat, float* __restrict__ out) {
   const int width = concat ? nh * f : f;
-  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (idx >= n * width) return;
-  int64_t i = idx / width;
-  int c = (int)(idx % width);
-  const float* r = o + i * (int64_t)nh * fp;
-  if (concat) {
-    out[idx] = r[(c / f) * fp + (c % f)];
-  } else {
-    float s = 0.f;
-    for (int h = 0; h < nh; ++h) s += r[h * fp + c];
-    out[idx] = s / (float)nh;   // torch.mean(dim=1): sum then divide
+  for (int64_t i = (int64_t)blockIdx.x * kMergeRows + threadIdx.y; i < n; i += (int64_t)gridDim.x * kMergeRows) {
+    const float* r = o + i * (int64_t)nh * fp;
+    float* w = out + i * (int64_t)width;
+    if (concat) {
+      for (int h = 0; h < nh; ++h)
+        for (int j = threadIdx.x; j < f; j += 32) w[h * f + j] = r[h * fp + j];
+    } else {
+      for (int c = threadIdx.x; c < f; c += 32) {
+        float s = 0.f;
+        for (int h = 0; h < nh; ++h) s += r[h * fp + c];
+        w[c] = s / (float)nh;   // torch.mean(dim=1): sum then divide
+      }
+    }
   }
 }
 
@@ -415,12 +421,13 @@ __global__ void out_glue_adjoint_kernel(const float* __restrict__ g, const float
 
 // Head-mean layers: the adjoint of mean(dim=1) hands every head the same vector g/NH, so it is stored ONCE as a padded
 // (n, fp) row that the backward kernels share across heads (go_shared) -- a quarter of the gather traffic at NH = 4.
-__global__ void head_mean_bwd_shared_kernel(const float* __restrict__ g, int64_t n, int nh, int f, int fp, float* __restrict__ go) {
-  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (idx >= n * fp) return;
-  const int64_t i = idx / fp;
-  const int j = (int)(idx - i * fp);
-  go[idx] = j < f ? g[i * (int64_t)f + j] / (float)nh : 0.f;
+__global__ void __launch_bounds__(256)
+head_mean_bwd_shared_kernel(const float* __restrict__ g, int64_t n, int nh, int f, int fp, float* __restrict__ go) {
+  for (int64_t i = (int64_t)blockIdx.x * kMergeRows + threadIdx.y; i < n; i += (int64_t)gridDim.x * kMergeRows) {
+    const float* r = g + i * (int64_t)f;
+    float* w = go + i * (int64_t)fp;
+    for (int j = threadIdx.x; j < fp; j += 32) w[j] = j < f ? r[j] / (float)nh : 0.f;
+  }
 }
 
 __global__ void head_merge_bwd_kernel(const float* __restrict__ g, int64_t n, int nh, int f, int fp, int concat,
@@ -582,7 +589,9 @@ extern "C" int gat_head_merge_fwd(const float* o_padded, int64_t n, int nh, int 
   GAT_CHECK_ARG(nh >= 1 && f >= 1 && fp >= f, "gat_head_merge_fwd: bad shape");
   int64_t total = n * (concat ? nh * f : f);
   if (total == 0) return GAT_OK;
-  head_merge_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(o_padded, n, nh, f, fp, concat, out);
+  const int64_t want_m = (n + kMergeRows - 1) / kMergeRows;
+  head_merge_fwd_kernel<<<(unsigned)(want_m < kNumSMs * 16 ? want_m : kNumSMs * 16), dim3(32, kMergeRows), 0, (cudaStream_t)stream>>>(
+      o_padded, n, nh, f, fp, concat, out);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }
@@ -633,7 +642,9 @@ extern "C" int gat_head_mean_bwd_shared(const float* grad_out, int64_t n, int nh
   GAT_CHECK_ARG(nh >= 1 && f >= 1 && fp >= f && fp % 4 == 0, "gat_head_mean_bwd_shared: bad shape");
   int64_t total = n * (int64_t)fp;
   if (total == 0) return GAT_OK;
-  head_mean_bwd_shared_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad_out, n, nh, f, fp, go_shared);
+  const int64_t want_m = (n + kMergeRows - 1) / kMergeRows;
+  head_mean_bwd_shared_kernel<<<(unsigned)(want_m < kNumSMs * 16 ? want_m : kNumSMs * 16), dim3(32, kMergeRows), 0, (cudaStream_t)stream>>>(
+      grad_out, n, nh, f, fp, go_shared);
   GAT_LAUNCH_CHECK();
   return GAT_OK;
 }
