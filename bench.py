@@ -378,6 +378,10 @@ def extras(g, _lib, lib, dev):
         out["ppi_epoch"] = {"metric": "ppi_epoch_time", "value": secs, "unit": "s", "higher_is_better": False, "steps_per_epoch": len(data),
                             "attention_penalty": 1.0, "last_step": {"loss": loss, "train_f1": f1},
                             "ms_per_step_breakdown_synchronised": {k: round(v, 3) for k, v in ppi_epoch.gpu_epoch.breakdown.items()}}
+        # the same epoch with the opt-in caller-side pieces: model_forward (skip / ELU in the layers' kernels, regulariser fused: no
+        # attention tensors) and the micro-F1 counted on the device instead of sklearn on host copies (same value)
+        secs2, (loss2, f12) = ppi_epoch.gpu_epoch(data, 2, 1.0, f1="gpu", fused=True)
+        out["ppi_epoch"]["with_model_forward_and_device_f1"] = {"value": secs2, "unit": "s", "last_step": {"loss": loss2, "train_f1": f12}}
     except Exception as exc:
         out["ppi_epoch"] = {"error": repr(exc)[:300]}
     return out

@@ -17,8 +17,8 @@ through the `gat_pytorch_b200` shim module at the repository root.
 """
 from .gat_layer import GATLayer  # noqa: F401
 from .graph import GLOBAL_CACHE, GraphStructure, StructureCache, build_structure  # noqa: F401
-from .glue import attention_norm, degree_scaled_attention, model_forward, neighbourhood_attention, neighbourhood_entropy  # noqa: F401
+from .glue import attention_norm, degree_scaled_attention, micro_f1, model_forward, neighbourhood_attention, neighbourhood_entropy  # noqa: F401
 from . import synth  # noqa: F401
 
 __all__ = ["GATLayer", "GraphStructure", "StructureCache", "build_structure", "GLOBAL_CACHE", "attention_norm", "neighbourhood_entropy",
-           "degree_scaled_attention", "neighbourhood_attention", "model_forward", "synth"]
+           "degree_scaled_attention", "neighbourhood_attention", "model_forward", "micro_f1", "synth"]

@@ -86,6 +86,7 @@ SIGNATURES = {
     "gat_edge_bwd_fused_bf16": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P,
                                    c_float, c_uint64, c_uint64, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
                                    _P, _P, _P, _P, c_int, c_int, c_int64, _P, c_size_t, _P]),
+    "gat_micro_f1_counts": (c_int, [_P, _P, c_int64, _P, _P]),
     "gat_attention_entropy": (c_int, [_P, _P, c_int64, _P, c_int, _P, _P, _P]),
     "gat_attention_degree_scaled": (c_int, [_P, _P, c_int64, _P, c_int, _P, _P]),
     "gat_attention_neighbourhood": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, _P, _P]),

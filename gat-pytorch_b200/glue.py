@@ -134,6 +134,26 @@ def model_forward(model, data, return_attention_weights=None, attention_norm=Fal
     return (x, edge_index, attention) + norm
 
 
+def micro_f1(logits: torch.Tensor, y_true: torch.Tensor) -> float:
+    """`sklearn.metrics.f1_score(y_pred=logits > 0, y_true=y_true, average="micro")` for multilabel indicator targets -- the metric
+    `PPI_GAT` logs in every training / validation / test step (ppi_gat.py:38, :48, :56) after copying both (n, classes) matrices to
+    the host -- from three integer counts taken on the device (include/gat_b200.h: gat_micro_f1_counts); one 24-byte read-back.
+    A maintainer replaces the `f1_score(...)` call with `micro_f1(out, batch.y)`."""
+    if not logits.is_cuda:
+        raise RuntimeError("gat_b200.micro_f1 runs on CUDA only; there is no CPU fallback")
+    if logits.shape != y_true.shape:
+        raise ValueError(f"logits {tuple(logits.shape)} and y_true {tuple(y_true.shape)} differ in shape")
+    lg = logits.detach().to(torch.float32).contiguous()
+    yt = y_true.detach().to(device=lg.device, dtype=torch.float32).contiguous()
+    with torch.cuda.device(lg.device):
+        counts = torch.empty(3, dtype=torch.int64, device=lg.device)
+        _lib.call("gat_micro_f1_counts", lg.data_ptr(), yt.data_ptr(), lg.numel(), counts.data_ptr(),
+                  torch.cuda.current_stream(lg.device).cuda_stream)
+    tp, fp, fn = (int(v) for v in counts.tolist())
+    den = 2 * tp + fp + fn
+    return 2.0 * tp / den if den else 0.0
+
+
 def _structure_for(edge_index: torch.Tensor, n_nodes: int | None, who: str):
     if not edge_index.is_cuda:
         raise RuntimeError(f"gat_b200.{who} runs on CUDA only; there is no CPU fallback")

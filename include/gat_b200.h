@@ -352,6 +352,12 @@ GAT_API int gat_attention_norm_scores(const int32_t* rowptr, const int32_t* col,
                                       const float* s_tgt, const float* gmax, const float* z, int nh, int const_attention,
                                       float* tsum, float* norm_out, void* workspace, size_t workspace_bytes, gat_stream_t stream);
 
+/* Micro-averaged F1 of a multilabel prediction, as the PPI task model logs it every step (ppi_gat.py:38, :48, :56:
+ * sklearn.metrics.f1_score(y_pred = out > 0, y_true = y, average="micro") on host copies of both (n, classes) matrices -- 29 of
+ * every 36 ms of a PPI-shaped training step).  counts[0..2] = TP, FP, FN over `count` elements (zeroed by the call; integer sums,
+ * exact); F1 = 2 TP / (2 TP + FP + FN), 0 when the denominator is 0 (sklearn's zero_division default). */
+GAT_API int gat_micro_f1_counts(const float* logits, const float* y_true, int64_t count, unsigned long long* counts, gat_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Visualisation feed.  Replaces the per-node `target_nodes == node_id` masks of
  * visualisation/entropy_histograms.py:103-115 and visualisation/weight_histograms.py:74-87 by one pass over the CSR of

@@ -291,3 +291,18 @@ def test_model_forward_with_fused_norm_equals_calc_attention_norm():
                         **{f"g:{k}": v.grad.clone() for k, v in model.named_parameters()}))
     for k in res[0]:
         assert _rel(res[1][k], res[0][k]) <= 2e-5, (k, _rel(res[1][k], res[0][k]))
+
+
+def test_micro_f1_equals_sklearn():
+    """gat_pytorch_b200.micro_f1 == the call PPI_GAT makes every step (ppi_gat.py:38), on PPI-shaped logits / labels and the edge
+    cases (nothing predicted, nothing true)."""
+    from sklearn.metrics import f1_score
+    from gat_pytorch_b200 import micro_f1
+    g = torch.Generator().manual_seed(3)
+    for n, c, bias in ((4800, 121, 0.0), (4800, 121, -1.5), (97, 7, 0.3), (1, 1, 0.0)):
+        out = torch.randn((n, c), generator=g) + bias
+        y = (torch.rand((n, c), generator=g) < 0.3).float()
+        want = f1_score(y_pred=out.numpy() > 0, y_true=y.numpy(), average="micro", zero_division=0)
+        assert abs(micro_f1(out.cuda(), y.cuda()) - want) < 1e-12, (n, c, bias)
+    z = torch.zeros((10, 5))
+    assert micro_f1((z - 1).cuda(), z.cuda()) == 0.0

@@ -42,8 +42,12 @@ def f1_micro(out, y):
     return f1_score(y_pred=out.detach().cpu().numpy() > 0, y_true=y.detach().cpu().numpy(), average="micro")
 
 
-def gpu_epoch(data, epochs, penalty):
+def gpu_epoch(data, epochs, penalty, f1="sklearn", fused=False):
+    """f1 = "sklearn": the reference's own call (ppi_gat.py:38); "gpu": gat_pytorch_b200.micro_f1 (same value, counted on the device).
+    fused: forward through gat_pytorch_b200.model_forward with the regulariser computed by the layers (no attention tensors)."""
     import gat_pytorch_b200 as g
+    import types
+    f1_fn = f1_micro if f1 == "sklearn" else (lambda out, y: g.micro_f1(out, y))
     dev = torch.device("cuda", 0)
     shapes, skip = g.synth.LAYER_SHAPES["ppi"], g.synth.SKIP["ppi"]
     torch.manual_seed(42)
@@ -52,22 +56,31 @@ def gpu_epoch(data, epochs, penalty):
     dd = [(x.to(dev), ei.to(dev), y.to(dev)) for x, ei, y in data]
     lib = g._lib.load() if hasattr(g, "_lib") else None
 
+    model = types.SimpleNamespace(gat_layer_list=layers, skip_layer_list=torch.nn.ModuleList([torch.nn.Identity() for s_ in skip if s_]),
+                                  add_skip_connection=list(skip), heads_concat_per_layer=[c for (_fi, _nh, _f, c) in shapes],
+                                  num_heads_per_layer=[1] + [nh for (_fi, nh, _f, _c) in shapes],
+                                  head_output_features_per_layer=[shapes[0][0]] + [f for (_fi, _nh, f, _c) in shapes],
+                                  dropout=0.0, training=True)
+
     def step(x, ei, y):
-        att = []
-        h = x
-        for i, layer in enumerate(layers):
-            inp = h
-            h, (ei, a) = layer(h, ei, return_attention_weights=True)        # GATModel.py:166 (rewritten list feeds the next layer)
-            att.append(a)
-            if skip[i]:
-                h = h + inp                                                  # identity skip, GATModel.py:171-181
-            if i != len(layers) - 1:
-                h = F.elu(h)
+        if fused:
+            h, norm = g.model_forward(model, types.SimpleNamespace(x=x, edge_index=ei), attention_norm=True)
+        else:
+            att = []
+            h = x
+            for i, layer in enumerate(layers):
+                inp = h
+                h, (ei, a) = layer(h, ei, return_attention_weights=True)        # GATModel.py:166 (rewritten list feeds the next layer)
+                att.append(a)
+                if skip[i]:
+                    h = h + inp                                                  # identity skip, GATModel.py:171-181
+                if i != len(layers) - 1:
+                    h = F.elu(h)
+            norm = g.attention_norm(ei, att)
         loss = F.binary_cross_entropy_with_logits(h, y)
-        norm = g.attention_norm(ei, att)
         if penalty != 0.0:
             loss = loss + penalty * norm
-        f1 = f1_micro(h, y)
+        f1 = f1_fn(h, y)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
