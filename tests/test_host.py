@@ -167,6 +167,16 @@ def test_c_abi_rejects_bad_arguments_with_a_message_before_touching_the_device()
     assert lib.gat_gemm_tc_supported(0, 1, 100, 64, 1024, 1024, 1024, 64) == 1
     with pytest.raises(RuntimeError, match="gat_scores_fwd"):
         _lib.call("gat_scores_fwd", None, 10, 64, None, None, 9, None, None, None)
+    # round-2 entry points: the output glue, the fused regulariser, the bf16 coverage query, the device micro-F1
+    assert lib.gat_out_glue_adjoint(None, None, 4, 8, 1, 0.5, 1, None, None) != 0 and b"gat_out_glue_adjoint" in lib.gat_last_error()
+    assert lib.gat_head_merge_fwd_glue(None, 4, 2, 4, 4, 1, None, 0, 1, 1.5, 0, None, None) != 0 and b"dropout" in lib.gat_last_error()
+    assert lib.gat_attention_norm_scores(None, None, 4, 8, None, None, None, None, 4, 0, None, None, None, 0, None) != 0
+    assert b"gat_attention_norm_scores" in lib.gat_last_error()
+    assert lib.gat_micro_f1_counts(None, None, 8, None, None) != 0 and b"gat_micro_f1_counts" in lib.gat_last_error()
+    assert lib.gat_f32_round_bf16(None, None, 8, None) != 0 and b"gat_f32_round_bf16" in lib.gat_last_error()
+    # bf16 kernels: NH <= 4, padded rows of 132..256 floats, unshared gradient (products-class shapes); everything else rounds
+    assert lib.gat_edge_bf16_native(4, 64, 0) == 1 and lib.gat_edge_bf16_native(4, 48, 0) == 1
+    assert lib.gat_edge_bf16_native(4, 48, 1) == 0 and lib.gat_edge_bf16_native(8, 8, 0) == 0 and lib.gat_edge_bf16_native(4, 256, 0) == 0
 
 
 def test_model_forward_folds_the_glue_as_documented():

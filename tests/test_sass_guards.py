@@ -25,6 +25,7 @@ FWD = "edge_fwd_kernelILi32ELi2ELi4ELb0ELb0E"                      # products hi
 BWD = "edge_bwd_main_kernelILi32ELi2ELi4ELb0ELb1ELb1ELb0ELb0E"     # fused backward, FULL rows
 BWD_GS = "edge_bwd_main_kernelILi32ELi2ELi4ELb0ELb1ELb0ELb1ELb0E"  # head-mean layer, staged rows
 BWD_HM = "edge_bwd_hm4_kernelILi3ELb1EE"                             # head-mean layer (4 heads), short rows: lane = (edge slot, head, quarter)
+ROWDOT = "edge_bwd_rowdot_kernelILi4ELb0EE"                         # per-node S = <dOut, out> pass, plain instantiation (3 CTAs/SM)
 GEMM_NT = "gemm_tc_kernelILi128ELb0E"
 GEMM_PAIR = "gemm_pair_kernel"
 
@@ -66,7 +67,7 @@ def _op(ins):
     return (t[1] if t[0].startswith("@") else t[0])
 
 
-@pytest.mark.parametrize("sub,max_regs", [(FWD, 80), (BWD, 80), (BWD_GS, 80), (BWD_HM, 80), (GEMM_NT, 128), (GEMM_PAIR, 200)])
+@pytest.mark.parametrize("sub,max_regs", [(FWD, 80), (BWD, 80), (BWD_GS, 80), (BWD_HM, 80), (ROWDOT, 80), (GEMM_NT, 128), (GEMM_PAIR, 200)])
 def test_hot_kernels_fit_their_register_budget_without_spills(resources, sub, max_regs):
     regs, stack = resources[_mangled(sub)]
     # the pair GEMM keeps one loop counter on the stack (8 bytes, outside the hot loops); everything else must be spill-free
