@@ -312,3 +312,75 @@ def test_cuda_backend_implements_the_backend_interface():
             continue
         assert hasattr(CudaBackend, name), name
         assert list(inspect.signature(fn).parameters) == list(inspect.signature(getattr(CudaBackend, name)).parameters), name
+
+
+def _model_worker(rank, world, port, balance, replicate, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from _oracle_backend import OracleBackend
+        from gat_pytorch_b200 import synth
+        from gat_pytorch_b200.partition import PartitionedGAT
+        x, ei, shapes, weights = _model_inputs(synth)
+        model = PartitionedGAT(shapes, weights, torch.from_numpy(x), torch.from_numpy(ei), torch.device("cpu"), backend=OracleBackend(),
+                               balance=balance, replicate_input=replicate)
+        loss = model.step_resident()
+        total = loss.detach().clone()
+        dist.all_reduce(total)
+        e2e = model.step_e2e()                     # fresh upload (edge exchange, structure, x all-gather) + the same step
+        ret[rank] = dict(loss=float(total), e2e=float(e2e), bounds=model.plan.bounds, rows=model.plan.rows, n_edges=model.n_edges_global,
+                         x_full=model.x_full is not None, out=model.last_out.numpy(),
+                         grads=[(l.W.weight.grad.numpy().copy(), l.a.weight.grad.numpy().copy()) for l in model.layers])
+    finally:
+        dist.destroy_process_group()
+
+
+def _model_inputs(synth):
+    """A 3-layer stack of the products pattern in miniature (concat, concat, four-head head mean) on the adversarial graph, sorted
+    by degree so that equal node ranges would be badly unbalanced."""
+    rng = np.random.default_rng(11)
+    x, ei = synth.adversarial()
+    shapes = [(x.shape[1], 2, 8, True), (16, 2, 8, True), (16, 4, 3, False)]
+    weights = [(synth.xavier_uniform(rng, nh * f, f_in), synth.xavier_uniform(rng, nh, 2 * nh * f)) for (f_in, nh, f, _c) in shapes]
+    return x, ei.astype(np.int64), shapes, weights
+
+
+@pytest.mark.parametrize("balance,replicate", [("edges", True), ("edges", False), ("nodes", True)])
+def test_partitioned_model_matches_the_single_process_stack(balance, replicate):
+    """bench.py's multi-GPU model end to end on 2 gloo ranks with the oracle backend: distributed edge-list upload, edge-balanced
+    (or equal) destination ranges, the first layer on a replicated input (or exchanged like the others), ELU between layers, the
+    head-mean output layer with ONE shared gradient row per target, loss share per rank, parameter gradients summed over ranks --
+    against the torch port of the reference formulation in fp64 (loss, output rows, every dW / da)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port
+    from gat_pytorch_b200 import synth
+    world = 2
+    ret = mp.Manager().dict()
+    port = 29800 + (os.getpid() % 50)
+    mp.spawn(_model_worker, args=(world, port, balance, replicate, ret), nprocs=world, join=True)
+    x, ei, shapes, weights = _model_inputs(synth)
+    ws = [(torch.from_numpy(w).double().requires_grad_(True), torch.from_numpy(a).double().requires_grad_(True)) for w, a in weights]
+    h = torch.from_numpy(x).double()
+    eit = torch.from_numpy(ei)
+    for i, ((w, a), (_fi, nh, f, concat)) in enumerate(zip(ws, shapes)):
+        h, _, _ = torch_port.layer_forward(h, eit, w, a, nh, f, concat)
+        if i != len(shapes) - 1:
+            h = torch.nn.functional.elu(h)
+    loss = h.square().mean()
+    loss.backward()
+    loss = loss.detach()
+    rel = lambda got, want: float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))   # noqa: E731
+    out = np.concatenate([ret[r]["out"] for r in range(world)])
+    assert out.shape == tuple(h.shape) and rel(out, h.detach().numpy()) < 1e-5
+    for r in range(world):
+        assert abs(ret[r]["loss"] - float(loss)) < 1e-6 * abs(float(loss)) + 1e-12
+        assert abs(ret[r]["e2e"] - float(loss)) < 1e-6 * abs(float(loss)) + 1e-12
+        assert ret[r]["x_full"] == replicate
+        assert (ret[r]["bounds"] is not None) == (balance == "edges")
+        for (gw, ga), (w, a) in zip(ret[r]["grads"], ws):
+            assert rel(gw, w.grad.numpy()) < 2e-5 and rel(ga, a.grad.numpy()) < 2e-5
+    assert sum(ret[r]["rows"] for r in range(world)) == x.shape[0]
+    assert ret[0]["n_edges"] == int(torch_port.rewrite_edges(eit).size(1))
