@@ -238,3 +238,15 @@ def test_model_forward_folds_the_glue_as_documented():
     m2 = model([True], [False], [4], [1, 2], [8, 4], 0.0)
     model_forward(m2, types.SimpleNamespace(x=torch.arange(48.).view(6, 8), edge_index=data.edge_index))
     assert calls[0]["skip"] == (6, 4) and calls[0]["act"] is None
+
+
+def test_head_groups_cover_every_head_within_the_kernel_limits():
+    """gat_layer._head_groups: layers beyond the edge kernels' limits (more than 8 heads, more than 1024 floats per padded row) are
+    processed in consecutive head groups that each fit."""
+    from gat_pytorch_b200.gat_layer import MAX_HEADS, MAX_ROW_FLOATS, _head_groups
+    for nh, fp in [(9, 8), (12, 8), (16, 72), (4, 300), (10, 128), (64, 4), (3, 1024), (8, 128), (1, 4)]:
+        groups = _head_groups(nh, fp)
+        assert groups[0][0] == 0 and groups[-1][1] == nh
+        assert all(a[1] == b[0] for a, b in zip(groups, groups[1:]))
+        assert all(0 < h1 - h0 <= MAX_HEADS and (h1 - h0) * fp <= MAX_ROW_FLOATS for h0, h1 in groups)
+    assert _head_groups(8, 128) == [(0, 8)]          # exactly at the limits: one group

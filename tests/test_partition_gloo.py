@@ -348,8 +348,8 @@ def _model_inputs(synth):
     return x, ei.astype(np.int64), shapes, weights
 
 
-@pytest.mark.parametrize("balance,replicate", [("edges", True), ("edges", False), ("nodes", True)])
-def test_partitioned_model_matches_the_single_process_stack(balance, replicate):
+@pytest.mark.parametrize("balance,replicate,world", [("edges", True, 2), ("edges", False, 2), ("nodes", True, 2), ("edges", True, 3)])
+def test_partitioned_model_matches_the_single_process_stack(balance, replicate, world):
     """bench.py's multi-GPU model end to end on 2 gloo ranks with the oracle backend: distributed edge-list upload, edge-balanced
     (or equal) destination ranges, the first layer on a replicated input (or exchanged like the others), ELU between layers, the
     head-mean output layer with ONE shared gradient row per target, loss share per rank, parameter gradients summed over ranks --
@@ -357,7 +357,6 @@ def test_partitioned_model_matches_the_single_process_stack(balance, replicate):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch_port
     from gat_pytorch_b200 import synth
-    world = 2
     ret = mp.Manager().dict()
     port = 29800 + (os.getpid() % 50)
     mp.spawn(_model_worker, args=(world, port, balance, replicate, ret), nprocs=world, join=True)
