@@ -250,3 +250,28 @@ def test_head_groups_cover_every_head_within_the_kernel_limits():
         assert all(a[1] == b[0] for a, b in zip(groups, groups[1:]))
         assert all(0 < h1 - h0 <= MAX_HEADS and (h1 - h0) * fp <= MAX_ROW_FLOATS for h0, h1 in groups)
     assert _head_groups(8, 128) == [(0, 8)]          # exactly at the limits: one group
+
+
+@pytest.mark.skipif(__import__("shutil").which("gcc") is None, reason="needs gcc")
+def test_layer_descriptor_layout_matches_the_header(tmp_path):
+    """struct gat_layer_desc crosses the C ABI by pointer: the ctypes mirror in _lib.py must agree with the header field by field
+    (size and every offset), checked by compiling a C program against include/gat_b200.h -- a mismatch would corrupt pointers
+    silently on the GPU box."""
+    import ctypes
+    import subprocess
+    from gat_pytorch_b200 import _lib
+    names = [n for n, _ in _lib.LayerDesc._fields_]
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "gat_b200.h"\nint main(void) {\n  printf("%zu\\n", sizeof(gat_layer_desc));\n'
+           + "".join(f'  printf("{n} %zu\\n", offsetof(gat_layer_desc, {n}));\n' for n in names) + "  return 0;\n}\n")
+    (tmp_path / "t.c").write_text(src)
+    exe = str(tmp_path / "t")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(tmp_path / "t.c"), "-o", exe],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr          # the header is plain C (no C++ / CUDA types in the boundary)
+    lines = subprocess.run([exe], capture_output=True, text=True).stdout.split()
+    assert int(lines[0]) == ctypes.sizeof(_lib.LayerDesc)
+    for name, off in zip(lines[1::2], lines[2::2]):
+        assert getattr(_lib.LayerDesc, name).offset == int(off), name
+    # and no field of the header is missing from the mirror: the struct's size leaves no room for one
+    last = names[-1]
+    assert getattr(_lib.LayerDesc, last).offset + getattr(_lib.LayerDesc, last).size == ctypes.sizeof(_lib.LayerDesc)
