@@ -275,3 +275,33 @@ def test_layer_descriptor_layout_matches_the_header(tmp_path):
     # and no field of the header is missing from the mirror: the struct's size leaves no room for one
     last = names[-1]
     assert getattr(_lib.LayerDesc, last).offset + getattr(_lib.LayerDesc, last).size == ctypes.sizeof(_lib.LayerDesc)
+
+
+def test_binding_argument_counts_match_the_header():
+    """Every prototype of include/gat_b200.h against its ctypes signature in _lib.SIGNATURES: same number of parameters, pointer
+    parameters bound as pointers, 64-bit integers as 64-bit (a wrong count or width passes garbage across the C ABI)."""
+    import ctypes
+    import re
+    from gat_pytorch_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "gat_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = re.findall(r"GAT_API\s+([\w\s\*]+?)\s*\b(gat_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 50
+    seen = set()
+    for _ret, name, args in protos:
+        seen.add(name)
+        params = [a.strip() for a in args.replace("\n", " ").split(",")]
+        if params == ["void"] or params == [""]:
+            params = []
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for p, t in zip(params, argtypes):
+            if "*" in p or "gat_stream_t" in p:
+                assert t is ctypes.c_void_p, (name, p, t)
+            elif re.search(r"\b(int64_t|uint64_t|size_t)\b", p):
+                assert ctypes.sizeof(t) == 8 and t is not ctypes.c_void_p and t is not ctypes.c_double, (name, p, t)
+            elif re.search(r"\bfloat\b", p):
+                assert t is ctypes.c_float, (name, p, t)
+            elif re.search(r"\bint\b", p):
+                assert t is ctypes.c_int, (name, p, t)
+    assert seen == set(_lib.SIGNATURES), (seen ^ set(_lib.SIGNATURES))
