@@ -14,8 +14,12 @@ source ids) and the transposed CSR of ITS edges.  W and a are replicated.  Per l
             local GEMMs; ALL-REDUCE(sum) of dW, dA_src, dA_tgt
 
 The forward is bit-identical to the single-GPU forward (same rows, same edge order inside a row, same
-M); parameter gradients agree to fp32 reduction-order noise.  Equal node ranges are used so that the
-all-gather is uniform; with the id-permuted synthetic graphs this is also edge-balanced.
+M); parameter gradients agree to fp32 reduction-order noise.  Ranges are edge-balanced by default
+(`edge_balanced_bounds` / `make_balanced_plan`: the kernels then run on slab ids, so the gathered buffers stay uniform);
+`make_plan` gives equal node ranges.  The two wide exchanges run inside our kernels over NVLink peer memory (projection ->
+all-gather by TMA stores, source-major backward -> reduce-scatter by bulk-copy pushes); the first layer of a model can skip
+them altogether on a replicated input (`PartitionedGATLayer.forward_replicated`).  `dropout`, `const_attention` and
+`return_attention_weights` follow the reference layer.
 
 The numerical work goes through a `backend` object with one method per C-ABI entry point.  The product
 backend is `CudaBackend` (libgat_b200.so; raises without CUDA).  tests/ inject an oracle-based backend to
